@@ -1,0 +1,307 @@
+"""CPU oracle for the fvGP training hot path -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+A numpy/scipy restatement of the reference algorithm for every row of SURVEY.md
+section 8(a).  Only `tests/`, `__graft_entry__.smoke()` and the CPU-baseline / reference
+arm of `bench.py` may import this module; the product (`fvgp_b200/`) never does and
+fails loudly when its CUDA library is missing.
+
+Pinning: `tests/golden/make_golden.py` runs the UNMODIFIED reference (imported from
+/root/reference through `tests/golden/ref_shim.py`) on seeded inputs and commits the
+outputs under `tests/golden/*.npz`; `tests/test_oracle_golden.py` checks every function
+below against those vectors (bit-exact for the gp2Scale pattern and values, <=1e-13
+relative for dense K, <=1e-10 relative for LML / gradient).  Parity is therefore PINNED
+for the dense path and for gp2Scale with an exact log-determinant.  The stochastic
+(imate SLQ) log-determinant is un-vendored third-party arithmetic with no value-pinning
+test in the reference: "parity unpinned" for that one quantity; it is checked against
+the exact log-determinant instead.
+
+All citations are file:line into /root/reference/fvgp/.
+"""
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+SQRT3 = np.sqrt(3.0)
+SQRT5 = np.sqrt(5.0)
+
+
+# --------------------------------------------------------------------------- a2
+def distance_matrix(x1, x2):
+    """Isotropic Euclidean distance, kernels.py:440-458 (square, accumulate per axis, sqrt)."""
+    acc = np.zeros((len(x1), len(x2)))
+    for i in range(x1.shape[1]):
+        acc += (x1[:, i][:, None] - x2[:, i][None, :]) ** 2
+    return np.sqrt(acc)
+
+
+def anisotropic_distance_matrix(x1, x2, scales):
+    """Axis-scaled distance, kernels.py:461-481: |dx_i / scales[i]|**2 summed in axis order."""
+    acc = np.zeros((len(x1), len(x2)))
+    for i in range(x1.shape[1]):
+        acc += np.abs(np.subtract.outer(x1[:, i], x2[:, i]) / scales[i]) ** 2
+    return np.sqrt(acc)
+
+
+# --------------------------------------------------------------------------- a3
+def squared_exponential(d, length):
+    """kernels.py:16-33."""
+    return np.exp(-(d ** 2) / (2.0 * (length ** 2)))
+
+
+def exponential(d, length):
+    """kernels.py:56-74."""
+    return np.exp(-d / length)
+
+
+def matern32(d, length):
+    """kernels.py:98-118 (matern_kernel_diff1)."""
+    a = (SQRT3 * d) / length
+    return (1.0 + a) * np.exp(-a)
+
+
+def matern52(d, length):
+    """kernels.py:166-188 (matern_kernel_diff2)."""
+    return (1.0 + (SQRT5 * d) / length + (5.0 * d ** 2) / (3.0 * length ** 2)) * np.exp(-(SQRT5 * d) / length)
+
+
+RADIAL = {"se": squared_exponential, "exp": exponential, "matern32": matern32, "matern52": matern52}
+
+
+# --------------------------------------------------------------------------- a1
+def default_kernel(x1, x2, hps):
+    """ARD Matern-3/2, gp_prior.py:376-400: hps[0] * matern32(aniso distance with hps[1:], 1)."""
+    return hps[0] * matern32(anisotropic_distance_matrix(x1, x2, hps[1:]), 1.0)
+
+
+# --------------------------------------------------------------------------- a4
+def default_kernel_gradient(x1, x2, hps):
+    """d default_kernel / d hps, shape (H,U,V); gp_prior.py:421-436 with kernels.py:121-141.
+
+    The length-scale derivative is evaluated in the reference's own form
+    dadl*ea - (1+a)*dadl*ea with dadl = sqrt3 * (-dx_i^2 / (hps_i^3 d)), zero where d == 0.
+    """
+    d = anisotropic_distance_matrix(x1, x2, hps[1:])
+    out = np.zeros((len(hps), len(x1), len(x2)))
+    nz = d != 0.0
+    a = SQRT3 * d
+    ea = np.exp(-a)
+    for i in range(x1.shape[1]):
+        dd = np.zeros_like(d)
+        dx2 = np.abs(np.subtract.outer(x1[:, i], x2[:, i])) ** 2
+        dd[nz] = -dx2[nz] / (hps[1 + i] ** 3 * d[nz])
+        dadl = SQRT3 * dd
+        out[1 + i] = hps[0] * (dadl * ea - (1.0 + a) * dadl * ea)
+    out[0] = matern32(d, 1.0)
+    return out
+
+
+# --------------------------------------------------------------------------- a6 / a7
+def default_noise(y):
+    """gp_likelihood.py:102-104: (mean(|y|)/100)^2 for every point."""
+    return np.full(len(y), (np.mean(np.abs(y)) / 100.0) ** 2)
+
+
+def add_kv(K, V):
+    """gp_kv.py:640-669: K + diag(V) for a vector V (dense copy+fill_diagonal, sparse setdiag)."""
+    if sp.issparse(K):
+        KV = K.copy().tocsr()
+        KV.setdiag(K.diagonal() + V)
+        return KV
+    KV = K.copy()
+    np.fill_diagonal(KV, np.diag(K) + V)
+    return KV
+
+
+# --------------------------------------------------------------------------- a8-a10
+class NonPositiveDefinite(Exception):
+    """Mirrors NonPositiveDefiniteError, gp_lin_alg.py:27-58."""
+
+
+def chol_factor(KV):
+    """gp_lin_alg.py:237-269: scipy cho_factor(lower=True)."""
+    try:
+        c, _ = sla.cho_factor(KV, lower=True)
+    except np.linalg.LinAlgError as exc:
+        raise NonPositiveDefinite(str(exc)) from exc
+    return c
+
+
+def chol_solve(c, b):
+    """gp_lin_alg.py:289-328."""
+    return sla.cho_solve((c, True), b)
+
+
+def chol_logdet(c):
+    """gp_lin_alg.py:331-360: 2 * sum(log|diag|)."""
+    return 2.0 * np.sum(np.log(np.abs(np.diag(c))))
+
+
+# --------------------------------------------------------------------------- a12
+def log_likelihood_from(KVinvY, logdet, y_minus_m):
+    """gp_marginal_likelihood.py:171-178; the quadratic form is averaged over y columns."""
+    n, r = y_minus_m.shape
+    l1 = np.sum(y_minus_m * KVinvY) / r
+    return -0.5 * (l1 + logdet + n * np.log(2.0 * np.pi))
+
+
+def dense_log_likelihood(x, y, hps, noise=None, kernel=default_kernel, mean=None):
+    """Full dense LML: K-fill, +V, Cholesky, solve, logdet."""
+    y = y.reshape(len(y), -1)
+    K = kernel(x, x, hps)
+    V = default_noise(y) if noise is None else noise
+    m = np.full(len(x), np.mean(y)) if mean is None else mean       # gp_prior.py:449-458
+    c = chol_factor(add_kv(K, V))
+    ym = y - m[:, None]
+    return log_likelihood_from(chol_solve(c, ym), chol_logdet(c), ym)
+
+
+# --------------------------------------------------------------------------- a13
+def dense_neg_log_likelihood_gradient(x, y, hps, noise=None, component=0,
+                                      kernel=default_kernel, kernel_grad=default_kernel_gradient,
+                                      mean=None, dm_dh=None, economical=False):
+    """Gradient of -LML, gp_marginal_likelihood.py:224-309.
+
+    economical=False follows the reference literally: stacked LU solves of KV against
+    dK/dh (gp_lin_alg.py:1581-1626), trace of each.  economical=True is the algebraically
+    identical tr(KV^-1 dK) = sum(KV^-1 o dK) used for larger N on the CPU baseline.
+    The `dL_dHm[i] == 0.0` switch of :301-308 is kept.
+    """
+    y = y.reshape(len(y), -1)
+    n, H = len(x), len(hps)
+    K = kernel(x, x, hps)
+    V = default_noise(y) if noise is None else noise
+    m = np.full(n, np.mean(y)) if mean is None else mean
+    KV = add_kv(K, V)
+    c = chol_factor(KV)
+    b = chol_solve(c, y - m[:, None])[:, component]
+    dK = kernel_grad(x, x, hps)                     # noise derivative is zero (gp_likelihood.py:112-120)
+    dm = np.zeros((H, n)) if dm_dh is None else dm_dh
+    grad = np.zeros(H)
+    if economical:
+        KVinv = chol_solve(c, np.eye(n))
+    for i in range(H):
+        gm = -dm[i] @ b
+        if gm == 0.0:
+            quad = b @ dK[i] @ b
+            tr = np.sum(KVinv * dK[i]) if economical else np.trace(np.linalg.solve(KV, dK[i]))
+            grad[i] = -0.5 * (quad - tr)
+        grad[i] += gm
+    return grad
+
+
+# --------------------------------------------------------------------------- a16
+def wendland_block(x1, x2, hps):
+    """Dense compact-support block, kernels.py:502-528 (the DEFINING gp2Scale oracle).
+
+    s accumulates ((x1_i - x2_i) / hps[1+i])**2 in axis order, each numpy ufunc rounding
+    separately; d = min(1, sqrt(s)); value = hps[0] * (1-d)**8 * (32 d**3 + 25 d**2 + 8 d + 1).
+    """
+    s = np.zeros((len(x1), len(x2)))
+    for i in range(x1.shape[1]):
+        s += (np.subtract.outer(x1[:, i], x2[:, i]) / hps[1 + i]) ** 2
+    d = np.sqrt(s)
+    d[d > 1.0] = 1.0
+    return hps[0] * (1.0 - d) ** 8 * (32.0 * d ** 3 + 25.0 * d ** 2 + 8.0 * d + 1.0)
+
+
+# --------------------------------------------------------------------------- a18 / a19
+def chunk_ranges(n, batch):
+    """gp2Scale_covariance.py:48-61: chunks of at most `batch`, remainder last."""
+    batch = max(1, int(batch))
+    return [(s, min(s + batch, n)) for s in range(0, n, batch)]
+
+
+def gp2scale_covariance(x1, x2, hps, batch=10000, kernel=wendland_block, symmetric=None):
+    """Blockwise sparse assembly, gp2Scale_covariance.py:136-170, 240-287, 313-431.
+
+    Per block: dense kernel, np.nonzero pattern; symmetric diagonal blocks keep row<=col;
+    off-diagonal entries are mirrored; COO -> canonical CSR (sorted int32 indices).
+    """
+    if symmetric is None:
+        symmetric = x1 is x2
+    n1, n2 = len(x1), len(x2)
+    rows, cols, vals = [], [], []
+    for (i0, i1) in chunk_ranges(n1, batch):
+        for (j0, j1) in chunk_ranges(n2, batch):
+            if symmetric and i0 > j0:
+                continue
+            blk = np.asarray(kernel(x1[i0:i1], x2[j0:j1], hps))
+            r, c = np.nonzero(blk)
+            v = blk[r, c]
+            if symmetric and i0 == j0:
+                keep = r <= c
+                r, c, v = r[keep], c[keep], v[keep]
+            r = r + i0
+            c = c + j0
+            rows.append(r), cols.append(c), vals.append(v)
+            if symmetric:
+                off = r != c
+                rows.append(c[off]), cols.append(r[off]), vals.append(v[off])
+    if not rows:
+        return sp.csr_matrix((n1, n2))
+    idx = np.int32 if max(n1, n2) < 2 ** 31 else np.int64          # :107-114
+    K = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows).astype(idx),
+                                              np.concatenate(cols).astype(idx))), shape=(n1, n2))
+    return K.tocsr()
+
+
+# --------------------------------------------------------------------------- a20
+def sparse_cg(KV, b, rtol=1e-5, x0=None, maxiter=None, M=None):
+    """gp_lin_alg.py:1213-1291: scipy cg per right-hand-side column, atol=0."""
+    b = b.reshape(len(b), -1)
+    out = np.empty_like(b, dtype=float)
+    iters = []
+    for c in range(b.shape[1]):
+        count = [0]
+        sol, _ = spla.cg(KV, b[:, c], x0=None if x0 is None else x0[:, c], rtol=rtol, atol=0.0,
+                         maxiter=maxiter, M=M, callback=lambda _x: count.__setitem__(0, count[0] + 1))
+        out[:, c] = sol
+        iters.append(count[0])
+    return out, iters
+
+
+def sparse_lu_solve_logdet(KV, b):
+    """Exact sparse reference (mode sparseLU), gp_lin_alg.py:203-230 + LU logdet."""
+    lu = spla.splu(KV.tocsc())
+    logdet = float(np.sum(np.log(np.abs(lu.L.diagonal()))) + np.sum(np.log(np.abs(lu.U.diagonal()))))
+    return lu.solve(b), logdet
+
+
+def gp2scale_log_likelihood(x, y, hps, noise, batch=10000, exact=True, rtol=1e-10):
+    """gp2Scale LML with the exact sparse-LU logdet."""
+    y = y.reshape(len(y), -1)
+    K = gp2scale_covariance(x, x, hps, batch=batch, symmetric=True)
+    KV = add_kv(K, noise)
+    m = np.full(len(x), np.mean(y))
+    ym = y - m[:, None]
+    alpha, logdet = sparse_lu_solve_logdet(KV, ym)
+    if not exact:
+        alpha, _ = sparse_cg(KV, ym, rtol=rtol)
+    return log_likelihood_from(alpha.reshape(ym.shape), logdet, ym)
+
+
+# --------------------------------------------------------------------------- a23
+def fvgp_transform(x, y, noise=None):
+    """fvGP index-set transform, fvgp.py:626-660: task-major stacking, NaN y dropped."""
+    n, tasks = y.shape
+    xs, ys, vs = [], [], []
+    for t in range(tasks):
+        keep = ~np.isnan(y[:, t])
+        xs.append(np.column_stack([x[keep], np.full(int(keep.sum()), float(t))]))
+        ys.append(y[keep, t])
+        if noise is not None:
+            vs.append(noise[keep, t])
+    return np.vstack(xs), np.concatenate(ys), (np.concatenate(vs) if noise is not None else None)
+
+
+# --------------------------------------------------------------------------- posterior (8f #1)
+def posterior_mean_cov(x, y, hps, noise, x_pred, kernel=default_kernel):
+    """gp_posterior.py:139-182, 229-288 (dense): mean = k^T KV^-1 (y-m) + m, S = kk - k^T KV^-1 k."""
+    y = y.reshape(len(y), -1)
+    m0 = np.mean(y)
+    c = chol_factor(add_kv(kernel(x, x, hps), noise))
+    k = kernel(x, x_pred, hps)
+    mean = k.T @ chol_solve(c, y - m0) + m0
+    S = kernel(x_pred, x_pred, hps) - k.T @ chol_solve(c, k)
+    return mean[:, 0], S
