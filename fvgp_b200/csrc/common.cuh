@@ -1,0 +1,66 @@
+// Shared helpers for the fvgp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define FVGP_ERR_CUDA (-1)
+#define FVGP_ERR_ARG (-2)
+
+#define FVGP_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      fprintf(stderr, "[fvgp_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), \
+              __FILE__, __LINE__, cudaGetErrorString(_e));                              \
+      return FVGP_ERR_CUDA;                                                             \
+    }                                                                                   \
+  } while (0)
+
+#define FVGP_LAUNCH_OK() FVGP_CUDA_OK(cudaGetLastError())
+
+#define FVGP_REQUIRE(cond)                                                           \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      fprintf(stderr, "[fvgp_b200] bad argument: %s (%s:%d)\n", #cond, __FILE__, __LINE__); \
+      return FVGP_ERR_ARG;                                                           \
+    }                                                                                \
+  } while (0)
+
+namespace fvgp {
+
+constexpr int kMaxDim = 8;  // input-space dimensionality supported by the fused kernels
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic CTA-wide sum; result valid in thread 0. `red` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (wid == 0) {
+    v = lane < nw ? red[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace fvgp

@@ -1,0 +1,380 @@
+// Dense FP64 factorisation suite: recursive blocked Cholesky (POTRF), triangular solves
+// (POTRS), log-determinant, and the inverse from the factor (POTRI = TRTRI + LAUUM).
+//
+// Reference behaviour being replaced (lbl-camera/fvGP):
+//   calculate_Chol_factor  gp_lin_alg.py:237-269   scipy cho_factor(lower=True)
+//   calculate_Chol_solve   gp_lin_alg.py:289-328   cho_solve
+//   calculate_Chol_logdet  gp_lin_alg.py:331-360   2*sum(log|diag|)
+//   calculate_inv_from_chol gp_lin_alg.py:1558, and the KV^-1 that the gradient's trace
+//   term needs (gp_marginal_likelihood.py:273-274 obtains it through batched LU solves).
+//
+// Design: everything above 64x64 is recursion over ONE tensor-core GEMM kernel
+// (dgemm.cuh, DMMA.8x8x4), so >98% of the N^3/3 (+2N^3/3) flops run at GEMM speed with
+// the large inner dimensions a cache-oblivious recursion gives (K up to N/2).  Only the
+// 64x64 diagonal tiles are factored by a warp-cooperative shared-memory kernel, which
+// also emits each tile's inverse; triangular solves against a tile are then GEMMs with
+// that inverse (no scalar TRSM anywhere).  All operations are in place on the lower
+// triangle of the row-major matrix.
+#include "../../include/fvgp_b200.h"
+#include "dgemm.cuh"
+
+namespace fvgp {
+
+constexpr int TS = 64;  // diagonal tile size
+constexpr size_t POTRF_TILE_SMEM = (2 * TS * (TS + 1) + TS) * sizeof(double);
+
+// ----------------------------------------------------------------------------------------------
+// 64x64 diagonal tile: Cholesky + inverse of the factor, one CTA, all in shared memory.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) potrf_tile_kernel(double* A, long long ld, int nt, double* dinv,
+                                                         int* info, int global_row0) {
+  extern __shared__ __align__(16) double tile_smem[];
+  double(*T)[TS + 1] = reinterpret_cast<double(*)[TS + 1]>(tile_smem);
+  double(*Inv)[TS + 1] = reinterpret_cast<double(*)[TS + 1]>(tile_smem + TS * (TS + 1));
+  double* Dg = tile_smem + 2 * TS * (TS + 1);
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TS * TS; idx += 256) {
+    const int r = idx / TS, c = idx % TS;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < nt && c <= r) v = A[(long long)r * ld + c];
+    T[r][c] = v;
+  }
+  __syncthreads();
+  const int ri = tid >> 2, part = tid & 3;  // row owned in the trailing update, 4 threads per row
+  for (int j = 0; j < TS; ++j) {
+    const double d = T[j][j];
+    if (!(d > 0.0) && tid == 0) atomicCAS(info, 0, global_row0 + j + 1);
+    const double s = sqrt(d);
+    if (tid == j) Dg[j] = s;
+    if (tid > j && tid < TS) T[tid][j] = T[tid][j] / s;
+    __syncthreads();
+    if (ri > j) {
+      const double lij = T[ri][j];
+      for (int k = j + 1 + part; k <= ri; k += 4) T[ri][k] -= lij * T[k][j];
+    }
+    __syncthreads();
+  }
+  // Inverse of the lower factor: column c of Inv solves L x = e_c; 4 lanes share a column.
+  {
+    const int c = tid >> 2;
+    for (int i = 0; i < TS; ++i) {
+      double acc = 0.0;
+      if (i > c)
+        for (int k = c + part; k < i; k += 4) acc += T[i][k] * Inv[k][c];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) Inv[i][c] = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - acc) / Dg[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TS * TS; idx += 256) {
+    const int r = idx / TS, c = idx % TS;
+    dinv[idx] = Inv[r][c];
+    if (r < nt && c < nt) A[(long long)r * ld + c] = (c < r) ? T[r][c] : ((c == r) ? Dg[r] : 0.0);
+  }
+}
+
+// dst (rows x cols, ldd) <- src (lds)
+__global__ void copy2d_kernel(double* dst, long long ldd, const double* src, long long lds, int rows, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * 16;
+  if (c >= cols) return;
+  for (int r = r0; r < min(r0 + 16, rows); ++r) dst[(long long)r * ldd + c] = src[(long long)r * lds + c];
+}
+
+// Zero the strict upper part inside every 128x128 diagonal block (the GEMM k-trims assume
+// triangular operands carry explicit zeros there).
+__global__ void zero_upper_diag_blocks_kernel(double* A, long long ld, int n) {
+  const int b0 = blockIdx.x * BM;
+  for (int idx = threadIdx.x; idx < BM * BM; idx += blockDim.x) {
+    const int r = idx / BM, c = idx % BM;
+    if (c > r && b0 + c < n && b0 + r < n) A[(long long)(b0 + r) * ld + b0 + c] = 0.0;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Single right-hand-side triangular solves: one launch per 64-wide tile, leaf solve by the
+// stored tile inverse fused with the rank-64 update of the remaining vector.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict__ L, long long ld, int n, int j0,
+                                                       const double* __restrict__ dinv, double* w, double* z) {
+  __shared__ double yj[TS], zj[TS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = min(TS, n - j0);
+  if (tid < TS) yj[tid] = tid < nt ? w[j0 + tid] : 0.0;
+  __syncthreads();
+  {
+    const int r = tid >> 2, part = tid & 3;
+    double acc = 0.0;
+    for (int k = part; k <= r; k += 4) acc += dinv[r * TS + k] * yj[k];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) {
+      zj[r] = acc;
+      if (blockIdx.x == 0 && r < nt) z[j0 + r] = acc;
+    }
+  }
+  __syncthreads();
+  const int rest0 = j0 + TS;
+  const double z0 = zj[lane], z1 = zj[lane + 32];
+  for (int i = rest0 + blockIdx.x * 64 + warp; i < min(n, rest0 + (int)(blockIdx.x + 1) * 64); i += 8) {
+    const double* row = L + (long long)i * ld + j0;
+    double acc = row[lane] * z0 + row[lane + 32] * z1;
+    acc = warp_sum(acc);
+    if (lane == 0) w[i] -= acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict__ L, long long ld, int n, int j0,
+                                                       const double* __restrict__ dinv, double* z, double* x) {
+  __shared__ double zj[TS], xj[TS];
+  const int tid = threadIdx.x;
+  const int nt = min(TS, n - j0);
+  if (tid < TS) zj[tid] = tid < nt ? z[j0 + tid] : 0.0;
+  __syncthreads();
+  {
+    const int c = tid >> 2, part = tid & 3;
+    double acc = 0.0;
+    for (int r = c + part; r < TS; r += 4) acc += dinv[r * TS + c] * zj[r];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) {
+      xj[c] = acc;
+      if (blockIdx.x == 0 && c < nt) x[j0 + c] = acc;
+    }
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + tid;
+  if (c < j0) {
+    double acc = 0.0;
+    for (int r = 0; r < nt; ++r) acc += L[(long long)(j0 + r) * ld + c] * xj[r];
+    z[c] -= acc;
+  }
+}
+
+__global__ void __launch_bounds__(1024) logdet_kernel(const double* __restrict__ L, long long ld, int n, double* out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) s += log(fabs(L[(long long)i * ld + i]));
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = 2.0 * s;
+}
+
+__global__ void __launch_bounds__(1024) dot_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                   long long n, double* out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) s += a[i] * b[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host-side recursion
+// ----------------------------------------------------------------------------------------------
+struct Ctx {
+  cudaStream_t st;
+  double* dinv;        // per-64-tile inverses, tile t at dinv + t*4096
+  int* info;
+  double* work;        // scratch panel for trtri / lauum
+  int err;
+};
+
+static inline int split(int n) {
+  if (n > 2 * TS) {
+    int h = ((n / 2 + BM / 2) / BM) * BM;
+    if (h < BM) h = BM;
+    if (h >= n) h -= BM;
+    return h;
+  }
+  return TS;
+}
+
+#define REC_OK(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+// B (m x n) <- B * L^-T, L the n x n lower factor whose first row is global row `row0`.
+static int trsm_rt_rec(Ctx& c, double* B, long long ldb, int m, const double* L, long long ld, int n, int row0) {
+  if (m <= 0) return 0;
+  if (n <= TS) {
+    const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
+    return launch_gemm<false, false>(c.st, B, ldb, tile, TS, B, ldb, m, n, n, 1.0, 0.0, 0);
+  }
+  const int n1 = split(n), n2 = n - n1;
+  REC_OK(trsm_rt_rec(c, B, ldb, m, L, ld, n1, row0));
+  REC_OK((launch_gemm<false, false>(c.st, B, ldb, L + (long long)n1 * ld, ld, B + n1, ldb, m, n2, n1, -1.0, 1.0, 0)));
+  return trsm_rt_rec(c, B + n1, ldb, m, L + (long long)n1 * ld + n1, ld, n2, row0 + n1);
+}
+
+// B (m x n) <- B * L^-1 (the L^T x = z direction for row-stored right-hand sides).
+static int trsm_rn_rec(Ctx& c, double* B, long long ldb, int m, const double* L, long long ld, int n, int row0) {
+  if (m <= 0) return 0;
+  if (n <= TS) {
+    const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
+    return launch_gemm<false, true>(c.st, B, ldb, tile, TS, B, ldb, m, n, n, 1.0, 0.0, 0);
+  }
+  const int n1 = split(n), n2 = n - n1;
+  REC_OK(trsm_rn_rec(c, B + n1, ldb, m, L + (long long)n1 * ld + n1, ld, n2, row0 + n1));
+  REC_OK((launch_gemm<false, true>(c.st, B + n1, ldb, L + (long long)n1 * ld, ld, B, ldb, m, n1, n2, -1.0, 1.0, 0)));
+  return trsm_rn_rec(c, B, ldb, m, L, ld, n1, row0);
+}
+
+static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
+  if (n <= TS) {
+    potrf_tile_kernel<<<1, 256, POTRF_TILE_SMEM, c.st>>>(A, ld, n, c.dinv + (long long)(row0 / TS) * TS * TS, c.info,
+                                                          row0);
+    FVGP_LAUNCH_OK();
+    return 0;
+  }
+  const int n1 = split(n), n2 = n - n1;
+  double* A21 = A + (long long)n1 * ld;
+  double* A22 = A21 + n1;
+  REC_OK(potrf_rec(c, A, ld, n1, row0));
+  REC_OK(trsm_rt_rec(c, A21, ld, n2, A, ld, n1, row0));
+  REC_OK((launch_gemm<false, false>(c.st, A21, ld, A21, ld, A22, ld, n2, n2, n1, -1.0, 1.0, GEMM_LOWER)));
+  return potrf_rec(c, A22, ld, n2, row0 + n1);
+}
+
+// L -> L^-1 in place (lower).  Needs explicit zeros above the diagonal inside diagonal blocks.
+static int trtri_rec(Ctx& c, double* L, long long ld, int n, int row0) {
+  if (n <= TS) {
+    const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
+    copy2d_kernel<<<dim3(1, (n + 15) / 16), 64, 0, c.st>>>(L, ld, tile, TS, n, n);
+    FVGP_LAUNCH_OK();
+    return 0;
+  }
+  const int n1 = split(n), n2 = n - n1;
+  double* L21 = L + (long long)n1 * ld;
+  double* L22 = L21 + n1;
+  REC_OK(trtri_rec(c, L, ld, n1, row0));
+  REC_OK(trtri_rec(c, L22, ld, n2, row0 + n1));
+  // W = L21 * M11   (M11 lower: k >= column)
+  REC_OK((launch_gemm<false, true>(c.st, L21, ld, L, ld, c.work, n1, n2, n1, n1, 1.0, 0.0, GEMM_KB_FROM_N)));
+  // L21 = -M22 * W  (M22 lower: k <= row)
+  return launch_gemm<false, true>(c.st, L22, ld, c.work, n1, L21, ld, n2, n1, n2, -1.0, 0.0, GEMM_KE_FROM_M);
+}
+
+// lower(M) <- lower(M^T M) in place.
+static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
+  if (n <= BM) return launch_gemm<true, true>(c.st, M, ld, M, ld, M, ld, n, n, n, 1.0, 0.0, 0);
+  const int n1 = split(n), n2 = n - n1;
+  double* M21 = M + (long long)n1 * ld;
+  double* M22 = M21 + n1;
+  REC_OK(lauum_rec(c, M, ld, n1));
+  // P11 += M21^T M21
+  REC_OK((launch_gemm<true, true>(c.st, M21, ld, M21, ld, M, ld, n1, n1, n2, 1.0, 1.0, GEMM_LOWER)));
+  // W = M22^T M21  (M22 lower: k >= row of the output)
+  REC_OK((launch_gemm<true, true>(c.st, M22, ld, M21, ld, c.work, n1, n2, n1, n2, 1.0, 0.0, GEMM_KB_FROM_M)));
+  copy2d_kernel<<<dim3((n1 + 255) / 256, (n2 + 15) / 16), 256, 0, c.st>>>(M21, ld, c.work, n1, n2, n1);
+  FVGP_LAUNCH_OK();
+  return lauum_rec(c, M22, ld, n2);
+}
+
+}  // namespace fvgp
+
+using namespace fvgp;
+
+extern "C" {
+
+int fvgp_version(void) { return 100; }
+
+int64_t fvgp_chol_workspace_len(int64_t n) { return ((n + TS - 1) / TS) * (int64_t)TS * TS; }
+
+int64_t fvgp_potri_workspace_len(int64_t n) {
+  const int64_t h = n / 2 + BM + 2;
+  return h * h;
+}
+
+int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream) {
+  FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{st, d_tileinv, d_info, nullptr, 0};
+  static bool configured = false;
+  if (!configured) {
+    FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)POTRF_TILE_SMEM));
+    configured = true;
+  }
+  FVGP_CUDA_OK(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+  int r = potrf_rec(c, d_A, lda, (int)n, 0);
+  if (r != 0) return r;
+  int info = 0;
+  FVGP_CUDA_OK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  return info;
+}
+
+int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B, int nrhs,
+                     int64_t ldb, double* d_work, void* stream) {
+  FVGP_REQUIRE(n > 0 && nrhs >= 0 && ldb >= n && lda % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nrhs > 4) {
+    FVGP_REQUIRE(ldb % 2 == 0);
+    Ctx c{st, const_cast<double*>(d_tileinv), nullptr, nullptr, 0};
+    int r = trsm_rt_rec(c, d_B, ldb, nrhs, d_L, lda, (int)n, 0);   // rows of B <- rows * L^-T  (L y = b)
+    if (r != 0) return r;
+    return trsm_rn_rec(c, d_B, ldb, nrhs, d_L, lda, (int)n, 0);    // rows <- rows * L^-1      (L^T x = y)
+  }
+  double* w = d_work;
+  double* z = d_work + n;
+  const int tiles = (int)((n + TS - 1) / TS);
+  for (int r = 0; r < nrhs; ++r) {
+    double* b = d_B + (int64_t)r * ldb;
+    FVGP_CUDA_OK(cudaMemcpyAsync(w, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    for (int t = 0; t < tiles; ++t) {
+      const int j0 = t * TS;
+      const int rest = (int)n - (j0 + TS);
+      const int grid = rest > 0 ? (rest + 63) / 64 : 1;
+      fwd_step_kernel<<<grid, 256, 0, st>>>(d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, w, z);
+    }
+    FVGP_LAUNCH_OK();
+    for (int t = tiles - 1; t >= 0; --t) {
+      const int j0 = t * TS;
+      const int grid = j0 > 0 ? (j0 + 255) / 256 : 1;
+      bwd_step_kernel<<<grid, 256, 0, st>>>(d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, z, b);
+    }
+    FVGP_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratch1, double* h_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  logdet_kernel<<<1, 1024, 0, st>>>(d_L, lda, (int)n, d_scratch1);
+  FVGP_LAUNCH_OK();
+  FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_scratch1, sizeof(double), cudaMemcpyDeviceToHost, st));
+  FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int fvgp_dot(const double* d_a, const double* d_b, int64_t n, double* d_scratch1, double* h_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  dot_kernel<<<1, 1024, 0, st>>>(d_a, d_b, n, d_scratch1);
+  FVGP_LAUNCH_OK();
+  FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_scratch1, sizeof(double), cudaMemcpyDeviceToHost, st));
+  FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_work, void* stream) {
+  FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{st, const_cast<double*>(d_tileinv), nullptr, d_work, 0};
+  zero_upper_diag_blocks_kernel<<<(unsigned)((n + BM - 1) / BM), 256, 0, st>>>(d_L, lda, (int)n);
+  FVGP_LAUNCH_OK();
+  int r = trtri_rec(c, d_L, lda, (int)n, 0);
+  if (r != 0) return r;
+  return lauum_rec(c, d_L, lda, (int)n);
+}
+
+int fvgp_dgemm_nt(const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C, int64_t ldc, int m,
+                  int n, int k, double alpha, double beta, int lower, void* stream) {
+  return launch_gemm<false, false>((cudaStream_t)stream, d_A, lda, d_B, ldb, d_C, ldc, m, n, k, alpha, beta,
+                                   lower ? GEMM_LOWER : 0);
+}
+
+}  // extern "C"

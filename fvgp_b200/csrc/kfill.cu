@@ -1,0 +1,417 @@
+// Dense covariance assembly and gradient traces.
+//
+//   fvgp_kfill_dense           K = amp * f(||(x1-x2)*inv_scale|| / length) (+ noise on the diagonal)
+//                              replaces gp_prior.py:376-400, kernels.py:16-188, :440-481, gp_kv.py:640-669
+//   fvgp_kgrad_trace_matern32  sum_ij (Kinv - b b^T)_ij dK_ij/dtheta_h with dK regenerated per tile
+//                              replaces gp_prior.py:421-436 + gp_marginal_likelihood.py:264-306
+//   fvgp_kgrad_dense_matern32  materialised dK/dtheta (kernel_function_grad seam)
+//
+// K-fill is HBM-write bound (8 bytes per entry) with the FP64 pipe a close second
+// (~40 DP instructions per entry: sqrt + exp).  The symmetric mode therefore evaluates
+// only the upper tile triangle: a 64x64 tile is stored directly from registers (each
+// warp store covers 256 contiguous bytes of one row) and, transposed through padded
+// shared memory, a second time as the mirror tile with one TMA bulk store
+// (cp.async.bulk.global.shared::cta) per 512-byte row, double buffered so the stores of
+// tile t drain under the arithmetic of tile t+1.  Differences are taken directly
+// (x1-x2), never through the |x|^2+|y|^2-2xy expansion: the expansion loses the 1e-12
+// relative entry accuracy once coordinates exceed ~40 length scales (hard part 3).
+#include "../../include/fvgp_b200.h"
+#include "common.cuh"
+
+namespace fvgp {
+
+constexpr int FT = 64;             // tile edge
+constexpr int FT_STRIDE = FT + 2;  // even (16-byte rows for the bulk copy)
+constexpr int FILL_THREADS = 256;
+
+static int g_use_bulk_store = 1;
+
+struct FillParams {
+  const double* x1;
+  const double* x2;
+  const double* noise;
+  double* K;
+  long long n1, n2, ldk;
+  double amp, c_arg, c_aux;  // kind-specific constants
+  double inv_scale[kMaxDim];
+  int dim, mode;
+  long long tiles_i, tiles_j, ntiles;
+  int bulk;
+};
+
+__device__ __forceinline__ void tri_index(long long id, long long& a, long long& b) {
+  a = (long long)((sqrt(8.0 * (double)id + 1.0) - 1.0) * 0.5);
+  while (a * (a + 1) / 2 > id) --a;
+  while ((a + 1) * (a + 2) / 2 <= id) ++a;
+  b = id - a * (a + 1) / 2;
+}
+
+template <int KIND>
+__device__ __forceinline__ double radial_value(double s, double amp, double c_arg, double c_aux) {
+  // s = squared scaled distance
+  if (KIND == FVGP_K_SQEXP) return amp * exp(-s * c_arg);  // c_arg = 1/(2 l^2)
+  const double d = sqrt(s);
+  if (KIND == FVGP_K_DISTANCE) return d;
+  if (KIND == FVGP_K_MATERN32) {
+    const double a = c_arg * d;  // c_arg = sqrt(3)/l
+    return amp * ((1.0 + a) * exp(-a));
+  }
+  if (KIND == FVGP_K_MATERN52) {
+    const double a = c_arg * d;  // c_arg = sqrt(5)/l, c_aux = 5/(3 l^2)
+    return amp * ((1.0 + a + c_aux * s) * exp(-a));
+  }
+  if (KIND == FVGP_K_EXP) return amp * exp(-d * c_arg);  // c_arg = 1/l
+  // Wendland (dense form, kernels.py:355-378)
+  const double dd = fmin(d * c_arg, 1.0);
+  const double u = 1.0 - dd;
+  const double u2 = u * u, u4 = u2 * u2;
+  return amp * (u4 * u4) * (32.0 * dd * dd * dd + 25.0 * dd * dd + 8.0 * dd + 1.0);
+}
+
+template <int DIM>
+__device__ __forceinline__ double sqdist(const double* a, const double* b, const double* inv, int dim) {
+  double s = 0.0;
+  if (DIM > 0) {
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      const double t = (a[i] - b[i]) * inv[i];
+      s = fma(t, t, s);
+    }
+  } else {
+    for (int i = 0; i < dim; ++i) {
+      const double t = (a[i] - b[i]) * inv[i];
+      s = fma(t, t, s);
+    }
+  }
+  return s;
+}
+
+__device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc, unsigned bytes) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(ssrc));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+}
+
+template <int KIND, int DIM>
+__global__ void __launch_bounds__(FILL_THREADS) kfill_kernel(const FillParams p) {
+  extern __shared__ __align__(128) double stage[];  // 2 x FT x FT_STRIDE
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  double inv[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < p.dim) ? p.inv_scale[i] : 0.0;
+  const int dim = p.dim;
+
+  int mit = 0;  // mirror-tile counter: selects the staging buffer (bulk groups are committed per mirror tile)
+  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    long long ti, tj;
+    if (p.mode == FVGP_FILL_FULL) {
+      ti = tile / p.tiles_j;
+      tj = tile - ti * p.tiles_j;
+    } else {
+      long long a, b;
+      tri_index(tile, a, b);
+      if (p.mode == FVGP_FILL_SYMMETRIC) ti = b, tj = a; else ti = a, tj = b;
+    }
+    const bool mirror = (p.mode == FVGP_FILL_SYMMETRIC) && (tj > ti);
+    double* sT = stage + (mit & 1) * (FT * FT_STRIDE);
+    if (mirror) {
+      ++mit;
+      // the bulk stores issued from this buffer two tiles ago must have finished reading it
+      if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+      __syncthreads();
+    }
+    const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
+    const long long ca = c0 + lane, cb = c0 + lane + 32;
+    double xa[D], xb[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      xa[i] = (ca < p.n2 && (DIM > 0 || i < dim)) ? p.x2[ca * dim + i] : 0.0;
+      xb[i] = (cb < p.n2 && (DIM > 0 || i < dim)) ? p.x2[cb * dim + i] : 0.0;
+    }
+#pragma unroll 2
+    for (int rr = 0; rr < 8; ++rr) {
+      const long long r = r0 + rr;
+      if (r >= p.n1) break;
+      double xr[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? p.x1[r * dim + i] : 0.0;
+      double va = radial_value<KIND>(sqdist<DIM>(xr, xa, inv, dim), p.amp, p.c_arg, p.c_aux);
+      double vb = radial_value<KIND>(sqdist<DIM>(xr, xb, inv, dim), p.amp, p.c_arg, p.c_aux);
+      if (p.noise != nullptr) {
+        if (r == ca) va += p.noise[r];
+        if (r == cb) vb += p.noise[r];
+      }
+      double* krow = p.K + r * p.ldk;
+      if (ca < p.n2) krow[ca] = va;
+      if (cb < p.n2) krow[cb] = vb;
+      if (mirror) {
+        const int lr = warp * 8 + rr;
+        sT[lane * FT_STRIDE + lr] = va;
+        sT[(lane + 32) * FT_STRIDE + lr] = vb;
+      }
+    }
+    if (mirror) {
+      // mirror tile: rows c0.. of K, columns ti*FT .. ti*FT+63 (always a full 64 because ti < tj)
+      if (p.bulk) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();
+        if (tid < FT) {
+          const long long grow = c0 + tid;
+          if (grow < p.n2) bulk_store_row(p.K + grow * p.ldk + ti * FT, sT + tid * FT_STRIDE, FT * 8);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+      } else {
+        __syncthreads();
+#pragma unroll 2
+        for (int rr = 0; rr < 8; ++rr) {
+          const long long grow = c0 + warp * 8 + rr;
+          if (grow >= p.n2) break;
+          double* krow = p.K + grow * p.ldk + ti * FT;
+          krow[lane] = sT[(warp * 8 + rr) * FT_STRIDE + lane];
+          krow[lane + 32] = sT[(warp * 8 + rr) * FT_STRIDE + lane + 32];
+        }
+      }
+    }
+  }
+  if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+
+template <int KIND>
+static int launch_fill_dim(const FillParams& p, cudaStream_t st) {
+  const size_t smem = 2 * FT * FT_STRIDE * sizeof(double);
+  const long long max_ctas = (long long)sm_count() * 3;
+  const unsigned grid = (unsigned)(p.ntiles < max_ctas ? p.ntiles : max_ctas);
+#define FVGP_FILL_CASE(DIMV)                                                                              \
+  {                                                                                                       \
+    static bool cfg = false;                                                                              \
+    if (!cfg) {                                                                                           \
+      FVGP_CUDA_OK(cudaFuncSetAttribute(kfill_kernel<KIND, DIMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                      \
+      cfg = true;                                                                                         \
+    }                                                                                                     \
+    kfill_kernel<KIND, DIMV><<<grid, FILL_THREADS, smem, st>>>(p);                                        \
+  }
+  switch (p.dim) {
+    case 1: FVGP_FILL_CASE(1) break;
+    case 2: FVGP_FILL_CASE(2) break;
+    case 3: FVGP_FILL_CASE(3) break;
+    case 4: FVGP_FILL_CASE(4) break;
+    default: FVGP_FILL_CASE(0) break;
+  }
+#undef FVGP_FILL_CASE
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Gradient traces for the default ARD Matern-3/2 kernel.
+// ----------------------------------------------------------------------------------------------
+struct TraceParams {
+  const double* x;
+  const double* Kinv;
+  const double* b;
+  double* partials;
+  long long n, ld, ntiles;
+  double inv_len[kMaxDim];
+  int dim;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(FILL_THREADS) kgrad_trace_kernel(const TraceParams p) {
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  const int dim = p.dim;
+  const double sqrt3 = 1.7320508075688772;
+  double inv[D], acc[D + 1];
+#pragma unroll
+  for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < dim) ? p.inv_len[i] : 0.0;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) acc[i] = 0.0;
+
+  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    long long ti, tj;
+    tri_index(tile, ti, tj);  // tj <= ti
+    const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
+    const long long cc[2] = {c0 + lane, c0 + lane + 32};
+    double xc[2][D], bc[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const bool ok = cc[q] < p.n;
+      bc[q] = ok ? p.b[cc[q]] : 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) xc[q][i] = (ok && (DIM > 0 || i < dim)) ? p.x[cc[q] * dim + i] : 0.0;
+    }
+    for (int rr = 0; rr < 8; ++rr) {
+      const long long r = r0 + rr;
+      if (r >= p.n) break;
+      const double br = p.b[r];
+      double xr[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? p.x[r * dim + i] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const long long c = cc[q];
+        if (c > r || c >= p.n) continue;  // lower triangle only
+        const double w = (p.Kinv[r * p.ld + c] - br * bc[q]) * ((c == r) ? 1.0 : 2.0);
+        double t2[D], s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const double t = (xr[i] - xc[q][i]) * inv[i];
+          t2[i] = t * t;
+          s += t2[i];
+        }
+        const double a = sqrt3 * sqrt(s);
+        const double ea = exp(-a);
+        const double wea = w * ea;
+        acc[0] = fma(wea, 1.0 + a, acc[0]);
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[1 + i] = fma(wea, t2[i], acc[1 + i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i <= D; ++i) {
+    const double v = block_sum(acc[i], red);
+    if (tid == 0 && (DIM > 0 || i <= dim)) p.partials[(long long)blockIdx.x * (dim + 1) + i] = v;
+  }
+}
+
+// out[h] = scale[h] * sum_cta partials[cta][h]; fixed order -> deterministic.
+__global__ void trace_reduce_kernel(const double* partials, int nctas, int H, double amp, const double* inv_len_dev,
+                                    double* out) {
+  __shared__ double red[32];
+  for (int h = 0; h < H; ++h) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nctas; i += blockDim.x) s += partials[(long long)i * H + h];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[h] = (h == 0) ? s : s * 3.0 * amp * inv_len_dev[h - 1];
+    __syncthreads();
+  }
+}
+
+__global__ void kgrad_dense_kernel(const double* __restrict__ x1, long long n1, const double* __restrict__ x2,
+                                   long long n2, int dim, double amp, const double* __restrict__ len, double* out) {
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long r = blockIdx.y;
+  if (c >= n2 || r >= n1) return;
+  const double sqrt3 = 1.7320508075688772;
+  double s = 0.0, dx2[kMaxDim];
+  for (int i = 0; i < dim; ++i) {
+    const double dx = fabs(x1[r * dim + i] - x2[c * dim + i]);
+    const double t = dx / len[i];
+    dx2[i] = dx * dx;
+    s += t * t;
+  }
+  const double d = sqrt(s), a = sqrt3 * d, ea = exp(-a);
+  const long long plane = n1 * n2, at = r * n2 + c;
+  out[at] = (1.0 + a) * ea;
+  for (int i = 0; i < dim; ++i) {
+    double v = 0.0;
+    if (d != 0.0) {
+      const double dadl = sqrt3 * (-dx2[i] / (len[i] * len[i] * len[i] * d));
+      v = amp * (dadl * ea - (1.0 + a) * dadl * ea);  // gp_prior.py:431-434, kernels.py:137-141
+    }
+    out[(1 + i) * plane + at] = v;
+  }
+}
+
+}  // namespace fvgp
+
+using namespace fvgp;
+
+extern "C" {
+
+// test / profiling hook: 0 = plain coalesced stores for the mirror tile, 1 = TMA bulk stores
+int fvgp_set_bulk_store(int on) {
+  const int old = g_use_bulk_store;
+  g_use_bulk_store = on ? 1 : 0;
+  return old;
+}
+
+int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2, int dim,
+                     double amp, const double* h_inv_scale, double length, const double* d_noise, double* d_K,
+                     int64_t ldk, void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n1 >= 0 && n2 >= 0 && ldk >= n2);
+  FVGP_REQUIRE(mode == FVGP_FILL_FULL || (n1 == n2));
+  if (n1 == 0 || n2 == 0) return 0;
+  FillParams p;
+  p.x1 = d_x1, p.x2 = d_x2, p.noise = d_noise, p.K = d_K;
+  p.n1 = n1, p.n2 = n2, p.ldk = ldk, p.amp = amp, p.dim = dim, p.mode = mode;
+  for (int i = 0; i < kMaxDim; ++i) p.inv_scale[i] = i < dim ? h_inv_scale[i] : 0.0;
+  p.tiles_i = (n1 + FT - 1) / FT;
+  p.tiles_j = (n2 + FT - 1) / FT;
+  p.ntiles = mode == FVGP_FILL_FULL ? p.tiles_i * p.tiles_j : p.tiles_i * (p.tiles_i + 1) / 2;
+  p.bulk = (g_use_bulk_store && mode == FVGP_FILL_SYMMETRIC && ldk % 2 == 0 && ((uintptr_t)d_K % 16 == 0)) ? 1 : 0;
+  p.c_arg = 0.0, p.c_aux = 0.0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case FVGP_K_MATERN32: p.c_arg = sqrt(3.0) / length; return launch_fill_dim<FVGP_K_MATERN32>(p, st);
+    case FVGP_K_MATERN52:
+      p.c_arg = sqrt(5.0) / length, p.c_aux = 5.0 / (3.0 * length * length);
+      return launch_fill_dim<FVGP_K_MATERN52>(p, st);
+    case FVGP_K_SQEXP: p.c_arg = 1.0 / (2.0 * length * length); return launch_fill_dim<FVGP_K_SQEXP>(p, st);
+    case FVGP_K_EXP: p.c_arg = 1.0 / length; return launch_fill_dim<FVGP_K_EXP>(p, st);
+    case FVGP_K_WENDLAND: p.c_arg = 1.0 / length; return launch_fill_dim<FVGP_K_WENDLAND>(p, st);
+    case FVGP_K_DISTANCE: return launch_fill_dim<FVGP_K_DISTANCE>(p, st);
+    default: FVGP_REQUIRE(!"unknown kernel kind");
+  }
+  return 0;
+}
+
+static inline long long trace_grid(int64_t n) {
+  const long long t = (n + FT - 1) / FT, ntiles = t * (t + 1) / 2;
+  const long long cap = (long long)sm_count() * 4;
+  return ntiles < cap ? ntiles : cap;
+}
+
+int64_t fvgp_kgrad_partials_len(int64_t n, int dim) { return (trace_grid(n) + 2) * (dim + 1) + kMaxDim; }
+
+int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const double* h_theta, const double* d_Kinv,
+                              int64_t ld, const double* d_b, double* d_partials, double* h_out, void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  TraceParams p;
+  p.x = d_x, p.Kinv = d_Kinv, p.b = d_b, p.partials = d_partials, p.n = n, p.ld = ld, p.dim = dim;
+  const long long t = (n + FT - 1) / FT;
+  p.ntiles = t * (t + 1) / 2;
+  double inv_len[kMaxDim];
+  for (int i = 0; i < kMaxDim; ++i) inv_len[i] = p.inv_len[i] = i < dim ? 1.0 / h_theta[1 + i] : 0.0;
+  const unsigned grid = (unsigned)trace_grid(n);
+  switch (dim) {
+    case 1: kgrad_trace_kernel<1><<<grid, FILL_THREADS, 0, st>>>(p); break;
+    case 2: kgrad_trace_kernel<2><<<grid, FILL_THREADS, 0, st>>>(p); break;
+    case 3: kgrad_trace_kernel<3><<<grid, FILL_THREADS, 0, st>>>(p); break;
+    case 4: kgrad_trace_kernel<4><<<grid, FILL_THREADS, 0, st>>>(p); break;
+    default: kgrad_trace_kernel<0><<<grid, FILL_THREADS, 0, st>>>(p); break;
+  }
+  FVGP_LAUNCH_OK();
+  const int H = dim + 1;
+  double* d_out = d_partials + (long long)grid * H;
+  double* d_invlen = d_out + H;
+  FVGP_CUDA_OK(cudaMemcpyAsync(d_invlen, inv_len, dim * sizeof(double), cudaMemcpyHostToDevice, st));
+  trace_reduce_kernel<<<1, 256, 0, st>>>(d_partials, (int)grid, H, h_theta[0], d_invlen, d_out);
+  FVGP_LAUNCH_OK();
+  FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_out, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+  FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int fvgp_kgrad_dense_matern32(const double* d_x1, int64_t n1, const double* d_x2, int64_t n2, int dim,
+                              const double* h_theta, double* d_out, void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n1 > 0 && n2 > 0 && n1 < 65536ll * 32768);
+  cudaStream_t st = (cudaStream_t)stream;
+  // length scales go through a tiny device buffer at the tail of the output's first row? no: use a managed copy
+  double* d_len = nullptr;
+  FVGP_CUDA_OK(cudaMallocAsync((void**)&d_len, kMaxDim * sizeof(double), st));
+  FVGP_CUDA_OK(cudaMemcpyAsync(d_len, h_theta + 1, dim * sizeof(double), cudaMemcpyHostToDevice, st));
+  dim3 grid((unsigned)((n2 + 255) / 256), (unsigned)n1);
+  FVGP_REQUIRE(n1 <= 65535);
+  kgrad_dense_kernel<<<grid, 256, 0, st>>>(d_x1, n1, d_x2, n2, dim, h_theta[0], d_len, d_out);
+  FVGP_LAUNCH_OK();
+  FVGP_CUDA_OK(cudaFreeAsync(d_len, st));
+  return 0;
+}
+
+}  // extern "C"

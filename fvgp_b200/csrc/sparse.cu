@@ -1,0 +1,756 @@
+// gp2Scale on the device: compact-support (Wendland) covariance straight to canonical CSR,
+// CSR SpMV, preconditioned CG and the Lanczos recurrences of the SLQ log-determinant.
+//
+// Reference behaviour being replaced (lbl-camera/fvGP):
+//   kernels.py:502-528          wendland_anisotropic_gp2Scale_cpu   (dense B x B block per dask task)
+//   gp2Scale_covariance.py:136-170, :240-287   np.nonzero pattern, triu mask, mirror, COO -> CSR sort
+//   gp_kv.py:655-661            K + diag(V) via setdiag
+//   gp_lin_alg.py:1213-1291     calculate_sparse_conj_grad -> scipy.sparse.linalg.cg
+//   gp_lin_alg.py:604-622       block-Jacobi preconditioner
+//   gp_lin_alg.py:1103-1181     calculate_random_logdet -> imate SLQ (device part: Lanczos)
+//
+// Bit-exact sparsity: an entry is stored iff the reference's value is non-zero, which is
+// s < 1 for s = sum_i ((x1_i - x2_i) / theta_i)^2 accumulated in axis order with every
+// operation rounded separately (numpy never fuses).  The predicate below uses the
+// __dsub_rn/__ddiv_rn/__dmul_rn/__dadd_rn intrinsics, which ptxas may not contract.
+// Tile and point-vs-tile bounding-box culls run the SAME operation sequence on the
+// coordinate gaps; every operation is monotone, so gap_s >= 1 implies s >= 1 for every
+// pair in the tile and the cull never changes the pattern (no epsilon margins).
+//
+// Layout: 32-point row tiles (one warp each) against 32-point column tiles, column tiles
+// grouped into super tiles of 32 for a two-level box cull.  Inside a surviving tile pair
+// the warp walks the rows; lanes hold the 32 columns, hits are compacted with
+// ballot + popc prefix so each row's entries land in ascending column order -- the CSR
+// is canonical by construction, no sort, no atomics, deterministic.
+#include "../../include/fvgp_b200.h"
+#include "common.cuh"
+
+namespace fvgp {
+
+constexpr int WT = 32;          // points per tile
+constexpr int WS = 32;          // tiles per super tile
+constexpr int W_WARPS = 4;      // row tiles per CTA
+
+struct WendlandParams {
+  const double* x1;
+  const double* x2;
+  const double* aabb1;
+  const double* aabb2;
+  const long long* indptr;
+  const double* noise;
+  long long* rowcount;
+  int* indices;
+  double* data;
+  long long n1, n2, tiles1, tiles2, super2;
+  double amp;
+  double theta[kMaxDim];
+  int dim;
+};
+
+// Bounding boxes: tile t -> lo[dim], hi[dim] at aabb + t*2*dim; super tiles follow the tiles.
+__global__ void aabb_tiles_kernel(const double* __restrict__ x, long long n, int dim, double* aabb, long long tiles) {
+  const long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= tiles) return;
+  const long long r = t * WT + lane;
+  for (int i = 0; i < dim; ++i) {
+    double lo = r < n ? x[r * dim + i] : INFINITY, hi = r < n ? x[r * dim + i] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      aabb[t * 2 * dim + i] = lo;
+      aabb[t * 2 * dim + dim + i] = hi;
+    }
+  }
+}
+
+__global__ void aabb_super_kernel(double* aabb, int dim, long long tiles, long long supers) {
+  const long long s = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= supers) return;
+  const long long t = s * WS + lane;
+  double* out = aabb + tiles * 2 * dim + s * 2 * dim;
+  for (int i = 0; i < dim; ++i) {
+    double lo = t < tiles ? aabb[t * 2 * dim + i] : INFINITY, hi = t < tiles ? aabb[t * 2 * dim + dim + i] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) out[i] = lo, out[dim + i] = hi;
+  }
+}
+
+// s for the per-axis gaps between two boxes, in the reference's operation order.
+template <int DIM>
+__device__ __forceinline__ double box_gap_s(const double* lo1, const double* hi1, const double* lo2, const double* hi2,
+                                            const double* theta) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    const double g = fmax(0.0, fmax(__dsub_rn(lo2[i], hi1[i]), __dsub_rn(lo1[i], hi2[i])));
+    const double t = __ddiv_rn(g, theta[i]);
+    s = __dadd_rn(s, __dmul_rn(t, t));
+  }
+  return s;
+}
+
+template <int DIM, bool FILL>
+__global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const WendlandParams p) {
+  __shared__ double xs[W_WARPS][WT][DIM];
+  __shared__ long long cursor[W_WARPS][WT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tile = blockIdx.x * (long long)W_WARPS + warp;
+  if (tile >= p.tiles1) return;  // whole warp exits together; no CTA-wide barriers below
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  double theta[DIM], lo1[DIM], hi1[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    theta[i] = p.theta[i];
+    lo1[i] = p.aabb1[tile * 2 * DIM + i];
+    hi1[i] = p.aabb1[tile * 2 * DIM + DIM + i];
+  }
+  const long long r_mine = tile * WT + lane;
+  const int rows_here = (int)min((long long)WT, p.n1 - tile * WT);
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) xs[warp][lane][i] = r_mine < p.n1 ? p.x1[r_mine * DIM + i] : 0.0;
+  cursor[warp][lane] = (FILL && r_mine < p.n1) ? p.indptr[r_mine] : 0;
+  __syncwarp();
+
+  const double* tile_boxes = p.aabb2;
+  const double* super_boxes = p.aabb2 + p.tiles2 * 2 * DIM;
+
+  for (long long s0 = 0; s0 < p.super2; s0 += 32) {
+    const long long sidx = s0 + lane;
+    bool keep = false;
+    if (sidx < p.super2) {
+      const double* bx = super_boxes + sidx * 2 * DIM;
+      double lo2[DIM], hi2[DIM];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) lo2[i] = bx[i], hi2[i] = bx[DIM + i];
+      keep = box_gap_s<DIM>(lo1, hi1, lo2, hi2, theta) < 1.0;
+    }
+    unsigned smask = __ballot_sync(0xffffffffu, keep);
+    while (smask) {
+      const int sb = __ffs(smask) - 1;
+      smask &= smask - 1;
+      const long long t_idx = (s0 + sb) * WS + lane;
+      bool keep_t = false;
+      if (t_idx < p.tiles2) {
+        const double* bx = tile_boxes + t_idx * 2 * DIM;
+        double lo2[DIM], hi2[DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) lo2[i] = bx[i], hi2[i] = bx[DIM + i];
+        keep_t = box_gap_s<DIM>(lo1, hi1, lo2, hi2, theta) < 1.0;
+      }
+      unsigned tmask = __ballot_sync(0xffffffffu, keep_t);
+      while (tmask) {
+        const int tb = __ffs(tmask) - 1;
+        tmask &= tmask - 1;
+        const long long ct = (s0 + sb) * WS + tb;
+        const long long c = ct * WT + lane;
+        const bool c_ok = c < p.n2;
+        double xc[DIM], lo2[DIM], hi2[DIM];
+        const double* bx = tile_boxes + ct * 2 * DIM;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+          xc[i] = c_ok ? p.x2[c * DIM + i] : 0.0;
+          lo2[i] = bx[i];
+          hi2[i] = bx[DIM + i];
+        }
+        for (int rr = 0; rr < rows_here; ++rr) {
+          double xr[DIM];
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) xr[i] = xs[warp][rr][i];
+          // point-vs-box cull (warp-uniform): the row point as a degenerate box
+          if (box_gap_s<DIM>(xr, xr, lo2, hi2, theta) >= 1.0) continue;
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) {
+            const double t = __ddiv_rn(__dsub_rn(xr[i], xc[i]), theta[i]);
+            s = __dadd_rn(s, __dmul_rn(t, t));
+          }
+          double v = 0.0;
+          if (c_ok && s < 1.0) {
+            const double d = __dsqrt_rn(s);
+            const double u = 1.0 - d;
+            const double u2 = u * u, u4 = u2 * u2;
+            const double d2 = d * d;
+            const double poly = ((32.0 * (d2 * d) + 25.0 * d2) + 8.0 * d) + 1.0;
+            v = (p.amp * (u4 * u4)) * poly;
+          }
+          const bool hit = v != 0.0;
+          const unsigned hmask = __ballot_sync(0xffffffffu, hit);
+          if (hmask == 0u) continue;
+          if (FILL) {
+            if (hit) {
+              const long long r = tile * WT + rr;
+              const long long pos = cursor[warp][rr] + __popc(hmask & lt_mask);
+              if (p.noise != nullptr && r == c) v += p.noise[r];
+              p.indices[pos] = (int)c;
+              p.data[pos] = v;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) cursor[warp][rr] += __popc(hmask);
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (!FILL) {
+    __syncwarp();
+    if (r_mine < p.n1) p.rowcount[r_mine] = cursor[warp][lane];
+  }
+}
+
+// ---------------------------------------------------------------------------- exclusive scan (int64)
+constexpr int SCAN_CHUNK = 2048;
+
+__global__ void __launch_bounds__(256) scan_block_sums_kernel(const long long* __restrict__ in, long long n,
+                                                              long long* sums) {
+  __shared__ long long red[256];
+  const long long base = blockIdx.x * (long long)SCAN_CHUNK;
+  long long s = 0;
+  for (int k = threadIdx.x; k < SCAN_CHUNK; k += 256)
+    if (base + k < n) s += in[base + k];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[blockIdx.x] = red[0];
+}
+
+__global__ void scan_sums_kernel(long long* sums, long long nblk) {  // single thread: nblk is small
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    long long run = 0;
+    for (long long i = 0; i < nblk; ++i) {
+      const long long v = sums[i];
+      sums[i] = run;
+      run += v;
+    }
+    sums[nblk] = run;
+  }
+}
+
+__global__ void __launch_bounds__(256) scan_apply_kernel(const long long* __restrict__ in, long long n,
+                                                         const long long* __restrict__ sums, long long* out,
+                                                         long long nblk) {
+  __shared__ long long part[256];
+  const long long base = blockIdx.x * (long long)SCAN_CHUNK + threadIdx.x * 8;
+  long long v[8], s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 256 thread sums
+  for (int o = 1; o < 256; o <<= 1) {
+    long long add = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  long long run = sums[blockIdx.x] + part[threadIdx.x] - s;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == nblk - 1 && threadIdx.x == 0) out[n] = sums[nblk];
+}
+
+// ---------------------------------------------------------------------------- SpMV and Krylov kernels
+constexpr int KR_THREADS = 256;
+
+struct KrylovScalars {
+  double rho, rho_old, pq, rr, atol, alpha, beta, bnorm2;
+  int done, iters;
+  unsigned counter[4];
+};
+
+__device__ __forceinline__ double csr_row_dot(const long long* __restrict__ indptr, const int* __restrict__ idx,
+                                              const double* __restrict__ val, const double* __restrict__ x,
+                                              long long row, int lane) {
+  const long long b = indptr[row], e = indptr[row + 1];
+  double s = 0.0;
+  for (long long k = b + lane; k < e; k += 32) s = fma(val[k], x[idx[k]], s);
+  return warp_sum(s);
+}
+
+__global__ void __launch_bounds__(KR_THREADS) spmv_kernel(long long n, const long long* __restrict__ indptr,
+                                                          const int* __restrict__ idx, const double* __restrict__ val,
+                                                          const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const double s = csr_row_dot(indptr, idx, val, x, row, lane);
+    if (lane == 0) y[row] = s;
+  }
+}
+
+// Deterministic grid-wide sums: every CTA publishes its partial, the last CTA to arrive adds
+// them in index order.  Returns true in the finishing CTA (all its threads), totals in out[].
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double* partials, unsigned* counter, double (&out)[NV]) {
+  __shared__ double red[32];
+  __shared__ bool last;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const double s = block_sum(v[q], red);
+    if (threadIdx.x == 0) partials[(size_t)q * gridDim.x + blockIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return false;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double s = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += partials[(size_t)q * gridDim.x + i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) red[0] = s;
+    __syncthreads();
+    out[q] = red[0];
+    __syncthreads();
+  }
+  return true;
+}
+
+// r = b - A x ; bnorm2 = b.b ; rr = r.r ; sets the absolute tolerance and the done flag.
+__global__ void __launch_bounds__(KR_THREADS) pcg_init_kernel(long long n, const long long* __restrict__ indptr,
+                                                              const int* __restrict__ idx,
+                                                              const double* __restrict__ val,
+                                                              const double* __restrict__ b, const double* __restrict__ x,
+                                                              double* __restrict__ r, double rtol, KrylovScalars* sc,
+                                                              double* partials) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double v[2] = {0.0, 0.0};
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const double ax = csr_row_dot(indptr, idx, val, x, row, lane);
+    if (lane == 0) {
+      const double bi = b[row], ri = bi - ax;
+      r[row] = ri;
+      v[0] += bi * bi;
+      v[1] += ri * ri;
+    }
+  }
+  double tot[2];
+  if (grid_sum<2>(v, partials, &sc->counter[0], tot) && threadIdx.x == 0) {
+    sc->bnorm2 = tot[0];
+    sc->rr = tot[1];
+    sc->atol = rtol * sqrt(tot[0]);
+    sc->rho = 0.0, sc->rho_old = 0.0, sc->iters = 0;
+    sc->done = (sqrt(tot[1]) < sc->atol || tot[0] == 0.0) ? 1 : 0;  // scipy: ||r|| < atol at loop top
+  }
+}
+
+// z = M r (block-Jacobi, 32x32 symmetric inverse blocks) or z = r ; rho = r.z ; beta = rho/rho_old
+__global__ void __launch_bounds__(KR_THREADS) pcg_precond_kernel(long long n, const double* __restrict__ blocks,
+                                                                 const double* __restrict__ r, double* __restrict__ z,
+                                                                 KrylovScalars* sc, double* partials) {
+  if (sc->done) return;
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nblk = (n + 31) / 32;
+  double v[1] = {0.0};
+  for (long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblk; blk += warps) {
+    const long long i = blk * 32 + lane;
+    const double ri = i < n ? r[i] : 0.0;
+    double zi = ri;
+    if (blocks != nullptr) {
+      const double* B = blocks + blk * 1024;
+      zi = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) zi = fma(B[j * 32 + lane], __shfl_sync(0xffffffffu, ri, j), zi);
+    }
+    if (i < n) {
+      z[i] = zi;
+      v[0] += ri * zi;
+    }
+  }
+  double tot[1];
+  if (grid_sum<1>(v, partials, &sc->counter[1], tot) && threadIdx.x == 0) {
+    sc->rho_old = sc->rho;
+    sc->rho = tot[0];
+    sc->beta = sc->iters > 0 ? tot[0] / sc->rho_old : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(KR_THREADS) pcg_update_p_kernel(long long n, const double* __restrict__ z,
+                                                                  double* __restrict__ p, const KrylovScalars* sc) {
+  if (sc->done) return;
+  const double beta = sc->beta;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = z[i] + beta * p[i];
+}
+
+// q = A p ; pq = p.q ; alpha = rho / pq
+__global__ void __launch_bounds__(KR_THREADS) pcg_spmv_kernel(long long n, const long long* __restrict__ indptr,
+                                                              const int* __restrict__ idx,
+                                                              const double* __restrict__ val,
+                                                              const double* __restrict__ p, double* __restrict__ q,
+                                                              KrylovScalars* sc, double* partials) {
+  if (sc->done) return;
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double v[1] = {0.0};
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const double s = csr_row_dot(indptr, idx, val, p, row, lane);
+    if (lane == 0) {
+      q[row] = s;
+      v[0] += s * p[row];
+    }
+  }
+  double tot[1];
+  if (grid_sum<1>(v, partials, &sc->counter[2], tot) && threadIdx.x == 0) {
+    sc->pq = tot[0];
+    sc->alpha = sc->rho / tot[0];
+  }
+}
+
+// x += alpha p ; r -= alpha q ; rr = r.r ; iteration count ; convergence flag
+__global__ void __launch_bounds__(KR_THREADS) pcg_update_xr_kernel(long long n, const double* __restrict__ p,
+                                                                   const double* __restrict__ q,
+                                                                   double* __restrict__ x, double* __restrict__ r,
+                                                                   KrylovScalars* sc, double* partials, int maxiter) {
+  if (sc->done) return;
+  const double alpha = sc->alpha;
+  double v[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    v[0] += ri * ri;
+  }
+  double tot[1];
+  if (grid_sum<1>(v, partials, &sc->counter[3], tot) && threadIdx.x == 0) {
+    sc->rr = tot[0];
+    sc->iters += 1;
+    if (sqrt(tot[0]) < sc->atol) sc->done = 1;
+    else if (sc->iters >= maxiter) sc->done = 2;
+  }
+}
+
+// Dense 32x32 diagonal blocks of the CSR matrix, inverted in shared memory (Gauss-Jordan, SPD).
+__global__ void __launch_bounds__(128) bjacobi_build_kernel(long long n, const long long* __restrict__ indptr,
+                                                            const int* __restrict__ idx,
+                                                            const double* __restrict__ val, double* blocks) {
+  __shared__ double Bs[4][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long blk = blockIdx.x * 4ll + warp;
+  const long long nblk = (n + 31) / 32;
+  if (blk >= nblk) return;
+  double(*B)[33] = Bs[warp];
+  for (int j = 0; j < 32; ++j) B[lane][j] = (j == lane) ? 1.0 : 0.0;  // identity padding for the ragged tail
+  __syncwarp();
+  const long long row = blk * 32 + lane, c0 = blk * 32;
+  if (row < n) {
+    bool any = false;
+    for (long long k = indptr[row]; k < indptr[row + 1]; ++k) {
+      const long long c = idx[k];
+      if (c >= c0 && c < c0 + 32) {
+        if (!any) B[lane][lane] = 0.0, any = true;
+        B[lane][c - c0] += val[k];
+      }
+    }
+  }
+  __syncwarp();
+  for (int k = 0; k < 32; ++k) {
+    const double piv = 1.0 / B[k][k];
+    __syncwarp();
+    const double f = B[lane][k];
+    if (lane == k) {
+      for (int j = 0; j < 32; ++j) B[k][j] = (j == k) ? piv : B[k][j] * piv;
+    }
+    __syncwarp();
+    if (lane != k) {
+      for (int j = 0; j < 32; ++j) B[lane][j] = (j == k) ? -f * piv : B[lane][j] - f * B[k][j];
+    }
+    __syncwarp();
+  }
+  double* out = blocks + blk * 1024;
+  for (int j = 0; j < 32; ++j) out[j * 32 + lane] = 0.5 * (B[j][lane] + B[lane][j]);  // symmetrised
+}
+
+// ---------------------------------------------------------------------------- Lanczos (SLQ)
+__device__ __forceinline__ double rademacher(unsigned long long seed, unsigned long long probe, unsigned long long i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (probe * 0x100000001B3ull + i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (z & 1ull) ? 1.0 : -1.0;
+}
+
+__global__ void lanczos_start_kernel(long long n, unsigned long long seed, unsigned long long probe, double* v,
+                                     double* vprev, KrylovScalars* sc) {
+  const double s = rsqrt((double)n);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    v[i] = rademacher(seed, probe, (unsigned long long)i) * s;
+    vprev[i] = 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->beta = 0.0;
+}
+
+// w = A v - beta_prev * vprev ; alpha = w.v
+__global__ void __launch_bounds__(KR_THREADS) lanczos_spmv_kernel(long long n, const long long* __restrict__ indptr,
+                                                                  const int* __restrict__ idx,
+                                                                  const double* __restrict__ val,
+                                                                  const double* __restrict__ v,
+                                                                  const double* __restrict__ vprev,
+                                                                  double* __restrict__ w, KrylovScalars* sc,
+                                                                  double* partials) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const double beta = sc->beta;
+  double acc[1] = {0.0};
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const double s = csr_row_dot(indptr, idx, val, v, row, lane);
+    if (lane == 0) {
+      const double wi = s - beta * vprev[row];
+      w[row] = wi;
+      acc[0] += wi * v[row];
+    }
+  }
+  double tot[1];
+  if (grid_sum<1>(acc, partials, &sc->counter[0], tot) && threadIdx.x == 0) sc->alpha = tot[0];
+}
+
+// w -= alpha v ; beta = ||w||
+__global__ void __launch_bounds__(KR_THREADS) lanczos_axpy_kernel(long long n, const double* __restrict__ v,
+                                                                  double* __restrict__ w, KrylovScalars* sc,
+                                                                  double* partials, double* out_alpha,
+                                                                  double* out_beta) {
+  const double alpha = sc->alpha;
+  double acc[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double wi = fma(-alpha, v[i], w[i]);
+    w[i] = wi;
+    acc[0] += wi * wi;
+  }
+  double tot[1];
+  if (grid_sum<1>(acc, partials, &sc->counter[1], tot) && threadIdx.x == 0) {
+    sc->beta = sqrt(tot[0]);
+    *out_alpha = alpha;
+    *out_beta = sc->beta;
+  }
+}
+
+// vprev = v ; v = w / beta
+__global__ void lanczos_shift_kernel(long long n, double* v, double* vprev, const double* w, const KrylovScalars* sc) {
+  const double inv = sc->beta > 0.0 ? 1.0 / sc->beta : 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    vprev[i] = v[i];
+    v[i] = w[i] * inv;
+  }
+}
+
+static inline unsigned krylov_grid() { return (unsigned)sm_count() * 4u; }
+
+template <bool FILL>
+static int launch_wendland(const WendlandParams& p, cudaStream_t st) {
+  const unsigned grid = (unsigned)((p.tiles1 + W_WARPS - 1) / W_WARPS);
+  switch (p.dim) {
+    case 1: wendland_csr_kernel<1, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
+    case 2: wendland_csr_kernel<2, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
+    case 3: wendland_csr_kernel<3, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
+    case 4: wendland_csr_kernel<4, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
+    case 5: wendland_csr_kernel<5, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
+    case 6: wendland_csr_kernel<6, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
+    default: FVGP_REQUIRE(!"gp2Scale Wendland supports 1..6 input dimensions");
+  }
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+static int fill_wendland_params(WendlandParams& p, const double* d_x1, int64_t n1, const double* d_aabb1,
+                                const double* d_x2, int64_t n2, const double* d_aabb2, int dim,
+                                const double* h_theta) {
+  FVGP_REQUIRE(dim >= 1 && dim <= 6 && n1 >= 0 && n2 >= 0 && n2 < (1ll << 31));
+  p.x1 = d_x1, p.x2 = d_x2, p.aabb1 = d_aabb1, p.aabb2 = d_aabb2;
+  p.n1 = n1, p.n2 = n2, p.dim = dim, p.amp = h_theta[0];
+  p.tiles1 = (n1 + WT - 1) / WT, p.tiles2 = (n2 + WT - 1) / WT, p.super2 = (p.tiles2 + WS - 1) / WS;
+  for (int i = 0; i < kMaxDim; ++i) p.theta[i] = i < dim ? h_theta[1 + i] : 1.0;
+  p.indptr = nullptr, p.noise = nullptr, p.rowcount = nullptr, p.indices = nullptr, p.data = nullptr;
+  return 0;
+}
+
+
+}  // namespace fvgp
+
+using namespace fvgp;
+
+extern "C" {
+
+int64_t fvgp_wendland_aabb_len(int64_t n, int dim) {
+  const int64_t tiles = (n + WT - 1) / WT, supers = (tiles + WS - 1) / WS;
+  return (tiles + supers) * 2 * dim;
+}
+
+int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim);
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t tiles = (n + WT - 1) / WT, supers = (tiles + WS - 1) / WS;
+  aabb_tiles_kernel<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, st>>>(d_x, n, dim, d_aabb, tiles);
+  FVGP_LAUNCH_OK();
+  aabb_super_kernel<<<(unsigned)((supers * 32 + 255) / 256), 256, 0, st>>>(d_aabb, dim, tiles, supers);
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+int fvgp_wendland_csr_count(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
+                            const double* d_aabb2, int dim, const double* h_theta, int64_t* d_rowcount,
+                            void* stream) {
+  WendlandParams p;
+  int r = fill_wendland_params(p, d_x1, n1, d_aabb1, d_x2, n2, d_aabb2, dim, h_theta);
+  if (r != 0) return r;
+  if (n1 == 0) return 0;
+  p.rowcount = (long long*)d_rowcount;
+  return launch_wendland<false>(p, (cudaStream_t)stream);
+}
+
+int fvgp_wendland_csr_fill(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
+                           const double* d_aabb2, int dim, const double* h_theta, const int64_t* d_indptr,
+                           const double* d_noise_diag, int32_t* d_indices, double* d_data, void* stream) {
+  WendlandParams p;
+  int r = fill_wendland_params(p, d_x1, n1, d_aabb1, d_x2, n2, d_aabb2, dim, h_theta);
+  if (r != 0) return r;
+  if (n1 == 0) return 0;
+  p.indptr = (const long long*)d_indptr, p.noise = d_noise_diag, p.indices = d_indices, p.data = d_data;
+  return launch_wendland<true>(p, (cudaStream_t)stream);
+}
+
+int64_t fvgp_scan_scratch_len(int64_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 2; }
+
+int fvgp_exclusive_scan_i64(const int64_t* d_counts, int64_t n, int64_t* d_indptr, int64_t* d_scratch,
+                            int64_t* h_total, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) {
+    FVGP_CUDA_OK(cudaMemsetAsync(d_indptr, 0, sizeof(int64_t), st));
+    if (h_total) *h_total = 0;
+    return 0;
+  }
+  const long long nblk = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  scan_block_sums_kernel<<<(unsigned)nblk, 256, 0, st>>>((const long long*)d_counts, n, (long long*)d_scratch);
+  scan_sums_kernel<<<1, 32, 0, st>>>((long long*)d_scratch, nblk);
+  scan_apply_kernel<<<(unsigned)nblk, 256, 0, st>>>((const long long*)d_counts, n, (const long long*)d_scratch,
+                                                    (long long*)d_indptr, nblk);
+  FVGP_LAUNCH_OK();
+  if (h_total) {
+    FVGP_CUDA_OK(cudaMemcpyAsync(h_total, d_scratch + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+int fvgp_csr_spmv(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                  const double* d_x, double* d_y, void* stream) {
+  if (n <= 0) return 0;
+  const long long want = (n * 32 + KR_THREADS - 1) / KR_THREADS;
+  const unsigned grid = (unsigned)(want < (long long)sm_count() * 16 ? want : (long long)sm_count() * 16);
+  spmv_kernel<<<grid, KR_THREADS, 0, (cudaStream_t)stream>>>(n, (const long long*)d_indptr, d_indices, d_data, d_x,
+                                                             d_y);
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+int64_t fvgp_bjacobi_len(int64_t n) { return ((n + 31) / 32) * 1024; }
+
+int fvgp_bjacobi_build(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                       double* d_blocks, void* stream) {
+  if (n <= 0) return 0;
+  const long long nblk = (n + 31) / 32;
+  bjacobi_build_kernel<<<(unsigned)((nblk + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      n, (const long long*)d_indptr, d_indices, d_data, d_blocks);
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+// work layout: r | z | p | q | partials (2*grid) | KrylovScalars
+int64_t fvgp_pcg_work_len(int64_t n) { return 4 * n + 2 * (int64_t)krylov_grid() + 64; }
+
+int fvgp_pcg(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+             const double* d_precond, const double* d_b, double* d_x, double rtol, int maxiter, double* d_work,
+             int* h_iters, double* h_relres, void* stream) {
+  FVGP_REQUIRE(n > 0 && maxiter > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = krylov_grid();
+  double* r = d_work;
+  double* z = r + n;
+  double* p = z + n;
+  double* q = p + n;
+  double* partials = q + n;
+  KrylovScalars* sc = (KrylovScalars*)(partials + 2 * grid);
+  const long long* ip = (const long long*)d_indptr;
+  FVGP_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(KrylovScalars), st));
+  FVGP_CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(double), st));
+  pcg_init_kernel<<<grid, KR_THREADS, 0, st>>>(n, ip, d_indices, d_data, d_b, d_x, r, rtol, sc, partials);
+  FVGP_LAUNCH_OK();
+  KrylovScalars h;
+  int launched = 0;
+  const int batch = 16;
+  for (;;) {
+    FVGP_CUDA_OK(cudaMemcpyAsync(&h, sc, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, st));
+    FVGP_CUDA_OK(cudaStreamSynchronize(st));
+    if (h.done || launched >= maxiter) break;
+    for (int k = 0; k < batch && launched < maxiter; ++k, ++launched) {
+      pcg_precond_kernel<<<grid, KR_THREADS, 0, st>>>(n, d_precond, r, z, sc, partials);
+      pcg_update_p_kernel<<<grid, KR_THREADS, 0, st>>>(n, z, p, sc);
+      pcg_spmv_kernel<<<grid, KR_THREADS, 0, st>>>(n, ip, d_indices, d_data, p, q, sc, partials);
+      pcg_update_xr_kernel<<<grid, KR_THREADS, 0, st>>>(n, p, q, d_x, r, sc, partials, maxiter);
+    }
+    FVGP_LAUNCH_OK();
+  }
+  if (h_iters) *h_iters = h.iters;
+  if (h_relres) *h_relres = h.bnorm2 > 0.0 ? sqrt(h.rr / h.bnorm2) : 0.0;
+  return h.done == 1 ? 0 : 1;
+}
+
+// work layout: v | vprev | w | partials (grid) | KrylovScalars | alpha[degree] | beta[degree]
+int64_t fvgp_lanczos_work_len(int64_t n, int degree) { return 3 * n + (int64_t)krylov_grid() + 64 + 2 * degree; }
+
+int fvgp_lanczos_tridiag(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                         int degree, int probe0, int nprobes, uint64_t seed, double* d_work, double* h_alpha,
+                         double* h_beta, void* stream) {
+  FVGP_REQUIRE(n > 0 && degree > 0 && nprobes >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = krylov_grid();
+  double* v = d_work;
+  double* vprev = v + n;
+  double* w = vprev + n;
+  double* partials = w + n;
+  KrylovScalars* sc = (KrylovScalars*)(partials + grid);
+  double* d_alpha = (double*)(sc) + 32;
+  double* d_beta = d_alpha + degree;
+  const long long* ip = (const long long*)d_indptr;
+  for (int pr = 0; pr < nprobes; ++pr) {
+    FVGP_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(KrylovScalars), st));
+    lanczos_start_kernel<<<grid, KR_THREADS, 0, st>>>(n, seed, (unsigned long long)(probe0 + pr), v, vprev, sc);
+    for (int j = 0; j < degree; ++j) {
+      lanczos_spmv_kernel<<<grid, KR_THREADS, 0, st>>>(n, ip, d_indices, d_data, v, vprev, w, sc, partials);
+      lanczos_axpy_kernel<<<grid, KR_THREADS, 0, st>>>(n, v, w, sc, partials, d_alpha + j, d_beta + j);
+      lanczos_shift_kernel<<<grid, KR_THREADS, 0, st>>>(n, v, vprev, w, sc);
+    }
+    FVGP_LAUNCH_OK();
+    FVGP_CUDA_OK(cudaMemcpyAsync(h_alpha + (size_t)pr * degree, d_alpha, degree * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    FVGP_CUDA_OK(cudaMemcpyAsync(h_beta + (size_t)pr * degree, d_beta, degree * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+"""Device operators of the hot path: thin, typed wrappers over the C ABI.
+
+Everything here takes / returns torch CUDA tensors (float64) and enqueues on torch's
+current stream.  No arithmetic is done in Python or by torch kernels on these paths.
+"""
+import ctypes
+from ctypes import c_double, c_int, c_int64
+
+import numpy as np
+
+from . import _lib as L
+
+
+# ------------------------------------------------------------------------------ dense K
+def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL, out=None):
+    """K = amp * f(||(x1-x2)*inv_scale|| / length) [+ diag(noise)].  Returns (buffer, ld);
+    buffer[:, :n2] is the matrix (gp_prior.py:376-400, kernels.py:16-188, gp_kv.py:640-669)."""
+    lib = L.load()
+    n1, n2, dim = x1.shape[0], x2.shape[0], x1.shape[1]
+    if out is None:
+        buf, ld = L.dev_matrix(n1, n2)
+    else:
+        buf, ld = out
+    _, inv_p = L.dvec(inv_scale)
+    st = lib.fvgp_kfill_dense(kind, mode, L.ptr(x1), n1, L.ptr(x2), n2, dim, float(amp), inv_p, float(length),
+                              L.ptr(noise), L.ptr(buf), ld, L.stream_ptr())
+    L.check(st, "fvgp_kfill_dense")
+    return buf, ld
+
+
+def kgrad_dense_matern32(x1, x2, theta):
+    lib = L.load()
+    n1, n2, dim = x1.shape[0], x2.shape[0], x1.shape[1]
+    out = L.dev_empty((dim + 1, n1, n2))
+    _, th = L.dvec(theta)
+    L.check(lib.fvgp_kgrad_dense_matern32(L.ptr(x1), n1, L.ptr(x2), n2, dim, th, L.ptr(out), L.stream_ptr()),
+            "fvgp_kgrad_dense_matern32")
+    return out
+
+
+def kgrad_trace_matern32(x, theta, kinv_buf, ld, b):
+    """sum_ij (Kinv - b b^T)_ij dK_ij/dtheta_h for the default kernel; returns ndarray (dim+1,)."""
+    lib = L.load()
+    n, dim = x.shape
+    partials = L.dev_empty((int(lib.fvgp_kgrad_partials_len(n, dim)),))
+    _, th = L.dvec(theta)
+    out = (c_double * (dim + 1))()
+    L.check(lib.fvgp_kgrad_trace_matern32(L.ptr(x), n, dim, th, L.ptr(kinv_buf), ld, L.ptr(b), L.ptr(partials), out,
+                                          L.stream_ptr()), "fvgp_kgrad_trace_matern32")
+    return np.array(out[:], dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------ dense factorisation
+class CholFactor:
+    """Lower Cholesky factor resident on the device (+ the tile inverses potrs/potri need)."""
+
+    def __init__(self, buf, ld, n, tileinv):
+        self.buf, self.ld, self.n, self.tileinv = buf, ld, n, tileinv
+        self.inverted = False
+
+    def lower(self):
+        torch = L._torch()
+        return torch.tril(self.buf[:, :self.n])
+
+
+def potrf(buf, ld, n):
+    """In-place lower Cholesky (gp_lin_alg.py:237-269).  Raises NonPositiveDefiniteError."""
+    lib = L.load()
+    torch = L._torch()
+    tileinv = L.dev_empty((int(lib.fvgp_chol_workspace_len(n)),))
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = L.check(lib.fvgp_potrf_lower(L.ptr(buf), n, ld, L.ptr(tileinv), L.ptr(info), L.stream_ptr()),
+                 "fvgp_potrf_lower")
+    if st > 0:
+        raise L.NonPositiveDefiniteError(st, n)
+    return CholFactor(buf, ld, n, tileinv)
+
+
+def potrs(factor, rhs_t):
+    """Solve KV X = B in place.  rhs_t: (nrhs, n) C-contiguous device tensor = B^T (gp_lin_alg.py:289-328)."""
+    lib = L.load()
+    assert not factor.inverted
+    nrhs, n = rhs_t.shape
+    assert n == factor.n and rhs_t.is_contiguous()
+    if nrhs > 4 and n % 2:            # GEMM path needs an even row stride
+        ldb = n + 1
+        padded = L.dev_empty((nrhs, ldb))
+        padded[:, :n] = rhs_t
+        work = L.dev_empty((2 * n,))
+        L.check(lib.fvgp_potrs_lower(L.ptr(factor.buf), n, factor.ld, L.ptr(factor.tileinv), L.ptr(padded), nrhs, ldb,
+                                     L.ptr(work), L.stream_ptr()), "fvgp_potrs_lower")
+        rhs_t.copy_(padded[:, :n])
+        return rhs_t
+    work = L.dev_empty((2 * n,))
+    L.check(lib.fvgp_potrs_lower(L.ptr(factor.buf), n, factor.ld, L.ptr(factor.tileinv), L.ptr(rhs_t), nrhs, n,
+                                 L.ptr(work), L.stream_ptr()), "fvgp_potrs_lower")
+    return rhs_t
+
+
+def chol_logdet(factor):
+    lib = L.load()
+    scratch = L.dev_empty((1,))
+    out = c_double()
+    L.check(lib.fvgp_chol_logdet(L.ptr(factor.buf), factor.n, factor.ld, L.ptr(scratch), ctypes.byref(out),
+                                 L.stream_ptr()), "fvgp_chol_logdet")
+    return out.value
+
+
+def potri(factor):
+    """Lower triangle of the factor buffer <- lower triangle of KV^-1 (gp_lin_alg.py:1558)."""
+    lib = L.load()
+    work = L.dev_empty((int(lib.fvgp_potri_workspace_len(factor.n)),))
+    L.check(lib.fvgp_potri_lower(L.ptr(factor.buf), factor.n, factor.ld, L.ptr(factor.tileinv), L.ptr(work),
+                                 L.stream_ptr()), "fvgp_potri_lower")
+    factor.inverted = True
+    return factor
+
+
+def dot(a, b):
+    lib = L.load()
+    scratch = L.dev_empty((1,))
+    out = c_double()
+    L.check(lib.fvgp_dot(L.ptr(a), L.ptr(b), a.numel(), L.ptr(scratch), ctypes.byref(out), L.stream_ptr()), "fvgp_dot")
+    return out.value
+
+
+def dgemm_nt(A, B, C, alpha=1.0, beta=0.0, lower=False):
+    """C = alpha A B^T + beta C on row-major 2-D device tensors (strides taken from the tensors)."""
+    lib = L.load()
+    m, k = A.shape
+    n = B.shape[0]
+    L.check(lib.fvgp_dgemm_nt(L.ptr(A), A.stride(0), L.ptr(B), B.stride(0), L.ptr(C), C.stride(0), m, n, k,
+                              float(alpha), float(beta), int(lower), L.stream_ptr()), "fvgp_dgemm_nt")
+    return C
+
+
+# ------------------------------------------------------------------------------ gp2Scale sparse
+class DeviceCSR:
+    """Canonical CSR on the device: int64 indptr, int32 sorted indices, float64 data."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data, self.shape = indptr, indices, data, shape
+
+    @property
+    def nnz(self):
+        return int(self.data.numel())
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        idx_t = np.int32 if (self.nnz < 2 ** 31 and max(self.shape) < 2 ** 31) else np.int64
+        return sp.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy().astype(idx_t, copy=False),
+                              self.indptr.cpu().numpy().astype(idx_t)), shape=self.shape)
+
+
+def wendland_aabb(x):
+    lib = L.load()
+    n, dim = x.shape
+    boxes = L.dev_empty((max(1, int(lib.fvgp_wendland_aabb_len(n, dim))),))
+    L.check(lib.fvgp_wendland_aabb(L.ptr(x), n, dim, L.ptr(boxes), L.stream_ptr()), "fvgp_wendland_aabb")
+    return boxes
+
+
+def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None):
+    """k(x1, x2) for the compact-support Wendland kernel as canonical CSR (bit-exact pattern).
+
+    Replaces the per-block dask tasks + host assembly (gp2Scale_covariance.py:136-287); `noise`
+    fuses K + diag(V) (gp_kv.py:655-661)."""
+    lib = L.load()
+    torch = L._torch()
+    n1, dim = x1.shape
+    n2 = x2.shape[0]
+    same = x1.data_ptr() == x2.data_ptr() and n1 == n2
+    if boxes1 is None:
+        boxes1 = wendland_aabb(x1)
+    if boxes2 is None:
+        boxes2 = boxes1 if same else wendland_aabb(x2)
+    _, th = L.dvec(theta)
+    counts = torch.zeros(max(n1, 1), dtype=torch.int64, device="cuda")
+    st = L.stream_ptr()
+    L.check(lib.fvgp_wendland_csr_count(L.ptr(x1), n1, L.ptr(boxes1), L.ptr(x2), n2, L.ptr(boxes2), dim, th,
+                                        L.ptr(counts), st), "fvgp_wendland_csr_count")
+    indptr = torch.empty(n1 + 1, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(int(lib.fvgp_scan_scratch_len(n1)), dtype=torch.int64, device="cuda")
+    total = c_int64()
+    L.check(lib.fvgp_exclusive_scan_i64(L.ptr(counts), n1, L.ptr(indptr), L.ptr(scratch), ctypes.byref(total), st),
+            "fvgp_exclusive_scan_i64")
+    nnz = total.value
+    indices = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    data = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    if nnz:
+        L.check(lib.fvgp_wendland_csr_fill(L.ptr(x1), n1, L.ptr(boxes1), L.ptr(x2), n2, L.ptr(boxes2), dim, th,
+                                           L.ptr(indptr), L.ptr(noise), L.ptr(indices), L.ptr(data), st),
+                "fvgp_wendland_csr_fill")
+    return DeviceCSR(indptr, indices, data, (n1, n2))
+
+
+def spmv(A, x, y=None):
+    lib = L.load()
+    if y is None:
+        y = L.dev_empty((A.shape[0],))
+    L.check(lib.fvgp_csr_spmv(A.shape[0], L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.data), L.ptr(x), L.ptr(y),
+                              L.stream_ptr()), "fvgp_csr_spmv")
+    return y
+
+
+def bjacobi(A):
+    lib = L.load()
+    blocks = L.dev_empty((int(lib.fvgp_bjacobi_len(A.shape[0])),))
+    L.check(lib.fvgp_bjacobi_build(A.shape[0], L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.data), L.ptr(blocks),
+                                   L.stream_ptr()), "fvgp_bjacobi_build")
+    return blocks
+
+
+def pcg(A, b, x0=None, rtol=1e-5, maxiter=None, precond=None):
+    """scipy.sparse.linalg.cg semantics (gp_lin_alg.py:1284-1288). Returns (x, info, iters, relres)."""
+    lib = L.load()
+    torch = L._torch()
+    n = A.shape[0]
+    x = torch.zeros(n, dtype=torch.float64, device="cuda") if x0 is None else x0.clone().contiguous()
+    work = L.dev_empty((int(lib.fvgp_pcg_work_len(n)),))
+    iters, relres = c_int(), c_double()
+    if maxiter is None:
+        maxiter = 10 * n
+    st = L.check(lib.fvgp_pcg(n, L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.data), L.ptr(precond), L.ptr(b), L.ptr(x),
+                              float(rtol), int(maxiter), L.ptr(work), ctypes.byref(iters), ctypes.byref(relres),
+                              L.stream_ptr()), "fvgp_pcg")
+    return x, st, iters.value, relres.value
+
+
+def slq_logdet(A, degree=20, probes=30, seed=0):
+    """Stochastic Lanczos quadrature estimate of log det A (gp_lin_alg.py:1103-1181, imate slq).
+
+    Device: Lanczos three-term recurrences (SpMV bound).  Host: eigen-decomposition of the
+    `degree` x `degree` tridiagonals (microseconds).  Returns (estimate, variance_of_mean, samples)."""
+    lib = L.load()
+    n = A.shape[0]
+    degree = int(min(degree, n))
+    work = L.dev_empty((int(lib.fvgp_lanczos_work_len(n, degree)),))
+    alpha = np.zeros(probes * degree)
+    beta = np.zeros(probes * degree)
+    L.check(lib.fvgp_lanczos_tridiag(n, L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.data), degree, 0, probes,
+                                     int(seed), L.ptr(work), alpha.ctypes.data_as(ctypes.POINTER(c_double)),
+                                     beta.ctypes.data_as(ctypes.POINTER(c_double)), L.stream_ptr()),
+            "fvgp_lanczos_tridiag")
+    samples = np.empty(probes)
+    for p in range(probes):
+        a = alpha[p * degree:(p + 1) * degree]
+        b = beta[p * degree:(p + 1) * degree - 1]
+        m = degree
+        small = np.nonzero(b < 1e-12 * max(1.0, np.abs(a).max()))[0]      # invariant subspace found early
+        if small.size:
+            m = int(small[0]) + 1
+        T = np.diag(a[:m]) + np.diag(b[:m - 1], 1) + np.diag(b[:m - 1], -1)
+        lam, vec = np.linalg.eigh(T)
+        samples[p] = n * np.sum(vec[0, :] ** 2 * np.log(np.maximum(lam, 1e-300)))
+    est = float(samples.mean())
+    var = float(samples.var(ddof=1) / probes) if probes > 1 else float("nan")
+    return est, var, samples

@@ -1,0 +1,161 @@
+/* fvgp_b200 -- C ABI of the B200-native fvGP training hot path.
+ *
+ * Drop-in boundary.  Every entry point replaces one Python-level
+ * function of the reference on the LML(+gradient) path; the reference function is cited
+ * as file:line into lbl-camera/fvGP.  The reference is pure Python, so the binding a
+ * maintainer adds is a ctypes stub; `fvgp_b200/_lib.py` is ours.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.
+ *  - pointers named d_* are DEVICE pointers (owned by the caller, e.g. torch tensors);
+ *    pointers named h_* are HOST pointers (small parameter vectors / scalar results).
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.  Functions
+ *    that return a scalar through an h_* pointer synchronise that stream once.
+ *  - matrices are C-order (row-major) float64 with leading dimension ld* in elements;
+ *    ld must be even and bases 16-byte aligned.
+ *  - return value: 0 ok; >0 = 1-based index of the first non-positive pivot (-> the
+ *    reference's NonPositiveDefiniteError, gp_lin_alg.py:27-58); <0 CUDA / argument error.
+ *  - no global mutable state besides one-time kernel attribute set-up; re-entrant across
+ *    streams of one device.
+ */
+#ifndef FVGP_B200_H
+#define FVGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- radial kernel families: value = amp * f(d / length), d = ||(x1 - x2) * inv_scale|| */
+enum fvgp_kernel_kind {
+  FVGP_K_MATERN32 = 0, /* kernels.py:98-118  matern_kernel_diff1; default kernel gp_prior.py:376-400 */
+  FVGP_K_MATERN52 = 1, /* kernels.py:166-188 matern_kernel_diff2 */
+  FVGP_K_SQEXP = 2,    /* kernels.py:16-33   squared_exponential_kernel */
+  FVGP_K_EXP = 3,      /* kernels.py:56-74   exponential_kernel */
+  FVGP_K_WENDLAND = 4, /* kernels.py:355-378 wendland_anisotropic (dense form) */
+  FVGP_K_DISTANCE = 5  /* kernels.py:440-481 get_(anisotropic_)distance_matrix: value = d */
+};
+
+enum fvgp_fill_mode {
+  FVGP_FILL_FULL = 0,      /* every entry of the n1 x n2 matrix */
+  FVGP_FILL_SYMMETRIC = 1, /* x1 == x2: evaluate upper tiles once, write tile + transpose */
+  FVGP_FILL_LOWER = 2      /* x1 == x2: tiles on/below the diagonal only (input of potrf) */
+};
+
+int fvgp_version(void);
+/* test / profiling hook: mirror tiles of the symmetric K-fill through TMA bulk stores (1, default)
+ * or plain coalesced stores (0).  Returns the previous setting. */
+int fvgp_set_bulk_store(int on);
+
+/* Dense covariance assembly fused with the noise diagonal.
+ * Replaces GPprior._default_kernel (gp_prior.py:376-400), kernels.get_distance_matrix /
+ * get_anisotropic_distance_matrix (kernels.py:440-481) + the radial kernels
+ * (kernels.py:16-188), and GPkv.addKV for vector noise (gp_kv.py:640-669).
+ * h_inv_scale[dim]: 1/length-scale per axis (all 1.0 = isotropic).  d_noise may be NULL. */
+int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2, int dim,
+                     double amp, const double* h_inv_scale, double length, const double* d_noise, double* d_K,
+                     int64_t ldk, void* stream);
+
+/* Gradient traces without materialising dK/dtheta (gp_marginal_likelihood.py:256-309 with
+ * gp_prior.py:421-436): for the default ARD Matern-3/2 kernel and theta = (amp, l_1..l_dim)
+ *   h_out[h] = sum_ij W_ij * dK_ij/dtheta_h,   W = Kinv - b b^T  (lower triangle of d_Kinv is read)
+ * so that grad(-LML)_h = 0.5 * h_out[h].  d_partials: workspace of fvgp_kgrad_partials_len() doubles. */
+int64_t fvgp_kgrad_partials_len(int64_t n, int dim);
+int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const double* h_theta, const double* d_Kinv,
+                              int64_t ld, const double* d_b, double* d_partials, double* h_out, void* stream);
+
+/* Dense dK/dtheta materialised, (dim+1) x n1 x n2 (GPprior._default_kernel_analytical_gradient,
+ * gp_prior.py:421-436) -- the kernel_function_grad seam (gp_prior.py:236-240). */
+int fvgp_kgrad_dense_matern32(const double* d_x1, int64_t n1, const double* d_x2, int64_t n2, int dim,
+                              const double* h_theta, double* d_out, void* stream);
+
+/* ---- dense FP64 factorisation (gp_lin_alg.py:237-360, :1558) */
+int64_t fvgp_chol_workspace_len(int64_t n);  /* doubles: per-64-tile inverses kept by potrf   */
+int64_t fvgp_potri_workspace_len(int64_t n); /* doubles: scratch panel of trtri / lauum       */
+
+/* calculate_Chol_factor (gp_lin_alg.py:237-269): in-place lower Cholesky of the lower
+ * triangle of d_A.  d_tileinv (fvgp_chol_workspace_len doubles) receives the inverses of the
+ * 64x64 diagonal tiles and must be passed unchanged to potrs / potri.  d_info: one int. */
+int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream);
+
+/* calculate_Chol_solve (gp_lin_alg.py:289-328): solve (L L^T) X = B in place.  d_B holds
+ * nrhs right-hand sides, each contiguous with stride ldb (i.e. B^T in C order).
+ * d_work: 2*n doubles. */
+int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B, int nrhs,
+                     int64_t ldb, double* d_work, void* stream);
+
+/* calculate_Chol_logdet (gp_lin_alg.py:331-360): 2 * sum log|L_ii| -> *h_out. */
+int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratch1, double* h_out, void* stream);
+
+/* calculate_inv_from_chol (gp_lin_alg.py:1558) / the trace term's KV^-1
+ * (gp_marginal_likelihood.py:273-274): lower triangle of d_L <- lower triangle of (L L^T)^-1. */
+int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_work, void* stream);
+
+/* Plain tensor-core GEMM exposed for tests / roofline measurement:
+ * C = alpha * A * B^T + beta * C with A (m x k) and B (n x k) row-major. lower!=0: lower tiles only. */
+int fvgp_dgemm_nt(const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C, int64_t ldc, int m,
+                  int n, int k, double alpha, double beta, int lower, void* stream);
+
+/* sum_i a_i * b_i -> *h_out (quadratic form of gp_marginal_likelihood.py:175). */
+int fvgp_dot(const double* d_a, const double* d_b, int64_t n, double* d_scratch1, double* h_out, void* stream);
+
+/* ---- gp2Scale: compact-support covariance straight to canonical CSR
+ * Replaces wendland_anisotropic_gp2Scale_cpu (kernels.py:502-528) evaluated per block by
+ * block_triplets / block_to_coo (gp2Scale_covariance.py:136-170) and the host assembly
+ * assemble_triplets (gp2Scale_covariance.py:240-287), and addKV's setdiag (gp_kv.py:655-661).
+ * Pass 1 counts entries per row; the caller scans counts into d_indptr (int64 or int32 is
+ * the caller's choice for the final matrix; the kernels use int64 offsets); pass 2 fills
+ * sorted column indices + values.  Pattern is bit-exact w.r.t. the reference predicate. */
+int64_t fvgp_wendland_aabb_len(int64_t n, int dim); /* doubles per point set for tile bounding boxes */
+int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, void* stream);
+int fvgp_wendland_csr_count(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
+                            const double* d_aabb2, int dim, const double* h_theta, int64_t* d_rowcount,
+                            void* stream);
+int fvgp_wendland_csr_fill(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
+                           const double* d_aabb2, int dim, const double* h_theta, const int64_t* d_indptr,
+                           const double* d_noise_diag, int32_t* d_indices, double* d_data, void* stream);
+/* exclusive scan of n counts into n+1 offsets (d_indptr[0] = 0); *h_total = nnz. */
+int fvgp_exclusive_scan_i64(const int64_t* d_counts, int64_t n, int64_t* d_indptr, int64_t* d_scratch,
+                            int64_t* h_total, void* stream);
+int64_t fvgp_scan_scratch_len(int64_t n);
+
+/* ---- sparse solve (gp_lin_alg.py:1213-1291 calculate_sparse_conj_grad -> scipy cg) */
+int fvgp_csr_spmv(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                  const double* d_x, double* d_y, void* stream);
+
+/* Block-Jacobi preconditioner: inverses of the dense bs x bs diagonal blocks of the CSR
+ * matrix (cf. calculate_sparse_preconditioner "block_jacobi", gp_lin_alg.py:604-622). bs = 32. */
+int64_t fvgp_bjacobi_len(int64_t n);
+int fvgp_bjacobi_build(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                       double* d_blocks, void* stream);
+
+/* Preconditioned CG, scipy semantics: x0 given in d_x, stop when ||r||_2 < rtol*||b||_2
+ * (checked at the top of each iteration), atol = 0.  d_precond: fvgp_bjacobi_build output
+ * or NULL (plain CG).  d_work: fvgp_pcg_work_len(n) doubles.
+ * h_iters / h_relres receive iteration count and final relative residual.
+ * Returns 0 on convergence, 1 if maxiter was reached (scipy's info > 0). */
+int64_t fvgp_pcg_work_len(int64_t n);
+int fvgp_pcg(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+             const double* d_precond, const double* d_b, double* d_x, double rtol, int maxiter, double* d_work,
+             int* h_iters, double* h_relres, void* stream);
+
+/* Stochastic Lanczos quadrature log-determinant (calculate_random_logdet,
+ * gp_lin_alg.py:1103-1181 -> imate slq): Rademacher probes (counter-based, `seed`),
+ * `degree` Lanczos steps each, full reorthogonalisation off (imate orthogonalize=0).
+ * Device part: the Lanczos recurrences; outputs the tridiagonal coefficients
+ * h_alpha[probe*degree + j], h_beta[probe*degree + j] for the host-side quadrature.
+ * d_work: fvgp_lanczos_work_len(n, degree) doubles. */
+int64_t fvgp_lanczos_work_len(int64_t n, int degree);
+int fvgp_lanczos_tridiag(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
+                         int degree, int probe0, int nprobes, uint64_t seed, double* d_work, double* h_alpha,
+                         double* h_beta, void* stream);
+
+/* ---- measurement only: register-resident FP64 issue-rate probes (which: 0 = DMMA.8x8x4,
+ * 1 = DFMA) giving the FP64 roofline denominator of the box.  d_scratch: 148*8*256 doubles. */
+int fvgp_bench_fp64_peak(int which, int ctas_per_sm, int iters, double* d_scratch, double* h_tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVGP_B200_H */
