@@ -22,9 +22,11 @@ _SIGNATURES = {
     "fvgp_set_bulk_store": (c_int, [c_int]),
     "fvgp_kfill_dense": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_double, POINTER(c_double),
                                  c_double, _P, _P, c_int64, _P]),
+    "fvgp_radial_elementwise": (c_int, [c_int, _P, c_int64, c_double, c_double, _P, _P]),
     "fvgp_kgrad_partials_len": (c_int64, [c_int64, c_int]),
     "fvgp_kgrad_trace_matern32": (c_int, [_P, c_int64, c_int, POINTER(c_double), _P, c_int64, _P, _P,
                                           POINTER(c_double), _P]),
+    "fvgp_trace_sym_product": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, POINTER(c_double), _P]),
     "fvgp_kgrad_dense_matern32": (c_int, [_P, c_int64, _P, c_int64, c_int, POINTER(c_double), _P, _P]),
     "fvgp_chol_workspace_len": (c_int64, [c_int64]),
     "fvgp_potri_workspace_len": (c_int64, [c_int64]),

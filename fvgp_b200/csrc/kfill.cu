@@ -291,6 +291,44 @@ __global__ void trace_reduce_kernel(const double* partials, int nctas, int H, do
   }
 }
 
+// Radial kernel applied elementwise to a user-supplied distance array (the fvgp.kernels
+// functions called on a plain ndarray instead of on get_distance_matrix's result).
+template <int KIND>
+__global__ void radial_elementwise_kernel(const double* __restrict__ d, long long count, double amp, double c_arg,
+                                          double c_aux, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const double v = d[i];
+    out[i] = radial_value<KIND>(v * v, amp, c_arg, c_aux);
+  }
+}
+
+// sum_ij (Kinv - b b^T)_ij * dK_ij for a materialised symmetric dK (user kernels with their own
+// gradient function); only the lower triangles are read.  One partial per CTA.
+__global__ void __launch_bounds__(256) trace_sym_product_kernel(const double* __restrict__ Kinv, long long ld,
+                                                                const double* __restrict__ b,
+                                                                const double* __restrict__ dK, long long lddk,
+                                                                long long n, double* partials) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (long long r = blockIdx.x; r < n; r += gridDim.x) {
+    const double br = b[r];
+    for (long long c = threadIdx.x; c <= r; c += blockDim.x) {
+      const double w = (Kinv[r * ld + c] - br * b[c]) * ((c == r) ? 1.0 : 2.0);
+      acc = fma(w, dK[r * lddk + c], acc);
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+__global__ void sum_partials_kernel(const double* partials, int count, double* out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s += partials[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
 __global__ void kgrad_dense_kernel(const double* __restrict__ x1, long long n1, const double* __restrict__ x2,
                                    long long n2, int dim, double amp, const double* __restrict__ len, double* out) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -360,6 +398,35 @@ int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const d
   return 0;
 }
 
+int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, double amp, double length, double* d_out,
+                            void* stream) {
+  if (count <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long want = (count + 255) / 256, cap = (long long)sm_count() * 16;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  switch (kind) {
+    case FVGP_K_MATERN32:
+      radial_elementwise_kernel<FVGP_K_MATERN32><<<grid, 256, 0, st>>>(d_dist, count, amp, sqrt(3.0) / length, 0.0, d_out);
+      break;
+    case FVGP_K_MATERN52:
+      radial_elementwise_kernel<FVGP_K_MATERN52><<<grid, 256, 0, st>>>(d_dist, count, amp, sqrt(5.0) / length,
+                                                                        5.0 / (3.0 * length * length), d_out);
+      break;
+    case FVGP_K_SQEXP:
+      radial_elementwise_kernel<FVGP_K_SQEXP><<<grid, 256, 0, st>>>(d_dist, count, amp, 1.0 / (2.0 * length * length), 0.0, d_out);
+      break;
+    case FVGP_K_EXP:
+      radial_elementwise_kernel<FVGP_K_EXP><<<grid, 256, 0, st>>>(d_dist, count, amp, 1.0 / length, 0.0, d_out);
+      break;
+    case FVGP_K_WENDLAND:
+      radial_elementwise_kernel<FVGP_K_WENDLAND><<<grid, 256, 0, st>>>(d_dist, count, amp, 1.0 / length, 0.0, d_out);
+      break;
+    default: FVGP_REQUIRE(!"unknown kernel kind");
+  }
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
 static inline long long trace_grid(int64_t n) {
   const long long t = (n + FT - 1) / FT, ntiles = t * (t + 1) / 2;
   const long long cap = (long long)sm_count() * 4;
@@ -394,6 +461,19 @@ int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const doubl
   trace_reduce_kernel<<<1, 256, 0, st>>>(d_partials, (int)grid, H, h_theta[0], d_invlen, d_out);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_out, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+  FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int fvgp_trace_sym_product(const double* d_Kinv, int64_t ld, const double* d_b, const double* d_dK, int64_t lddk,
+                           int64_t n, double* d_partials, double* h_out, void* stream) {
+  FVGP_REQUIRE(n > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)(n < (int64_t)sm_count() * 8 ? n : (int64_t)sm_count() * 8);
+  trace_sym_product_kernel<<<grid, 256, 0, st>>>(d_Kinv, ld, d_b, d_dK, lddk, n, d_partials);
+  sum_partials_kernel<<<1, 256, 0, st>>>(d_partials, grid, d_partials + grid);
+  FVGP_LAUNCH_OK();
+  FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_partials + grid, sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }

@@ -1,0 +1,67 @@
+"""Data container (reference: fvgp/gp_data.py:6-59).  Host-side bookkeeping only."""
+import numpy as np
+
+
+class GPdata:
+    def __init__(self, x_data, y_data, args=None, noise_variances=None, ram_economy=False, gp2Scale=False,
+                 compute_device="gpu", dask_client=None):
+        assert isinstance(x_data, (np.ndarray, list)), "wrong format in x_data"
+        assert isinstance(y_data, np.ndarray) and np.ndim(y_data) in (1, 2), "wrong format in y_data"
+        assert noise_variances is None or isinstance(noise_variances, np.ndarray), "wrong format in noise_variances"
+        assert len(x_data) == len(y_data), "x_data and y_data do not have the same lengths."
+        if isinstance(x_data, np.ndarray):
+            assert np.ndim(x_data) == 2, "x_data must be a 2-d array"
+            self.Euclidean = True
+            self.index_set_dim = x_data.shape[1]
+            x_data = np.ascontiguousarray(x_data, dtype=np.float64)
+        else:
+            self.Euclidean = False
+            self.index_set_dim = 1
+        if np.ndim(y_data) == 1:
+            y_data = y_data.reshape(-1, 1)                          # gp_data.py:24
+        if noise_variances is not None:
+            assert np.ndim(noise_variances) == 1, "noise_variances must be a 1-d array"
+            assert np.all(noise_variances > 0.0), "Negative or zero measurement variances communicated to fvgp."
+        self.x_data = x_data
+        self.y_data = np.ascontiguousarray(y_data, dtype=np.float64)
+        self.noise_variances = noise_variances
+        self.args = {} if args is None else args
+        self.ram_economy = ram_economy
+        self.gp2Scale = gp2Scale
+        self.compute_device = compute_device
+        self.dask_client = dask_client
+        self._x_dev = None
+
+    @property
+    def point_number(self):
+        return len(self.x_data)
+
+    def x_device(self):
+        """x_data resident on the GPU (uploaded once, 8*N*D bytes)."""
+        if self._x_dev is None:
+            from . import _lib as L
+            self._x_dev = L.to_dev(self.x_data)
+        return self._x_dev
+
+    def update(self, x_new, y_new, noise_variances_new=None, append=True):
+        """gp_data.py:93-116."""
+        if np.ndim(y_new) == 1:
+            y_new = y_new.reshape(-1, 1)
+        if append:
+            if self.noise_variances is not None:
+                if noise_variances_new is None:
+                    raise Exception("Please provide noise_variances in the data update.")
+                self.noise_variances = np.append(self.noise_variances, noise_variances_new)
+            self.x_data = np.vstack([self.x_data, x_new]) if self.Euclidean else self.x_data + x_new
+            self.y_data = np.vstack([self.y_data, y_new])
+        else:
+            self.x_data, self.y_data, self.noise_variances = x_new, y_new, noise_variances_new
+        if self.Euclidean:
+            self.x_data = np.ascontiguousarray(self.x_data, dtype=np.float64)
+        self._x_dev = None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_x_dev"] = None
+        state["dask_client"] = None
+        return state

@@ -1,0 +1,217 @@
+"""The `fvgp.kernels` names, evaluated on the B200 (reference: fvgp/kernels.py).
+
+Drop-in usage is unchanged -- e.g. the examples' user kernel
+
+    def skernel(x1, x2, hps):
+        return hps[0] * squared_exponential_kernel(get_distance_matrix(x1, x2), hps[1])
+
+-- but nothing is computed when these functions are called: `get_distance_matrix`
+returns a lazy `Distance`, the radial kernels wrap it into a lazy `Radial`, and scalar
+multiplication folds into its amplitude.  The GP then evaluates the whole expression in
+ONE fused CUDA kernel (distance + radial function + noise diagonal, straight into the
+layout the Cholesky wants) instead of the reference's D+4 full N x N numpy passes.
+`np.asarray(expr)` materialises any lazy object as a host ndarray, so code that goes on
+to do its own numpy arithmetic on the result keeps working.
+
+Only the kernels on the hot path named by the task are provided (SURVEY.md section 2 rows
+1-2): squared exponential, exponential, Matern-3/2, Matern-5/2, their distance builders
+and the anisotropic Wendland functions.  The remaining reference kernels (periodic,
+linear, polynomial, non-stationary, Wasserstein, ...) are outside this build's scope.
+"""
+import numpy as np
+
+from . import _lib as L
+from . import ops
+
+__all__ = ["squared_exponential_kernel", "exponential_kernel", "matern_kernel_diff1", "matern_kernel_diff2",
+           "get_distance_matrix", "get_anisotropic_distance_matrix", "wendland_anisotropic",
+           "wendland_anisotropic_gp2Scale_cpu", "wendland_anisotropic_gp2Scale_gpu", "matern_kernel_diff1_grad"]
+
+
+def _device_points(x):
+    """Upload (and cache per ndarray object) a point set."""
+    torch = L._torch()
+    if isinstance(x, torch.Tensor):
+        return x.to(device="cuda", dtype=torch.float64).contiguous()
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    return L.to_dev(x)
+
+
+class _Lazy:
+    """Base of the lazy covariance expressions."""
+    ndim = 2
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.to_host()
+        return out.astype(dtype) if dtype is not None else out
+
+    def to_host(self):
+        buf, _ = self.materialize()
+        return buf[:, :self.shape[1]].cpu().numpy()
+
+    def to_device(self):
+        buf, _ = self.materialize()
+        return buf[:, :self.shape[1]]
+
+    # numpy-style fallbacks: any arithmetic we cannot fold materialises on the host
+    def __add__(self, other):
+        return np.asarray(self) + np.asarray(other)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return np.asarray(self) - np.asarray(other)
+
+    def __rsub__(self, other):
+        return np.asarray(other) - np.asarray(self)
+
+    def __pow__(self, p):
+        return np.asarray(self) ** p
+
+    def __getitem__(self, item):
+        return np.asarray(self)[item]
+
+
+class Distance(_Lazy):
+    """Lazy pairwise (axis-scaled) Euclidean distance between two point sets."""
+
+    def __init__(self, x1, x2, inv_scale):
+        self.x1, self.x2 = x1, x2
+        self.same = x1 is x2
+        self.inv_scale = np.asarray(inv_scale, dtype=np.float64)
+        self.shape = (len(x1), len(x2))
+
+    def materialize(self, mode=L.FILL_FULL, noise=None, out=None):
+        d1 = _device_points(self.x1)
+        d2 = d1 if self.same else _device_points(self.x2)
+        return ops.kfill(L.K_DISTANCE, d1, d2, 1.0, self.inv_scale, 1.0, noise=noise, mode=mode, out=out)
+
+
+class Radial(_Lazy):
+    """Lazy amp * f(distance / length)."""
+
+    def __init__(self, dist, kind, length, amp=1.0):
+        self.dist, self.kind, self.length, self.amp = dist, kind, float(length), float(amp)
+        self.shape = dist.shape
+
+    def __mul__(self, s):
+        if np.isscalar(s) or (isinstance(s, np.ndarray) and s.ndim == 0):
+            return Radial(self.dist, self.kind, self.length, self.amp * float(s))
+        return np.asarray(self) * np.asarray(s)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, s):
+        if np.isscalar(s):
+            return Radial(self.dist, self.kind, self.length, self.amp / float(s))
+        return np.asarray(self) / np.asarray(s)
+
+    def materialize(self, mode=L.FILL_FULL, noise=None, out=None, x1_dev=None, x2_dev=None):
+        d = self.dist
+        d1 = x1_dev if x1_dev is not None else _device_points(d.x1)
+        d2 = x2_dev if x2_dev is not None else (d1 if d.same else _device_points(d.x2))
+        return ops.kfill(self.kind, d1, d2, self.amp, d.inv_scale, self.length, noise=noise, mode=mode, out=out)
+
+
+def _elementwise(kind, distance, length):
+    """Radial kernel of a caller-supplied distance array / scalar, evaluated on the device."""
+    lib = L.load()
+    arr = np.asarray(distance, dtype=np.float64)
+    d = L.to_dev(arr.reshape(-1))
+    out = L.dev_empty((d.numel(),))
+    L.check(lib.fvgp_radial_elementwise(kind, L.ptr(d), d.numel(), 1.0, float(length), L.ptr(out), L.stream_ptr()),
+            "fvgp_radial_elementwise")
+    res = out.cpu().numpy().reshape(arr.shape)
+    return res if arr.ndim else float(res)
+
+
+def _radial(kind, distance, length):
+    if isinstance(distance, Distance):
+        return Radial(distance, kind, length)
+    return _elementwise(kind, distance, length)
+
+
+def get_distance_matrix(x1, x2):
+    """Pairwise Euclidean distances (kernels.py:440-458), lazy."""
+    x1, x2 = np.asarray(x1), np.asarray(x2)
+    return Distance(x1, x2 if x2 is not x1 else x1, np.ones(x1.shape[1]))
+
+
+def get_anisotropic_distance_matrix(x1, x2, hps):
+    """Axis-scaled distances, hps = per-axis length scales (kernels.py:461-481), lazy."""
+    x1, x2 = np.asarray(x1), np.asarray(x2)
+    return Distance(x1, x2 if x2 is not x1 else x1, 1.0 / np.asarray(hps, dtype=np.float64)[:x1.shape[1]])
+
+
+def squared_exponential_kernel(distance, length):
+    """exp(-d^2 / (2 l^2)) (kernels.py:16-33)."""
+    return _radial(L.K_SQEXP, distance, length)
+
+
+def exponential_kernel(distance, length):
+    """exp(-d / l) (kernels.py:56-74)."""
+    return _radial(L.K_EXP, distance, length)
+
+
+def matern_kernel_diff1(distance, length):
+    """(1 + sqrt3 d/l) exp(-sqrt3 d/l) (kernels.py:98-118)."""
+    return _radial(L.K_MATERN32, distance, length)
+
+
+def matern_kernel_diff2(distance, length):
+    """(1 + sqrt5 d/l + 5 d^2/(3 l^2)) exp(-sqrt5 d/l) (kernels.py:166-188)."""
+    return _radial(L.K_MATERN52, distance, length)
+
+
+def matern_kernel_diff1_grad(distance, dist_der):
+    """kernels.py:121-141, host-side helper for user gradient functions (O(size) numpy)."""
+    a = np.sqrt(3.0) * np.asarray(distance)
+    dadl = np.sqrt(3.0) * np.asarray(dist_der)
+    ea = np.exp(-a)
+    return dadl * ea - (1.0 + a) * dadl * ea
+
+
+def wendland_anisotropic(x1, x2, hyperparameters):
+    """Dense anisotropic Wendland kernel (kernels.py:355-378), lazy."""
+    hps = np.asarray(hyperparameters, dtype=np.float64)
+    x1, x2 = np.asarray(x1), np.asarray(x2)
+    d = Distance(x1, x2 if x2 is not x1 else x1, 1.0 / hps[1:1 + x1.shape[1]])
+    return Radial(d, L.K_WENDLAND, 1.0, hps[0])
+
+
+class SparseWendland:
+    """Lazy compact-support covariance; the GP turns it into a device CSR in two kernel
+    passes (count, fill) -- see ops.wendland_csr."""
+
+    def __init__(self, x1, x2, hps):
+        self.x1, self.x2, self.hps = x1, x2, np.asarray(hps, dtype=np.float64)
+        self.same = x1 is x2
+        self.shape = (len(x1), len(x2))
+
+    def to_device_csr(self, noise=None, x1_dev=None, x2_dev=None, boxes1=None, boxes2=None):
+        d1 = x1_dev if x1_dev is not None else _device_points(self.x1)
+        d2 = x2_dev if x2_dev is not None else (d1 if self.same else _device_points(self.x2))
+        return ops.wendland_csr(d1, d2, self.hps, noise=noise, boxes1=boxes1, boxes2=boxes2)
+
+    def tocsr(self):
+        return self.to_device_csr().to_scipy()
+
+    def toarray(self):
+        return self.tocsr().toarray()
+
+    def __array__(self, dtype=None, copy=None):
+        return self.toarray()
+
+
+def wendland_anisotropic_gp2Scale_cpu(x1, x2, hps):
+    """The default gp2Scale kernel (kernels.py:502-528).  Name kept for drop-in use; it runs on
+    the GPU, in FP64, with the reference's exact rounding sequence for the support predicate."""
+    x1, x2 = np.asarray(x1), np.asarray(x2)
+    return SparseWendland(x1, x2 if x2 is not x1 else x1, hps)
+
+
+def wendland_anisotropic_gp2Scale_gpu(x1, x2, hps, args=None):
+    """kernels.py:539-591 computes this in float32 on torch/cupy; here it is the same FP64 kernel."""
+    return wendland_anisotropic_gp2Scale_cpu(x1, x2, hps)

@@ -50,6 +50,17 @@ def kgrad_trace_matern32(x, theta, kinv_buf, ld, b):
     return np.array(out[:], dtype=np.float64)
 
 
+def trace_sym_product(kinv_buf, ld, b, dK):
+    """sum_ij (Kinv - b b^T)_ij dK_ij for a materialised symmetric dK (device, row-major 2-D tensor)."""
+    lib = L.load()
+    n = b.numel()
+    partials = L.dev_empty((148 * 8 * 2 + 8,))
+    out = c_double()
+    L.check(lib.fvgp_trace_sym_product(L.ptr(kinv_buf), ld, L.ptr(b), L.ptr(dK), dK.stride(0), n, L.ptr(partials),
+                                       ctypes.byref(out), L.stream_ptr()), "fvgp_trace_sym_product")
+    return out.value
+
+
 # ------------------------------------------------------------------------------ dense factorisation
 class CholFactor:
     """Lower Cholesky factor resident on the device (+ the tile inverses potrs/potri need)."""

@@ -57,6 +57,10 @@ int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const d
                      double amp, const double* h_inv_scale, double length, const double* d_noise, double* d_K,
                      int64_t ldk, void* stream);
 
+/* The radial kernels of kernels.py:16-188 applied elementwise to a caller-supplied distance array. */
+int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, double amp, double length, double* d_out,
+                            void* stream);
+
 /* Gradient traces without materialising dK/dtheta (gp_marginal_likelihood.py:256-309 with
  * gp_prior.py:421-436): for the default ARD Matern-3/2 kernel and theta = (amp, l_1..l_dim)
  *   h_out[h] = sum_ij W_ij * dK_ij/dtheta_h,   W = Kinv - b b^T  (lower triangle of d_Kinv is read)
@@ -64,6 +68,11 @@ int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const d
 int64_t fvgp_kgrad_partials_len(int64_t n, int dim);
 int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const double* h_theta, const double* d_Kinv,
                               int64_t ld, const double* d_b, double* d_partials, double* h_out, void* stream);
+
+/* Same trace against a MATERIALISED symmetric dK (user kernel_function_grad, gp_prior.py:236-240):
+ * *h_out = sum_ij (Kinv - b b^T)_ij dK_ij.  d_partials: 148*8 + 1 doubles. */
+int fvgp_trace_sym_product(const double* d_Kinv, int64_t ld, const double* d_b, const double* d_dK, int64_t lddk,
+                           int64_t n, double* d_partials, double* h_out, void* stream);
 
 /* Dense dK/dtheta materialised, (dim+1) x n1 x n2 (GPprior._default_kernel_analytical_gradient,
  * gp_prior.py:421-436) -- the kernel_function_grad seam (gp_prior.py:236-240). */
