@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the fvGP training hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (ours;  torchrun launches N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): LML + gradient evaluations per second on config C2 -- single-task GP,
+3-D inputs, N = 50 000, default anisotropic Matern-3/2 kernel, dense FP64 Cholesky.  One "step"
+is one evaluation of log_likelihood(theta_k) AND neg_log_likelihood_gradient(theta_k) at a new
+theta_k (synthetic data of SURVEY.md section 8d, seeded).
+
+  value        evals/s with x / y / noise resident in HBM, timed with CUDA events on the launching
+               stream, barrier + synchronize on both sides, max over ranks.
+  e2e          same metric through the public API with HOST buffers: every step re-uploads x from
+               pinned host memory and reads LML and gradient back (copies inside the timed region).
+  roofline     dominant kernel = the DMMA GEMM behind POTRF + POTRI: algorithmic N^3 flop / (CUDA-event
+               time of the potrf + potri phases); peak = DMMA issue rate measured live in this run
+               (MEASURED_PEAKS.json has no FP64 figure).  roofline_kfill: the K-assembly kernel against HBM.
+  cpu_baseline the numpy/scipy oracle port of the reference algorithm on the host cores, on a bounded
+               sample (smaller N), extrapolated with N^3 (the reference gradient needs (3H+3) 8 N^2 bytes
+               = 300 GB at N = 50k and cannot run); reported, not the target.
+N > 1: hyperparameter proposals are independent evaluations (MCMC / DE populations), so each rank
+evaluates its own theta sequence on a replica of the data -- no data-path collective ("weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def synthetic_c2(n, seed=2):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, 3))
+    y = np.sin(5 * x[:, 0]) * np.cos(3 * x[:, 1]) + x[:, 2] + 0.1 * rng.standard_normal(n)
+    return x, y, np.full(n, 1e-2)
+
+
+def theta_k(k, rank=0):
+    return np.array([1.0, .3, .4, .5]) * (1.0 + 0.02 * ((k + 7 * rank) % 20))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline_step(x, y, noise, theta, orc):
+    """Reference algorithm (stacked LU solves of KV against dK/dtheta) on the host cores."""
+    lml = orc.dense_log_likelihood(x, y, theta, noise)
+    grad = orc.dense_neg_log_likelihood_gradient(x, y, theta, noise, economical=False)
+    return lml, grad
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (numpy/scipy oracle port; the reference itself is
+    pure Python and absent on the GPU box) timed on the host cores, bounded sample, N^3-extrapolated."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import fvgp_oracle as orc
+    ns = args.cpu_sample_n
+    x, y, noise = synthetic_c2(ns)
+    for k in range(min(args.warmup, 1)):
+        cpu_baseline_step(x, y, noise, theta_k(k), orc)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_baseline_step(x, y, noise, theta_k(k), orc)
+    per = (time.perf_counter() - t0) / args.steps
+    scale = (args.n / ns) ** 3
+    value = 1.0 / (per * scale)
+    cores = os.cpu_count()
+    sample = (f"oracle port of the reference algorithm (K-fill numpy, scipy cho_factor, H stacked LU solves) at N={ns}: "
+              f"{per:.2f} s per LML+gradient on {cores} host threads; extrapolated x(N/{ns})^3 to N={args.n} "
+              f"(the reference gradient needs ~{(3 * 4 + 3) * 8 * args.n ** 2 / 1e9:.0f} GB at N={args.n})")
+    line = {"impl": "reference", "metric": "LML+gradient evals/s (dense, N=50k, 3D, ARD Matern-3/2)",
+            "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"C2: single-task GP, 3-D input, N={args.n}, anisotropic Matern-3/2 (default kernel), dense FP64 "
+                        f"Cholesky, LML + hyperparameter gradient per step",
+            "n": args.n, "dim": 3, "hyperparameters": 4, "parallelism": f"replicas x{args.gpus} (one theta proposal per GPU)",
+            "l2_policy": f"inputs larger than L2: K is {8 * args.n ** 2 / 1e9:.1f} GB"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=50000)
+    ap.add_argument("--cpu-sample-n", type=int, default=3000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from fvgp_b200 import GP, ops, parallel
+    from fvgp_b200 import _lib as L
+    rank, local_rank, world = parallel.init()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    lib = L.load()
+    n = args.n
+    x, y, noise = synthetic_c2(n)
+    x_pinned = torch.from_numpy(x).pin_memory()
+    gp = GP(x, y, init_hyperparameters=theta_k(0), noise_variances=noise)
+    H = 4
+
+    def step(k):
+        th = theta_k(k, rank)
+        return gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for k in range(args.warmup):
+        step(k)
+    sampler = ClockSampler(local_rank)
+    parallel.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = lib.fvgp_launch_count()
+    ops.start_phase_timing()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        out = step(args.warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    phases = ops.stop_phase_timing()
+    launches = lib.fvgp_launch_count() - launches0
+    clocks = sampler.summary()
+    t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    # ---- end to end: host buffers in, host results out ---------------------------------------
+    parallel.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        gp.data._x_dev = x_pinned.cuda(non_blocking=True)          # H2D of this step's inputs
+        lml, grad = step(args.warmup + args.steps + k)
+        assert np.isfinite(lml) and np.all(np.isfinite(grad))
+    torch.cuda.synchronize()
+    t_e2e = parallel.max_over_ranks(time.perf_counter() - t0)
+    h2d = x.nbytes + 2 * n * 8                                      # x, y - m, noise diagonal
+    d2h = n * 8 + 8 + 4 + H * 8                                     # KVinvY, logdet, potrf status, traces
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (DMMA GEMM inside potrf + potri) ----------------------
+    import ctypes
+    scratch = L.dev_empty((148 * 8 * 256,))
+    pk = ctypes.c_double()
+    lib.fvgp_bench_fp64_peak(0, 2, 20000, L.ptr(scratch), ctypes.byref(pk), L.stream_ptr())
+    t_tensor = (phases.get("potrf", 0.0) + phases.get("potri", 0.0)) / args.steps
+    achieved = n ** 3 / t_tensor / 1e12
+    roofline = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri", "achieved": achieved,
+                "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value, "traffic": None,
+                "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
+                "algorithmic_flops_per_step": float(n) ** 3,
+                "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    out_buf = L.dev_matrix(n, n)
+    xd, nd = gp.data.x_device(), L.to_dev(noise)
+    th = theta_k(1)
+    best = 1e30
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.kfill(L.K_MATERN32, xd, xd, th[0], 1 / th[1:], 1.0, noise=nd, mode=L.FILL_SYMMETRIC, out=out_buf)
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    kfill_gbs = 8.0 * n * n / best / 1e9
+    roofline_kfill = {"bound": "hbm", "kernel": "kfill_kernel<MATERN32,3> symmetric (full square + noise diagonal)",
+                      "achieved": kfill_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": kfill_gbs / hbm_peak,
+                      "traffic": None, "peak_source": hbm_src, "algorithmic_bytes": 8.0 * n * n}
+    del out_buf
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import fvgp_oracle as orc
+        ns = args.cpu_sample_n
+        xs, ys, vs = synthetic_c2(ns)
+        t0 = time.perf_counter()
+        cpu_baseline_step(xs, ys, vs, theta_k(1), orc)
+        per = time.perf_counter() - t0
+        cpu = {"value": 1.0 / (per * (n / ns) ** 3), "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle port of the reference algorithm, one LML+gradient at N={ns} took {per:.2f} s on "
+                         f"{os.cpu_count()} host threads, extrapolated x(N/{ns})^3 to N={n}"}
+
+    line = {"metric": "LML+gradient evals/s (dense, N=50k, 3D, ARD Matern-3/2)",
+            "value": world * args.steps / t_dev, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": world * args.steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_kfill": roofline_kfill,
+            "cpu_baseline": cpu, "last_lml": out[0]}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

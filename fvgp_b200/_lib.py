@@ -19,6 +19,7 @@ FILL_FULL, FILL_SYMMETRIC, FILL_LOWER = range(3)
 _P = c_void_p
 _SIGNATURES = {
     "fvgp_version": (c_int, []),
+    "fvgp_launch_count": (ctypes.c_ulonglong, []),
     "fvgp_set_bulk_store": (c_int, [c_int]),
     "fvgp_kfill_dense": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_double, POINTER(c_double),
                                  c_double, _P, _P, c_int64, _P]),

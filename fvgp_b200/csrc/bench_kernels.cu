@@ -54,8 +54,8 @@ int fvgp_bench_fp64_peak(int which, int ctas_per_sm, int iters, double* d_scratc
   FVGP_CUDA_OK(cudaEventCreate(&e1));
   for (int rep = 0; rep < 3; ++rep) {  // last repetition is the timed one
     FVGP_CUDA_OK(cudaEventRecord(e0, st));
-    if (which == 0) dmma_peak_kernel<<<grid, 256, 0, st>>>(d_scratch, iters);
-    else dfma_peak_kernel<<<grid, 256, 0, st>>>(d_scratch, iters);
+    if (which == 0) launch(dmma_peak_kernel, grid, 256, 0, st, d_scratch, iters);
+    else launch(dfma_peak_kernel, grid, 256, 0, st, d_scratch, iters);
     FVGP_CUDA_OK(cudaEventRecord(e1, st));
     FVGP_CUDA_OK(cudaEventSynchronize(e1));
   }

@@ -27,7 +27,18 @@
     }                                                                                \
   } while (0)
 
+#include <utility>
+
 namespace fvgp {
+
+// Every kernel of the library is launched through this helper so that the number of launches
+// (bench.py's "gpu_launches") is counted, not estimated.
+extern unsigned long long g_launches;
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  kernel<<<grid, block, smem, st>>>(std::forward<Args>(args)...);
+  ++g_launches;
+}
 
 constexpr int kMaxDim = 8;  // input-space dimensionality supported by the fused kernels
 

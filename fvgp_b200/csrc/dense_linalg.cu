@@ -20,6 +20,8 @@
 
 namespace fvgp {
 
+unsigned long long g_launches = 0;
+
 constexpr int TS = 64;  // diagonal tile size
 constexpr size_t POTRF_TILE_SMEM = (2 * TS * (TS + 1) + TS) * sizeof(double);
 
@@ -225,7 +227,7 @@ static int trsm_rn_rec(Ctx& c, double* B, long long ldb, int m, const double* L,
 
 static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
   if (n <= TS) {
-    potrf_tile_kernel<<<1, 256, POTRF_TILE_SMEM, c.st>>>(A, ld, n, c.dinv + (long long)(row0 / TS) * TS * TS, c.info,
+    launch(potrf_tile_kernel, 1, 256, POTRF_TILE_SMEM, c.st, A, ld, n, c.dinv + (long long)(row0 / TS) * TS * TS, c.info,
                                                           row0);
     FVGP_LAUNCH_OK();
     return 0;
@@ -243,7 +245,7 @@ static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
 static int trtri_rec(Ctx& c, double* L, long long ld, int n, int row0) {
   if (n <= TS) {
     const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
-    copy2d_kernel<<<dim3(1, (n + 15) / 16), 64, 0, c.st>>>(L, ld, tile, TS, n, n);
+    launch(copy2d_kernel, dim3(1, (n + 15) / 16), 64, 0, c.st, L, ld, tile, TS, n, n);
     FVGP_LAUNCH_OK();
     return 0;
   }
@@ -269,7 +271,7 @@ static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
   REC_OK((launch_gemm<true, true>(c.st, M21, ld, M21, ld, M, ld, n1, n1, n2, 1.0, 1.0, GEMM_LOWER)));
   // W = M22^T M21  (M22 lower: k >= row of the output)
   REC_OK((launch_gemm<true, true>(c.st, M22, ld, M21, ld, c.work, n1, n2, n1, n2, 1.0, 0.0, GEMM_KB_FROM_M)));
-  copy2d_kernel<<<dim3((n1 + 255) / 256, (n2 + 15) / 16), 256, 0, c.st>>>(M21, ld, c.work, n1, n2, n1);
+  launch(copy2d_kernel, dim3((n1 + 255) / 256, (n2 + 15) / 16), 256, 0, c.st, M21, ld, c.work, n1, n2, n1);
   FVGP_LAUNCH_OK();
   return lauum_rec(c, M22, ld, n2);
 }
@@ -281,6 +283,8 @@ using namespace fvgp;
 extern "C" {
 
 int fvgp_version(void) { return 100; }
+
+unsigned long long fvgp_launch_count(void) { return g_launches; }
 
 int64_t fvgp_chol_workspace_len(int64_t n) { return ((n + TS - 1) / TS) * (int64_t)TS * TS; }
 
@@ -329,13 +333,13 @@ int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_
       const int j0 = t * TS;
       const int rest = (int)n - (j0 + TS);
       const int grid = rest > 0 ? (rest + 63) / 64 : 1;
-      fwd_step_kernel<<<grid, 256, 0, st>>>(d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, w, z);
+      launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, w, z);
     }
     FVGP_LAUNCH_OK();
     for (int t = tiles - 1; t >= 0; --t) {
       const int j0 = t * TS;
       const int grid = j0 > 0 ? (j0 + 255) / 256 : 1;
-      bwd_step_kernel<<<grid, 256, 0, st>>>(d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, z, b);
+      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, z, b);
     }
     FVGP_LAUNCH_OK();
   }
@@ -344,7 +348,7 @@ int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_
 
 int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratch1, double* h_out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  logdet_kernel<<<1, 1024, 0, st>>>(d_L, lda, (int)n, d_scratch1);
+  launch(logdet_kernel, 1, 1024, 0, st, d_L, lda, (int)n, d_scratch1);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_scratch1, sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
@@ -353,7 +357,7 @@ int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratc
 
 int fvgp_dot(const double* d_a, const double* d_b, int64_t n, double* d_scratch1, double* h_out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  dot_kernel<<<1, 1024, 0, st>>>(d_a, d_b, n, d_scratch1);
+  launch(dot_kernel, 1, 1024, 0, st, d_a, d_b, n, d_scratch1);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_scratch1, sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
@@ -364,7 +368,7 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
   FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   Ctx c{st, const_cast<double*>(d_tileinv), nullptr, d_work, 0};
-  zero_upper_diag_blocks_kernel<<<(unsigned)((n + BM - 1) / BM), 256, 0, st>>>(d_L, lda, (int)n);
+  launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, st, d_L, lda, (int)n);
   FVGP_LAUNCH_OK();
   int r = trtri_rec(c, d_L, lda, (int)n, 0);
   if (r != 0) return r;

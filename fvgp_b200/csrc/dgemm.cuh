@@ -237,7 +237,7 @@ inline int launch_gemm(cudaStream_t st, const double* A, long long lda, const do
   } else {
     tiles = (long long)p.tiles_m * p.tiles_n;
   }
-  dgemm_mma_kernel<A_MN, B_MN><<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  launch(dgemm_mma_kernel<A_MN, B_MN>, (unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, st, p);
   FVGP_LAUNCH_OK();
   return 0;
 }

@@ -190,7 +190,7 @@ static int launch_fill_dim(const FillParams& p, cudaStream_t st) {
                                         (int)smem));                                                      \
       cfg = true;                                                                                         \
     }                                                                                                     \
-    kfill_kernel<KIND, DIMV><<<grid, FILL_THREADS, smem, st>>>(p);                                        \
+    launch(kfill_kernel<KIND, DIMV>, grid, FILL_THREADS, smem, st, p);                                        \
   }
   switch (p.dim) {
     case 1: FVGP_FILL_CASE(1) break;
@@ -406,20 +406,20 @@ int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, doubl
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   switch (kind) {
     case FVGP_K_MATERN32:
-      radial_elementwise_kernel<FVGP_K_MATERN32><<<grid, 256, 0, st>>>(d_dist, count, amp, sqrt(3.0) / length, 0.0, d_out);
+      launch(radial_elementwise_kernel<FVGP_K_MATERN32>, grid, 256, 0, st, d_dist, count, amp, sqrt(3.0) / length, 0.0, d_out);
       break;
     case FVGP_K_MATERN52:
-      radial_elementwise_kernel<FVGP_K_MATERN52><<<grid, 256, 0, st>>>(d_dist, count, amp, sqrt(5.0) / length,
+      launch(radial_elementwise_kernel<FVGP_K_MATERN52>, grid, 256, 0, st, d_dist, count, amp, sqrt(5.0) / length,
                                                                         5.0 / (3.0 * length * length), d_out);
       break;
     case FVGP_K_SQEXP:
-      radial_elementwise_kernel<FVGP_K_SQEXP><<<grid, 256, 0, st>>>(d_dist, count, amp, 1.0 / (2.0 * length * length), 0.0, d_out);
+      launch(radial_elementwise_kernel<FVGP_K_SQEXP>, grid, 256, 0, st, d_dist, count, amp, 1.0 / (2.0 * length * length), 0.0, d_out);
       break;
     case FVGP_K_EXP:
-      radial_elementwise_kernel<FVGP_K_EXP><<<grid, 256, 0, st>>>(d_dist, count, amp, 1.0 / length, 0.0, d_out);
+      launch(radial_elementwise_kernel<FVGP_K_EXP>, grid, 256, 0, st, d_dist, count, amp, 1.0 / length, 0.0, d_out);
       break;
     case FVGP_K_WENDLAND:
-      radial_elementwise_kernel<FVGP_K_WENDLAND><<<grid, 256, 0, st>>>(d_dist, count, amp, 1.0 / length, 0.0, d_out);
+      launch(radial_elementwise_kernel<FVGP_K_WENDLAND>, grid, 256, 0, st, d_dist, count, amp, 1.0 / length, 0.0, d_out);
       break;
     default: FVGP_REQUIRE(!"unknown kernel kind");
   }
@@ -447,18 +447,18 @@ int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const doubl
   for (int i = 0; i < kMaxDim; ++i) inv_len[i] = p.inv_len[i] = i < dim ? 1.0 / h_theta[1 + i] : 0.0;
   const unsigned grid = (unsigned)trace_grid(n);
   switch (dim) {
-    case 1: kgrad_trace_kernel<1><<<grid, FILL_THREADS, 0, st>>>(p); break;
-    case 2: kgrad_trace_kernel<2><<<grid, FILL_THREADS, 0, st>>>(p); break;
-    case 3: kgrad_trace_kernel<3><<<grid, FILL_THREADS, 0, st>>>(p); break;
-    case 4: kgrad_trace_kernel<4><<<grid, FILL_THREADS, 0, st>>>(p); break;
-    default: kgrad_trace_kernel<0><<<grid, FILL_THREADS, 0, st>>>(p); break;
+    case 1: launch(kgrad_trace_kernel<1>, grid, FILL_THREADS, 0, st, p); break;
+    case 2: launch(kgrad_trace_kernel<2>, grid, FILL_THREADS, 0, st, p); break;
+    case 3: launch(kgrad_trace_kernel<3>, grid, FILL_THREADS, 0, st, p); break;
+    case 4: launch(kgrad_trace_kernel<4>, grid, FILL_THREADS, 0, st, p); break;
+    default: launch(kgrad_trace_kernel<0>, grid, FILL_THREADS, 0, st, p); break;
   }
   FVGP_LAUNCH_OK();
   const int H = dim + 1;
   double* d_out = d_partials + (long long)grid * H;
   double* d_invlen = d_out + H;
   FVGP_CUDA_OK(cudaMemcpyAsync(d_invlen, inv_len, dim * sizeof(double), cudaMemcpyHostToDevice, st));
-  trace_reduce_kernel<<<1, 256, 0, st>>>(d_partials, (int)grid, H, h_theta[0], d_invlen, d_out);
+  launch(trace_reduce_kernel, 1, 256, 0, st, d_partials, (int)grid, H, h_theta[0], d_invlen, d_out);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_out, H * sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
@@ -470,8 +470,8 @@ int fvgp_trace_sym_product(const double* d_Kinv, int64_t ld, const double* d_b, 
   FVGP_REQUIRE(n > 0);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)(n < (int64_t)sm_count() * 8 ? n : (int64_t)sm_count() * 8);
-  trace_sym_product_kernel<<<grid, 256, 0, st>>>(d_Kinv, ld, d_b, d_dK, lddk, n, d_partials);
-  sum_partials_kernel<<<1, 256, 0, st>>>(d_partials, grid, d_partials + grid);
+  launch(trace_sym_product_kernel, grid, 256, 0, st, d_Kinv, ld, d_b, d_dK, lddk, n, d_partials);
+  launch(sum_partials_kernel, 1, 256, 0, st, d_partials, grid, d_partials + grid);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_partials + grid, sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
@@ -488,7 +488,7 @@ int fvgp_kgrad_dense_matern32(const double* d_x1, int64_t n1, const double* d_x2
   FVGP_CUDA_OK(cudaMemcpyAsync(d_len, h_theta + 1, dim * sizeof(double), cudaMemcpyHostToDevice, st));
   dim3 grid((unsigned)((n2 + 255) / 256), (unsigned)n1);
   FVGP_REQUIRE(n1 <= 65535);
-  kgrad_dense_kernel<<<grid, 256, 0, st>>>(d_x1, n1, d_x2, n2, dim, h_theta[0], d_len, d_out);
+  launch(kgrad_dense_kernel, grid, 256, 0, st, d_x1, n1, d_x2, n2, dim, h_theta[0], d_len, d_out);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaFreeAsync(d_len, st));
   return 0;

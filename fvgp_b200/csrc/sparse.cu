@@ -562,12 +562,12 @@ template <bool FILL>
 static int launch_wendland(const WendlandParams& p, cudaStream_t st) {
   const unsigned grid = (unsigned)((p.tiles1 + W_WARPS - 1) / W_WARPS);
   switch (p.dim) {
-    case 1: wendland_csr_kernel<1, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
-    case 2: wendland_csr_kernel<2, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
-    case 3: wendland_csr_kernel<3, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
-    case 4: wendland_csr_kernel<4, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
-    case 5: wendland_csr_kernel<5, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
-    case 6: wendland_csr_kernel<6, FILL><<<grid, W_WARPS * 32, 0, st>>>(p); break;
+    case 1: launch(wendland_csr_kernel<1, FILL>, grid, W_WARPS * 32, 0, st, p); break;
+    case 2: launch(wendland_csr_kernel<2, FILL>, grid, W_WARPS * 32, 0, st, p); break;
+    case 3: launch(wendland_csr_kernel<3, FILL>, grid, W_WARPS * 32, 0, st, p); break;
+    case 4: launch(wendland_csr_kernel<4, FILL>, grid, W_WARPS * 32, 0, st, p); break;
+    case 5: launch(wendland_csr_kernel<5, FILL>, grid, W_WARPS * 32, 0, st, p); break;
+    case 6: launch(wendland_csr_kernel<6, FILL>, grid, W_WARPS * 32, 0, st, p); break;
     default: FVGP_REQUIRE(!"gp2Scale Wendland supports 1..6 input dimensions");
   }
   FVGP_LAUNCH_OK();
@@ -603,9 +603,9 @@ int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, vo
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t tiles = (n + WT - 1) / WT, supers = (tiles + WS - 1) / WS;
-  aabb_tiles_kernel<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, st>>>(d_x, n, dim, d_aabb, tiles);
+  launch(aabb_tiles_kernel, (unsigned)((tiles * 32 + 255) / 256), 256, 0, st, d_x, n, dim, d_aabb, tiles);
   FVGP_LAUNCH_OK();
-  aabb_super_kernel<<<(unsigned)((supers * 32 + 255) / 256), 256, 0, st>>>(d_aabb, dim, tiles, supers);
+  launch(aabb_super_kernel, (unsigned)((supers * 32 + 255) / 256), 256, 0, st, d_aabb, dim, tiles, supers);
   FVGP_LAUNCH_OK();
   return 0;
 }
@@ -643,9 +643,9 @@ int fvgp_exclusive_scan_i64(const int64_t* d_counts, int64_t n, int64_t* d_indpt
     return 0;
   }
   const long long nblk = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
-  scan_block_sums_kernel<<<(unsigned)nblk, 256, 0, st>>>((const long long*)d_counts, n, (long long*)d_scratch);
-  scan_sums_kernel<<<1, 32, 0, st>>>((long long*)d_scratch, nblk);
-  scan_apply_kernel<<<(unsigned)nblk, 256, 0, st>>>((const long long*)d_counts, n, (const long long*)d_scratch,
+  launch(scan_block_sums_kernel, (unsigned)nblk, 256, 0, st, (const long long*)d_counts, n, (long long*)d_scratch);
+  launch(scan_sums_kernel, 1, 32, 0, st, (long long*)d_scratch, nblk);
+  launch(scan_apply_kernel, (unsigned)nblk, 256, 0, st, (const long long*)d_counts, n, (const long long*)d_scratch,
                                                     (long long*)d_indptr, nblk);
   FVGP_LAUNCH_OK();
   if (h_total) {
@@ -660,7 +660,7 @@ int fvgp_csr_spmv(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, 
   if (n <= 0) return 0;
   const long long want = (n * 32 + KR_THREADS - 1) / KR_THREADS;
   const unsigned grid = (unsigned)(want < (long long)sm_count() * 16 ? want : (long long)sm_count() * 16);
-  spmv_kernel<<<grid, KR_THREADS, 0, (cudaStream_t)stream>>>(n, (const long long*)d_indptr, d_indices, d_data, d_x,
+  launch(spmv_kernel, grid, KR_THREADS, 0, (cudaStream_t)stream, n, (const long long*)d_indptr, d_indices, d_data, d_x,
                                                              d_y);
   FVGP_LAUNCH_OK();
   return 0;
@@ -672,7 +672,7 @@ int fvgp_bjacobi_build(int64_t n, const int64_t* d_indptr, const int32_t* d_indi
                        double* d_blocks, void* stream) {
   if (n <= 0) return 0;
   const long long nblk = (n + 31) / 32;
-  bjacobi_build_kernel<<<(unsigned)((nblk + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+  launch(bjacobi_build_kernel, (unsigned)((nblk + 3) / 4), 128, 0, (cudaStream_t)stream, 
       n, (const long long*)d_indptr, d_indices, d_data, d_blocks);
   FVGP_LAUNCH_OK();
   return 0;
@@ -696,7 +696,7 @@ int fvgp_pcg(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const
   const long long* ip = (const long long*)d_indptr;
   FVGP_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(KrylovScalars), st));
   FVGP_CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(double), st));
-  pcg_init_kernel<<<grid, KR_THREADS, 0, st>>>(n, ip, d_indices, d_data, d_b, d_x, r, rtol, sc, partials);
+  launch(pcg_init_kernel, grid, KR_THREADS, 0, st, n, ip, d_indices, d_data, d_b, d_x, r, rtol, sc, partials);
   FVGP_LAUNCH_OK();
   KrylovScalars h;
   int launched = 0;
@@ -706,10 +706,10 @@ int fvgp_pcg(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const
     FVGP_CUDA_OK(cudaStreamSynchronize(st));
     if (h.done || launched >= maxiter) break;
     for (int k = 0; k < batch && launched < maxiter; ++k, ++launched) {
-      pcg_precond_kernel<<<grid, KR_THREADS, 0, st>>>(n, d_precond, r, z, sc, partials);
-      pcg_update_p_kernel<<<grid, KR_THREADS, 0, st>>>(n, z, p, sc);
-      pcg_spmv_kernel<<<grid, KR_THREADS, 0, st>>>(n, ip, d_indices, d_data, p, q, sc, partials);
-      pcg_update_xr_kernel<<<grid, KR_THREADS, 0, st>>>(n, p, q, d_x, r, sc, partials, maxiter);
+      launch(pcg_precond_kernel, grid, KR_THREADS, 0, st, n, d_precond, r, z, sc, partials);
+      launch(pcg_update_p_kernel, grid, KR_THREADS, 0, st, n, z, p, sc);
+      launch(pcg_spmv_kernel, grid, KR_THREADS, 0, st, n, ip, d_indices, d_data, p, q, sc, partials);
+      launch(pcg_update_xr_kernel, grid, KR_THREADS, 0, st, n, p, q, d_x, r, sc, partials, maxiter);
     }
     FVGP_LAUNCH_OK();
   }
@@ -737,11 +737,11 @@ int fvgp_lanczos_tridiag(int64_t n, const int64_t* d_indptr, const int32_t* d_in
   const long long* ip = (const long long*)d_indptr;
   for (int pr = 0; pr < nprobes; ++pr) {
     FVGP_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(KrylovScalars), st));
-    lanczos_start_kernel<<<grid, KR_THREADS, 0, st>>>(n, seed, (unsigned long long)(probe0 + pr), v, vprev, sc);
+    launch(lanczos_start_kernel, grid, KR_THREADS, 0, st, n, seed, (unsigned long long)(probe0 + pr), v, vprev, sc);
     for (int j = 0; j < degree; ++j) {
-      lanczos_spmv_kernel<<<grid, KR_THREADS, 0, st>>>(n, ip, d_indices, d_data, v, vprev, w, sc, partials);
-      lanczos_axpy_kernel<<<grid, KR_THREADS, 0, st>>>(n, v, w, sc, partials, d_alpha + j, d_beta + j);
-      lanczos_shift_kernel<<<grid, KR_THREADS, 0, st>>>(n, v, vprev, w, sc);
+      launch(lanczos_spmv_kernel, grid, KR_THREADS, 0, st, n, ip, d_indices, d_data, v, vprev, w, sc, partials);
+      launch(lanczos_axpy_kernel, grid, KR_THREADS, 0, st, n, v, w, sc, partials, d_alpha + j, d_beta + j);
+      launch(lanczos_shift_kernel, grid, KR_THREADS, 0, st, n, v, vprev, w, sc);
     }
     FVGP_LAUNCH_OK();
     FVGP_CUDA_OK(cudaMemcpyAsync(h_alpha + (size_t)pr * degree, d_alpha, degree * sizeof(double),

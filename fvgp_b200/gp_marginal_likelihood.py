@@ -1,0 +1,155 @@
+"""Log marginal likelihood and its gradient (reference: fvgp/gp_marginal_likelihood.py).
+
+log_likelihood            :137-179   L = -1/2 ( (y-m)^T KV^-1 (y-m) / r + log|KV| + n log 2 pi )
+neg_log_likelihood_gradient :224-309 g_i = -1/2 ( b^T dK_i b - tr(KV^-1 dK_i) )
+
+The reference forms dK/dtheta as H dense N x N arrays and obtains the traces through
+H stacked LU solves (gp_lin_alg.py:1581-1626): (3H+3) N^2 doubles and H*(8/3) N^3 flops.
+Here KV^-1 comes from the Cholesky factor on the tensor cores (2/3 N^3 flops, in place) and
+tr(KV^-1 dK_i) - b^T dK_i b = sum((KV^-1 - b b^T) o dK_i) is reduced tile by tile with dK_i
+regenerated in registers, so nothing of size H x N x N ever exists.
+"""
+import numpy as np
+
+from . import _lib as L
+from . import ops
+
+
+class GPMarginalLikelihood:
+    def __init__(self, data, prior, likelihood, trainer, kv):
+        self.data, self.prior, self.likelihood, self.trainer, self.kv = data, prior, likelihood, trainer, kv
+        self._warm_start_KVinvY = None
+
+    @property
+    def args(self):
+        return self.data.args
+
+    def _x0(self):
+        if not bool(self.args.get("sparse_krylov_warm_start", False)):
+            return None
+        for cand in (self._warm_start_KVinvY, self.kv.KVinvY):
+            if cand is not None and cand.shape == self.data.y_data.shape:
+                return cand
+        return None
+
+    # ------------------------------------------------------------------------------------------
+    def log_likelihood(self, hyperparameters=None):
+        y = self.data.y_data
+        if hyperparameters is None:
+            m, KVinvY, logdet = self.prior.m, self.kv.KVinvY, self.kv.logdet_KV
+        else:
+            hps = np.asarray(hyperparameters, dtype=np.float64)
+            V = self.likelihood.calculate_V(self.data.x_data, hps)
+            m = self.prior.compute_mean(self.data.x_data, hps)
+            try:
+                ev = self.kv.evaluate(hps, V, m, x0=self._x0(), want_factor=False)
+            except Exception as e:
+                raise Exception(f"Linear algebra failed for hyperparameters {hyperparameters}: {e}") from e
+            KVinvY, logdet = ev.KVinvY, ev.logdet
+            if bool(self.args.get("sparse_krylov_warm_start", False)):
+                self._warm_start_KVinvY = np.array(KVinvY, copy=True)
+        y_mean = y - m[:, None]
+        l1 = np.sum(y_mean * KVinvY) / y_mean.shape[1]
+        return float(-0.5 * (l1 + logdet + len(y) * np.log(2.0 * np.pi)))
+
+    def log_likelihood_variance(self):
+        v = getattr(self.kv, "last_logdet_variance", None)
+        return None if v is None else 0.25 * float(v)
+
+    def neg_log_likelihood(self, hyperparameters=None):
+        return -self.log_likelihood(hyperparameters=hyperparameters)
+
+    # ------------------------------------------------------------------------------------------
+    def neg_log_likelihood_gradient(self, hyperparameters=None, component=0):
+        if self.data.gp2Scale:
+            raise Exception("Can't compute neg_log_likelihood_gradient for gp2Scale")      # :240
+        hps = np.asarray(self.trainer.hyperparameters if hyperparameters is None else hyperparameters,
+                         dtype=np.float64)
+        x = self.data.x_data
+        n, H = len(x), len(hps)
+        V = self.likelihood.calculate_V(x, hps)
+        m = self.prior.compute_mean(x, hps)
+        ev = self.kv.evaluate(hps, V, m, want_logdet=False)
+        if ev.factor is None:
+            return self._gradient_host(hps, V, ev, component)
+        b_dev = ev.alpha_dev[component].contiguous()
+        b = ev.KVinvY[:, component]
+        ops.potri(ev.factor)                                   # lower(buf) <- lower(KV^-1)
+        fused = self.prior.default_kernel and self.prior.kernel_grad is None
+        if fused:
+            traces = ops.kgrad_trace_matern32(self.data.x_device(), hps, ev.factor.buf, ev.factor.ld, b_dev)
+        dV = self.likelihood.calculate_V_grad(x, hps)
+        have_dV = np.any(dV != 0.0)
+        if have_dV:
+            assert np.ndim(dV) == 2, "noise gradient must be 2-d (one diagonal per hyperparameter) on the GPU path"
+            wdiag = ev.factor.buf[:, :n].diagonal().cpu().numpy() - b * b
+        dm = self.prior.dm_dh(x, hps)
+        grad = np.zeros(H)
+        for i in range(H):
+            gm = float(-dm[i] @ b)
+            if gm == 0.0:                                      # the reference's switch, :301-308
+                if fused:
+                    t = traces[i]
+                else:
+                    dK = self.prior.dk_dh(x, x, hps, direction=i) if self.data.ram_economy \
+                        else self._dk_all(x, hps)[i]
+                    t = ops.trace_sym_product(ev.factor.buf, ev.factor.ld, b_dev, L.to_dev(np.asarray(dK)))
+                if have_dV:
+                    t += float(np.sum(wdiag * dV[i]))
+                grad[i] = 0.5 * t
+            grad[i] += gm
+        self._dk_cache = None
+        return grad
+
+    _dk_cache = None
+
+    def _dk_all(self, x, hps):
+        if self._dk_cache is None:
+            try:
+                self._dk_cache = self.prior.dk_dh(x, x, hps)
+            except Exception as e:
+                raise Exception("The gradient evaluation dK/dh + dNoise/dh was not successful. That normally means "
+                                "the combination of ram_economy and definition of the gradient function is wrong.") from e
+        return self._dk_cache
+
+    def _gradient_host(self, hps, V, ev, component):
+        """Custom-callable linalg modes: the reference algorithm on host arrays (user-supplied solver)."""
+        x = self.data.x_data
+        KV = self.kv.addKV(self.prior.compute_prior_covariance_matrix(x, hps), V)
+        b = ev.KVinvY[:, component]
+        dK = np.asarray(self.prior.dk_dh(x, x, hps))
+        dV = self.likelihood.calculate_V_grad(x, hps)
+        dm = self.prior.dm_dh(x, hps)
+        obj = self.kv.mode[0](KV)
+        grad = np.zeros(len(hps))
+        for i in range(len(hps)):
+            gm = float(-dm[i] @ b)
+            if gm == 0.0:
+                dKi = dK[i] + (np.diag(dV[i]) if np.ndim(dV[i]) == 1 else dV[i])
+                grad[i] = -0.5 * (b @ dKi @ b - np.trace(np.asarray(self.kv.mode[1](obj, dKi))))
+            grad[i] += gm
+        return grad
+
+    # ------------------------------------------------------------------------------------------
+    def neg_log_likelihood_hessian(self, hyperparameters=None):
+        """Forward finite difference of the gradient, eps = 1e-6 (:312-336)."""
+        hps = np.asarray(self.trainer.hyperparameters if hyperparameters is None else hyperparameters, dtype=float)
+        H = len(hps)
+        out = np.zeros((H, H))
+        g0 = self.neg_log_likelihood_gradient(hyperparameters=hps)
+        for i in range(H):
+            hp = np.array(hps)
+            hp[i] += 1e-6
+            out[i, i:] = ((self.neg_log_likelihood_gradient(hyperparameters=hp) - g0) / 1e-6)[i:]
+        return out + out.T - np.diag(np.diag(out))
+
+    def test_log_likelihood_gradient(self, hyperparameters, epsilon=1e-6):
+        """Finite-difference vs analytic gradient of +LML (:338-364)."""
+        thps = np.array(hyperparameters, dtype=float)
+        fd = np.empty(len(thps))
+        base = self.log_likelihood(hyperparameters=thps)
+        for i in range(len(thps)):
+            t = np.array(thps)
+            t[i] += epsilon
+            fd[i] = (self.log_likelihood(hyperparameters=t) - base) / epsilon
+        return fd, -self.neg_log_likelihood_gradient(hyperparameters=thps)

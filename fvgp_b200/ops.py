@@ -10,6 +10,39 @@ import numpy as np
 
 from . import _lib as L
 
+# Optional phase timer (bench.py): CUDA-event pairs on torch's current stream around each operator.
+PHASES = None
+
+
+class _Phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PHASES is not None:
+            torch = L._torch()
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PHASES is not None:
+            self.e1.record()
+            PHASES.setdefault(self.name, []).append((self.e0, self.e1))
+
+
+def start_phase_timing():
+    global PHASES
+    PHASES = {}
+
+
+def stop_phase_timing():
+    """Returns {phase: total seconds}; synchronises."""
+    global PHASES
+    L._torch().cuda.synchronize()
+    out = {k: sum(a.elapsed_time(b) for a, b in v) * 1e-3 for k, v in (PHASES or {}).items()}
+    PHASES = None
+    return out
+
 
 # ------------------------------------------------------------------------------ dense K
 def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL, out=None):
@@ -22,8 +55,9 @@ def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL
     else:
         buf, ld = out
     _, inv_p = L.dvec(inv_scale)
-    st = lib.fvgp_kfill_dense(kind, mode, L.ptr(x1), n1, L.ptr(x2), n2, dim, float(amp), inv_p, float(length),
-                              L.ptr(noise), L.ptr(buf), ld, L.stream_ptr())
+    with _Phase("kfill"):
+        st = lib.fvgp_kfill_dense(kind, mode, L.ptr(x1), n1, L.ptr(x2), n2, dim, float(amp), inv_p, float(length),
+                                  L.ptr(noise), L.ptr(buf), ld, L.stream_ptr())
     L.check(st, "fvgp_kfill_dense")
     return buf, ld
 
@@ -45,8 +79,9 @@ def kgrad_trace_matern32(x, theta, kinv_buf, ld, b):
     partials = L.dev_empty((int(lib.fvgp_kgrad_partials_len(n, dim)),))
     _, th = L.dvec(theta)
     out = (c_double * (dim + 1))()
-    L.check(lib.fvgp_kgrad_trace_matern32(L.ptr(x), n, dim, th, L.ptr(kinv_buf), ld, L.ptr(b), L.ptr(partials), out,
-                                          L.stream_ptr()), "fvgp_kgrad_trace_matern32")
+    with _Phase("kgrad_trace"):
+        L.check(lib.fvgp_kgrad_trace_matern32(L.ptr(x), n, dim, th, L.ptr(kinv_buf), ld, L.ptr(b), L.ptr(partials),
+                                              out, L.stream_ptr()), "fvgp_kgrad_trace_matern32")
     return np.array(out[:], dtype=np.float64)
 
 
@@ -80,8 +115,9 @@ def potrf(buf, ld, n):
     torch = L._torch()
     tileinv = L.dev_empty((int(lib.fvgp_chol_workspace_len(n)),))
     info = torch.zeros(1, dtype=torch.int32, device="cuda")
-    st = L.check(lib.fvgp_potrf_lower(L.ptr(buf), n, ld, L.ptr(tileinv), L.ptr(info), L.stream_ptr()),
-                 "fvgp_potrf_lower")
+    with _Phase("potrf"):
+        st = L.check(lib.fvgp_potrf_lower(L.ptr(buf), n, ld, L.ptr(tileinv), L.ptr(info), L.stream_ptr()),
+                     "fvgp_potrf_lower")
     if st > 0:
         raise L.NonPositiveDefiniteError(st, n)
     return CholFactor(buf, ld, n, tileinv)
@@ -103,8 +139,9 @@ def potrs(factor, rhs_t):
         rhs_t.copy_(padded[:, :n])
         return rhs_t
     work = L.dev_empty((2 * n,))
-    L.check(lib.fvgp_potrs_lower(L.ptr(factor.buf), n, factor.ld, L.ptr(factor.tileinv), L.ptr(rhs_t), nrhs, n,
-                                 L.ptr(work), L.stream_ptr()), "fvgp_potrs_lower")
+    with _Phase("potrs"):
+        L.check(lib.fvgp_potrs_lower(L.ptr(factor.buf), n, factor.ld, L.ptr(factor.tileinv), L.ptr(rhs_t), nrhs, n,
+                                     L.ptr(work), L.stream_ptr()), "fvgp_potrs_lower")
     return rhs_t
 
 
@@ -121,8 +158,9 @@ def potri(factor):
     """Lower triangle of the factor buffer <- lower triangle of KV^-1 (gp_lin_alg.py:1558)."""
     lib = L.load()
     work = L.dev_empty((int(lib.fvgp_potri_workspace_len(factor.n)),))
-    L.check(lib.fvgp_potri_lower(L.ptr(factor.buf), factor.n, factor.ld, L.ptr(factor.tileinv), L.ptr(work),
-                                 L.stream_ptr()), "fvgp_potri_lower")
+    with _Phase("potri"):
+        L.check(lib.fvgp_potri_lower(L.ptr(factor.buf), factor.n, factor.ld, L.ptr(factor.tileinv), L.ptr(work),
+                                     L.stream_ptr()), "fvgp_potri_lower")
     factor.inverted = True
     return factor
 

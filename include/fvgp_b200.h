@@ -44,6 +44,8 @@ enum fvgp_fill_mode {
 };
 
 int fvgp_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long fvgp_launch_count(void);
 /* test / profiling hook: mirror tiles of the symmetric K-fill through TMA bulk stores (1, default)
  * or plain coalesced stores (0).  Returns the previous setting. */
 int fvgp_set_bulk_store(int on);

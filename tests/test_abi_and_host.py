@@ -1,0 +1,147 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/*.h declares, the
+product path fails loudly without a GPU, and the host-side logic mirrors the reference."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "fvgp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fvgp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fvgp_b200 import _lib
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (fvgp_[a-z0-9_]+)", out))
+    missing = [s for s in syms if s not in exported]
+    assert not missing, missing
+    assert set(_lib.EXPORTED_SYMBOLS) == set(syms), set(_lib.EXPORTED_SYMBOLS) ^ set(syms)
+    assert lib.fvgp_version() >= 100
+    # size helpers are pure host functions: callable without a GPU
+    assert lib.fvgp_chol_workspace_len(130) == 3 * 64 * 64
+    assert lib.fvgp_wendland_aabb_len(100, 3) == (4 + 1) * 6
+    assert lib.fvgp_bjacobi_len(33) == 2 * 1024
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fvgp_b200 import GP, NativeLibraryError
+    with pytest.warns(UserWarning):
+        with pytest.raises(NativeLibraryError):
+            GP(np.random.rand(8, 2), np.random.rand(8), init_hyperparameters=np.ones(3))
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fvgp_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, f
+
+
+def test_fvgp_transform_matches_reference(golden):
+    from fvgp_b200.fvgp import fvGP
+    g = golden("multitask")
+    xi, yf, vf = fvGP._transform_index_set(g["x"], g["y"], g["noise"])
+    assert np.array_equal(xi, g["x_index"]) and np.array_equal(yf, g["y_flat"][:, 0]) and np.array_equal(vf, g["v_flat"])
+
+
+def test_cartesian_product_is_task_major():
+    from fvgp_b200.gp_posterior import GPposterior
+    x = np.arange(6.0).reshape(3, 2)
+    out = GPposterior.cartesian_product(x, np.array([0.0, 1.0]))
+    ref = np.array([np.append(x[i], t) for t in (0.0, 1.0) for i in range(3)])      # gp_posterior.py:586-606
+    assert np.array_equal(out, ref)
+
+
+def test_lazy_kernel_algebra():
+    from fvgp_b200 import kernels as K
+    from fvgp_b200 import _lib as L
+    x = np.random.rand(5, 2)
+    d = K.get_distance_matrix(x, x)
+    assert isinstance(d, K.Distance) and d.same and np.all(d.inv_scale == 1.0)
+    r = 2.0 * K.squared_exponential_kernel(d, 0.3) * 1.5
+    assert isinstance(r, K.Radial) and r.kind == L.K_SQEXP and r.amp == 3.0 and r.length == 0.3
+    a = K.get_anisotropic_distance_matrix(x, np.random.rand(4, 2), np.array([.5, .25]))
+    assert not a.same and np.allclose(a.inv_scale, [2.0, 4.0]) and a.shape == (5, 4)
+    assert K.matern_kernel_diff1(a, 1.0).kind == L.K_MATERN32
+    assert K.matern_kernel_diff2(a, 1.0).kind == L.K_MATERN52
+    assert K.exponential_kernel(a, 1.0).kind == L.K_EXP
+    w = K.wendland_anisotropic_gp2Scale_cpu(x, x, np.array([1.0, .1, .1]))
+    assert isinstance(w, K.SparseWendland) and w.same
+
+
+def test_gp2scale_mode_thresholds():
+    """gp_kv.py:182-188 (tests/test_fvgp.py:5110)."""
+    from fvgp_b200.gp_kv import GPkv, resolve_gp2scale_linalg_mode
+
+    class D:
+        x_data = np.zeros((3000, 1))
+        args = {}
+    kv = GPkv.__new__(GPkv)
+    kv.data, kv.linalg_mode = D(), None
+    assert kv._set_gp2Scale_mode(int(0.00005 * 3000 ** 2)) == "sparseLU"
+    assert kv._set_gp2Scale_mode(int(0.01 * 3000 ** 2)) == "sparseMINRES"
+    D.x_data = np.zeros((1500, 1))
+    assert kv._set_gp2Scale_mode(int(0.01 * 1500 ** 2)) == "Chol"
+    kv.linalg_mode = "sparseCG"
+    assert kv._set_gp2Scale_mode(10) == "sparseCG"
+    assert resolve_gp2scale_linalg_mode("sparseCGpre_ilu", {})[0] == "sparseCGpre"
+    assert resolve_gp2scale_linalg_mode("sparseCGpre_ilu", {})[1]["sparse_preconditioner_type"] == "ilu"
+
+
+def test_addKV_formats():
+    """gp_kv.py:640-669 (tests/test_fvgp.py:4231)."""
+    import scipy.sparse as sp
+    from fvgp_b200.gp_kv import GPkv
+    K = np.arange(9.0).reshape(3, 3)
+    V = np.array([.1, .2, .3])
+    assert np.allclose(GPkv.addKV(K, V), K + np.diag(V))
+    assert np.allclose(GPkv.addKV(K, np.diag(V)), K + np.diag(V))
+    assert np.allclose(GPkv.addKV(sp.csr_matrix(K), V).toarray(), K + np.diag(V))
+
+
+def test_training_drivers_on_a_toy_objective():
+    from fvgp_b200.gp_training import GPtraining
+    tr = GPtraining(None, np.array([0.5, 0.5]))
+    target = np.array([0.3, 0.7])
+    bounds = np.array([[0.0, 1.0], [0.0, 1.0]])
+
+    def nll(h):
+        return float(np.sum((h - target) ** 2))
+    out = tr.train(objective_function=nll, objective_function_gradient=lambda h: 2 * (h - target),
+                   hyperparameter_bounds=bounds, init_hyperparameters=np.array([.5, .5]), method="local", max_iter=50)
+    assert np.allclose(out, target, atol=1e-4)
+    out = tr.train(objective_function=nll, hyperparameter_bounds=bounds, init_hyperparameters=np.array([.5, .5]),
+                   method="global", max_iter=40, pop_size=10)
+    assert np.allclose(out, target, atol=1e-2)
+    out = tr.train(objective_function=lambda h: -200 * nll(h), hyperparameter_bounds=bounds,
+                   init_hyperparameters=np.array([.5, .5]), method="mcmc", max_iter=1500, mcmc_args={"seed": 1})
+    assert np.allclose(out, target, atol=0.05) and tr.mcmc_info["acceptance rate"] > 0.05
+    out = tr.train(objective_function=nll, objective_function_gradient=lambda h: 2 * (h - target),
+                   hyperparameter_bounds=bounds, init_hyperparameters=np.array([.5, .5]), method="adam", max_iter=400)
+    assert np.allclose(out, target, atol=2e-2)
+    with pytest.raises(Exception):
+        tr.train(objective_function=nll, hyperparameter_bounds=bounds, init_hyperparameters=np.array([2., 2.]))
+
+
+def test_bench_reference_arm_prints_contract_line():
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-n", "400"], capture_output=True, text=True, timeout=300)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

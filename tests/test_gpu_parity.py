@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path, called through the reference-facing API (GP / fvGP / kernels) and the
+C ABI, against the golden fixtures made by the unmodified reference and against the oracle.
+
+Tolerances (BASELINE.json north_star): K entries <= 1e-12 relative, LML and gradient <= 1e-8
+relative, gp2Scale sparsity pattern bit-exact."""
+import os
+import pickle
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+warnings.filterwarnings("ignore")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def fv():
+    import torch
+    assert torch.cuda.is_available()
+    import fvgp_b200
+    from fvgp_b200 import _lib
+    _lib.load()
+    return fvgp_b200
+
+
+def test_kernel_probe_sections_pass(fv):
+    """Every low-level kernel check of tests/gpu_probe.py (shapes, edge cases, modes) must pass."""
+    os.environ["PROBE_ONLY"] = "__none__"
+    sys.argv = [sys.argv[0], "--quick"]
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gpu_probe as gp
+    for fn in (gp._gemm_shapes, gp._kfill, gp._chol, gp._lml, gp._sparse):
+        gp.FAILS.clear()
+        fn()
+        assert not gp.FAILS, (fn.__name__, gp.FAILS)
+
+
+def test_dense_kernels_entrywise(fv, golden):
+    from fvgp_b200 import kernels as K
+    from fvgp_b200.gp_prior import GPprior
+    g = golden("dense_kernels")
+    x1, x2, h = g["x1"], g["x2"], g["hps"]
+    assert rel(np.asarray(GPprior._default_kernel(x1, x2, h)), g["default_12"]) <= 1e-12
+    assert rel(np.asarray(GPprior._default_kernel(x1, x1, h)), g["default_11"]) <= 1e-12
+    assert rel(np.asarray(K.get_distance_matrix(x1, x2)), g["d_iso"]) <= 1e-13
+    assert rel(np.asarray(K.get_anisotropic_distance_matrix(x1, x2, h[1:])), g["d_ani"]) <= 1e-13
+    for nm, f in (("se", K.squared_exponential_kernel), ("exp", K.exponential_kernel),
+                  ("matern32", K.matern_kernel_diff1), ("matern52", K.matern_kernel_diff2)):
+        assert rel(np.asarray(f(K.get_distance_matrix(x1, x2), 0.37)), g[nm + "_iso"]) <= 1e-12, nm
+        assert rel(np.asarray(f(K.get_anisotropic_distance_matrix(x1, x2, h[1:]), 1.3)), g[nm + "_ani"]) <= 1e-12, nm
+        assert rel(f(g["d_iso"], 0.37), g[nm + "_iso"]) <= 1e-12, nm          # plain-ndarray call path
+    assert rel(np.asarray(GPprior._default_kernel(g["c1_x"], g["c1_x"], g["c1_hps"])), g["c1_K"]) <= 1e-12
+
+
+def test_default_kernel_gradient_dense(fv, golden):
+    from fvgp_b200 import GP
+    g = golden("dense_kernels")
+    x1, x2, h = g["x1"], g["x2"], g["hps"]
+    gp = GP(x1, np.zeros(len(x1)) + np.arange(len(x1)) * 0.1, init_hyperparameters=h, noise_variances=np.full(len(x1), .1))
+    d11 = gp.prior.dk_dh(x1, x1, h)
+    d12 = gp.prior.dk_dh(x1, x2, h)
+    assert np.max(np.abs(d11 - g["default_grad_11"])) <= 1e-12
+    assert np.max(np.abs(d12 - g["default_grad_12"])) <= 1e-12
+    assert np.max(np.abs(gp.prior.dk_dh(x1, x2, h, direction=2) - g["default_grad_12"][2])) <= 1e-12
+
+
+@pytest.mark.parametrize("tag", ["c1", "c2"])
+def test_dense_gp_against_reference(fv, golden, tag):
+    from fvgp_b200 import GP
+    g = golden("dense_lml_" + tag)
+    x, y, nz = g["x"], g["y"], g["noise"]
+    gp = GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz)
+    assert abs(gp.log_likelihood() / g["lml_h0_state"] - 1) <= 1e-8
+    for hk in ("h0", "h1"):
+        assert abs(gp.log_likelihood(g[hk]) / g["lml_" + hk] - 1) <= 1e-8
+        assert rel(gp.neg_log_likelihood_gradient(g[hk]), g["grad_" + hk]) <= 1e-8
+        assert abs(gp.neg_log_likelihood(g[hk]) + g["lml_" + hk]) <= 1e-8 * abs(g["lml_" + hk])
+    assert rel(gp.kv.KVinvY, g["KVinvY_h0"]) <= 1e-7
+    assert abs(gp.kv.logdet_KV / g["logdet_h0"] - 1) <= 1e-10
+    assert rel(gp.K, fv.gp_prior.GPprior._default_kernel(x, x, g["h0"]).to_host()) == 0.0
+    pm = gp.posterior_mean(g["x_pred"])
+    assert np.allclose(pm["m(x)"], g["post_mean"], rtol=1e-8, atol=1e-10)
+    pc = gp.posterior_covariance(g["x_pred"])
+    assert np.allclose(pc["S"], g["post_S"], rtol=1e-6, atol=1e-9)
+    assert np.allclose(pc["v(x)"], g["post_var"], rtol=1e-6, atol=1e-9)
+    assert gp.posterior_covariance(g["x_pred"], variance_only=True)["S"] is None
+    # analytic gradient agrees with finite differences of our own LML (gp_marginal_likelihood.py:338-364)
+    fd, an = gp.test_log_likelihood_gradient(g["h1"])
+    assert np.allclose(fd, an, rtol=2e-3, atol=1e-3)
+    # default noise (gp_likelihood.py:102-104)
+    gpd = GP(x[:200], y[:200], init_hyperparameters=g["h0"])
+    assert abs(gpd.log_likelihood(g["h1"]) / g["lml_default_noise"] - 1) <= 1e-8
+    # user kernel composed from fvgp.kernels names (examples' skernel): fused lazily, same LML
+    from fvgp_b200.kernels import get_distance_matrix, squared_exponential_kernel
+
+    def se(x1, x2, h):
+        return h[0] * squared_exponential_kernel(get_distance_matrix(x1, x2), h[1])
+    gps = GP(x[:300], y[:300], init_hyperparameters=g["se_hps"], noise_variances=nz[:300], kernel_function=se)
+    assert abs(gps.log_likelihood(g["se_hps"] * 1.1) / g["lml_se"] - 1) <= 1e-8
+    # ... and its gradient through finite-difference dK (gp_prior.py:438-447) stays consistent with FD of the LML
+    gr = gps.neg_log_likelihood_gradient(g["se_hps"])
+    fd, _ = gps.test_log_likelihood_gradient(g["se_hps"])
+    assert np.allclose(-gr, fd, rtol=5e-2, atol=5e-2)
+
+
+def test_set_hyperparameters_update_data_and_pickle(fv, golden):
+    from fvgp_b200 import GP
+    g = golden("dense_lml_c2")
+    x, y, nz = g["x"], g["y"], g["noise"]
+    gp = GP(x[:400], y[:400], init_hyperparameters=g["h0"], noise_variances=nz[:400])
+    gp.update_gp_data(x[400:], y[400:], noise_variances_new=nz[400:], append=True)
+    assert abs(gp.log_likelihood() / g["lml_h0"] - 1) <= 1e-8
+    gp.set_hyperparameters(g["h1"])
+    assert abs(gp.log_likelihood() / g["lml_h1"] - 1) <= 1e-8
+    K0, m0 = gp.K.copy(), gp.posterior_mean(g["x_pred"])["m(x)"]
+    gp2 = pickle.loads(pickle.dumps(gp))                                   # tests/test_fvgp.py:1108
+    assert np.array_equal(gp2.K, K0) and np.array_equal(gp2.V, gp.V)
+    assert np.allclose(gp2.posterior_mean(g["x_pred"])["m(x)"], m0, rtol=1e-12)
+
+
+def test_linalg_modes_and_custom_callables(fv, golden):
+    """tests/test_fvgp.py:357, :4188, :5030."""
+    import scipy.linalg as sla
+    from fvgp_b200 import GP
+    g = golden("dense_lml_c1")
+    x, y, nz = g["x"][:200], g["y"][:200], g["noise"][:200]
+    base = GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz)
+    ref = base.log_likelihood(g["h1"])
+    for mode in ("CholInv", "Inv"):
+        gp = GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz, linalg_mode=mode)
+        assert abs(gp.log_likelihood(g["h1"]) / ref - 1) <= 1e-10
+        assert np.allclose(gp.kv.KVinv @ gp.kv.KV, np.eye(200), atol=1e-8)
+    calls = (lambda KV: sla.cho_factor(KV, lower=True), lambda f, b: sla.cho_solve(f, b),
+             lambda f: 2 * np.sum(np.log(np.diag(f[0]))))
+    gp = GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz, linalg_mode=calls)
+    assert abs(gp.log_likelihood(g["h1"]) / ref - 1) <= 1e-10
+    assert rel(gp.neg_log_likelihood_gradient(g["h1"]), base.neg_log_likelihood_gradient(g["h1"])) <= 1e-7
+    with pytest.raises(Exception):
+        GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz, linalg_mode="nonsense")
+
+
+def test_non_positive_definite_raises(fv):
+    from fvgp_b200 import GP
+
+    def bad_kernel(x1, x2, h):
+        return -np.ones((len(x1), len(x2)))
+    with pytest.raises(Exception, match="positive definite"):
+        GP(np.random.rand(70, 2), np.random.rand(70), init_hyperparameters=np.ones(3), noise_variances=np.full(70, 1e-3),
+           kernel_function=bad_kernel)
+
+
+def test_multitask_against_reference(fv, golden):
+    from fvgp_b200 import fvGP
+    g = golden("multitask")
+    gp = fvGP(g["x"], g["y"], init_hyperparameters=g["h"], noise_variances=g["noise"])
+    assert np.array_equal(gp.x_data, g["x_index"]) and np.array_equal(gp.y_data, g["y_flat"])
+    assert abs(gp.log_likelihood(g["h1"]) / g["lml"] - 1) <= 1e-8
+    assert rel(gp.neg_log_likelihood_gradient(g["h1"]), g["grad"]) <= 1e-8
+    pm = gp.posterior_mean(g["x_pred"])
+    assert np.allclose(pm["m(x)"], g["post_mean"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(pm["m(x)_flat"], g["post_mean_flat"], rtol=1e-8, atol=1e-10)
+    pc = gp.posterior_covariance(g["x_pred"])
+    assert pc["v(x)"].shape == (7, 3) and pc["S"].shape == (7, 7, 3, 3)
+
+
+@pytest.mark.parametrize("tag", ["t3152", "c4small"])
+def test_gp2scale_against_reference(fv, golden, tag):
+    from fvgp_b200 import GP
+    g = golden("gp2scale_" + tag)
+    x, y, nz = g["x"], g["y"], g["noise"]
+    gp = GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz, gp2Scale=True, linalg_mode="sparseLU")
+    K = gp.K
+    assert K.indices.dtype == np.int32 and K.has_sorted_indices
+    assert np.array_equal(K.indptr, g["indptr"]) and np.array_equal(K.indices, g["indices"])      # bit-exact
+    if "data" in g:
+        assert rel(K.data, g["data"]) <= 1e-12
+    else:
+        assert rel(K.data[:2000], g["data_head"]) <= 1e-12 and abs(K.data.sum() / g["data_sum"] - 1) <= 1e-13
+    K1 = gp.prior.compute_prior_covariance_matrix(x, g["h1"])
+    assert np.array_equal(K1.indptr, g["h1_indptr"]) and np.array_equal(K1.indices, g["h1_indices"])
+    assert (K != K.T).nnz == 0
+    for hk in ("h0", "h1"):
+        assert abs(gp.log_likelihood(g[hk]) / g["lml_" + hk] - 1) <= 1e-8
+    assert rel(gp.kv.KVinvY, g["KVinvY_h0"]) <= 1e-6
+    assert np.allclose(gp.posterior_mean(g["x_pred"])["m(x)"], g["post_mean"], rtol=1e-7, atol=1e-9)
+    assert np.allclose(gp.posterior_covariance(g["x_pred"])["v(x)"], g["post_var"], rtol=1e-6, atol=1e-8)
+    with pytest.raises(Exception, match="gp2Scale"):
+        gp.neg_log_likelihood_gradient(g["h0"])                       # gp_marginal_likelihood.py:240
+    # Krylov modes: tight CG reproduces the exact solve; SLQ logdet within its own error bars
+    for mode in ("sparseCG", "sparseCGpre"):
+        gpk = GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz, gp2Scale=True, linalg_mode=mode,
+                 args={"sparse_cg_tol": 1e-11, "random_logdet_lanczos_degree": 30,
+                       "random_logdet_min_num_samples": 40, "random_logdet_error_rtol": 0.003})
+        assert np.allclose(gpk.kv.KVinvY, g["KVinvY_h0"], rtol=1e-6, atol=1e-8 * np.abs(g["KVinvY_h0"]).max())
+        sd = np.sqrt(gpk.kv.last_logdet_variance)
+        assert abs(gpk.kv.logdet_KV - g["logdet_h0"]) <= 5 * sd + 0.01 * abs(g["logdet_h0"])
+        assert gpk.marginal_likelihood.log_likelihood_variance() is not None
+
+
+def test_gp2scale_edge_cases(fv):
+    from fvgp_b200 import _lib as L, ops
+    h = np.array([2.0, .4, .35])
+    far = ops.wendland_csr(L.to_dev(np.zeros((5, 2))), L.to_dev(np.ones((4, 2)) * 10), h)
+    assert far.nnz == 0 and far.to_scipy().shape == (5, 4)                 # disjoint boxes (test_fvgp.py:1737)
+    one = L.to_dev(np.array([[0.3, 0.3]]))
+    K = ops.wendland_csr(one, one, h).to_scipy()
+    assert K.nnz == 1 and K[0, 0] == 2.0                                   # diagonal == amplitude (test_fvgp.py:1724)
+    dup = L.to_dev(np.tile(np.array([[0.5, 0.5]]), (70, 1)))               # coincident points: dense 70x70 block
+    K = ops.wendland_csr(dup, dup, h).to_scipy()
+    assert K.nnz == 4900 and np.all(K.data == 2.0)
+
+
+def test_size_independent_properties_at_scale(fv):
+    """Properties that need no oracle: symmetry, L L^T = KV, KV KV^-1 = I, mirrored sparsity."""
+    import torch
+    from fvgp_b200 import _lib as L, ops
+    rng = np.random.default_rng(9)
+    n = 6000
+    x = L.to_dev(rng.random((n, 3)))
+    noise = L.to_dev(np.full(n, 1e-2))
+    h = np.array([1.0, .3, .4, .5])
+    full, _ = ops.kfill(L.K_MATERN32, x, x, h[0], 1 / h[1:], 1.0, noise=noise, mode=L.FILL_SYMMETRIC)
+    KV = full[:, :n].clone()
+    assert torch.equal(KV, KV.T)                                            # mirror tiles are bitwise transposes
+    ref, _ = ops.kfill(L.K_MATERN32, x, x, h[0], 1 / h[1:], 1.0, noise=noise, mode=L.FILL_FULL)
+    assert torch.equal(KV, ref[:, :n])
+    f = ops.potrf(full, _, n)
+    Lw = f.lower()
+    assert float((Lw @ Lw.T - KV).abs().max()) <= 1e-12 * float(KV.abs().max()) * 50
+    ops.potri(f)
+    low = torch.tril(f.buf[:, :n])
+    Kinv = low + torch.tril(low, -1).T
+    assert float((Kinv @ KV - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max()) <= 1e-9
+    ns = 50000
+    xs = rng.random((ns, 3))
+    xs = L.to_dev(xs[np.lexsort((xs[:, 2] // .1, xs[:, 1] // .1, xs[:, 0] // .1))])
+    A = ops.wendland_csr(xs, xs, np.array([1.0, .05, .05, .05])).to_scipy()
+    assert (A != A.T).nnz == 0 and np.all(A.diagonal() == 1.0) and A.has_sorted_indices
+    shuffled = ops.wendland_csr(xs.flip(0).contiguous(), xs.flip(0).contiguous(), np.array([1.0, .05, .05, .05])).to_scipy()
+    assert shuffled.nnz == A.nnz                                            # ordering changes the layout, not the set
