@@ -22,27 +22,39 @@ namespace fvgp {
 
 unsigned long long g_launches = 0;
 
-constexpr int TS = 64;  // diagonal tile size
-constexpr size_t POTRF_TILE_SMEM = (2 * TS * (TS + 1) + TS) * sizeof(double);
+constexpr int TS = 128;  // diagonal tile handled by one CTA (Cholesky + inverse of the factor)
+constexpr int VS = 64;   // block width of the single-right-hand-side solves
+constexpr int TP = TS + 1;
+constexpr int HP = TS / 2 + 1;
+constexpr size_t POTRF_TILE_SMEM = (size_t(TS) * TP + 2 * (TS / 2) * HP + TS) * sizeof(double);  // ~198 KB
 
 // ----------------------------------------------------------------------------------------------
-// 64x64 diagonal tile: Cholesky + inverse of the factor, one CTA, all in shared memory.
+// 128x128 diagonal tile, one CTA of 512 threads, everything in shared memory:
+//   1. right-looking Cholesky, 4 threads per row in the trailing update;
+//   2. inverses of the two 64x64 diagonal blocks of the factor by forward substitution
+//      (column per 4 lanes, both blocks concurrently);
+//   3. the off-diagonal block of the inverse, -D^-1 C A^-1, staged in the unused upper-right
+//      quadrant of the tile.
+// Emits L (lower, explicit zeros above the diagonal) in place and the full 128x128 inverse of L,
+// so that every triangular solve against this tile is ONE tensor-core GEMM with K = 128.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) potrf_tile_kernel(double* A, long long ld, int nt, double* dinv,
+__global__ void __launch_bounds__(512) potrf_tile_kernel(double* A, long long ld, int nt, double* dinv,
                                                          int* info, int global_row0) {
   extern __shared__ __align__(16) double tile_smem[];
-  double(*T)[TS + 1] = reinterpret_cast<double(*)[TS + 1]>(tile_smem);
-  double(*Inv)[TS + 1] = reinterpret_cast<double(*)[TS + 1]>(tile_smem + TS * (TS + 1));
-  double* Dg = tile_smem + 2 * TS * (TS + 1);
+  double(*T)[TP] = reinterpret_cast<double(*)[TP]>(tile_smem);
+  double(*InvA)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP);
+  double(*InvD)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP + (TS / 2) * HP);
+  double* Dg = tile_smem + TS * TP + 2 * (TS / 2) * HP;
+  constexpr int H = TS / 2;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < TS * TS; idx += 256) {
+  for (int idx = tid; idx < TS * TS; idx += 512) {
     const int r = idx / TS, c = idx % TS;
     double v = (r == c) ? 1.0 : 0.0;
     if (r < nt && c <= r) v = A[(long long)r * ld + c];
     T[r][c] = v;
   }
   __syncthreads();
-  const int ri = tid >> 2, part = tid & 3;  // row owned in the trailing update, 4 threads per row
+  const int ri = tid >> 2, part = tid & 3;
   for (int j = 0; j < TS; ++j) {
     const double d = T[j][j];
     if (!(d > 0.0) && tid == 0) atomicCAS(info, 0, global_row0 + j + 1);
@@ -56,23 +68,51 @@ __global__ void __launch_bounds__(256) potrf_tile_kernel(double* A, long long ld
     }
     __syncthreads();
   }
-  // Inverse of the lower factor: column c of Inv solves L x = e_c; 4 lanes share a column.
-  {
-    const int c = tid >> 2;
-    for (int i = 0; i < TS; ++i) {
+  {  // inverses of the diagonal blocks: column (tid>>2) of block (tid>>8)
+    const int c = (tid >> 2) & (H - 1), base = (tid >> 8) * H;
+    double(*Inv)[HP] = (tid >> 8) ? InvD : InvA;
+    for (int i = 0; i < H; ++i) {
       double acc = 0.0;
       if (i > c)
-        for (int k = c + part; k < i; k += 4) acc += T[i][k] * Inv[k][c];
+        for (int k = c + part; k < i; k += 4) acc += T[base + i][base + k] * Inv[k][c];
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (part == 0) Inv[i][c] = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - acc) / Dg[i];
+      if (part == 0) Inv[i][c] = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - acc) / Dg[base + i];
       __syncwarp();
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < TS * TS; idx += 256) {
+  {  // E = C A^-1 into T[0..63][64..127]  (C = T[64+i][k])
+    const int i = tid >> 3, j0 = (tid & 7) * 8;
+    double e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = 0.0;
+    for (int k = 0; k < H; ++k) {
+      const double cik = T[H + i][k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) e[u] = fma(cik, InvA[k][j0 + u], e[u]);   // InvA[k][j] = 0 for k < j
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) T[i][H + j0 + u] = e[u];
+  }
+  __syncthreads();
+  {  // F = -D^-1 E  -> dinv[64+i][j]
+    const int i = tid >> 3, j0 = (tid & 7) * 8;
+    double f[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] = 0.0;
+    for (int k = 0; k <= i; ++k) {
+      const double dik = InvD[i][k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = fma(dik, T[k][H + j0 + u], f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dinv[(H + i) * TS + j0 + u] = -f[u];
+  }
+  for (int idx = tid; idx < TS * TS; idx += 512) {
     const int r = idx / TS, c = idx % TS;
-    dinv[idx] = Inv[r][c];
+    if (r < H) dinv[idx] = (c < H) ? InvA[r][c] : 0.0;
+    else if (c >= H) dinv[idx] = InvD[r - H][c - H];
     if (r < nt && c < nt) A[(long long)r * ld + c] = (c < r) ? T[r][c] : ((c == r) ? Dg[r] : 0.0);
   }
 }
@@ -101,15 +141,15 @@ __global__ void zero_upper_diag_blocks_kernel(double* A, long long ld, int n) {
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict__ L, long long ld, int n, int j0,
                                                        const double* __restrict__ dinv, double* w, double* z) {
-  __shared__ double yj[TS], zj[TS];
+  __shared__ double yj[VS], zj[VS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nt = min(TS, n - j0);
-  if (tid < TS) yj[tid] = tid < nt ? w[j0 + tid] : 0.0;
+  const int nt = min(VS, n - j0);
+  if (tid < VS) yj[tid] = tid < nt ? w[j0 + tid] : 0.0;
   __syncthreads();
   {
     const int r = tid >> 2, part = tid & 3;
     double acc = 0.0;
-    for (int k = part; k <= r; k += 4) acc += dinv[r * TS + k] * yj[k];
+    for (int k = part; k <= r; k += 4) acc += dinv[r * TS + k] * yj[k];  // dinv: 64x64 block, ld = TS
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (part == 0) {
@@ -118,7 +158,7 @@ __global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict_
     }
   }
   __syncthreads();
-  const int rest0 = j0 + TS;
+  const int rest0 = j0 + VS;
   const double z0 = zj[lane], z1 = zj[lane + 32];
   for (int i = rest0 + blockIdx.x * 64 + warp; i < min(n, rest0 + (int)(blockIdx.x + 1) * 64); i += 8) {
     const double* row = L + (long long)i * ld + j0;
@@ -130,15 +170,15 @@ __global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict_
 
 __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict__ L, long long ld, int n, int j0,
                                                        const double* __restrict__ dinv, double* z, double* x) {
-  __shared__ double zj[TS], xj[TS];
+  __shared__ double zj[VS], xj[VS];
   const int tid = threadIdx.x;
-  const int nt = min(TS, n - j0);
-  if (tid < TS) zj[tid] = tid < nt ? z[j0 + tid] : 0.0;
+  const int nt = min(VS, n - j0);
+  if (tid < VS) zj[tid] = tid < nt ? z[j0 + tid] : 0.0;
   __syncthreads();
   {
     const int c = tid >> 2, part = tid & 3;
     double acc = 0.0;
-    for (int r = c + part; r < TS; r += 4) acc += dinv[r * TS + c] * zj[r];
+    for (int r = c + part; r < VS; r += 4) acc += dinv[r * TS + c] * zj[r];
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (part == 0) {
@@ -183,14 +223,11 @@ struct Ctx {
   int err;
 };
 
-static inline int split(int n) {
-  if (n > 2 * TS) {
-    int h = ((n / 2 + BM / 2) / BM) * BM;
-    if (h < BM) h = BM;
-    if (h >= n) h -= BM;
-    return h;
-  }
-  return TS;
+static inline int split(int n) {  // n > TS: first part is a multiple of 128, at least 128, less than n
+  int h = ((n / 2 + BM / 2) / BM) * BM;
+  if (h < BM) h = BM;
+  if (h >= n) h -= BM;
+  return h;
 }
 
 #define REC_OK(expr)          \
@@ -227,7 +264,7 @@ static int trsm_rn_rec(Ctx& c, double* B, long long ldb, int m, const double* L,
 
 static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
   if (n <= TS) {
-    launch(potrf_tile_kernel, 1, 256, POTRF_TILE_SMEM, c.st, A, ld, n, c.dinv + (long long)(row0 / TS) * TS * TS, c.info,
+    launch(potrf_tile_kernel, 1, 512, POTRF_TILE_SMEM, c.st, A, ld, n, c.dinv + (long long)(row0 / TS) * TS * TS, c.info,
                                                           row0);
     FVGP_LAUNCH_OK();
     return 0;
@@ -245,7 +282,7 @@ static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
 static int trtri_rec(Ctx& c, double* L, long long ld, int n, int row0) {
   if (n <= TS) {
     const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
-    launch(copy2d_kernel, dim3(1, (n + 15) / 16), 64, 0, c.st, L, ld, tile, TS, n, n);
+    launch(copy2d_kernel, dim3(1, (n + 15) / 16), 128, 0, c.st, L, ld, tile, TS, n, n);
     FVGP_LAUNCH_OK();
     return 0;
   }
@@ -325,21 +362,24 @@ int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_
   }
   double* w = d_work;
   double* z = d_work + n;
-  const int tiles = (int)((n + TS - 1) / TS);
+  const int tiles = (int)((n + VS - 1) / VS);
+  auto block_inv = [&](int t) {  // 64x64 diagonal sub-block of the 128x128 tile inverse (leading dimension TS)
+    return d_tileinv + (int64_t)(t / 2) * TS * TS + (t % 2) * ((int64_t)VS * TS + VS);
+  };
   for (int r = 0; r < nrhs; ++r) {
     double* b = d_B + (int64_t)r * ldb;
     FVGP_CUDA_OK(cudaMemcpyAsync(w, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     for (int t = 0; t < tiles; ++t) {
-      const int j0 = t * TS;
-      const int rest = (int)n - (j0 + TS);
+      const int j0 = t * VS;
+      const int rest = (int)n - (j0 + VS);
       const int grid = rest > 0 ? (rest + 63) / 64 : 1;
-      launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, w, z);
+      launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), w, z);
     }
     FVGP_LAUNCH_OK();
     for (int t = tiles - 1; t >= 0; --t) {
-      const int j0 = t * TS;
+      const int j0 = t * VS;
       const int grid = j0 > 0 ? (j0 + 255) / 256 : 1;
-      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, d_tileinv + (int64_t)t * TS * TS, z, b);
+      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), z, b);
     }
     FVGP_LAUNCH_OK();
   }

@@ -146,11 +146,54 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  // Per-thread copy descriptors, computed once: every k-tile except a ragged last one is a pure
+  // pointer bump (the generic path costs ~150 integer instructions per k-tile and sat between the
+  // barrier and the first DMMA of every warp).
+  const double* a_src[4];
+  const double* b_src[4];
+  int a_bytes[4], b_bytes[4], a_off[4], b_off[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = tid + GEMM_THREADS * q;
+    if (!A_MN) {
+      const int r = c >> 3, kc = (c & 7) * 2;
+      a_off[q] = r * KMAJ_STRIDE + kc;
+      a_bytes[q] = (m0 + r < p.M) ? 16 : 0;
+      a_src[q] = a_bytes[q] ? p.A + (long long)(m0 + r) * p.lda + kb + kc : p.A;
+    } else {
+      const int kk = c >> 6, mc = (c & 63) * 2;
+      a_off[q] = kk * MNMAJ_STRIDE + mc;
+      a_bytes[q] = 8 * min(max(p.M - (m0 + mc), 0), 2);
+      a_src[q] = a_bytes[q] ? p.A + (long long)(kb + kk) * p.lda + m0 + mc : p.A;
+    }
+    if (!B_MN) {
+      const int r = c >> 3, kc = (c & 7) * 2;
+      b_off[q] = r * KMAJ_STRIDE + kc;
+      b_bytes[q] = (n0 + r < p.N) ? 16 : 0;
+      b_src[q] = b_bytes[q] ? p.B + (long long)(n0 + r) * p.ldb + kb + kc : p.B;
+    } else {
+      const int kk = c >> 6, nc = (c & 63) * 2;
+      b_off[q] = kk * MNMAJ_STRIDE + nc;
+      b_bytes[q] = 8 * min(max(p.N - (n0 + nc), 0), 2);
+      b_src[q] = b_bytes[q] ? p.B + (long long)(kb + kk) * p.ldb + n0 + nc : p.B;
+    }
+  }
+  const long long a_step = A_MN ? (long long)BK * p.lda : BK;
+  const long long b_step = B_MN ? (long long)BK * p.ldb : BK;
+
   auto issue = [&](int kt) {
     double* st = smem + (kt % GEMM_STAGES) * STAGE_DOUBLES;
     const int k0 = kb + kt * BK;
-    load_operand<A_MN>(st, p.A, p.lda, m0, p.M, k0, ke, tid);
-    load_operand<B_MN>(st + OPERAND_DOUBLES, p.B, p.ldb, n0, p.N, k0, ke, tid);
+    if (k0 + BK <= ke) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        cp_async16(st + a_off[q], a_src[q] + (a_bytes[q] ? kt * a_step : 0), a_bytes[q]);
+        cp_async16(st + OPERAND_DOUBLES + b_off[q], b_src[q] + (b_bytes[q] ? kt * b_step : 0), b_bytes[q]);
+      }
+    } else {
+      load_operand<A_MN>(st, p.A, p.lda, m0, p.M, k0, ke, tid);
+      load_operand<B_MN>(st + OPERAND_DOUBLES, p.B, p.ldb, n0, p.N, k0, ke, tid);
+    }
   };
 
 #pragma unroll
@@ -162,8 +205,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
   for (int kt = 0; kt < kt_total; ++kt) {
     cp_async_wait<GEMM_STAGES - 2>();
     __syncthreads();
-    if (kt + GEMM_STAGES - 1 < kt_total) issue(kt + GEMM_STAGES - 1);
-    cp_async_commit();
 
     const double* As = smem + (kt % GEMM_STAGES) * STAGE_DOUBLES;
     const double* Bs = As + OPERAND_DOUBLES;
@@ -180,6 +221,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      if (kk == 0) {
+        // refill the stage freed by the barrier above only after this warp has fed the tensor pipe
+        if (kt + GEMM_STAGES - 1 < kt_total) issue(kt + GEMM_STAGES - 1);
+        cp_async_commit();
+      }
     }
   }
   cp_async_wait<0>();

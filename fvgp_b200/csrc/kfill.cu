@@ -46,21 +46,58 @@ __device__ __forceinline__ void tri_index(long long id, long long& a, long long&
   b = id - a * (a + 1) / 2;
 }
 
+// ---- lean FP64 math for the fill: the kernel is instruction-issue bound, not DP-pipe bound, with
+// libdevice's exp/sqrt (64-bit immediates are rebuilt with UMOV pairs, slow-path branches around
+// every call).  Coefficients live in constant memory so each DFMA takes its constant operand
+// straight from the constant bank; no special cases are needed because the argument of exp is
+// always <= 0 and the argument of sqrt is clamped positive.  Both are accurate to ~1 ulp
+// (tests compare K entries with the reference at 1e-12 relative).
+__constant__ double kExpC[12] = {2.5022322536502990E-008, 2.7630903488173108E-007, 2.7557514545882439E-006,
+                                 2.4801491039099165E-005, 1.9841269589115497E-004, 1.3888888945916380E-003,
+                                 8.3333333334550432E-003, 4.1666666666519754E-002, 1.6666666666666477E-001,
+                                 5.0000000000000122E-001, 1.0, 1.0};
+__constant__ double kExpK[4] = {1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01,
+                                -2.31904681384629956e-17};
+
+__device__ __forceinline__ double exp_nonpos(double x) {  // x <= 0
+  const double t = fma(x, kExpK[0], kExpK[1]);
+  const int n = __double2loint(t);
+  const double nf = t - kExpK[1];
+  double r = fma(nf, kExpK[2], x);
+  r = fma(nf, kExpK[3], r);
+  double p = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) p = fma(p, r, kExpC[i]);
+  const double scaled = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  return x < -708.0 ? 0.0 : scaled;
+}
+
+__device__ __forceinline__ double sqrt_pos(double s) {  // s > 0, finite
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double g = s * y, h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  const double d = fma(-g, g, s);
+  return fma(d, h, g);
+}
+
 template <int KIND>
 __device__ __forceinline__ double radial_value(double s, double amp, double c_arg, double c_aux) {
   // s = squared scaled distance
-  if (KIND == FVGP_K_SQEXP) return amp * exp(-s * c_arg);  // c_arg = 1/(2 l^2)
-  const double d = sqrt(s);
+  if (KIND == FVGP_K_SQEXP) return amp * exp_nonpos(-s * c_arg);  // c_arg = 1/(2 l^2)
+  const double d = (KIND == FVGP_K_DISTANCE || KIND == FVGP_K_WENDLAND) ? sqrt(s) : sqrt_pos(fmax(s, 1e-300));
   if (KIND == FVGP_K_DISTANCE) return d;
   if (KIND == FVGP_K_MATERN32) {
     const double a = c_arg * d;  // c_arg = sqrt(3)/l
-    return amp * ((1.0 + a) * exp(-a));
+    return amp * ((1.0 + a) * exp_nonpos(-a));
   }
   if (KIND == FVGP_K_MATERN52) {
     const double a = c_arg * d;  // c_arg = sqrt(5)/l, c_aux = 5/(3 l^2)
-    return amp * ((1.0 + a + c_aux * s) * exp(-a));
+    return amp * ((1.0 + a + c_aux * s) * exp_nonpos(-a));
   }
-  if (KIND == FVGP_K_EXP) return amp * exp(-d * c_arg);  // c_arg = 1/l
+  if (KIND == FVGP_K_EXP) return amp * exp_nonpos(-d * c_arg);  // c_arg = 1/l
   // Wendland (dense form, kernels.py:355-378)
   const double dd = fmin(d * c_arg, 1.0);
   const double u = 1.0 - dd;
@@ -92,6 +129,45 @@ __device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc,
                : "memory");
 }
 
+// One 64x64 tile: warp w owns rows 8w..8w+7, lane l owns columns l and l+32 (two 256-byte
+// coalesced row segments per warp store).  INTERIOR tiles carry no bounds checks and no noise test.
+template <int KIND, int DIM, bool INTERIOR>
+__device__ __forceinline__ void fill_tile(const FillParams& p, long long ti, long long tj, bool mirror, double* sT,
+                                          const double* inv, int lane, int warp) {
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  const int dim = p.dim;
+  const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
+  const long long ca = c0 + lane, cb = ca + 32;
+  double xa[D], xb[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    xa[i] = ((INTERIOR || ca < p.n2) && (DIM > 0 || i < dim)) ? p.x2[ca * dim + i] : 0.0;
+    xb[i] = ((INTERIOR || cb < p.n2) && (DIM > 0 || i < dim)) ? p.x2[cb * dim + i] : 0.0;
+  }
+  const double* xrow = p.x1 + r0 * dim;
+  double* krow = p.K + r0 * p.ldk + ca;
+  double* srow = sT + lane * FT_STRIDE + warp * 8;
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    if (!INTERIOR && r0 + rr >= p.n1) break;
+    double xr[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? xrow[rr * dim + i] : 0.0;
+    double va = radial_value<KIND>(sqdist<DIM>(xr, xa, inv, dim), p.amp, p.c_arg, p.c_aux);
+    double vb = radial_value<KIND>(sqdist<DIM>(xr, xb, inv, dim), p.amp, p.c_arg, p.c_aux);
+    if (!INTERIOR && p.noise != nullptr) {
+      if (r0 + rr == ca) va += p.noise[ca];
+      if (r0 + rr == cb) vb += p.noise[cb];
+    }
+    if (INTERIOR || ca < p.n2) krow[rr * p.ldk] = va;
+    if (INTERIOR || cb < p.n2) krow[rr * p.ldk + 32] = vb;
+    if (mirror) {
+      srow[rr] = va;
+      srow[32 * FT_STRIDE + rr] = vb;
+    }
+  }
+}
+
 template <int KIND, int DIM>
 __global__ void __launch_bounds__(FILL_THREADS) kfill_kernel(const FillParams p) {
   extern __shared__ __align__(128) double stage[];  // 2 x FT x FT_STRIDE
@@ -100,7 +176,6 @@ __global__ void __launch_bounds__(FILL_THREADS) kfill_kernel(const FillParams p)
   double inv[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < p.dim) ? p.inv_scale[i] : 0.0;
-  const int dim = p.dim;
 
   int mit = 0;  // mirror-tile counter: selects the staging buffer (bulk groups are committed per mirror tile)
   for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -121,38 +196,12 @@ __global__ void __launch_bounds__(FILL_THREADS) kfill_kernel(const FillParams p)
       if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
       __syncthreads();
     }
-    const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
-    const long long ca = c0 + lane, cb = c0 + lane + 32;
-    double xa[D], xb[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      xa[i] = (ca < p.n2 && (DIM > 0 || i < dim)) ? p.x2[ca * dim + i] : 0.0;
-      xb[i] = (cb < p.n2 && (DIM > 0 || i < dim)) ? p.x2[cb * dim + i] : 0.0;
-    }
-#pragma unroll 2
-    for (int rr = 0; rr < 8; ++rr) {
-      const long long r = r0 + rr;
-      if (r >= p.n1) break;
-      double xr[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? p.x1[r * dim + i] : 0.0;
-      double va = radial_value<KIND>(sqdist<DIM>(xr, xa, inv, dim), p.amp, p.c_arg, p.c_aux);
-      double vb = radial_value<KIND>(sqdist<DIM>(xr, xb, inv, dim), p.amp, p.c_arg, p.c_aux);
-      if (p.noise != nullptr) {
-        if (r == ca) va += p.noise[r];
-        if (r == cb) vb += p.noise[r];
-      }
-      double* krow = p.K + r * p.ldk;
-      if (ca < p.n2) krow[ca] = va;
-      if (cb < p.n2) krow[cb] = vb;
-      if (mirror) {
-        const int lr = warp * 8 + rr;
-        sT[lane * FT_STRIDE + lr] = va;
-        sT[(lane + 32) * FT_STRIDE + lr] = vb;
-      }
-    }
+    const bool interior = (ti + 1) * FT <= p.n1 && (tj + 1) * FT <= p.n2 && (p.noise == nullptr || ti != tj);
+    if (interior) fill_tile<KIND, DIM, true>(p, ti, tj, mirror, sT, inv, lane, warp);
+    else fill_tile<KIND, DIM, false>(p, ti, tj, mirror, sT, inv, lane, warp);
     if (mirror) {
-      // mirror tile: rows c0.. of K, columns ti*FT .. ti*FT+63 (always a full 64 because ti < tj)
+      // mirror tile: rows tj*FT.. of K, columns ti*FT .. ti*FT+63 (always a full 64 because ti < tj)
+      const long long c0 = tj * FT;
       if (p.bulk) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
@@ -262,8 +311,8 @@ __global__ void __launch_bounds__(FILL_THREADS) kgrad_trace_kernel(const TracePa
           t2[i] = t * t;
           s += t2[i];
         }
-        const double a = sqrt3 * sqrt(s);
-        const double ea = exp(-a);
+        const double a = sqrt3 * sqrt_pos(fmax(s, 1e-300));
+        const double ea = exp_nonpos(-a);
         const double wea = w * ea;
         acc[0] = fma(wea, 1.0 + a, acc[0]);
 #pragma unroll

@@ -173,12 +173,18 @@ def dot(a, b):
     return out.value
 
 
+def _ld(t):
+    """Row stride of a 2-D tensor; torch reports arbitrary strides for size-1 dimensions."""
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1] + (t.shape[1] % 2)
+
+
 def dgemm_nt(A, B, C, alpha=1.0, beta=0.0, lower=False):
     """C = alpha A B^T + beta C on row-major 2-D device tensors (strides taken from the tensors)."""
     lib = L.load()
     m, k = A.shape
     n = B.shape[0]
-    L.check(lib.fvgp_dgemm_nt(L.ptr(A), A.stride(0), L.ptr(B), B.stride(0), L.ptr(C), C.stride(0), m, n, k,
+    assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
+    L.check(lib.fvgp_dgemm_nt(L.ptr(A), _ld(A), L.ptr(B), _ld(B), L.ptr(C), _ld(C), m, n, k,
                               float(alpha), float(beta), int(lower), L.stream_ptr()), "fvgp_dgemm_nt")
     return C
 

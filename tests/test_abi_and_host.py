@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTED_SYMBOLS) == set(syms), set(_lib.EXPORTED_SYMBOLS) ^ set(syms)
     assert lib.fvgp_version() >= 100
     # size helpers are pure host functions: callable without a GPU
-    assert lib.fvgp_chol_workspace_len(130) == 3 * 64 * 64
+    assert lib.fvgp_chol_workspace_len(130) == 2 * 128 * 128
     assert lib.fvgp_wendland_aabb_len(100, 3) == (4 + 1) * 6
     assert lib.fvgp_bjacobi_len(33) == 2 * 1024
 
