@@ -43,6 +43,22 @@ def synthetic_c2(n, seed=2):
     return x, y, np.full(n, 1e-2)
 
 
+def synthetic_c4(n, seed=4):
+    """uniform points in the unit cube, Morton-ordered (the permutation is part of the
+    workload definition and is applied before the CPU baseline too), ~100 neighbours inside the support."""
+    from fvgp_b200.utils import morton_order
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, 3))
+    x = np.ascontiguousarray(x[morton_order(x)])
+    y = np.sin(8 * np.linalg.norm(x, axis=1)) + 0.1 * rng.standard_normal(n)
+    return x, y, np.full(n, 1e-2)
+
+
+def theta_c4(k, n, rank=0):
+    base = 0.029 * (1e6 / n) ** (1.0 / 3.0)            # keeps ~102 nnz/row when n is reduced for tests
+    return np.array([1.0, base, base, base]) * np.array([1.0] + [1.0 + 0.005 * ((k + 3 * rank) % 10 - 5)] * 3)
+
+
 def theta_k(k, rank=0):
     return np.array([1.0, .3, .4, .5]) * (1.0 + 0.02 * ((k + 7 * rank) % 20))
 
@@ -115,6 +131,118 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_c4(args):
+    """Secondary workload (not the driver's headline line): gp2Scale LML evaluations per second, N = 1M,
+    3-D, anisotropic Wendland, K assembled straight to CSR on the device, block-Jacobi PCG + SLQ logdet.
+    There is no gradient under gp2Scale in the reference (gp_marginal_likelihood.py:240)."""
+    n = args.n
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        from oracle import fvgp_oracle as orc
+        import scipy.sparse.linalg as spla
+        ns = min(n, 20000)
+        x, y, noise = synthetic_c4(ns)
+        th = theta_c4(0, ns)
+        t0 = time.perf_counter()
+        K = orc.gp2scale_covariance(x, x, th, batch=2000, symmetric=True)      # the DEFINING dense-block path
+        t_fill = time.perf_counter() - t0
+        KV = orc.add_kv(K, noise)
+        t0 = time.perf_counter()
+        sol, iters = orc.sparse_cg(KV, (y - y.mean())[:, None], rtol=1e-5)
+        t_cg = time.perf_counter() - t0
+        per = t_fill * (n / ns) ** 2 + t_cg * (n / ns)
+        line = {"impl": "reference", "metric": "gp2Scale LML evals/s (N=1M, 3D, Wendland)", "value": 1.0 / per,
+                "unit": "evals/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": per * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4: gp2Scale N={n}", "n": n},
+                "cpu_baseline": {"value": 1.0 / per, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"oracle port at N={ns}: dense-block fill {t_fill:.1f} s (x(N/{ns})^2), scipy cg "
+                                           f"{t_cg:.2f} s / {iters[0]} iterations (x N/{ns}); the stochastic logdet (imate) is "
+                                           f"not available and not included"},
+                "e2e": {"value": 1.0 / per, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    from fvgp_b200 import GP, ops, parallel
+    from fvgp_b200 import _lib as L
+    rank, local_rank, world = parallel.init()
+    lib = L.load()
+    x, y, noise = synthetic_c4(n)
+    mode_args = {"sparse_cg_tol": 1e-5, "random_logdet_lanczos_degree": 20, "random_logdet_min_num_samples": 10,
+                 "random_logdet_max_num_samples": 10}
+    t0 = time.perf_counter()
+    gp = GP(x, y, init_hyperparameters=theta_c4(0, n), noise_variances=noise, gp2Scale=True,
+            linalg_mode="sparseCGpre", args=mode_args)
+    t_ctor = time.perf_counter() - t0
+    for k in range(args.warmup):
+        gp.log_likelihood(theta_c4(k + 1, n, rank))
+    parallel.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.fvgp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        lml = gp.log_likelihood(theta_c4(args.warmup + k + 1, n, rank))
+    e1.record()
+    torch.cuda.synchronize()
+    t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = lib.fvgp_launch_count() - launches0
+    # phase breakdown of one evaluation
+    xd = gp.data.x_device()
+    th = theta_c4(1, n)
+    nd = L.to_dev(noise)
+
+    def timed(fn, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) * 1e-3)
+        return best, out
+    t_fill, KV = timed(lambda: ops.wendland_csr(xd, xd, th, noise=nd))
+    v = L.to_dev(y - y.mean())
+    yv = L.dev_empty((n,))
+    t_spmv, _ = timed(lambda: ops.spmv(KV, v, yv), reps=10)
+    t_pre, M = timed(lambda: ops.bjacobi(KV))
+    t_cg, res = timed(lambda: ops.pcg(KV, v, rtol=1e-5, precond=M), reps=2)
+    t_cg0, res0 = timed(lambda: ops.pcg(KV, v, rtol=1e-5), reps=2)
+    t_slq, _ = timed(lambda: ops.slq_logdet(KV, degree=20, probes=10, seed=0), reps=1)
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    nnz = KV.nnz
+    spmv_gbs = (12.0 * nnz + 16.0 * n) / t_spmv / 1e9
+    fill_bytes = 12.0 * nnz + 4.0 * (n + 1) + 8.0 * n * 3
+    line = {"metric": "gp2Scale LML evals/s (N=1M, 3D, Wendland, sparse assembly + PCG + SLQ logdet)",
+            "value": world * args.steps / t_dev, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4: gp2Scale, 3-D input, N={n}, wendland_anisotropic, CSR assembly on device, "
+                                   f"block-Jacobi PCG rtol 1e-5, SLQ logdet (degree 20, 10 probes)", "n": n, "nnz": nnz,
+                       "nnz_per_row": nnz / n, "l2_policy": f"CSR is {12 * nnz / 1e9:.2f} GB > L2"},
+            "gpu_launches": int(launches), "constructor_seconds": t_ctor, "last_lml": lml,
+            "phases_seconds": {"csr_count+scan+fill": t_fill, "spmv": t_spmv, "bjacobi_build": t_pre,
+                               "pcg_bjacobi": t_cg, "pcg_bjacobi_iters": res[2], "pcg_plain": t_cg0,
+                               "pcg_plain_iters": res0[2], "slq_10x20": t_slq},
+            "roofline": {"bound": "hbm", "kernel": "spmv_kernel (CSR-vector), the inner kernel of PCG and SLQ",
+                         "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s", "frac": spmv_gbs / hbm, "traffic": None,
+                         "algorithmic_bytes": 12.0 * nnz + 16.0 * n},
+            "roofline_fill": {"bound": "hbm", "kernel": "wendland_csr_kernel count + fill (output-sensitive bytes)",
+                              "achieved": fill_bytes / t_fill / 1e9, "peak": hbm, "unit": "GB/s",
+                              "frac": fill_bytes / t_fill / 1e9 / hbm, "algorithmic_bytes": fill_bytes}}
+    print(json.dumps(line), flush=True)
+
+
 def workload_config(args):
     return {"workload": f"C2: single-task GP, 3-D input, N={args.n}, anisotropic Matern-3/2 (default kernel), dense FP64 "
                         f"Cholesky, LML + hyperparameter gradient per step",
@@ -131,7 +259,13 @@ def main():
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--cpu-sample-n", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 (default, the headline): dense N=50k LML+gradient; c4: gp2Scale N=1M LML")
     args = ap.parse_args()
+    if args.workload == "c4":
+        if args.n == 50000:
+            args.n = 1000000
+        return run_c4(args)
     if args.impl == "reference":
         return run_reference(args)
 

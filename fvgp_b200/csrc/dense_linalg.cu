@@ -26,7 +26,7 @@ constexpr int TS = 128;  // diagonal tile handled by one CTA (Cholesky + inverse
 constexpr int VS = 64;   // block width of the single-right-hand-side solves
 constexpr int TP = TS + 1;
 constexpr int HP = TS / 2 + 1;
-constexpr size_t POTRF_TILE_SMEM = (size_t(TS) * TP + 2 * (TS / 2) * HP + TS) * sizeof(double);  // ~198 KB
+constexpr size_t POTRF_TILE_SMEM = (size_t(TS) * TP + 2 * (TS / 2) * HP + 2 * TS) * sizeof(double);  // ~198 KB
 
 // ----------------------------------------------------------------------------------------------
 // 128x128 diagonal tile, one CTA of 512 threads, everything in shared memory:
@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(512) potrf_tile_kernel(double* A, long long ld
   double(*InvA)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP);
   double(*InvD)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP + (TS / 2) * HP);
   double* Dg = tile_smem + TS * TP + 2 * (TS / 2) * HP;
+  double* RDg = Dg + TS;  // reciprocals of the diagonal
   constexpr int H = TS / 2;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < TS * TS; idx += 512) {
@@ -58,13 +59,32 @@ __global__ void __launch_bounds__(512) potrf_tile_kernel(double* A, long long ld
   for (int j = 0; j < TS; ++j) {
     const double d = T[j][j];
     if (!(d > 0.0) && tid == 0) atomicCAS(info, 0, global_row0 + j + 1);
-    const double s = sqrt(d);
-    if (tid == j) Dg[j] = s;
-    if (tid > j && tid < TS) T[tid][j] = T[tid][j] / s;
+    // 1/sqrt(d) by MUFU.RSQ64H + two Newton steps (the IEEE sqrt + divide pair is a ~500-cycle
+    // dependent chain in every one of the 128 column steps); column scaling becomes a multiply.
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const double e = fma(-(d * y), y, 1.0);
+      y = fma(0.5 * y, e, y);
+    }
+    double s = d * y;
+    s = fma(fma(-s, s, d), 0.5 * y, s);
+    if (tid == j) Dg[j] = s, RDg[j] = y;
+    if (tid > j && tid < TS) T[tid][j] *= y;
     __syncthreads();
     if (ri > j) {
       const double lij = T[ri][j];
-      for (int k = j + 1 + part; k <= ri; k += 4) T[ri][k] -= lij * T[k][j];
+      int k = j + 1 + part;
+      for (; k + 12 <= ri; k += 16) {  // loads first, then FMAs, then stores: no load-after-store serialisation
+        const double a0 = T[k][j], a1 = T[k + 4][j], a2 = T[k + 8][j], a3 = T[k + 12][j];
+        const double c0 = T[ri][k], c1 = T[ri][k + 4], c2 = T[ri][k + 8], c3 = T[ri][k + 12];
+        T[ri][k] = fma(-lij, a0, c0);
+        T[ri][k + 4] = fma(-lij, a1, c1);
+        T[ri][k + 8] = fma(-lij, a2, c2);
+        T[ri][k + 12] = fma(-lij, a3, c3);
+      }
+      for (; k <= ri; k += 4) T[ri][k] = fma(-lij, T[k][j], T[ri][k]);
     }
     __syncthreads();
   }
@@ -72,12 +92,19 @@ __global__ void __launch_bounds__(512) potrf_tile_kernel(double* A, long long ld
     const int c = (tid >> 2) & (H - 1), base = (tid >> 8) * H;
     double(*Inv)[HP] = (tid >> 8) ? InvD : InvA;
     for (int i = 0; i < H; ++i) {
-      double acc = 0.0;
-      if (i > c)
-        for (int k = c + part; k < i; k += 4) acc += T[base + i][base + k] * Inv[k][c];
+      double acc0 = 0.0, acc1 = 0.0;
+      if (i > c) {
+        int k = c + part;
+        for (; k + 4 < i; k += 8) {
+          acc0 = fma(T[base + i][base + k], Inv[k][c], acc0);
+          acc1 = fma(T[base + i][base + k + 4], Inv[k + 4][c], acc1);
+        }
+        for (; k < i; k += 4) acc0 = fma(T[base + i][base + k], Inv[k][c], acc0);
+      }
+      double acc = acc0 + acc1;
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (part == 0) Inv[i][c] = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - acc) / Dg[base + i];
+      if (part == 0) Inv[i][c] = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - acc) * RDg[base + i];
       __syncwarp();
     }
   }

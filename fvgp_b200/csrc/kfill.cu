@@ -147,7 +147,7 @@ __device__ __forceinline__ void fill_tile(const FillParams& p, long long ti, lon
   const double* xrow = p.x1 + r0 * dim;
   double* krow = p.K + r0 * p.ldk + ca;
   double* srow = sT + lane * FT_STRIDE + warp * 8;
-#pragma unroll
+#pragma unroll 2
   for (int rr = 0; rr < 8; ++rr) {
     if (!INTERIOR && r0 + rr >= p.n1) break;
     double xr[D];
@@ -169,15 +169,14 @@ __device__ __forceinline__ void fill_tile(const FillParams& p, long long ti, lon
 }
 
 template <int KIND, int DIM>
-__global__ void __launch_bounds__(FILL_THREADS) kfill_kernel(const FillParams p) {
-  extern __shared__ __align__(128) double stage[];  // 2 x FT x FT_STRIDE
+__global__ void __launch_bounds__(FILL_THREADS, 3) kfill_kernel(const FillParams p) {
+  extern __shared__ __align__(128) double stage[];  // FT x FT_STRIDE staging tile (symmetric mode only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
   double inv[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < p.dim) ? p.inv_scale[i] : 0.0;
 
-  int mit = 0;  // mirror-tile counter: selects the staging buffer (bulk groups are committed per mirror tile)
   for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     long long ti, tj;
     if (p.mode == FVGP_FILL_FULL) {
@@ -189,11 +188,11 @@ __global__ void __launch_bounds__(FILL_THREADS) kfill_kernel(const FillParams p)
       if (p.mode == FVGP_FILL_SYMMETRIC) ti = b, tj = a; else ti = a, tj = b;
     }
     const bool mirror = (p.mode == FVGP_FILL_SYMMETRIC) && (tj > ti);
-    double* sT = stage + (mit & 1) * (FT * FT_STRIDE);
+    double* sT = stage;
     if (mirror) {
-      ++mit;
-      // the bulk stores issued from this buffer two tiles ago must have finished reading it
-      if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+      // the bulk stores of this CTA's previous mirror tile must have finished READING the staging tile
+      // (a few hundred cycles; the other CTAs resident on the SM keep the pipes busy meanwhile)
+      if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
       __syncthreads();
     }
     const bool interior = (ti + 1) * FT <= p.n1 && (tj + 1) * FT <= p.n2 && (p.noise == nullptr || ti != tj);
@@ -228,17 +227,11 @@ __global__ void __launch_bounds__(FILL_THREADS) kfill_kernel(const FillParams p)
 
 template <int KIND>
 static int launch_fill_dim(const FillParams& p, cudaStream_t st) {
-  const size_t smem = 2 * FT * FT_STRIDE * sizeof(double);
-  const long long max_ctas = (long long)sm_count() * 3;
+  const size_t smem = p.mode == FVGP_FILL_SYMMETRIC ? FT * FT_STRIDE * sizeof(double) : 0;
+  const long long max_ctas = (long long)sm_count() * 4;
   const unsigned grid = (unsigned)(p.ntiles < max_ctas ? p.ntiles : max_ctas);
 #define FVGP_FILL_CASE(DIMV)                                                                              \
   {                                                                                                       \
-    static bool cfg = false;                                                                              \
-    if (!cfg) {                                                                                           \
-      FVGP_CUDA_OK(cudaFuncSetAttribute(kfill_kernel<KIND, DIMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)smem));                                                      \
-      cfg = true;                                                                                         \
-    }                                                                                                     \
     launch(kfill_kernel<KIND, DIMV>, grid, FILL_THREADS, smem, st, p);                                        \
   }
   switch (p.dim) {

@@ -13,9 +13,10 @@
 // s < 1 for s = sum_i ((x1_i - x2_i) / theta_i)^2 accumulated in axis order with every
 // operation rounded separately (numpy never fuses).  The predicate below uses the
 // __dsub_rn/__ddiv_rn/__dmul_rn/__dadd_rn intrinsics, which ptxas may not contract.
-// Tile and point-vs-tile bounding-box culls run the SAME operation sequence on the
-// coordinate gaps; every operation is monotone, so gap_s >= 1 implies s >= 1 for every
-// pair in the tile and the cull never changes the pattern (no epsilon margins).
+// Bounding-box culls (tile, super tile, point-vs-tile) and a per-pair pre-filter evaluate an
+// approximate s (reciprocal multiply + FMA) and discard only what is >= 1 + 1e-12, far outside
+// the few-ulp approximation error, so they can never remove a stored entry; every surviving
+// candidate is decided by the exact sequence.
 //
 // Layout: 32-point row tiles (one warp each) against 32-point column tiles, column tiles
 // grouped into super tiles of 32 for a two-level box cull.  Inside a surviving tile pair
@@ -84,16 +85,23 @@ __global__ void aabb_super_kernel(double* aabb, int dim, long long tiles, long l
   }
 }
 
-// s for the per-axis gaps between two boxes, in the reference's operation order.
+// Conservative cull margin: the culls and the pair pre-filter use reciprocal multiplies and FMAs
+// (relative error of a few ulp, << 1e-12).  A box / pair is discarded only when its approximate s is
+// >= 1 + kMargin, which implies the exactly-rounded reference s is > 1; everything below that
+// threshold is decided by the exact operation sequence.  The pattern is therefore bit-exact while
+// the slow IEEE divisions run only for the ~7 % of candidate pairs that are (almost) hits.
+#define FVGP_CULL_LIMIT (1.0 + 1e-12)
+
+// approximate s of the per-axis gaps between two boxes
 template <int DIM>
 __device__ __forceinline__ double box_gap_s(const double* lo1, const double* hi1, const double* lo2, const double* hi2,
-                                            const double* theta) {
+                                            const double* rinv) {
   double s = 0.0;
 #pragma unroll
   for (int i = 0; i < DIM; ++i) {
-    const double g = fmax(0.0, fmax(__dsub_rn(lo2[i], hi1[i]), __dsub_rn(lo1[i], hi2[i])));
-    const double t = __ddiv_rn(g, theta[i]);
-    s = __dadd_rn(s, __dmul_rn(t, t));
+    const double g = fmax(0.0, fmax(lo2[i] - hi1[i], lo1[i] - hi2[i]));
+    const double t = g * rinv[i];
+    s = fma(t, t, s);
   }
   return s;
 }
@@ -107,10 +115,11 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
   if (tile >= p.tiles1) return;  // whole warp exits together; no CTA-wide barriers below
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  double theta[DIM], lo1[DIM], hi1[DIM];
+  double theta[DIM], rinv[DIM], lo1[DIM], hi1[DIM];
 #pragma unroll
   for (int i = 0; i < DIM; ++i) {
     theta[i] = p.theta[i];
+    rinv[i] = 1.0 / fabs(p.theta[i]);
     lo1[i] = p.aabb1[tile * 2 * DIM + i];
     hi1[i] = p.aabb1[tile * 2 * DIM + DIM + i];
   }
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
       double lo2[DIM], hi2[DIM];
 #pragma unroll
       for (int i = 0; i < DIM; ++i) lo2[i] = bx[i], hi2[i] = bx[DIM + i];
-      keep = box_gap_s<DIM>(lo1, hi1, lo2, hi2, theta) < 1.0;
+      keep = box_gap_s<DIM>(lo1, hi1, lo2, hi2, rinv) < FVGP_CULL_LIMIT;
     }
     unsigned smask = __ballot_sync(0xffffffffu, keep);
     while (smask) {
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
         double lo2[DIM], hi2[DIM];
 #pragma unroll
         for (int i = 0; i < DIM; ++i) lo2[i] = bx[i], hi2[i] = bx[DIM + i];
-        keep_t = box_gap_s<DIM>(lo1, hi1, lo2, hi2, theta) < 1.0;
+        keep_t = box_gap_s<DIM>(lo1, hi1, lo2, hi2, rinv) < FVGP_CULL_LIMIT;
       }
       unsigned tmask = __ballot_sync(0xffffffffu, keep_t);
       while (tmask) {
@@ -167,21 +176,32 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
 #pragma unroll
           for (int i = 0; i < DIM; ++i) xr[i] = xs[warp][rr][i];
           // point-vs-box cull (warp-uniform): the row point as a degenerate box
-          if (box_gap_s<DIM>(xr, xr, lo2, hi2, theta) >= 1.0) continue;
-          double s = 0.0;
+          if (box_gap_s<DIM>(xr, xr, lo2, hi2, rinv) >= FVGP_CULL_LIMIT) continue;
+          double sa = 0.0;
 #pragma unroll
           for (int i = 0; i < DIM; ++i) {
-            const double t = __ddiv_rn(__dsub_rn(xr[i], xc[i]), theta[i]);
-            s = __dadd_rn(s, __dmul_rn(t, t));
+            const double t = (xr[i] - xc[i]) * rinv[i];
+            sa = fma(t, t, sa);
           }
+          const bool maybe = c_ok && sa < FVGP_CULL_LIMIT;
+          if (!__any_sync(0xffffffffu, maybe)) continue;
           double v = 0.0;
-          if (c_ok && s < 1.0) {
-            const double d = __dsqrt_rn(s);
-            const double u = 1.0 - d;
-            const double u2 = u * u, u4 = u2 * u2;
-            const double d2 = d * d;
-            const double poly = ((32.0 * (d2 * d) + 25.0 * d2) + 8.0 * d) + 1.0;
-            v = (p.amp * (u4 * u4)) * poly;
+          if (maybe) {
+            // the reference's own sequence: subtract, TRUE divide, square, add -- each rounded separately
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+              const double t = __ddiv_rn(__dsub_rn(xr[i], xc[i]), theta[i]);
+              s = __dadd_rn(s, __dmul_rn(t, t));
+            }
+            if (s < 1.0) {
+              const double d = __dsqrt_rn(s);
+              const double u = 1.0 - d;
+              const double u2 = u * u, u4 = u2 * u2;
+              const double d2 = d * d;
+              const double poly = ((32.0 * (d2 * d) + 25.0 * d2) + 8.0 * d) + 1.0;
+              v = (p.amp * (u4 * u4)) * poly;
+            }
           }
           const bool hit = v != 0.0;
           const unsigned hmask = __ballot_sync(0xffffffffu, hit);

@@ -317,6 +317,12 @@ def _timings():
             print(f"  kfill {nm} bulk={bulk} n={n}: {t * 1e3:.2f} ms -> {bytes_ / t / 1e9:.0f} GB/s")
             RESULTS[f"kfill_{nm}_bulk{bulk}_gbs"] = bytes_ / t / 1e9
     L.load().fvgp_set_bulk_store(1)
+    x1d = dev(rng.random((n, 1)))
+    for mode, nm in ((L.FILL_SYMMETRIC, "symmetric"), (L.FILL_FULL, "full")):
+        t = cuda_time(lambda: ops.kfill(L.K_DISTANCE, x1d, x1d, 1.0, np.ones(1), 1.0, mode=mode, out=out), reps=5)
+        print(f"  store-path ceiling (1-D distance fill, {nm}): {8 * n * n / t / 1e9:.0f} GB/s")
+        t = cuda_time(lambda: ops.kfill(L.K_SQEXP, x, x, 1.0, 1 / hps[1:], 0.5, mode=mode, out=out), reps=5)
+        print(f"  squared-exponential fill ({nm}): {8 * n * n / t / 1e9:.0f} GB/s")
     t = cuda_time(lambda: out[0].fill_(1.0), reps=5)
     print(f"  torch fill_ same buffer: {out[0].numel() * 8 / t / 1e9:.0f} GB/s (write-only reference)")
     RESULTS["torch_fill_gbs"] = out[0].numel() * 8 / t / 1e9
