@@ -22,11 +22,14 @@ _SIGNATURES = {
     "fvgp_launch_count": (ctypes.c_ulonglong, []),
     "fvgp_set_bulk_store": (c_int, [c_int]),
     "fvgp_kfill_dense": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_double, POINTER(c_double),
-                                 c_double, _P, _P, c_int64, _P]),
+                                 POINTER(c_double), c_double, _P, _P, c_int64, _P]),
     "fvgp_radial_elementwise": (c_int, [c_int, _P, c_int64, c_double, c_double, _P, _P]),
     "fvgp_kgrad_partials_len": (c_int64, [c_int64, c_int]),
     "fvgp_kgrad_trace_matern32": (c_int, [_P, c_int64, c_int, POINTER(c_double), _P, c_int64, _P, _P,
                                           POINTER(c_double), _P]),
+    "fvgp_kgrad_block_partials_len": (c_int64, [c_int]),
+    "fvgp_kgrad_trace_block_matern32": (c_int, [_P, c_int64, _P, c_int64, c_int, POINTER(c_double), _P, c_int64, _P, _P,
+                                                c_int64, _P, _P, _P]),
     "fvgp_trace_sym_product": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, POINTER(c_double), _P]),
     "fvgp_kgrad_dense_matern32": (c_int, [_P, c_int64, _P, c_int64, c_int, POINTER(c_double), _P, _P]),
     "fvgp_chol_workspace_len": (c_int64, [c_int64]),
@@ -37,6 +40,14 @@ _SIGNATURES = {
     "fvgp_potri_lower": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "fvgp_dgemm_nt": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_double, c_double,
                               c_int, _P]),
+    "fvgp_dgemm": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_double,
+                           c_double, c_int, _P]),
+    "fvgp_trsm_right_lower_t": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, _P]),
+    "fvgp_trtri_lower": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
+    "fvgp_lauum_lower": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "fvgp_trsv_lower": (c_int, [_P, c_int64, c_int64, _P, _P, c_int, _P, _P]),
+    "fvgp_gemv_work_len": (c_int64, [c_int64, c_int64]),
+    "fvgp_gemv": (c_int, [c_int, _P, c_int64, c_int, c_int, c_double, _P, _P, _P, _P]),
     "fvgp_dot": (c_int, [_P, _P, c_int64, _P, POINTER(c_double), _P]),
     "fvgp_wendland_aabb_len": (c_int64, [c_int64, c_int]),
     "fvgp_wendland_aabb": (c_int, [_P, c_int64, c_int, _P, _P]),

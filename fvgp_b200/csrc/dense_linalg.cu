@@ -17,6 +17,7 @@
 // triangle of the row-major matrix.
 #include "../../include/fvgp_b200.h"
 #include "dgemm.cuh"
+#include <algorithm>
 
 namespace fvgp {
 
@@ -239,6 +240,53 @@ __global__ void __launch_bounds__(1024) dot_kernel(const double* __restrict__ a,
   if (threadIdx.x == 0) out[0] = s;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Matrix-vector products for the block-cyclic (multi-GPU) triangular solves: the panels of L that a
+// rank owns are m x n (n <= one block), row-major.  HBM-read bound (8*m*n bytes), deterministic.
+// ----------------------------------------------------------------------------------------------
+// y[i] += alpha * sum_j A[i][j] x[j]; one warp per row.
+__global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ A, long long lda, int m, int n,
+                                                     double alpha, const double* __restrict__ x, double* y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long i = (long long)blockIdx.x * 8 + warp; i < m; i += (long long)gridDim.x * 8) {
+    const double* row = A + i * lda;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc = fma(row[j], x[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[i] += alpha * acc;
+  }
+}
+
+// partial[chunk][j] = sum_{i in chunk} A[i][j] x[i]; thread = column, CTA = (column group, row chunk).
+constexpr int GEMVT_ROWS = 256;
+__global__ void __launch_bounds__(256) gemv_t_partial_kernel(const double* __restrict__ A, long long lda, int m, int n,
+                                                             const double* __restrict__ x, double* partial) {
+  __shared__ double xs[GEMVT_ROWS];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int i0 = blockIdx.y * GEMVT_ROWS, i1 = min(m, i0 + GEMVT_ROWS);
+  if (i0 + (int)threadIdx.x < i1) xs[threadIdx.x] = x[i0 + threadIdx.x];
+  __syncthreads();
+  if (j >= n) return;
+  double a0 = 0.0, a1 = 0.0;
+  int i = i0;
+  for (; i + 1 < i1; i += 2) {
+    a0 = fma(A[(long long)i * lda + j], xs[i - i0], a0);
+    a1 = fma(A[(long long)(i + 1) * lda + j], xs[i + 1 - i0], a1);
+  }
+  if (i < i1) a0 = fma(A[(long long)i * lda + j], xs[i - i0], a0);
+  partial[(long long)blockIdx.y * n + j] = a0 + a1;
+}
+
+__global__ void __launch_bounds__(256) gemv_t_reduce_kernel(const double* __restrict__ partial, int chunks, int n,
+                                                            double alpha, double* y) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partial[(long long)c * n + j];
+  y[j] += alpha * s;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Host-side recursion
 // ----------------------------------------------------------------------------------------------
@@ -446,6 +494,91 @@ int fvgp_dgemm_nt(const double* d_A, int64_t lda, const double* d_B, int64_t ldb
                   int n, int k, double alpha, double beta, int lower, void* stream) {
   return launch_gemm<false, false>((cudaStream_t)stream, d_A, lda, d_B, ldb, d_C, ldc, m, n, k, alpha, beta,
                                    lower ? GEMM_LOWER : 0);
+}
+
+
+/* ---- building blocks of the block-cyclic multi-GPU factorisation (fvgp_b200/sharded.py) ---- */
+
+int fvgp_dgemm(int a_mn, int b_mn, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C,
+               int64_t ldc, int m, int n, int k, double alpha, double beta, int flags, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!a_mn && !b_mn) return launch_gemm<false, false>(st, d_A, lda, d_B, ldb, d_C, ldc, m, n, k, alpha, beta, flags);
+  if (!a_mn && b_mn) return launch_gemm<false, true>(st, d_A, lda, d_B, ldb, d_C, ldc, m, n, k, alpha, beta, flags);
+  if (a_mn && b_mn) return launch_gemm<true, true>(st, d_A, lda, d_B, ldb, d_C, ldc, m, n, k, alpha, beta, flags);
+  FVGP_REQUIRE(!"operand layout (A MN-major, B K-major) is not instantiated");
+  return FVGP_ERR_ARG;
+}
+
+int fvgp_trsm_right_lower_t(double* d_B, int64_t ldb, int m, const double* d_L, int64_t ldl, int n,
+                            const double* d_tileinv, void* stream) {
+  FVGP_REQUIRE(n > 0 && m >= 0 && ldb % 2 == 0 && ldl % 2 == 0);
+  Ctx c{(cudaStream_t)stream, const_cast<double*>(d_tileinv), nullptr, nullptr, 0};
+  return trsm_rt_rec(c, d_B, ldb, m, d_L, ldl, n, 0);
+}
+
+int fvgp_trtri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_work, void* stream) {
+  FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{st, const_cast<double*>(d_tileinv), nullptr, d_work, 0};
+  launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, st, d_L, lda, (int)n);
+  FVGP_LAUNCH_OK();
+  return trtri_rec(c, d_L, lda, (int)n, 0);
+}
+
+int fvgp_lauum_lower(double* d_M, int64_t n, int64_t lda, double* d_work, void* stream) {
+  FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
+  Ctx c{(cudaStream_t)stream, nullptr, nullptr, d_work, 0};
+  return lauum_rec(c, d_M, lda, (int)n);
+}
+
+int fvgp_trsv_lower(const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_b, int transpose,
+                    double* d_work, void* stream) {
+  FVGP_REQUIRE(n > 0 && lda % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* w = d_work;
+  double* z = d_work + n;
+  const int tiles = (int)((n + VS - 1) / VS);
+  auto block_inv = [&](int t) {
+    return d_tileinv + (int64_t)(t / 2) * TS * TS + (t % 2) * ((int64_t)VS * TS + VS);
+  };
+  if (!transpose) {  // L z = b
+    FVGP_CUDA_OK(cudaMemcpyAsync(w, d_b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    for (int t = 0; t < tiles; ++t) {
+      const int j0 = t * VS;
+      const int rest = (int)n - (j0 + VS);
+      const int grid = rest > 0 ? (rest + 63) / 64 : 1;
+      launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), w, z);
+    }
+    FVGP_LAUNCH_OK();
+    FVGP_CUDA_OK(cudaMemcpyAsync(d_b, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  } else {  // L^T x = b
+    FVGP_CUDA_OK(cudaMemcpyAsync(z, d_b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    for (int t = tiles - 1; t >= 0; --t) {
+      const int j0 = t * VS;
+      const int grid = j0 > 0 ? (j0 + 255) / 256 : 1;
+      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), z, d_b);
+    }
+    FVGP_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int64_t fvgp_gemv_work_len(int64_t m, int64_t n) { return ((m + GEMVT_ROWS - 1) / GEMVT_ROWS) * n + 1; }
+
+int fvgp_gemv(int transpose, const double* d_A, int64_t lda, int m, int n, double alpha, const double* d_x,
+              double* d_y, double* d_work, void* stream) {
+  if (m <= 0 || n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!transpose) {
+    const int grid = (int)std::min<long long>(((long long)m + 7) / 8, (long long)sm_count() * 16);
+    launch(gemv_n_kernel, grid, 256, 0, st, d_A, lda, m, n, alpha, d_x, d_y);
+  } else {
+    const int chunks = (m + GEMVT_ROWS - 1) / GEMVT_ROWS;
+    launch(gemv_t_partial_kernel, dim3((n + 255) / 256, chunks), 256, 0, st, d_A, lda, m, n, d_x, d_work);
+    launch(gemv_t_reduce_kernel, (n + 255) / 256, 256, 0, st, d_work, chunks, n, alpha, d_y);
+  }
+  FVGP_LAUNCH_OK();
+  return 0;
 }
 
 }  // extern "C"

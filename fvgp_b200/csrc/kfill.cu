@@ -23,6 +23,7 @@ namespace fvgp {
 constexpr int FT = 64;             // tile edge
 constexpr int FT_STRIDE = FT + 2;  // even (16-byte rows for the bulk copy)
 constexpr int FILL_THREADS = 256;
+constexpr int STAGE_DOUBLES = FT * FT_STRIDE;
 
 static int g_use_bulk_store = 1;
 
@@ -33,10 +34,11 @@ struct FillParams {
   double* K;
   long long n1, n2, ldk;
   double amp, c_arg, c_aux;  // kind-specific constants
-  double inv_scale[kMaxDim];
+  double inv_scale[kMaxDim];  // centred path: inv_scale * (kind's argument constant)
+  double centre[kMaxDim];
   int dim, mode;
   long long tiles_i, tiles_j, ntiles;
-  int bulk;
+  int bulk, vec2;
 };
 
 __device__ __forceinline__ void tri_index(long long id, long long& a, long long& b) {
@@ -46,81 +48,72 @@ __device__ __forceinline__ void tri_index(long long id, long long& a, long long&
   b = id - a * (a + 1) / 2;
 }
 
-// ---- lean FP64 math for the fill: the kernel is instruction-issue bound, not DP-pipe bound, with
-// libdevice's exp/sqrt (64-bit immediates are rebuilt with UMOV pairs, slow-path branches around
-// every call).  Coefficients live in constant memory so each DFMA takes its constant operand
-// straight from the constant bank; no special cases are needed because the argument of exp is
-// always <= 0 and the argument of sqrt is clamped positive.  Both are accurate to ~1 ulp
-// (tests compare K entries with the reference at 1e-12 relative).
+// ---- lean FP64 math for the fill.  The kernel is bound by the FP64 pipe AND by instruction issue
+// (ncu: 37 DP + 37 other instructions per entry with libdevice-free but naive code), so every
+// special case is moved to the integer pipe and every constant comes from the constant bank:
+//   exp(-a), a >= 0 : Cody-Waite reduction + degree-11 Horner; the 2^n scaling is an integer add on
+//                     the high word with n clamped at -1022, so results below 2.3e-308 come back
+//                     as (sub)normal garbage of at most that magnitude instead of exactly 0;
+//   sqrt(s), s >= 0 : MUFU.RSQ64H on the high word (clamped to the smallest normal with an integer
+//                     max, which also makes s = 0 return exactly 0) + one Newton step + residual
+//                     correction, ~1 ulp.
+// Tests compare K entries with the reference at 1e-12 relative.
 __constant__ double kExpC[12] = {2.5022322536502990E-008, 2.7630903488173108E-007, 2.7557514545882439E-006,
                                  2.4801491039099165E-005, 1.9841269589115497E-004, 1.3888888945916380E-003,
                                  8.3333333334550432E-003, 4.1666666666519754E-002, 1.6666666666666477E-001,
                                  5.0000000000000122E-001, 1.0, 1.0};
-__constant__ double kExpK[4] = {1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01,
+__constant__ double kExpK[4] = {-1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01,
                                 -2.31904681384629956e-17};
 
-__device__ __forceinline__ double exp_nonpos(double x) {  // x <= 0
-  const double t = fma(x, kExpK[0], kExpK[1]);
-  const int n = __double2loint(t);
+__device__ __forceinline__ double exp_neg(double a) {  // exp(-a) for 0 <= a < 2^30
+  const double t = fma(a, kExpK[0], kExpK[1]);
+  int n = __double2loint(t);
   const double nf = t - kExpK[1];
-  double r = fma(nf, kExpK[2], x);
+  double r = fma(nf, kExpK[2], -a);
   r = fma(nf, kExpK[3], r);
   double p = kExpC[0];
 #pragma unroll
   for (int i = 1; i < 12; ++i) p = fma(p, r, kExpC[i]);
-  const double scaled = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-  return x < -708.0 ? 0.0 : scaled;
+  n = max(n, -1022);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
-__device__ __forceinline__ double sqrt_pos(double s) {  // s > 0, finite
+__device__ __forceinline__ double exp_nonpos(double x) {  // x <= 0 (trace kernel, elementwise kernels)
+  return exp_neg(fmin(-x, 1.0e9));
+}
+
+__device__ __forceinline__ double sqrt_pos(double s) {  // s >= 2.3e-308 (normal), finite
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-  double g = s * y, h = 0.5 * y;
+  double g = s * y;
+  const double h = 0.5 * y;
   const double r = fma(-h, g, 0.5);
   g = fma(g, r, g);
-  h = fma(h, r, h);
   const double d = fma(-g, g, s);
   return fma(d, h, g);
 }
 
-template <int KIND>
+// Value from the squared scaled distance s.  CENTRED: the kind's argument constant is already folded
+// into the coordinate scaling, so that a = sqrt(s) (or s) is the argument of exp directly.
+template <int KIND, bool CENTRED>
 __device__ __forceinline__ double radial_value(double s, double amp, double c_arg, double c_aux) {
-  // s = squared scaled distance
-  if (KIND == FVGP_K_SQEXP) return amp * exp_nonpos(-s * c_arg);  // c_arg = 1/(2 l^2)
-  const double d = (KIND == FVGP_K_DISTANCE || KIND == FVGP_K_WENDLAND) ? sqrt(s) : sqrt_pos(fmax(s, 1e-300));
+  if (KIND == FVGP_K_SQEXP) return amp * exp_neg(CENTRED ? s : fmin(s * c_arg, 1.0e9));  // c_arg = 1/(2 l^2)
+  const double d = ((KIND == FVGP_K_WENDLAND && !CENTRED) || KIND == FVGP_K_DISTANCE) ? sqrt(s) : sqrt_pos(s);
   if (KIND == FVGP_K_DISTANCE) return d;
   if (KIND == FVGP_K_MATERN32) {
-    const double a = c_arg * d;  // c_arg = sqrt(3)/l
-    return amp * ((1.0 + a) * exp_nonpos(-a));
+    const double a = CENTRED ? d : fmin(c_arg * d, 1.0e9);  // c_arg = sqrt(3)/l
+    return fma(amp, a, amp) * exp_neg(a);
   }
   if (KIND == FVGP_K_MATERN52) {
-    const double a = c_arg * d;  // c_arg = sqrt(5)/l, c_aux = 5/(3 l^2)
-    return amp * ((1.0 + a + c_aux * s) * exp_nonpos(-a));
+    const double a = CENTRED ? d : fmin(c_arg * d, 1.0e9);  // c_arg = sqrt(5)/l, c_aux = amp * 5/(3 l^2) | amp/3
+    return fma(c_aux, s, fma(amp, a, amp)) * exp_neg(a);
   }
-  if (KIND == FVGP_K_EXP) return amp * exp_nonpos(-d * c_arg);  // c_arg = 1/l
+  if (KIND == FVGP_K_EXP) return amp * exp_neg(CENTRED ? d : fmin(d * c_arg, 1.0e9));  // c_arg = 1/l
   // Wendland (dense form, kernels.py:355-378)
-  const double dd = fmin(d * c_arg, 1.0);
+  const double dd = fmin(CENTRED ? d : d * c_arg, 1.0);
   const double u = 1.0 - dd;
   const double u2 = u * u, u4 = u2 * u2;
   return amp * (u4 * u4) * (32.0 * dd * dd * dd + 25.0 * dd * dd + 8.0 * dd + 1.0);
-}
-
-template <int DIM>
-__device__ __forceinline__ double sqdist(const double* a, const double* b, const double* inv, int dim) {
-  double s = 0.0;
-  if (DIM > 0) {
-#pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-      const double t = (a[i] - b[i]) * inv[i];
-      s = fma(t, t, s);
-    }
-  } else {
-    for (int i = 0; i < dim; ++i) {
-      const double t = (a[i] - b[i]) * inv[i];
-      s = fma(t, t, s);
-    }
-  }
-  return s;
 }
 
 __device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc, unsigned bytes) {
@@ -129,75 +122,138 @@ __device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc,
                : "memory");
 }
 
-// One 64x64 tile: warp w owns rows 8w..8w+7, lane l owns columns l and l+32 (two 256-byte
-// coalesced row segments per warp store).  INTERIOR tiles carry no bounds checks and no noise test.
-template <int KIND, int DIM, bool INTERIOR>
+// One 64x64 tile.  Warp w owns rows 8w..8w+7; lane l owns the ADJACENT columns 2l, 2l+1, so a warp stores one
+// full 512-byte tile row with a single STG.128 per lane.  Rows are processed two at a time: four independent
+// sqrt/exp dependency chains per thread keep the FP64 pipe fed.  The warp's row coordinates are staged once per
+// tile in shared memory (already centred and scaled in the CENTRED variant): the inner loop then has no global
+// loads and, per entry, D subtractions + D fused multiply-adds for the distance.
+// INTERIOR tiles carry no bounds checks and no noise test.
+template <int KIND, int DIM, bool CENTRED, bool INTERIOR>
 __device__ __forceinline__ void fill_tile(const FillParams& p, long long ti, long long tj, bool mirror, double* sT,
-                                          const double* inv, int lane, int warp) {
+                                          double* sRow, int lane, int warp) {
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
-  const int dim = p.dim;
+  constexpr int DPAD = (D + 1) & ~1;
+  const int dim = DIM > 0 ? DIM : p.dim;
   const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
-  const long long ca = c0 + lane, cb = ca + 32;
+  const long long ca = c0 + 2 * lane, cb = ca + 1;
   double xa[D], xb[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    xa[i] = ((INTERIOR || ca < p.n2) && (DIM > 0 || i < dim)) ? p.x2[ca * dim + i] : 0.0;
-    xb[i] = ((INTERIOR || cb < p.n2) && (DIM > 0 || i < dim)) ? p.x2[cb * dim + i] : 0.0;
-  }
-  const double* xrow = p.x1 + r0 * dim;
-  double* krow = p.K + r0 * p.ldk + ca;
-  double* srow = sT + lane * FT_STRIDE + warp * 8;
-#pragma unroll 2
-  for (int rr = 0; rr < 8; ++rr) {
-    if (!INTERIOR && r0 + rr >= p.n1) break;
-    double xr[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? xrow[rr * dim + i] : 0.0;
-    double va = radial_value<KIND>(sqdist<DIM>(xr, xa, inv, dim), p.amp, p.c_arg, p.c_aux);
-    double vb = radial_value<KIND>(sqdist<DIM>(xr, xb, inv, dim), p.amp, p.c_arg, p.c_aux);
-    if (!INTERIOR && p.noise != nullptr) {
-      if (r0 + rr == ca) va += p.noise[ca];
-      if (r0 + rr == cb) vb += p.noise[cb];
+    const bool on = DIM > 0 || i < dim;
+    xa[i] = ((INTERIOR || ca < p.n2) && on) ? p.x2[ca * dim + i] : 0.0;
+    xb[i] = ((INTERIOR || cb < p.n2) && on) ? p.x2[cb * dim + i] : 0.0;
+    if (CENTRED) {
+      xa[i] = (xa[i] - p.centre[i]) * p.inv_scale[i];
+      xb[i] = (xb[i] - p.centre[i]) * p.inv_scale[i];
     }
-    if (INTERIOR || ca < p.n2) krow[rr * p.ldk] = va;
-    if (INTERIOR || cb < p.n2) krow[rr * p.ldk + 32] = vb;
-    if (mirror) {
-      srow[rr] = va;
-      srow[32 * FT_STRIDE + rr] = vb;
+  }
+  __syncwarp();  // the previous tile's reads of sRow are done
+  for (int idx = lane; idx < 8 * dim; idx += 32) {
+    const int rr = idx / dim, i = idx - rr * dim;
+    double v = (INTERIOR || r0 + rr < p.n1) ? p.x1[(r0 + rr) * dim + i] : 0.0;
+    if (CENTRED) v = (v - p.centre[i]) * p.inv_scale[i];
+    sRow[rr * DPAD + i] = v;
+  }
+  __syncwarp();
+  double* krow = p.K + r0 * p.ldk + ca;
+  double* srow = sT + (2 * lane) * FT_STRIDE + warp * 8;
+#pragma unroll 1
+  for (int rr = 0; rr < 8; rr += 2) {
+    if (!INTERIOR && r0 + rr >= p.n1) break;
+    // 1e-300 instead of 0: keeps the reciprocal square root finite for coincident points at no cost (the
+    // distance kind uses the IEEE square root and returns an exact 0)
+    constexpr double S0 = KIND == FVGP_K_DISTANCE ? 0.0 : 1e-300;
+    double s00 = S0, s01 = S0, s10 = S0, s11 = S0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (DIM > 0 || i < dim) {
+        const double x0 = sRow[rr * DPAD + i], x1 = sRow[(rr + 1) * DPAD + i];
+        double t00 = x0 - xa[i], t01 = x0 - xb[i], t10 = x1 - xa[i], t11 = x1 - xb[i];
+        if (!CENTRED) {
+          const double sc = p.inv_scale[i];
+          t00 *= sc, t01 *= sc, t10 *= sc, t11 *= sc;
+        }
+        s00 = fma(t00, t00, s00), s01 = fma(t01, t01, s01), s10 = fma(t10, t10, s10), s11 = fma(t11, t11, s11);
+      }
+    }
+    double v00 = radial_value<KIND, CENTRED>(s00, p.amp, p.c_arg, p.c_aux);
+    double v01 = radial_value<KIND, CENTRED>(s01, p.amp, p.c_arg, p.c_aux);
+    double v10 = radial_value<KIND, CENTRED>(s10, p.amp, p.c_arg, p.c_aux);
+    double v11 = radial_value<KIND, CENTRED>(s11, p.amp, p.c_arg, p.c_aux);
+    if (INTERIOR) {
+      if (p.vec2) {
+        *reinterpret_cast<double2*>(krow + rr * p.ldk) = make_double2(v00, v01);
+        *reinterpret_cast<double2*>(krow + (rr + 1) * p.ldk) = make_double2(v10, v11);
+      } else {
+        krow[rr * p.ldk] = v00, krow[rr * p.ldk + 1] = v01;
+        krow[(rr + 1) * p.ldk] = v10, krow[(rr + 1) * p.ldk + 1] = v11;
+      }
+    } else {
+      const long long ra = r0 + rr, rb = ra + 1;
+      if (p.noise != nullptr) {
+        if (ra == ca) v00 += p.noise[ca];
+        if (ra == cb) v01 += p.noise[cb];
+        if (rb == ca) v10 += p.noise[ca];
+        if (rb == cb) v11 += p.noise[cb];
+      }
+      if (ca < p.n2) krow[rr * p.ldk] = v00;
+      if (cb < p.n2) krow[rr * p.ldk + 1] = v01;
+      if (rb < p.n1) {
+        if (ca < p.n2) krow[(rr + 1) * p.ldk] = v10;
+        if (cb < p.n2) krow[(rr + 1) * p.ldk + 1] = v11;
+      }
+    }
+    if (mirror) {  // transposed staging tile: sT[column][row]
+      *reinterpret_cast<double2*>(srow + rr) = make_double2(v00, v10);
+      *reinterpret_cast<double2*>(srow + FT_STRIDE + rr) = make_double2(v01, v11);
     }
   }
 }
 
-template <int KIND, int DIM>
+template <int KIND, int DIM, bool CENTRED>
 __global__ void __launch_bounds__(FILL_THREADS, 3) kfill_kernel(const FillParams p) {
-  extern __shared__ __align__(128) double stage[];  // FT x FT_STRIDE staging tile (symmetric mode only)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // [8 warps][8 rows][DPAD] staged row coordinates, then two FT x FT_STRIDE staging tiles (symmetric mode only)
+  extern __shared__ __align__(128) double fill_smem[];
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
-  double inv[D];
-#pragma unroll
-  for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < p.dim) ? p.inv_scale[i] : 0.0;
+  constexpr int DPAD = (D + 1) & ~1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* sRow = fill_smem + warp * 8 * DPAD;
+  double* stage = fill_smem + 8 * 8 * DPAD;
+  int buf = 0;
 
-  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    long long ti, tj;
+  // Each CTA walks a CONTIGUOUS range of tiles: the (row block, column block) pair is decoded once (one FP64
+  // square root) and then advanced incrementally; consecutive tiles share a row / column block, so their
+  // coordinates stay in L1.
+  const long long per_cta = (p.ntiles + gridDim.x - 1) / gridDim.x;
+  long long tile = blockIdx.x * per_cta;
+  const long long tile_end = min(p.ntiles, tile + per_cta);
+  long long ia = 0, ib = 0;
+  if (tile < tile_end) {
     if (p.mode == FVGP_FILL_FULL) {
-      ti = tile / p.tiles_j;
-      tj = tile - ti * p.tiles_j;
+      ia = tile / p.tiles_j;
+      ib = tile - ia * p.tiles_j;
     } else {
-      long long a, b;
-      tri_index(tile, a, b);
-      if (p.mode == FVGP_FILL_SYMMETRIC) ti = b, tj = a; else ti = a, tj = b;
+      tri_index(tile, ia, ib);
+    }
+  }
+  for (; tile < tile_end; ++tile) {
+    long long ti = ia, tj = ib;
+    if (p.mode == FVGP_FILL_SYMMETRIC) ti = ib, tj = ia;
+    if (p.mode == FVGP_FILL_FULL) {
+      if (++ib == p.tiles_j) ib = 0, ++ia;
+    } else if (++ib > ia) {
+      ib = 0, ++ia;
     }
     const bool mirror = (p.mode == FVGP_FILL_SYMMETRIC) && (tj > ti);
-    double* sT = stage;
+    double* sT = stage + buf * STAGE_DOUBLES;
     if (mirror) {
-      // the bulk stores of this CTA's previous mirror tile must have finished READING the staging tile
-      // (a few hundred cycles; the other CTAs resident on the SM keep the pipes busy meanwhile)
-      if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      // the bulk stores that last used THIS staging buffer (two mirror tiles ago) must have finished reading it
+      if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
       __syncthreads();
     }
     const bool interior = (ti + 1) * FT <= p.n1 && (tj + 1) * FT <= p.n2 && (p.noise == nullptr || ti != tj);
-    if (interior) fill_tile<KIND, DIM, true>(p, ti, tj, mirror, sT, inv, lane, warp);
-    else fill_tile<KIND, DIM, false>(p, ti, tj, mirror, sT, inv, lane, warp);
+    if (interior) fill_tile<KIND, DIM, CENTRED, true>(p, ti, tj, mirror, sT, sRow, lane, warp);
+    else fill_tile<KIND, DIM, CENTRED, false>(p, ti, tj, mirror, sT, sRow, lane, warp);
     if (mirror) {
       // mirror tile: rows tj*FT.. of K, columns ti*FT .. ti*FT+63 (always a full 64 because ti < tj)
       const long long c0 = tj * FT;
@@ -209,6 +265,7 @@ __global__ void __launch_bounds__(FILL_THREADS, 3) kfill_kernel(const FillParams
           if (grow < p.n2) bulk_store_row(p.K + grow * p.ldk + ti * FT, sT + tid * FT_STRIDE, FT * 8);
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
+        buf ^= 1;
       } else {
         __syncthreads();
 #pragma unroll 2
@@ -225,21 +282,35 @@ __global__ void __launch_bounds__(FILL_THREADS, 3) kfill_kernel(const FillParams
   if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
 
+template <int KIND, int DIM, bool CENTRED>
+static void launch_fill_one(const FillParams& p, unsigned grid, cudaStream_t st) {
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  constexpr int DPAD = (D + 1) & ~1;
+  const size_t smem = (8 * 8 * DPAD + (p.mode == FVGP_FILL_SYMMETRIC ? 2 * STAGE_DOUBLES : 0)) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kfill_kernel<KIND, DIM, CENTRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((8 * 8 * DPAD + 2 * STAGE_DOUBLES) * sizeof(double)));
+    configured = true;
+  }
+  launch(kfill_kernel<KIND, DIM, CENTRED>, grid, FILL_THREADS, smem, st, p);
+}
+
 template <int KIND>
-static int launch_fill_dim(const FillParams& p, cudaStream_t st) {
-  const size_t smem = p.mode == FVGP_FILL_SYMMETRIC ? FT * FT_STRIDE * sizeof(double) : 0;
-  const long long max_ctas = (long long)sm_count() * 4;
+static int launch_fill_dim(const FillParams& p, bool centred, cudaStream_t st) {
+  const long long max_ctas = (long long)sm_count() * 3;
   const unsigned grid = (unsigned)(p.ntiles < max_ctas ? p.ntiles : max_ctas);
-#define FVGP_FILL_CASE(DIMV)                                                                              \
-  {                                                                                                       \
-    launch(kfill_kernel<KIND, DIMV>, grid, FILL_THREADS, smem, st, p);                                        \
+#define FVGP_FILL_CASE(DIMV)                                              \
+  {                                                                       \
+    if (centred) launch_fill_one<KIND, DIMV, true>(p, grid, st);          \
+    else launch_fill_one<KIND, DIMV, false>(p, grid, st);                 \
   }
   switch (p.dim) {
     case 1: FVGP_FILL_CASE(1) break;
     case 2: FVGP_FILL_CASE(2) break;
     case 3: FVGP_FILL_CASE(3) break;
     case 4: FVGP_FILL_CASE(4) break;
-    default: FVGP_FILL_CASE(0) break;
+    default: launch_fill_one<KIND, 0, false>(p, grid, st); break;
   }
 #undef FVGP_FILL_CASE
   FVGP_LAUNCH_OK();
@@ -333,6 +404,101 @@ __global__ void trace_reduce_kernel(const double* partials, int nctas, int H, do
   }
 }
 
+// Rectangular block of the same trace (multi-GPU block-cyclic layout, fvgp_b200/sharded.py): W is an m x n block of
+// KV^-1 whose rows belong to points x1 / entries b1 and columns to x2 / b2.  The first `diag_rows` rows form a
+// diagonal block aligned with the columns (only its lower triangle counts, the diagonal once); every other entry
+// stands for itself and its mirror image (weight 2).
+struct TraceBlockParams {
+  const double* x1;
+  const double* x2;
+  const double* W;
+  const double* b1;
+  const double* b2;
+  double* partials;
+  long long m, n, ld, tiles_j, ntiles;
+  long long diag_rows;
+  double inv_len[kMaxDim];
+  int dim;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(FILL_THREADS) kgrad_trace_block_kernel(const TraceBlockParams p) {
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  const int dim = p.dim;
+  const double sqrt3 = 1.7320508075688772;
+  double inv[D], acc[D + 1];
+#pragma unroll
+  for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < dim) ? p.inv_len[i] : 0.0;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) acc[i] = 0.0;
+  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long ti = tile / p.tiles_j, tj = tile - ti * p.tiles_j;
+    const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
+    if (r0 + 7 < p.diag_rows && c0 > r0 + 7) continue;  // strictly above the diagonal of the diagonal block
+    const long long cc[2] = {c0 + lane, c0 + lane + 32};
+    double xc[2][D], bc[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const bool ok = cc[q] < p.n;
+      bc[q] = ok ? p.b2[cc[q]] : 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) xc[q][i] = (ok && (DIM > 0 || i < dim)) ? p.x2[cc[q] * dim + i] : 0.0;
+    }
+    for (int rr = 0; rr < 8; ++rr) {
+      const long long r = r0 + rr;
+      if (r >= p.m) break;
+      const double br = p.b1[r];
+      double xr[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? p.x1[r * dim + i] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const long long c = cc[q];
+        if (c >= p.n) continue;
+        double weight = 2.0;
+        if (r < p.diag_rows) {
+          if (c > r) continue;
+          if (c == r) weight = 1.0;
+        }
+        const double w = (p.W[r * p.ld + c] - br * bc[q]) * weight;
+        double t2[D], s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const double t = (xr[i] - xc[q][i]) * inv[i];
+          t2[i] = t * t;
+          s += t2[i];
+        }
+        const double a = sqrt3 * sqrt_pos(fmax(s, 1e-300));
+        const double ea = exp_neg(fmin(a, 1.0e9));
+        const double wea = w * ea;
+        acc[0] = fma(wea, 1.0 + a, acc[0]);
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[1 + i] = fma(wea, t2[i], acc[1 + i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i <= D; ++i) {
+    const double v = block_sum(acc[i], red);
+    if (tid == 0 && (DIM > 0 || i <= dim)) p.partials[(long long)blockIdx.x * (dim + 1) + i] = v;
+  }
+}
+
+// accum[h] += scale[h] * sum_cta partials[cta][h]
+__global__ void trace_accumulate_kernel(const double* partials, int nctas, int H, double amp, const double* inv_len_dev,
+                                        double* accum) {
+  __shared__ double red[32];
+  for (int h = 0; h < H; ++h) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nctas; i += blockDim.x) s += partials[(long long)i * H + h];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) accum[h] += (h == 0) ? s : s * 3.0 * amp * inv_len_dev[h - 1];
+    __syncthreads();
+  }
+}
+
 // Radial kernel applied elementwise to a user-supplied distance array (the fvgp.kernels
 // functions called on a plain ndarray instead of on get_distance_matrix's result).
 template <int KIND>
@@ -340,7 +506,7 @@ __global__ void radial_elementwise_kernel(const double* __restrict__ d, long lon
                                           double c_aux, double* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const double v = d[i];
-    out[i] = radial_value<KIND>(v * v, amp, c_arg, c_aux);
+    out[i] = radial_value<KIND, false>(fmax(v * v, 1e-300), amp, c_arg, c_aux);
   }
 }
 
@@ -411,33 +577,50 @@ int fvgp_set_bulk_store(int on) {
 }
 
 int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2, int dim,
-                     double amp, const double* h_inv_scale, double length, const double* d_noise, double* d_K,
-                     int64_t ldk, void* stream) {
+                     double amp, const double* h_inv_scale, const double* h_centre, double length,
+                     const double* d_noise, double* d_K, int64_t ldk, void* stream) {
   FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n1 >= 0 && n2 >= 0 && ldk >= n2);
   FVGP_REQUIRE(mode == FVGP_FILL_FULL || (n1 == n2));
   if (n1 == 0 || n2 == 0) return 0;
   FillParams p;
   p.x1 = d_x1, p.x2 = d_x2, p.noise = d_noise, p.K = d_K;
   p.n1 = n1, p.n2 = n2, p.ldk = ldk, p.amp = amp, p.dim = dim, p.mode = mode;
-  for (int i = 0; i < kMaxDim; ++i) p.inv_scale[i] = i < dim ? h_inv_scale[i] : 0.0;
   p.tiles_i = (n1 + FT - 1) / FT;
   p.tiles_j = (n2 + FT - 1) / FT;
   p.ntiles = mode == FVGP_FILL_FULL ? p.tiles_i * p.tiles_j : p.tiles_i * (p.tiles_i + 1) / 2;
-  p.bulk = (g_use_bulk_store && mode == FVGP_FILL_SYMMETRIC && ldk % 2 == 0 && ((uintptr_t)d_K % 16 == 0)) ? 1 : 0;
+  p.vec2 = (ldk % 2 == 0 && ((uintptr_t)d_K % 16 == 0)) ? 1 : 0;
+  p.bulk = (g_use_bulk_store && mode == FVGP_FILL_SYMMETRIC && p.vec2) ? 1 : 0;
   p.c_arg = 0.0, p.c_aux = 0.0;
-  cudaStream_t st = (cudaStream_t)stream;
+  // Centred ("whitened") fast path: coordinates become (x - centre) * inv_scale * c with the kind's argument
+  // constant c folded in.  The caller vouches (by passing h_centre) that |x - centre| * inv_scale * c <= 512
+  // for every point, which bounds the extra relative error of an entry by ~2e-13.
+  const bool centred = h_centre != nullptr && dim <= 4;
+  double fold = 1.0;
   switch (kind) {
-    case FVGP_K_MATERN32: p.c_arg = sqrt(3.0) / length; return launch_fill_dim<FVGP_K_MATERN32>(p, st);
+    case FVGP_K_MATERN32: p.c_arg = sqrt(3.0) / length; fold = p.c_arg; break;
     case FVGP_K_MATERN52:
-      p.c_arg = sqrt(5.0) / length, p.c_aux = 5.0 / (3.0 * length * length);
-      return launch_fill_dim<FVGP_K_MATERN52>(p, st);
-    case FVGP_K_SQEXP: p.c_arg = 1.0 / (2.0 * length * length); return launch_fill_dim<FVGP_K_SQEXP>(p, st);
-    case FVGP_K_EXP: p.c_arg = 1.0 / length; return launch_fill_dim<FVGP_K_EXP>(p, st);
-    case FVGP_K_WENDLAND: p.c_arg = 1.0 / length; return launch_fill_dim<FVGP_K_WENDLAND>(p, st);
-    case FVGP_K_DISTANCE: return launch_fill_dim<FVGP_K_DISTANCE>(p, st);
+      p.c_arg = sqrt(5.0) / length, fold = p.c_arg;
+      p.c_aux = centred ? amp / 3.0 : amp * 5.0 / (3.0 * length * length);
+      break;
+    case FVGP_K_SQEXP: p.c_arg = 1.0 / (2.0 * length * length); fold = sqrt(p.c_arg); break;
+    case FVGP_K_EXP: p.c_arg = 1.0 / length; fold = p.c_arg; break;
+    case FVGP_K_WENDLAND: p.c_arg = 1.0 / length; fold = p.c_arg; break;
+    case FVGP_K_DISTANCE: break;
     default: FVGP_REQUIRE(!"unknown kernel kind");
   }
-  return 0;
+  for (int i = 0; i < kMaxDim; ++i) {
+    p.inv_scale[i] = i < dim ? h_inv_scale[i] * (centred ? fold : 1.0) : 0.0;
+    p.centre[i] = (centred && i < dim) ? h_centre[i] : 0.0;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case FVGP_K_MATERN32: return launch_fill_dim<FVGP_K_MATERN32>(p, centred, st);
+    case FVGP_K_MATERN52: return launch_fill_dim<FVGP_K_MATERN52>(p, centred, st);
+    case FVGP_K_SQEXP: return launch_fill_dim<FVGP_K_SQEXP>(p, centred, st);
+    case FVGP_K_EXP: return launch_fill_dim<FVGP_K_EXP>(p, centred, st);
+    case FVGP_K_WENDLAND: return launch_fill_dim<FVGP_K_WENDLAND>(p, centred, st);
+    default: return launch_fill_dim<FVGP_K_DISTANCE>(p, centred, st);
+  }
 }
 
 int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, double amp, double length, double* d_out,
@@ -452,7 +635,7 @@ int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, doubl
       break;
     case FVGP_K_MATERN52:
       launch(radial_elementwise_kernel<FVGP_K_MATERN52>, grid, 256, 0, st, d_dist, count, amp, sqrt(5.0) / length,
-                                                                        5.0 / (3.0 * length * length), d_out);
+                                                                        amp * 5.0 / (3.0 * length * length), d_out);
       break;
     case FVGP_K_SQEXP:
       launch(radial_elementwise_kernel<FVGP_K_SQEXP>, grid, 256, 0, st, d_dist, count, amp, 1.0 / (2.0 * length * length), 0.0, d_out);
@@ -504,6 +687,40 @@ int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const doubl
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_out, H * sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int64_t fvgp_kgrad_block_partials_len(int dim) { return (int64_t)(sm_count() * 4 + 2) * (dim + 1) + kMaxDim; }
+
+int fvgp_kgrad_trace_block_matern32(const double* d_x1, int64_t m, const double* d_x2, int64_t n, int dim,
+                                    const double* h_theta, const double* d_W, int64_t ldw, const double* d_b1,
+                                    const double* d_b2, int64_t diag_rows, double* d_partials, double* d_accum,
+                                    void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && m >= 0 && n >= 0 && diag_rows >= 0 && diag_rows <= m);
+  if (m == 0 || n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  TraceBlockParams p;
+  p.x1 = d_x1, p.x2 = d_x2, p.W = d_W, p.b1 = d_b1, p.b2 = d_b2, p.partials = d_partials;
+  p.m = m, p.n = n, p.ld = ldw, p.dim = dim, p.diag_rows = diag_rows;
+  p.tiles_j = (n + FT - 1) / FT;
+  p.ntiles = ((m + FT - 1) / FT) * p.tiles_j;
+  double inv_len[kMaxDim];
+  for (int i = 0; i < kMaxDim; ++i) inv_len[i] = p.inv_len[i] = i < dim ? 1.0 / h_theta[1 + i] : 0.0;
+  const long long cap = (long long)sm_count() * 4;
+  const unsigned grid = (unsigned)(p.ntiles < cap ? p.ntiles : cap);
+  switch (dim) {
+    case 1: launch(kgrad_trace_block_kernel<1>, grid, FILL_THREADS, 0, st, p); break;
+    case 2: launch(kgrad_trace_block_kernel<2>, grid, FILL_THREADS, 0, st, p); break;
+    case 3: launch(kgrad_trace_block_kernel<3>, grid, FILL_THREADS, 0, st, p); break;
+    case 4: launch(kgrad_trace_block_kernel<4>, grid, FILL_THREADS, 0, st, p); break;
+    default: launch(kgrad_trace_block_kernel<0>, grid, FILL_THREADS, 0, st, p); break;
+  }
+  FVGP_LAUNCH_OK();
+  const int H = dim + 1;
+  double* d_invlen = d_partials + (long long)(sm_count() * 4 + 2) * H;
+  FVGP_CUDA_OK(cudaMemcpyAsync(d_invlen, inv_len, dim * sizeof(double), cudaMemcpyHostToDevice, st));
+  launch(trace_accumulate_kernel, 1, 256, 0, st, d_partials, (int)grid, H, h_theta[0], d_invlen, d_accum);
+  FVGP_LAUNCH_OK();
   return 0;
 }
 

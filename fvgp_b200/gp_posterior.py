@@ -46,7 +46,8 @@ class GPposterior:
         if isinstance(res, K.SparseWendland):
             return "sparse", ops.wendland_csr(K._device_points(x_pred), xd, res.hps)
         if isinstance(res, K.Radial):                   # radial kernels are symmetric in their arguments
-            buf, _ = ops.kfill(res.kind, K._device_points(x_pred), xd, res.amp, res.dist.inv_scale, res.length)
+            buf, _ = ops.kfill(res.kind, K._device_points(x_pred), xd, res.amp, res.dist.inv_scale, res.length,
+                               bounds=res.dist.bounds())
             return "dense", buf[:, :len(x)]
         if sp.issparse(res):
             res = res.toarray()

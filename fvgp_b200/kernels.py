@@ -74,6 +74,23 @@ class _Lazy:
         return np.asarray(self)[item]
 
 
+_BOUNDS_CACHE = {}
+
+
+def point_bounds(x):
+    """Per-axis (lo, hi) of a host point set, cached per array (the training set is asked once per evaluation)."""
+    if not isinstance(x, np.ndarray) or x.ndim != 2 or x.size == 0:
+        return None
+    key = (id(x), x.shape, x.__array_interface__["data"][0])
+    hit = _BOUNDS_CACHE.get(key)
+    if hit is None:
+        if len(_BOUNDS_CACHE) > 16:
+            _BOUNDS_CACHE.clear()
+        hit = (x.min(axis=0), x.max(axis=0))
+        _BOUNDS_CACHE[key] = hit
+    return hit
+
+
 class Distance(_Lazy):
     """Lazy pairwise (axis-scaled) Euclidean distance between two point sets."""
 
@@ -83,10 +100,19 @@ class Distance(_Lazy):
         self.inv_scale = np.asarray(inv_scale, dtype=np.float64)
         self.shape = (len(x1), len(x2))
 
+    def bounds(self):
+        """Joint per-axis extent of both point sets (None if unknown)."""
+        b1 = point_bounds(self.x1)
+        b2 = b1 if self.same else point_bounds(self.x2)
+        if b1 is None or b2 is None:
+            return None
+        return np.minimum(b1[0], b2[0]), np.maximum(b1[1], b2[1])
+
     def materialize(self, mode=L.FILL_FULL, noise=None, out=None):
         d1 = _device_points(self.x1)
         d2 = d1 if self.same else _device_points(self.x2)
-        return ops.kfill(L.K_DISTANCE, d1, d2, 1.0, self.inv_scale, 1.0, noise=noise, mode=mode, out=out)
+        return ops.kfill(L.K_DISTANCE, d1, d2, 1.0, self.inv_scale, 1.0, noise=noise, mode=mode, out=out,
+                         bounds=self.bounds())
 
 
 class Radial(_Lazy):
@@ -112,7 +138,8 @@ class Radial(_Lazy):
         d = self.dist
         d1 = x1_dev if x1_dev is not None else _device_points(d.x1)
         d2 = x2_dev if x2_dev is not None else (d1 if d.same else _device_points(d.x2))
-        return ops.kfill(self.kind, d1, d2, self.amp, d.inv_scale, self.length, noise=noise, mode=mode, out=out)
+        return ops.kfill(self.kind, d1, d2, self.amp, d.inv_scale, self.length, noise=noise, mode=mode, out=out,
+                         bounds=d.bounds())
 
 
 def _elementwise(kind, distance, length):

@@ -45,9 +45,30 @@ def stop_phase_timing():
 
 
 # ------------------------------------------------------------------------------ dense K
-def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL, out=None):
+_FOLD = {L.K_MATERN32: np.sqrt(3.0), L.K_MATERN52: np.sqrt(5.0), L.K_SQEXP: np.sqrt(0.5), L.K_EXP: 1.0,
+         L.K_WENDLAND: 1.0, L.K_DISTANCE: 1.0}
+CENTRED_LIMIT = 512.0          # bound on |x - centre| * inv_scale * c for the centred fill
+
+
+def fill_centre(kind, inv_scale, length, bounds):
+    """Centre for the whitened K-fill, or None when the scaled half-extent of the points exceeds
+    CENTRED_LIMIT (then the fill takes coordinate differences first, like the reference).
+    bounds = (lo, hi): per-axis extent of ALL points involved (host arrays)."""
+    if bounds is None:
+        return None
+    lo, hi = (np.asarray(b, dtype=np.float64) for b in bounds)
+    if lo.size > 4 or not (np.all(np.isfinite(lo)) and np.all(np.isfinite(hi))):
+        return None
+    half = 0.5 * (hi - lo) * np.asarray(inv_scale, dtype=np.float64)[:lo.size] * (_FOLD[kind] / float(length))
+    if half.size and float(half.max()) > CENTRED_LIMIT:
+        return None
+    return 0.5 * (lo + hi)
+
+
+def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL, out=None, bounds=None):
     """K = amp * f(||(x1-x2)*inv_scale|| / length) [+ diag(noise)].  Returns (buffer, ld);
-    buffer[:, :n2] is the matrix (gp_prior.py:376-400, kernels.py:16-188, gp_kv.py:640-669)."""
+    buffer[:, :n2] is the matrix (gp_prior.py:376-400, kernels.py:16-188, gp_kv.py:640-669).
+    bounds: optional per-axis (lo, hi) of the points; enables the centred fast path when safe."""
     lib = L.load()
     n1, n2, dim = x1.shape[0], x2.shape[0], x1.shape[1]
     if out is None:
@@ -55,9 +76,14 @@ def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL
     else:
         buf, ld = out
     _, inv_p = L.dvec(inv_scale)
+    centre = fill_centre(kind, inv_scale, length, bounds)
+    if centre is not None:
+        _keep, centre_p = L.dvec(centre)
+    else:
+        centre_p = None
     with _Phase("kfill"):
-        st = lib.fvgp_kfill_dense(kind, mode, L.ptr(x1), n1, L.ptr(x2), n2, dim, float(amp), inv_p, float(length),
-                                  L.ptr(noise), L.ptr(buf), ld, L.stream_ptr())
+        st = lib.fvgp_kfill_dense(kind, mode, L.ptr(x1), n1, L.ptr(x2), n2, dim, float(amp), inv_p, centre_p,
+                                  float(length), L.ptr(noise), L.ptr(buf), ld, L.stream_ptr())
     L.check(st, "fvgp_kfill_dense")
     return buf, ld
 

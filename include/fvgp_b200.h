@@ -54,10 +54,15 @@ int fvgp_set_bulk_store(int on);
  * Replaces GPprior._default_kernel (gp_prior.py:376-400), kernels.get_distance_matrix /
  * get_anisotropic_distance_matrix (kernels.py:440-481) + the radial kernels
  * (kernels.py:16-188), and GPkv.addKV for vector noise (gp_kv.py:640-669).
- * h_inv_scale[dim]: 1/length-scale per axis (all 1.0 = isotropic).  d_noise may be NULL. */
+ * h_inv_scale[dim]: 1/length-scale per axis (all 1.0 = isotropic).  d_noise may be NULL.
+ * h_centre[dim] (may be NULL): a point c such that |x - c| * inv_scale / length * sqrt(5) <= 512 for every
+ * point of x1 and x2.  When given (and dim <= 4) the coordinates are centred and scaled once per tile and
+ * the per-entry distance is a difference of scaled coordinates (3 fewer FP64 operations per axis; the
+ * entry's extra relative error is bounded by ~2e-13).  NULL selects the reference's operation order
+ * ((x1 - x2) * inv_scale per entry). */
 int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const double* d_x2, int64_t n2, int dim,
-                     double amp, const double* h_inv_scale, double length, const double* d_noise, double* d_K,
-                     int64_t ldk, void* stream);
+                     double amp, const double* h_inv_scale, const double* h_centre, double length,
+                     const double* d_noise, double* d_K, int64_t ldk, void* stream);
 
 /* The radial kernels of kernels.py:16-188 applied elementwise to a caller-supplied distance array. */
 int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, double amp, double length, double* d_out,
@@ -70,6 +75,17 @@ int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, doubl
 int64_t fvgp_kgrad_partials_len(int64_t n, int dim);
 int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const double* h_theta, const double* d_Kinv,
                               int64_t ld, const double* d_b, double* d_partials, double* h_out, void* stream);
+
+/* One m x n block of the same trace for the block-cyclic multi-GPU layout: rows belong to (x1, b1), columns to
+ * (x2, b2); the first diag_rows rows are a diagonal block aligned with the columns (lower triangle only, diagonal
+ * weighted once), all other entries are weighted twice.  d_accum[h] (dim+1 doubles, device) += the block's
+ * contribution; no host synchronisation.  d_partials: fvgp_kgrad_block_partials_len(dim) doubles.
+ * NOTE: the memcpy of 1/length from a stack buffer is stream-ordered with pageable memory (synchronous copy-in). */
+int64_t fvgp_kgrad_block_partials_len(int dim);
+int fvgp_kgrad_trace_block_matern32(const double* d_x1, int64_t m, const double* d_x2, int64_t n, int dim,
+                                    const double* h_theta, const double* d_W, int64_t ldw, const double* d_b1,
+                                    const double* d_b2, int64_t diag_rows, double* d_partials, double* d_accum,
+                                    void* stream);
 
 /* Same trace against a MATERIALISED symmetric dK (user kernel_function_grad, gp_prior.py:236-240):
  * *h_out = sum_ij (Kinv - b b^T)_ij dK_ij.  d_partials: 148*8 + 1 doubles. */
@@ -102,6 +118,37 @@ int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratc
 /* calculate_inv_from_chol (gp_lin_alg.py:1558) / the trace term's KV^-1
  * (gp_marginal_likelihood.py:273-274): lower triangle of d_L <- lower triangle of (L L^T)^-1. */
 int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_work, void* stream);
+
+/* ---- building blocks of the 2-D block-cyclic multi-GPU factorisation (fvgp_b200/sharded.py).
+ * Each is the single-GPU piece of one step of the distributed POTRF / POTRS / POTRI that replaces
+ * calculate_Chol_factor / calculate_Chol_solve / the gradient's KV^-1 when KV exceeds one HBM. */
+enum fvgp_gemm_flags {
+  FVGP_GEMM_LOWER = 1,     /* square tile grid; tiles strictly above the diagonal are skipped */
+  FVGP_GEMM_KB_FROM_M = 2, /* k starts at the tile's first row    (A^T lower triangular) */
+  FVGP_GEMM_KB_FROM_N = 4, /* k starts at the tile's first column (B lower triangular)   */
+  FVGP_GEMM_KE_FROM_M = 8  /* k ends at the tile's last row       (A lower triangular)   */
+};
+/* C (m x n, row-major) = alpha * op(A) * op(B) + beta * C on the FP64 tensor cores (DMMA).
+ * a_mn = 0: A is m x k row-major (A[m][k]); a_mn = 1: A is stored k x m (A[k][m]).
+ * b_mn = 0: B is n x k row-major (B[n][k], i.e. C += A B^T); b_mn = 1: B is stored k x n.
+ * (a_mn, b_mn) = (1, 0) is not instantiated. */
+int fvgp_dgemm(int a_mn, int b_mn, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C,
+               int64_t ldc, int m, int n, int k, double alpha, double beta, int flags, void* stream);
+/* B (m x n) <- B * L^-T with L the n x n lower factor produced by fvgp_potrf_lower (+ its tile inverses). */
+int fvgp_trsm_right_lower_t(double* d_B, int64_t ldb, int m, const double* d_L, int64_t ldl, int n,
+                            const double* d_tileinv, void* stream);
+/* The two halves of fvgp_potri_lower: L <- L^-1 (lower), and lower(M) <- lower(M^T M). */
+int fvgp_trtri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_work, void* stream);
+int fvgp_lauum_lower(double* d_M, int64_t n, int64_t lda, double* d_work, void* stream);
+/* One triangular solve against the factor, in place on d_b: transpose = 0: L z = b; 1: L^T x = b.
+ * d_work: 2*n doubles. */
+int fvgp_trsv_lower(const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_b, int transpose,
+                    double* d_work, void* stream);
+/* y += alpha * A x (transpose = 0, A m x n row-major, x[n], y[m]) or y += alpha * A^T x (transpose = 1,
+ * x[m], y[n]); deterministic.  d_work: fvgp_gemv_work_len(m, n) doubles (transpose = 1 only). */
+int64_t fvgp_gemv_work_len(int64_t m, int64_t n);
+int fvgp_gemv(int transpose, const double* d_A, int64_t lda, int m, int n, double alpha, const double* d_x,
+              double* d_y, double* d_work, void* stream);
 
 /* Plain tensor-core GEMM exposed for tests / roofline measurement:
  * C = alpha * A * B^T + beta * C with A (m x k) and B (n x k) row-major. lower!=0: lower tiles only. */

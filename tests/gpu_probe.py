@@ -155,6 +155,15 @@ def _gemm_shapes():
             check("   padding column untouched", float(np.abs(c[:, n].cpu().numpy() - c0[:, n]).max()), 0.0)
 
 
+def elementwise_relerr(a, b):
+    """max_ij |a - b| / |b| over entries with b != 0 (plus the absolute error where b == 0)."""
+    a, b = np.asarray(a), np.asarray(b)
+    nz = b != 0
+    e1 = float(np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz]))) if nz.any() else 0.0
+    e0 = float(np.max(np.abs(a[~nz]))) if (~nz).any() else 0.0
+    return max(e1, e0)
+
+
 @section("dense K-fill vs oracle")
 def _kfill():
     rng = np.random.default_rng(5)
@@ -164,29 +173,43 @@ def _kfill():
         hps = np.concatenate([[1.7], 0.2 + rng.random(d)])
         dx1, dx2 = dev(x1), dev(x2)
         ref = orc.default_kernel(x1, x2, hps)
-        buf, ld = ops.kfill(L.K_MATERN32, dx1, dx2, hps[0], 1.0 / hps[1:], 1.0)
-        check(f"default kernel full {n1}x{n2} d={d}", relerr(buf[:, :n2].cpu().numpy(), ref), 1e-12)
-        if n1 == n2:
-            noise = rng.random(n1) * 0.1
-            refn = orc.add_kv(ref, noise)
-            for bulk in (1, 0):
-                L.load().fvgp_set_bulk_store(bulk)
+        both = np.vstack([x1, x2])
+        for bounds, tag in ((None, "exact-diff"), ((both.min(axis=0), both.max(axis=0)), "centred")):
+            buf, ld = ops.kfill(L.K_MATERN32, dx1, dx2, hps[0], 1.0 / hps[1:], 1.0, bounds=bounds)
+            err = elementwise_relerr(buf[:, :n2].cpu().numpy(), ref)
+            check(f"default kernel full {n1}x{n2} d={d} {tag} (max elementwise rel)", err, 1e-12)
+            if n1 == n2:
+                noise = rng.random(n1) * 0.1
+                refn = orc.add_kv(ref, noise)
+                for bulk in (1, 0):
+                    L.load().fvgp_set_bulk_store(bulk)
+                    buf, ld = ops.kfill(L.K_MATERN32, dx1, dx1, hps[0], 1.0 / hps[1:], 1.0, noise=dev(noise),
+                                        mode=L.FILL_SYMMETRIC, bounds=bounds)
+                    check(f"  symmetric+noise bulk={bulk} {tag}", elementwise_relerr(buf[:, :n2].cpu().numpy(), refn), 1e-12)
+                L.load().fvgp_set_bulk_store(1)
                 buf, ld = ops.kfill(L.K_MATERN32, dx1, dx1, hps[0], 1.0 / hps[1:], 1.0, noise=dev(noise),
-                                    mode=L.FILL_SYMMETRIC)
-                check(f"  symmetric+noise bulk={bulk}", relerr(buf[:, :n2].cpu().numpy(), refn), 1e-12)
-            L.load().fvgp_set_bulk_store(1)
-            buf, ld = ops.kfill(L.K_MATERN32, dx1, dx1, hps[0], 1.0 / hps[1:], 1.0, noise=dev(noise), mode=L.FILL_LOWER)
-            check("  lower+noise", relerr(np.tril(buf[:, :n2].cpu().numpy()), np.tril(refn)), 1e-12)
+                                    mode=L.FILL_LOWER, bounds=bounds)
+                check(f"  lower+noise {tag}", elementwise_relerr(np.tril(buf[:, :n2].cpu().numpy()), np.tril(refn)), 1e-12)
     x1, x2 = rng.random((150, 3)), rng.random((90, 3))
     dx1, dx2 = dev(x1), dev(x2)
     d_iso, d_ani = orc.distance_matrix(x1, x2), orc.anisotropic_distance_matrix(x1, x2, np.array([.3, .5, .9]))
     one = np.ones(3)
     check("distance iso", relerr(ops.kfill(L.K_DISTANCE, dx1, dx2, 1.0, one)[0][:, :90].cpu().numpy(), d_iso), 1e-13)
     check("distance aniso", relerr(ops.kfill(L.K_DISTANCE, dx1, dx2, 1.0, 1 / np.array([.3, .5, .9]))[0][:, :90].cpu().numpy(), d_ani), 1e-13)
+    bb = (np.zeros(3), np.ones(3))
+    check("distance iso centred", elementwise_relerr(ops.kfill(L.K_DISTANCE, dx1, dx2, 1.0, one, bounds=bb)[0][:, :90].cpu().numpy(), d_iso), 1e-12)
     for kind, nm in ((L.K_SQEXP, "se"), (L.K_EXP, "exp"), (L.K_MATERN32, "matern32"), (L.K_MATERN52, "matern52")):
         ref = 2.5 * orc.RADIAL[nm](d_iso, 0.37)
-        got = ops.kfill(kind, dx1, dx2, 2.5, one, 0.37)[0][:, :90].cpu().numpy()
-        check(f"{nm} iso", relerr(got, ref), 1e-12)
+        for bounds, tag in ((None, "exact-diff"), (bb, "centred")):
+            got = ops.kfill(kind, dx1, dx2, 2.5, one, 0.37, bounds=bounds)[0][:, :90].cpu().numpy()
+            check(f"{nm} iso {tag} (max elementwise rel)", elementwise_relerr(got, ref), 1e-12)
+    # far-apart / tiny length scale: underflow region and the CENTRED_LIMIT fallback
+    xs = np.vstack([rng.random((70, 2)), rng.random((70, 2)) + 50.0])
+    hs = np.array([1.0, .02, .03])
+    ref = orc.default_kernel(xs, xs, hs)
+    got = ops.kfill(L.K_MATERN32, dev(xs), dev(xs), hs[0], 1 / hs[1:], 1.0, bounds=(xs.min(0), xs.max(0)))[0][:, :140].cpu().numpy()
+    check("small length scale (fallback to exact-diff): |got| where ref underflows", float(np.abs(got[ref < 1e-290]).max()), 1e-290)
+    check("small length scale, elementwise rel where ref > 1e-290", elementwise_relerr(np.where(ref > 1e-290, got, 0), np.where(ref > 1e-290, ref, 0)), 1e-12)
     refw = orc.wendland_block(x1, x2, np.array([1.3, .3, .5, .9]))
     got = ops.kfill(L.K_WENDLAND, dx1, dx2, 1.3, 1 / np.array([.3, .5, .9]), 1.0)[0][:, :90].cpu().numpy()
     check("wendland dense (abs)", float(np.abs(got - refw).max()), 1e-14)
@@ -313,15 +336,18 @@ def _timings():
                              (L.FILL_LOWER, "lower", 4 * n * n)):
         for bulk in ((1, 0) if mode == L.FILL_SYMMETRIC else (1,)):
             L.load().fvgp_set_bulk_store(bulk)
-            t = cuda_time(lambda: ops.kfill(L.K_MATERN32, x, x, 1.0, 1 / hps[1:], 1.0, noise=noise, mode=mode, out=out), reps=5)
-            print(f"  kfill {nm} bulk={bulk} n={n}: {t * 1e3:.2f} ms -> {bytes_ / t / 1e9:.0f} GB/s")
-            RESULTS[f"kfill_{nm}_bulk{bulk}_gbs"] = bytes_ / t / 1e9
+            for bounds, tag in ((None, "exact"), ((np.zeros(3), np.ones(3)), "centred")):
+                t = cuda_time(lambda: ops.kfill(L.K_MATERN32, x, x, 1.0, 1 / hps[1:], 1.0, noise=noise, mode=mode, out=out,
+                                                bounds=bounds), reps=5)
+                print(f"  kfill {nm} {tag} bulk={bulk} n={n}: {t * 1e3:.2f} ms -> {bytes_ / t / 1e9:.0f} GB/s")
+                RESULTS[f"kfill_{nm}_{tag}_bulk{bulk}_gbs"] = bytes_ / t / 1e9
     L.load().fvgp_set_bulk_store(1)
     x1d = dev(rng.random((n, 1)))
     for mode, nm in ((L.FILL_SYMMETRIC, "symmetric"), (L.FILL_FULL, "full")):
         t = cuda_time(lambda: ops.kfill(L.K_DISTANCE, x1d, x1d, 1.0, np.ones(1), 1.0, mode=mode, out=out), reps=5)
         print(f"  store-path ceiling (1-D distance fill, {nm}): {8 * n * n / t / 1e9:.0f} GB/s")
-        t = cuda_time(lambda: ops.kfill(L.K_SQEXP, x, x, 1.0, 1 / hps[1:], 0.5, mode=mode, out=out), reps=5)
+        t = cuda_time(lambda: ops.kfill(L.K_SQEXP, x, x, 1.0, 1 / hps[1:], 0.5, mode=mode, out=out,
+                                        bounds=(np.zeros(3), np.ones(3))), reps=5)
         print(f"  squared-exponential fill ({nm}): {8 * n * n / t / 1e9:.0f} GB/s")
     t = cuda_time(lambda: out[0].fill_(1.0), reps=5)
     print(f"  torch fill_ same buffer: {out[0].numel() * 8 / t / 1e9:.0f} GB/s (write-only reference)")

@@ -27,9 +27,11 @@ elif what in ("kfill", "kfill_lower", "kfill_full"):
     x = L.to_dev(rng.random((n, 3)))
     noise = L.to_dev(np.full(n, 1e-2))
     out = L.dev_matrix(n, n)
+    bounds = None if os.environ.get("FVGP_EXACT_DIFF") else (np.zeros(3), np.ones(3))
     mode = {"kfill": L.FILL_SYMMETRIC, "kfill_lower": L.FILL_LOWER, "kfill_full": L.FILL_FULL}[what]
     for _ in range(reps):
-        ops.kfill(L.K_MATERN32, x, x, 1.0, 1 / np.array([.3, .4, .5]), 1.0, noise=noise, mode=mode, out=out)
+        ops.kfill(L.K_MATERN32, x, x, 1.0, 1 / np.array([.3, .4, .5]), 1.0, noise=noise, mode=mode, out=out,
+                  bounds=bounds)
 elif what == "trace":
     x = L.to_dev(rng.random((n, 3)))
     buf, ld = L.dev_matrix(n, n)
