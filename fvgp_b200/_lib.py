@@ -51,7 +51,7 @@ _SIGNATURES = {
     "fvgp_dot": (c_int, [_P, _P, c_int64, _P, POINTER(c_double), _P]),
     "fvgp_wendland_aabb_len": (c_int64, [c_int64, c_int]),
     "fvgp_wendland_aabb": (c_int, [_P, c_int64, c_int, _P, _P]),
-    "fvgp_wendland_csr_count": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P]),
+    "fvgp_wendland_csr_count": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P]),
     "fvgp_wendland_csr_fill": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P, _P,
                                        _P]),
     "fvgp_exclusive_scan_i64": (c_int, [_P, c_int64, _P, _P, POINTER(c_int64), _P]),

@@ -241,11 +241,12 @@ def wendland_aabb(x):
     return boxes
 
 
-def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None):
+def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None, stats=None):
     """k(x1, x2) for the compact-support Wendland kernel as canonical CSR (bit-exact pattern).
 
     Replaces the per-block dask tasks + host assembly (gp2Scale_covariance.py:136-287); `noise`
-    fuses K + diag(V) (gp_kv.py:655-661)."""
+    fuses K + diag(V) (gp_kv.py:655-661).  stats: optional int64 device tensor (1,), receives += the number
+    of 32x32 tile pairs the geometry pass tested."""
     lib = L.load()
     torch = L._torch()
     n1, dim = x1.shape
@@ -259,7 +260,7 @@ def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None):
     counts = torch.zeros(max(n1, 1), dtype=torch.int64, device="cuda")
     st = L.stream_ptr()
     L.check(lib.fvgp_wendland_csr_count(L.ptr(x1), n1, L.ptr(boxes1), L.ptr(x2), n2, L.ptr(boxes2), dim, th,
-                                        L.ptr(counts), st), "fvgp_wendland_csr_count")
+                                        L.ptr(counts), L.ptr(stats), st), "fvgp_wendland_csr_count")
     indptr = torch.empty(n1 + 1, dtype=torch.int64, device="cuda")
     scratch = torch.empty(int(lib.fvgp_scan_scratch_len(n1)), dtype=torch.int64, device="cuda")
     total = c_int64()
@@ -308,18 +309,20 @@ def pcg(A, b, x0=None, rtol=1e-5, maxiter=None, precond=None):
     return x, st, iters.value, relres.value
 
 
-def slq_logdet(A, degree=20, probes=30, seed=0):
+def slq_logdet(A, degree=20, probes=30, seed=0, probe0=0):
     """Stochastic Lanczos quadrature estimate of log det A (gp_lin_alg.py:1103-1181, imate slq).
 
     Device: Lanczos three-term recurrences (SpMV bound).  Host: eigen-decomposition of the
-    `degree` x `degree` tridiagonals (microseconds).  Returns (estimate, variance_of_mean, samples)."""
+    `degree` x `degree` tridiagonals (microseconds).  Probes probe0 .. probe0+probes-1 of the counter-based
+    Rademacher stream advance in lock step, up to 16 per sweep over the matrix (SpMM).
+    Returns (estimate, variance_of_mean, samples)."""
     lib = L.load()
     n = A.shape[0]
     degree = int(min(degree, n))
     work = L.dev_empty((int(lib.fvgp_lanczos_work_len(n, degree)),))
     alpha = np.zeros(probes * degree)
     beta = np.zeros(probes * degree)
-    L.check(lib.fvgp_lanczos_tridiag(n, L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.data), degree, 0, probes,
+    L.check(lib.fvgp_lanczos_tridiag(n, L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.data), degree, int(probe0), probes,
                                      int(seed), L.ptr(work), alpha.ctypes.data_as(ctypes.POINTER(c_double)),
                                      beta.ctypes.data_as(ctypes.POINTER(c_double)), L.stream_ptr()),
             "fvgp_lanczos_tridiag")

@@ -164,12 +164,15 @@ int fvgp_dot(const double* d_a, const double* d_b, int64_t n, double* d_scratch1
  * assemble_triplets (gp2Scale_covariance.py:240-287), and addKV's setdiag (gp_kv.py:655-661).
  * Pass 1 counts entries per row; the caller scans counts into d_indptr (int64 or int32 is
  * the caller's choice for the final matrix; the kernels use int64 offsets); pass 2 fills
- * sorted column indices + values.  Pattern is bit-exact w.r.t. the reference predicate. */
+ * sorted column indices (same geometry pass) and then the values (lane-dense kernel over the stored
+ * entries, reference operation order).  Pattern is bit-exact w.r.t. the reference predicate.
+ * d_stats (may be NULL): one int64 the count pass ADDS the number of 32x32 tile pairs it tested to
+ * (pair tests = 1024 x that; reported next to nnz as the cull efficiency). */
 int64_t fvgp_wendland_aabb_len(int64_t n, int dim); /* doubles per point set for tile bounding boxes */
 int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, void* stream);
 int fvgp_wendland_csr_count(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                             const double* d_aabb2, int dim, const double* h_theta, int64_t* d_rowcount,
-                            void* stream);
+                            int64_t* d_stats, void* stream);
 int fvgp_wendland_csr_fill(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                            const double* d_aabb2, int dim, const double* h_theta, const int64_t* d_indptr,
                            const double* d_noise_diag, int32_t* d_indices, double* d_data, void* stream);

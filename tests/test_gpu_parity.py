@@ -246,3 +246,126 @@ def test_size_independent_properties_at_scale(fv):
     assert (A != A.T).nnz == 0 and np.all(A.diagonal() == 1.0) and A.has_sorted_indices
     shuffled = ops.wendland_csr(xs.flip(0).contiguous(), xs.flip(0).contiguous(), np.array([1.0, .05, .05, .05])).to_scipy()
     assert shuffled.nnz == A.nnz                                            # ordering changes the layout, not the set
+
+
+def _random_spd_csr(rng, n, row_nnz):
+    """Symmetric, diagonally dominant CSR with ragged rows (some empty off-diagonals, some > 128 entries)."""
+    import scipy.sparse as sp
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        k = int(row_nnz[i])
+        c = rng.choice(n, size=min(k, n), replace=False)
+        rows += [i] * len(c)
+        cols += list(c)
+        vals += list(rng.standard_normal(len(c)))
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    A = A + A.T
+    A = A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)
+    A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+def _to_device_csr(A):
+    import torch
+    from fvgp_b200 import ops
+    return ops.DeviceCSR(torch.as_tensor(A.indptr.astype(np.int64)).cuda(), torch.as_tensor(A.indices.astype(np.int32)).cuda(),
+                         torch.as_tensor(A.data).cuda(), A.shape)
+
+
+def test_spmv_pcg_slq_on_ragged_matrix(fv):
+    """SpMV (4 strips in flight), the 3-kernel PCG and the batched Lanczos against scipy on a ragged SPD matrix."""
+    from fvgp_b200 import _lib as L, ops
+    from oracle import fvgp_oracle as orc
+    rng = np.random.default_rng(21)
+    n = 3001
+    row_nnz = rng.integers(0, 40, n)
+    row_nnz[::97] = 300                                   # rows longer than one 128-entry sweep
+    row_nnz[5:9] = 0
+    A = _random_spd_csr(rng, n, row_nnz)
+    Ad = _to_device_csr(A)
+    v = rng.standard_normal(n)
+    y = ops.spmv(Ad, L.to_dev(v)).cpu().numpy()
+    assert np.max(np.abs(y - A @ v)) <= 1e-13 * np.max(np.abs(A @ v))
+    b = rng.standard_normal(n)
+    for pre in (None, ops.bjacobi(Ad)):
+        for rtol in (1e-5, 1e-11):
+            x, info, iters, relres = ops.pcg(Ad, L.to_dev(b), rtol=rtol, precond=pre)
+            assert info == 0 and relres < rtol
+            assert np.linalg.norm(A @ x.cpu().numpy() - b) < rtol * np.linalg.norm(b) * 1.0001
+    ref, ref_iters = orc.sparse_cg(A, b[:, None], rtol=1e-5)
+    x, info, iters, relres = ops.pcg(Ad, L.to_dev(b), rtol=1e-5)
+    assert abs(iters - ref_iters[0]) <= 1                  # same recurrence and stopping rule as scipy cg
+    assert rel(x.cpu().numpy(), ref[:, 0]) <= 1e-4
+    _, info, iters, _ = ops.pcg(Ad, L.to_dev(b), rtol=1e-14, maxiter=3)
+    assert info == 1 and iters == 3                        # scipy: info > 0 when maxiter is reached
+    x0 = np.linalg.solve(A.toarray(), b)
+    _, info, iters, _ = ops.pcg(Ad, L.to_dev(b), x0=L.to_dev(x0), rtol=1e-8)
+    assert info == 0 and iters == 0                        # converged warm start: no update applied
+    # batched Lanczos (16 + 8 + 2 + 1 probes) == the same probes one at a time
+    est, var, samples = ops.slq_logdet(Ad, degree=25, probes=27, seed=3)
+    singles = np.array([ops.slq_logdet(Ad, degree=25, probes=1, seed=3, probe0=p)[2][0] for p in (0, 7, 15, 16, 23, 24, 26)])
+    assert rel(samples[[0, 7, 15, 16, 23, 24, 26]], singles) <= 1e-9
+    exact = np.linalg.slogdet(A.toarray())[1]
+    assert abs(est - exact) <= 6 * np.sqrt(var) + 0.01 * abs(exact)
+
+
+def test_gp2scale_value_underflow_pattern(fv):
+    """np.nonzero drops entries whose VALUE rounds to zero (gp2Scale_covariance.py:147): with a tiny
+    amplitude the near-edge pairs disappear from the pattern; the strict kernel variant replays that."""
+    from fvgp_b200 import _lib as L, ops
+    from oracle import fvgp_oracle as orc
+    rng = np.random.default_rng(8)
+    x = np.concatenate([rng.random((300, 1)), np.array([[0.0], [1.0 - 2.0 ** -20], [1.0 - 2.0 ** -30]])])
+    for amp in (1e-300, 1e-250, 1e-120, 3.0):
+        h = np.array([amp, 1.0])
+        ref = orc.gp2scale_covariance(x, x, h, batch=100, symmetric=True)
+        K = ops.wendland_csr(L.to_dev(x), L.to_dev(x), h).to_scipy()
+        assert np.array_equal(K.indptr, ref.indptr) and np.array_equal(K.indices, ref.indices), amp
+        normal = np.abs(ref.data) > 1e-290                            # subnormal values carry fewer digits
+        assert rel(K.data[normal], ref.data[normal]) <= 1e-12
+    assert ref.nnz > orc.gp2scale_covariance(x, x, np.array([1e-300, 1.0]), batch=100, symmetric=True).nnz
+
+
+def test_gp2scale_sliver_pairs(fv):
+    """Pairs whose s is within rounding of 1: the approximate test may not decide them, the exact sequence does."""
+    from fvgp_b200 import _lib as L, ops
+    from oracle import fvgp_oracle as orc
+    th = np.array([1.0, 0.3, 0.7])
+    base = np.array([0.25, 0.5])
+    ang = np.linspace(0, 2 * np.pi, 400, endpoint=False)
+    ring = base + np.stack([th[1] * np.cos(ang), th[2] * np.sin(ang)], axis=1)      # s == 1 up to rounding
+    pts = [base[None, :], ring]
+    for k in range(1, 4):
+        pts.append(np.nextafter(ring, base[None, :] + 0 * ring) if k == 1 else ring * (1 + (k - 2) * 2.0 ** -52))
+    x = np.concatenate(pts)
+    ref = orc.gp2scale_covariance(x, x, th, batch=500, symmetric=True)
+    K = ops.wendland_csr(L.to_dev(x), L.to_dev(x), th).to_scipy()
+    assert np.array_equal(K.indptr, ref.indptr) and np.array_equal(K.indices, ref.indices)
+    assert 0 < ref[0].nnz < len(x)                               # the ring really straddles the support edge
+
+
+def test_potrf_lookahead_ragged_size(fv):
+    """n >= 4 * 2048 takes the two-stream look-ahead factorisation; ragged last block; vs cuSOLVER."""
+    import torch
+    from fvgp_b200 import _lib as L, ops
+    rng = np.random.default_rng(12)
+    n = 8192 + 1111
+    x = L.to_dev(rng.random((n, 3)))
+    noise = L.to_dev(np.full(n, 1e-2))
+    h = np.array([1.0, .3, .4, .5])
+    buf, ld = ops.kfill(L.K_MATERN32, x, x, h[0], 1 / h[1:], 1.0, noise=noise, mode=L.FILL_SYMMETRIC)
+    ref = torch.linalg.cholesky(buf[:, :n])
+    f = ops.potrf(buf, ld, n)
+    err = float((f.lower() - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-11, err
+    rhs = L.to_dev(rng.standard_normal((1, n)))
+    sol = ops.potrs(f, rhs.clone())
+    ref_sol = torch.cholesky_solve(rhs.T.contiguous(), ref).T
+    assert float((sol - ref_sol).abs().max() / ref_sol.abs().max()) <= 1e-8
+    # failure inside a look-ahead panel is still reported with its global pivot index
+    bad, ld = ops.kfill(L.K_MATERN32, x, x, h[0], 1 / h[1:], 1.0, noise=noise, mode=L.FILL_SYMMETRIC)
+    bad[5000, 5000] = -1.0
+    with pytest.raises(L.NonPositiveDefiniteError) as ei:
+        ops.potrf(bad, ld, n)
+    assert ei.value.pivot == 5001
