@@ -1,6 +1,6 @@
 """Small single-purpose workloads for `ncu` captures (see profiles/README.md).
 
-    python tests/ncu_targets.py gemm|syrk|kfill|kfill_lower|trace|wendland|spmv [n]
+    python tests/ncu_targets.py gemm|syrk|kfill|kfill_lower|trace|wendland|spmv|slq|pcg [n]
 """
 import os
 import sys
@@ -39,13 +39,17 @@ elif what == "trace":
     b = L.to_dev(rng.standard_normal(n))
     for _ in range(reps):
         ops.kgrad_trace_matern32(x, np.array([1.0, .3, .4, .5]), buf, ld, b)
-elif what in ("wendland", "spmv"):
+elif what in ("wendland", "spmv", "slq", "pcg"):
     xs = rng.random((n, 3))
     xs = L.to_dev(xs[np.lexsort((xs[:, 2] // .05, xs[:, 1] // .05, xs[:, 0] // .05))])
     th = np.array([1.0, .029, .029, .029])
     th[1:] *= (1e6 / n) ** (1 / 3)
     for _ in range(reps if what == "wendland" else 1):
         K = ops.wendland_csr(xs, xs, th)
+    if what == "slq":
+        ops.slq_logdet(K, degree=3, probes=8, seed=0)
+    if what == "pcg":
+        ops.pcg(K, L.to_dev(rng.standard_normal(n)), rtol=1e-30, maxiter=3)
     if what == "spmv":
         v = L.to_dev(rng.standard_normal(n))
         y = L.dev_empty((n,))
