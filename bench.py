@@ -188,6 +188,16 @@ def run_c4(args):
     torch.cuda.synchronize()
     t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     launches = lib.fvgp_launch_count() - launches0
+    if args.profile_host and rank == 0:                      # where does the host side of one evaluation go?
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        gp.log_likelihood(theta_c4(args.warmup + args.steps + 2, n, rank))
+        torch.cuda.synchronize()
+        pr.disable()
+        with open(args.profile_host, "w") as fh:
+            pstats.Stats(pr, stream=fh).sort_stats("cumulative").print_stats(35)
     # phase breakdown of one evaluation
     xd = gp.data.x_device()
     th = theta_c4(1, n)
@@ -265,6 +275,7 @@ def main():
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--cpu-sample-n", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-host", default="", help="c4 only: write a cProfile of one evaluation to this file")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2 (default, the headline): dense N=50k LML+gradient; c4: gp2Scale N=1M LML")
     args = ap.parse_args()

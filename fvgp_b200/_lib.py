@@ -35,6 +35,7 @@ _SIGNATURES = {
     "fvgp_chol_workspace_len": (c_int64, [c_int64]),
     "fvgp_potri_workspace_len": (c_int64, [c_int64]),
     "fvgp_potrf_lower": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
+    "fvgp_potrs_work_len": (c_int64, [c_int64]),
     "fvgp_potrs_lower": (c_int, [_P, c_int64, c_int64, _P, _P, c_int, c_int64, _P, _P]),
     "fvgp_chol_logdet": (c_int, [_P, c_int64, c_int64, _P, POINTER(c_double), _P]),
     "fvgp_potri_lower": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
@@ -51,8 +52,9 @@ _SIGNATURES = {
     "fvgp_dot": (c_int, [_P, _P, c_int64, _P, POINTER(c_double), _P]),
     "fvgp_wendland_aabb_len": (c_int64, [c_int64, c_int]),
     "fvgp_wendland_aabb": (c_int, [_P, c_int64, c_int, _P, _P]),
-    "fvgp_wendland_csr_count": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P]),
-    "fvgp_wendland_csr_fill": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P, _P,
+    "fvgp_wendland_chunk_len": (c_int64, [c_int64, c_int64]),
+    "fvgp_wendland_csr_count": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
+    "fvgp_wendland_csr_fill": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P, _P, _P,
                                        _P]),
     "fvgp_exclusive_scan_i64": (c_int, [_P, c_int64, _P, _P, POINTER(c_int64), _P]),
     "fvgp_scan_scratch_len": (c_int64, [c_int64]),

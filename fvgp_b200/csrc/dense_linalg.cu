@@ -27,6 +27,7 @@ unsigned long long g_launches = 0;
 
 constexpr int TS = 128;  // diagonal tile handled by one CTA (Cholesky + inverse of the factor)
 constexpr int VS = 64;   // block width of the single-right-hand-side solves
+constexpr int VBLK = 2048;  // columns per block of the blocked single-right-hand-side solves
 constexpr int TP = TS + 1;
 constexpr int HP = TS / 2 + 1;
 constexpr size_t POTRF_TILE_SMEM = (size_t(TS) * TP + 2 * (TS / 2) * HP + 2 * TS) * sizeof(double);  // ~198 KB
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict_
 }
 
 __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict__ L, long long ld, int n, int j0,
-                                                       const double* __restrict__ dinv, double* z, double* x) {
+                                                       const double* __restrict__ dinv, double* z, double* x,
+                                                       int c_begin) {
   __shared__ double zj[VS], xj[VS];
   const int tid = threadIdx.x;
   const int nt = min(VS, n - j0);
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict_
     }
   }
   __syncthreads();
-  const int c = blockIdx.x * 256 + tid;
+  const int c = c_begin + blockIdx.x * 256 + tid;
   if (c < j0) {
     double acc = 0.0;
     for (int r = 0; r < nt; ++r) acc += L[(long long)(j0 + r) * ld + c] * xj[r];
@@ -430,14 +432,19 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
 }
 
 // Block width of the look-ahead factorisation; 0 disables it (pure recursion).  FVGP_POTRF_NB overrides.
+// Measured on B200 (profiles/r01/potrf_sweep.v4.log): N = 50 000: recursion 1468 ms, nb 1024 1472 ms, nb 2048
+// 1330 ms, nb 4096 1357 ms; N = 16 384: recursion 103 ms, nb 1024 89 ms, nb 2048 114 ms.
 static int potrf_block_width(int n) {
-  static int env = -1;
-  if (env < 0) {
+  static int env = -2;
+  if (env == -2) {
     const char* e = getenv("FVGP_POTRF_NB");
-    env = e ? atoi(e) : 2048;
+    env = e ? atoi(e) : -1;
     if (env > 0) env = std::max(BM, (env / BM) * BM);
   }
-  return (env > 0 && n >= 4 * env) ? env : 0;
+  if (env >= 0) return (env > 0 && n >= 4 * env) ? env : 0;
+  if (n >= 24576) return 2048;
+  if (n >= 6144) return 1024;
+  return 0;
 }
 
 // L -> L^-1 in place (lower).  Needs explicit zeros above the diagonal inside diagonal blocks.
@@ -487,6 +494,8 @@ unsigned long long fvgp_launch_count(void) { return g_launches; }
 
 int64_t fvgp_chol_workspace_len(int64_t n) { return ((n + TS - 1) / TS) * (int64_t)TS * TS; }
 
+int64_t fvgp_potrs_work_len(int64_t n) { return 2 * n + (VBLK / 256) * n + 64; }
+
 int64_t fvgp_potri_workspace_len(int64_t n) {
   const int64_t h = n / 2 + BM + 2;
   return h * h;
@@ -523,26 +532,49 @@ int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_
     if (r != 0) return r;
     return trsm_rn_rec(c, d_B, ldb, nrhs, d_L, lda, (int)n, 0);    // rows <- rows * L^-1      (L^T x = y)
   }
+  // Few right-hand sides: HBM-read bound (the lower triangle is read once per direction).  Blocks of VBLK
+  // columns: inside a block the 64-wide leaf steps (tile inverse + rank-64 update of the block's own rows),
+  // then ONE matrix-vector product with the whole panel below (forward) / left of (backward) the block, which
+  // streams >95 % of the factor at GEMV speed instead of in 782 latency-bound slivers.
   double* w = d_work;
   double* z = d_work + n;
-  const int tiles = (int)((n + VS - 1) / VS);
+  double* gemv_work = d_work + 2 * n;
   auto block_inv = [&](int t) {  // 64x64 diagonal sub-block of the 128x128 tile inverse (leading dimension TS)
     return d_tileinv + (int64_t)(t / 2) * TS * TS + (t % 2) * ((int64_t)VS * TS + VS);
   };
+  const int nblocks = (int)((n + VBLK - 1) / VBLK);
   for (int r = 0; r < nrhs; ++r) {
     double* b = d_B + (int64_t)r * ldb;
     FVGP_CUDA_OK(cudaMemcpyAsync(w, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    for (int t = 0; t < tiles; ++t) {
-      const int j0 = t * VS;
-      const int rest = (int)n - (j0 + VS);
-      const int grid = rest > 0 ? (rest + 63) / 64 : 1;
-      launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), w, z);
+    for (int blk = 0; blk < nblocks; ++blk) {  // L z = b
+      const int b0 = blk * VBLK, b1 = (int)std::min<int64_t>(n, b0 + VBLK);
+      for (int j0 = b0; j0 < b1; j0 += VS) {
+        const int rest = b1 - (j0 + VS);
+        const int grid = rest > 0 ? (rest + 63) / 64 : 1;
+        launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), w, z);
+      }
+      if (b1 < n) {
+        const int m = (int)n - b1;
+        const int grid = (int)std::min<long long>(((long long)m + 7) / 8, (long long)sm_count() * 16);
+        launch(gemv_n_kernel, grid, 256, 0, st, d_L + (int64_t)b1 * lda + b0, lda, m, b1 - b0, -1.0, z + b0, w + b1);
+      }
     }
     FVGP_LAUNCH_OK();
-    for (int t = tiles - 1; t >= 0; --t) {
-      const int j0 = t * VS;
-      const int grid = j0 > 0 ? (j0 + 255) / 256 : 1;
-      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), z, b);
+    for (int blk = nblocks - 1; blk >= 0; --blk) {  // L^T x = z
+      const int b0 = blk * VBLK, b1 = (int)std::min<int64_t>(n, b0 + VBLK);
+      const int last = b0 + ((b1 - b0 - 1) / VS) * VS;
+      for (int j0 = last; j0 >= b0; j0 -= VS) {
+        const int cols = j0 - b0;
+        const int grid = cols > 0 ? (cols + 255) / 256 : 1;
+        launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), z, b, b0);
+      }
+      if (b0 > 0) {  // z[0:b0] -= L[b0:b1, 0:b0]^T x[b0:b1]
+        const int m = b1 - b0;
+        const int chunks = (m + GEMVT_ROWS - 1) / GEMVT_ROWS;
+        launch(gemv_t_partial_kernel, dim3((b0 + 255) / 256, chunks), 256, 0, st, d_L + (int64_t)b0 * lda, lda, m, b0,
+               b + b0, gemv_work);
+        launch(gemv_t_reduce_kernel, (b0 + 255) / 256, 256, 0, st, gemv_work, chunks, b0, -1.0, z);
+      }
     }
     FVGP_LAUNCH_OK();
   }
@@ -644,7 +676,7 @@ int fvgp_trsv_lower(const double* d_L, int64_t n, int64_t lda, const double* d_t
     for (int t = tiles - 1; t >= 0; --t) {
       const int j0 = t * VS;
       const int grid = j0 > 0 ? (j0 + 255) / 256 : 1;
-      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), z, d_b);
+      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), z, d_b, 0);
     }
     FVGP_LAUNCH_OK();
   }

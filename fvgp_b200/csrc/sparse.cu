@@ -26,6 +26,7 @@
 // exclusive scan -> index pass (same geometry, writes column indices) -> value pass (lane-dense).
 #include "../../include/fvgp_b200.h"
 #include "common.cuh"
+#include <algorithm>
 
 namespace fvgp {
 
@@ -42,6 +43,9 @@ struct WendlandParams {
   const double* noise;
   long long* rowcount;
   long long* stats;
+  int* chunk;
+  long long supers_per_chunk;
+  int n_chunks;
   int* indices;
   double* data;
   long long n1, n2, tiles1, tiles2, super2;
@@ -134,9 +138,14 @@ __device__ __forceinline__ double wendland_value(double s, double amp) {
   return (amp * (u4 * u4)) * poly;
 }
 
-// One warp per 32-row tile.  Lanes hold the 32 columns of the current column tile; lane r also keeps the
-// running entry count (count pass) / write cursor (fill pass) of row r of the tile in a register, so a hit
-// costs one ballot, one shuffle and one predicated add -- no shared-memory traffic, no barriers.
+// One warp per UNIT = (32-row tile, chunk of the column super tiles).  Splitting the column range into up to 32
+// chunks bounds the work of one warp: a row tile whose 32 consecutive points straddle a jump of the
+// space-filling order has a huge bounding box and would otherwise test a large part of the matrix alone (ncu:
+// SMs busy 1/3 of the kernel's duration, the rest was the tail of a few such warps).  Units without a surviving
+// super tile cost one box test.  Lanes hold the 32 columns of the current column tile; lane r also keeps the
+// running entry count (count pass) / write cursor (index pass) of row r in a register, so a hit costs one
+// ballot, one shuffle and one predicated add -- no shared-memory traffic, no barriers.  Per-(chunk, row)
+// counts go to p.chunk; wendland_chunk_prefix_kernel turns them into per-chunk offsets and row totals.
 // STRICT (amp so small / large / non-finite that amp * (1-d)^8 * poly may round to 0 or inf): the hit
 // decision additionally evaluates the value and applies the reference's `value != 0` test (np.nonzero,
 // gp2Scale_covariance.py:147) for every candidate.
@@ -144,7 +153,9 @@ template <int DIM, bool FILL, bool STRICT>
 __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const WendlandParams p) {
   __shared__ double xs[W_WARPS][WT][DIM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long tile = blockIdx.x * (long long)W_WARPS + warp;
+  const long long unit = blockIdx.x * (long long)W_WARPS + warp;
+  const long long tile = unit / p.n_chunks;
+  const int chunk = (int)(unit - tile * p.n_chunks);
   if (tile >= p.tiles1) return;  // whole warp exits together; no CTA-wide barriers below
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -158,19 +169,19 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
   }
   const long long r_mine = tile * WT + lane;
   const int rows_here = (int)min((long long)WT, p.n1 - tile * WT);
-#pragma unroll
-  for (int i = 0; i < DIM; ++i) xs[warp][lane][i] = r_mine < p.n1 ? p.x1[r_mine * DIM + i] : 0.0;
-  long long cur = (FILL && r_mine < p.n1) ? p.indptr[r_mine] : 0;  // lane r: cursor of row r
+  long long cur = 0;  // lane r: entries of row r found by this unit (count) / write cursor of row r (fill)
   long long pairs = 0;
-  __syncwarp();
+  bool staged = false;
 
   const double* tile_boxes = p.aabb2;
   const double* super_boxes = p.aabb2 + p.tiles2 * 2 * DIM;
+  const long long s_begin = chunk * p.supers_per_chunk;
+  const long long s_end = min(p.super2, s_begin + p.supers_per_chunk);
 
-  for (long long s0 = 0; s0 < p.super2; s0 += 32) {
+  for (long long s0 = s_begin; s0 < s_end; s0 += 32) {
     const long long sidx = s0 + lane;
     bool keep = false;
-    if (sidx < p.super2) {
+    if (sidx < s_end) {
       const double* bx = super_boxes + sidx * 2 * DIM;
       double lo2[DIM], hi2[DIM];
 #pragma unroll
@@ -178,6 +189,13 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
       keep = box_gap_s<DIM>(lo1, hi1, lo2, hi2, rinv) < FVGP_CULL_LIMIT;
     }
     unsigned smask = __ballot_sync(0xffffffffu, keep);
+    if (smask != 0u && !staged) {  // first survivor: stage the row points, fetch the cursors
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) xs[warp][lane][i] = r_mine < p.n1 ? p.x1[r_mine * DIM + i] : 0.0;
+      if (FILL && r_mine < p.n1) cur = p.indptr[r_mine] + p.chunk[(long long)chunk * p.n1 + r_mine];
+      staged = true;
+      __syncwarp();
+    }
     while (smask) {
       const int sb = __ffs(smask) - 1;
       smask &= smask - 1;
@@ -234,9 +252,22 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
     }
   }
   if (!FILL) {
-    if (r_mine < p.n1) p.rowcount[r_mine] = cur;
-    if (p.stats != nullptr && lane == 0) atomicAdd((unsigned long long*)p.stats, (unsigned long long)pairs);
+    if (r_mine < p.n1) p.chunk[(long long)chunk * p.n1 + r_mine] = (int)cur;
+    if (p.stats != nullptr && lane == 0 && pairs != 0) atomicAdd((unsigned long long*)p.stats, (unsigned long long)pairs);
   }
+}
+
+// Per row: exclusive prefix of its per-chunk counts (in place) and the row total.
+__global__ void wendland_chunk_prefix_kernel(int* chunk, long long n1, int n_chunks, long long* rowcount) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= n1) return;
+  long long run = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int v = chunk[(long long)c * n1 + r];
+    chunk[(long long)c * n1 + r] = (int)run;
+    run += v;
+  }
+  rowcount[r] = run;
 }
 
 // Values of the stored entries, lane-dense: one warp per row walks the row's column indices.  The exact
@@ -348,16 +379,17 @@ __device__ __forceinline__ double csr_row_dot(const long long* __restrict__ indp
     const double v0 = val[k];
     const int i0 = idx[k];
     const double v1 = p1 ? val[k + 32] : 0.0;
-    const int i1 = p1 ? idx[k + 32] : i0;
+    const int i1 = p1 ? idx[k + 32] : 0;
     const double v2 = p2 ? val[k + 64] : 0.0;
-    const int i2 = p2 ? idx[k + 64] : i0;
+    const int i2 = p2 ? idx[k + 64] : 0;
     const double v3 = p3 ? val[k + 96] : 0.0;
-    const int i3 = p3 ? idx[k + 96] : i0;
-    const double x0 = x[i0], x1 = x[i1], x2 = x[i2], x3 = x[i3];
+    const int i3 = p3 ? idx[k + 96] : 0;
+    const double x0 = x[i0];
+    const double x1 = p1 ? x[i1] : 0.0, x2 = p2 ? x[i2] : 0.0, x3 = p3 ? x[i3] : 0.0;  // no gather for absent strips
     s0 = fma(v0, x0, s0);
-    if (p1) s1 = fma(v1, x1, s1);
-    if (p2) s2 = fma(v2, x2, s2);
-    if (p3) s3 = fma(v3, x3, s3);
+    s1 = fma(v1, x1, s1);
+    s2 = fma(v2, x2, s2);
+    s3 = fma(v3, x3, s3);
   }
   return warp_sum((s0 + s1) + (s2 + s3));
 }
@@ -740,6 +772,13 @@ __global__ void __launch_bounds__(KR_THREADS) lanczos_axpy_kernel(long long n, c
 
 static inline unsigned krylov_grid() { return (unsigned)sm_count() * 8u; }  // 8 x 256 threads = full occupancy
 
+// Column super tiles are cut into at most 32 chunks of a multiple of 32 super tiles each.
+static void wendland_chunking(int64_t n2, long long& supers_per_chunk, int& n_chunks) {
+  const long long tiles2 = (n2 + WT - 1) / WT, super2 = (tiles2 + WS - 1) / WS;
+  supers_per_chunk = 32 * std::max<long long>(1, (super2 + 1023) / 1024);
+  n_chunks = (int)std::max<long long>(1, (super2 + supers_per_chunk - 1) / supers_per_chunk);
+}
+
 // amp * (1-d)^8 * poly with (1-d)^8 >= 2^-424 and 1 <= poly <= 66 is a normal non-zero double for every
 // stored pair iff amp is moderately scaled; otherwise the reference's `value != 0` test must be replayed.
 static inline bool wendland_needs_strict(double amp) {
@@ -749,7 +788,7 @@ static inline bool wendland_needs_strict(double amp) {
 
 template <bool FILL>
 static int launch_wendland(const WendlandParams& p, cudaStream_t st) {
-  const unsigned grid = (unsigned)((p.tiles1 + W_WARPS - 1) / W_WARPS);
+  const unsigned grid = (unsigned)((p.tiles1 * p.n_chunks + W_WARPS - 1) / W_WARPS);
   const bool strict = wendland_needs_strict(p.amp);
 #define FVGP_WL(D)                                                                            \
   case D:                                                                                     \
@@ -788,6 +827,8 @@ static int fill_wendland_params(WendlandParams& p, const double* d_x1, int64_t n
   p.x1 = d_x1, p.x2 = d_x2, p.aabb1 = d_aabb1, p.aabb2 = d_aabb2;
   p.n1 = n1, p.n2 = n2, p.dim = dim, p.amp = h_theta[0];
   p.tiles1 = (n1 + WT - 1) / WT, p.tiles2 = (n2 + WT - 1) / WT, p.super2 = (p.tiles2 + WS - 1) / WS;
+  wendland_chunking(n2, p.supers_per_chunk, p.n_chunks);
+  p.chunk = nullptr;
   for (int i = 0; i < kMaxDim; ++i) p.theta[i] = i < dim ? h_theta[1 + i] : 1.0;
   p.indptr = nullptr, p.noise = nullptr, p.rowcount = nullptr, p.stats = nullptr, p.indices = nullptr, p.data = nullptr;
   return 0;
@@ -805,6 +846,13 @@ int64_t fvgp_wendland_aabb_len(int64_t n, int dim) {
   return (tiles + supers) * 2 * dim;
 }
 
+int64_t fvgp_wendland_chunk_len(int64_t n1, int64_t n2) {
+  long long spc;
+  int nc;
+  wendland_chunking(n2, spc, nc);
+  return (int64_t)nc * std::max<int64_t>(n1, 1);
+}
+
 int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, void* stream) {
   FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim);
   if (n <= 0) return 0;
@@ -819,23 +867,30 @@ int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, vo
 
 int fvgp_wendland_csr_count(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                             const double* d_aabb2, int dim, const double* h_theta, int64_t* d_rowcount,
-                            int64_t* d_stats, void* stream) {
+                            int32_t* d_chunk, int64_t* d_stats, void* stream) {
   WendlandParams p;
   int r = fill_wendland_params(p, d_x1, n1, d_aabb1, d_x2, n2, d_aabb2, dim, h_theta);
   if (r != 0) return r;
   if (n1 == 0) return 0;
-  p.rowcount = (long long*)d_rowcount, p.stats = (long long*)d_stats;
-  return launch_wendland<false>(p, (cudaStream_t)stream);
+  p.rowcount = (long long*)d_rowcount, p.stats = (long long*)d_stats, p.chunk = d_chunk;
+  r = launch_wendland<false>(p, (cudaStream_t)stream);
+  if (r != 0) return r;
+  launch(wendland_chunk_prefix_kernel, (unsigned)((n1 + 255) / 256), 256, 0, (cudaStream_t)stream, d_chunk, (long long)n1,
+         p.n_chunks, (long long*)d_rowcount);
+  FVGP_LAUNCH_OK();
+  return 0;
 }
 
 int fvgp_wendland_csr_fill(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                            const double* d_aabb2, int dim, const double* h_theta, const int64_t* d_indptr,
-                           const double* d_noise_diag, int32_t* d_indices, double* d_data, void* stream) {
+                           const int32_t* d_chunk, const double* d_noise_diag, int32_t* d_indices, double* d_data,
+                           void* stream) {
   WendlandParams p;
   int r = fill_wendland_params(p, d_x1, n1, d_aabb1, d_x2, n2, d_aabb2, dim, h_theta);
   if (r != 0) return r;
   if (n1 == 0) return 0;
   p.indptr = (const long long*)d_indptr, p.noise = d_noise_diag, p.indices = d_indices, p.data = d_data;
+  p.chunk = const_cast<int32_t*>(d_chunk);
   r = launch_wendland<true>(p, (cudaStream_t)stream);
   if (r != 0) return r;
   return launch_wendland_values(p, (cudaStream_t)stream);

@@ -33,10 +33,12 @@ def resolve_gp2scale_linalg_mode(mode, args):
 
 class Evaluation:
     """Result of one factor/solve/logdet pass; device objects are kept for the gradient / posterior."""
-    __slots__ = ("KVinvY", "logdet", "factor", "csr", "alpha_dev", "mode", "info")
+    __slots__ = ("KVinvY", "logdet", "factor", "csr", "alpha_dev", "mode", "info", "sharded", "serial")
 
     def __init__(self):
         self.KVinvY = self.logdet = self.factor = self.csr = self.alpha_dev = self.mode = None
+        self.sharded = None          # ShardedDenseEvaluator holding the block-cyclic factor (multi-GPU dense path)
+        self.serial = 0              # which evaluation of that evaluator this is (its matrix is reused in place)
         self.info = {}
 
 
@@ -122,6 +124,8 @@ class GPkv:
         if memo is not None and memo[0] == key and x0 is None:
             old = memo[1]
             usable = old.factor is None or not old.factor.inverted
+            if old.sharded is not None:
+                usable = self.sharded_current(old)
             if usable and want_logdet and old.logdet is None and old.factor is not None:
                 old.logdet = ops.chol_logdet(old.factor)
             if (usable or not want_factor) and (old.logdet is not None or not want_logdet):
@@ -143,6 +147,10 @@ class GPkv:
             ev.logdet = float(mode[2](obj)) if want_logdet else None
             ev.mode = mode
             return ev
+        if self._use_sharded(mode, V):
+            done = self._evaluate_sharded(ev, hps, V, m, y_mean)
+            if done is not None:
+                return done
         kind, obj = self.prior.device_KV(hps, V)
         if kind == "sparse":
             mode = self._set_gp2Scale_mode(obj.nnz) if self.gp2Scale else (mode or "sparseCG")
@@ -191,6 +199,51 @@ class GPkv:
         if want_logdet:
             ev.logdet = self._random_logdet(obj, ev)
         return ev
+
+    # ---- multi-GPU dense path: KV block-cyclic over the ranks of torch.distributed ----------------
+    def _use_sharded(self, mode, V):
+        """args["dense_sharded"]: True -> always (also on one rank); "auto"/unset -> when torch.distributed has
+        more than one rank AND KV + the inverse scratch would not fit one HBM.  Every rank must then call
+        log_likelihood / neg_log_likelihood_gradient collectively with the same hyperparameters."""
+        if self.gp2Scale or mode != "Chol" or V is None or np.ndim(V) != 1:
+            return False
+        want = self.args.get("dense_sharded", "auto")
+        if want is False:
+            return False
+        if want is True:
+            return True
+        try:
+            import torch.distributed as dist
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        except Exception:
+            world = 1
+        n = len(self.data.x_data)
+        return world > 1 and 10.0 * n * n > 0.9 * 180e9          # 8 N^2 matrix + 2 N^2 inverse scratch
+
+    def _evaluate_sharded(self, ev, hps, V, m, y_mean):
+        from . import kernels as K
+        from . import sharded
+        x = self.data.x_data
+        res = self.prior._call_kernel(x, x, np.asarray(hps, dtype=np.float64))
+        if not (isinstance(res, K.Radial) and res.dist.x1 is x and res.dist.x2 is x):
+            if self.args.get("dense_sharded") is True:
+                raise Exception("dense_sharded needs the default kernel or a kernel composed of fvgp_b200.kernels "
+                                "radial functions on get_(anisotropic_)distance_matrix")
+            return None
+        E = getattr(self, "_sharded_eval", None)
+        if E is None or E.n != len(x) or x is not self._sharded_x:       # new data object -> new layout
+            E = sharded.ShardedDenseEvaluator(x, self.data.y_data, V, nb=self.args.get("dense_sharded_block", None))
+            self._sharded_eval, self._sharded_x, self._sharded_serial = E, x, 0
+        E.y = np.ascontiguousarray(self.data.y_data, dtype=np.float64).reshape(len(x), -1)
+        out = E.evaluate(res.kind, res.amp, res.dist.inv_scale, res.length, m, noise=V)
+        self._sharded_serial += 1
+        ev.sharded, ev.serial, ev.mode = E, self._sharded_serial, "Chol"
+        ev.KVinvY, ev.logdet, ev.alpha_dev = out["alpha"], out["logdet"], out["alpha_dev"]
+        return ev
+
+    def sharded_current(self, ev):
+        """True while the evaluator's in-place matrix still belongs to evaluation `ev` and is un-inverted."""
+        return ev.sharded is not None and ev.serial == self._sharded_serial and ev.sharded._matrix().state == "factored"
 
     def _random_logdet(self, csr, ev=None):
         """SLQ estimate with the reference's argument keys (gp_lin_alg.py:1103-1181)."""
@@ -260,6 +313,12 @@ class GPkv:
         if callable_mode(self.mode):
             obj = self.mode[0](self.addKV(self.prior.K, self.likelihood.V))
             return np.asarray(self.mode[1](obj, b2)).reshape(b.shape)
+        if ev.sharded is not None:
+            if not self.sharded_current(ev):                    # the in-place matrix moved on: rebuild the state
+                self._memo = None
+                self._refresh()
+                ev = self.state
+            return ev.sharded.solve(b2).reshape(b.shape)
         if ev.factor is not None:
             if ev.factor.inverted:
                 self._refresh()
@@ -279,6 +338,10 @@ class GPkv:
 
     def solve_device(self, rhs_t):
         """In-place dense solve for (nrhs, N) device right-hand sides (posterior covariance)."""
+        if self.state.sharded is not None:
+            sol = self.solve(rhs_t.cpu().numpy().T)
+            rhs_t.copy_(L.to_dev(np.ascontiguousarray(sol.T)))
+            return rhs_t
         if self.state.factor.inverted:
             self._refresh()
         return ops.potrs(self.state.factor, rhs_t)
@@ -290,6 +353,7 @@ class GPkv:
         state = dict(self.__dict__)
         state["state"] = None                    # device buffers are rebuilt on first use after unpickling
         state["_memo"] = None
+        state["_sharded_eval"] = state["_sharded_x"] = None
         return state
 
     def __setstate__(self, state):

@@ -70,6 +70,8 @@ class GPMarginalLikelihood:
         V = self.likelihood.calculate_V(x, hps)
         m = self.prior.compute_mean(x, hps)
         ev = self.kv.evaluate(hps, V, m, want_logdet=False)
+        if ev.sharded is not None:
+            return self._gradient_sharded(hps, ev, component)
         if ev.factor is None:
             return self._gradient_host(hps, V, ev, component)
         b_dev = ev.alpha_dev[component].contiguous()
@@ -99,6 +101,25 @@ class GPMarginalLikelihood:
                 grad[i] = 0.5 * t
             grad[i] += gm
         self._dk_cache = None
+        return grad
+
+    def _gradient_sharded(self, hps, ev, component):
+        """Block-cyclic multi-GPU path (fvgp_b200/sharded.py): distributed TRTRI + LAUUM, block traces, one
+        all-reduce of H doubles.  Same host-side switch on the mean gradient as the single-GPU path."""
+        x = self.data.x_data
+        if not (self.prior.default_kernel and self.prior.kernel_grad is None):
+            raise Exception("the sharded dense gradient is implemented for the default kernel (analytic dK/dtheta)")
+        if np.any(self.likelihood.calculate_V_grad(x, hps) != 0.0):
+            raise Exception("noise-function gradients are not supported on the sharded dense path")
+        b = ev.KVinvY[:, component]
+        traces = ev.sharded.gradient_traces(hps, ev.alpha_dev[component])
+        dm = self.prior.dm_dh(x, hps)
+        grad = np.zeros(len(hps))
+        for i in range(len(hps)):
+            gm = float(-dm[i] @ b)
+            if gm == 0.0:                                      # the reference's switch, :301-308
+                grad[i] = 0.5 * traces[i]
+            grad[i] += gm
         return grad
 
     _dk_cache = None

@@ -159,12 +159,12 @@ def potrs(factor, rhs_t):
         ldb = n + 1
         padded = L.dev_empty((nrhs, ldb))
         padded[:, :n] = rhs_t
-        work = L.dev_empty((2 * n,))
+        work = L.dev_empty((int(lib.fvgp_potrs_work_len(n)),))
         L.check(lib.fvgp_potrs_lower(L.ptr(factor.buf), n, factor.ld, L.ptr(factor.tileinv), L.ptr(padded), nrhs, ldb,
                                      L.ptr(work), L.stream_ptr()), "fvgp_potrs_lower")
         rhs_t.copy_(padded[:, :n])
         return rhs_t
-    work = L.dev_empty((2 * n,))
+    work = L.dev_empty((int(lib.fvgp_potrs_work_len(n)),))
     with _Phase("potrs"):
         L.check(lib.fvgp_potrs_lower(L.ptr(factor.buf), n, factor.ld, L.ptr(factor.tileinv), L.ptr(rhs_t), nrhs, n,
                                      L.ptr(work), L.stream_ptr()), "fvgp_potrs_lower")
@@ -259,8 +259,9 @@ def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None, stats=None
     _, th = L.dvec(theta)
     counts = torch.zeros(max(n1, 1), dtype=torch.int64, device="cuda")
     st = L.stream_ptr()
+    chunk = torch.empty(int(lib.fvgp_wendland_chunk_len(n1, n2)), dtype=torch.int32, device="cuda")
     L.check(lib.fvgp_wendland_csr_count(L.ptr(x1), n1, L.ptr(boxes1), L.ptr(x2), n2, L.ptr(boxes2), dim, th,
-                                        L.ptr(counts), L.ptr(stats), st), "fvgp_wendland_csr_count")
+                                        L.ptr(counts), L.ptr(chunk), L.ptr(stats), st), "fvgp_wendland_csr_count")
     indptr = torch.empty(n1 + 1, dtype=torch.int64, device="cuda")
     scratch = torch.empty(int(lib.fvgp_scan_scratch_len(n1)), dtype=torch.int64, device="cuda")
     total = c_int64()
@@ -271,7 +272,7 @@ def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None, stats=None
     data = torch.empty(nnz, dtype=torch.float64, device="cuda")
     if nnz:
         L.check(lib.fvgp_wendland_csr_fill(L.ptr(x1), n1, L.ptr(boxes1), L.ptr(x2), n2, L.ptr(boxes2), dim, th,
-                                           L.ptr(indptr), L.ptr(noise), L.ptr(indices), L.ptr(data), st),
+                                           L.ptr(indptr), L.ptr(chunk), L.ptr(noise), L.ptr(indices), L.ptr(data), st),
                 "fvgp_wendland_csr_fill")
     return DeviceCSR(indptr, indices, data, (n1, n2))
 

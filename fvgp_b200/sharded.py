@@ -596,10 +596,16 @@ class ShardedDenseEvaluator:
             self.A = ShardedSPD(self.n, self.nb, self.grid, self.ops, self.comm)
         return self.A
 
-    def evaluate(self, kind, amp, inv_scale, length, mean, want_gradient_theta=None):
+    def evaluate(self, kind, amp, inv_scale, length, mean, want_gradient_theta=None, noise=None):
         """Returns dict(lml, alpha (N, r) ndarray, logdet[, traces]).  want_gradient_theta: the default
-        kernel's theta when its gradient traces are wanted."""
+        kernel's theta when its gradient traces are wanted.  noise: replaces the noise diagonal (noise functions
+        of the hyperparameters, gp_likelihood.py:89-94)."""
         from . import ops as single
+        if noise is not None:
+            noise = np.ascontiguousarray(noise, dtype=np.float64)
+            if self.noise is None or not np.array_equal(noise, self.noise):
+                self.noise = noise
+                self.noise_dev = self.ops.upload(noise)
         A = self._matrix()
         centre = single.fill_centre(kind, inv_scale, length, self.bounds)
         A.fill(kind, self.x_dev, self.x, amp, inv_scale, length, self.noise_dev, centre)
@@ -616,7 +622,23 @@ class ShardedDenseEvaluator:
         lml = float(-0.5 * (np.sum(ym * alpha) / r + logdet + self.n * np.log(2.0 * np.pi)))
         out = {"lml": lml, "alpha": alpha, "logdet": logdet, "alpha_dev": cols}
         if want_gradient_theta is not None:
-            A.invert()
-            out["traces"] = A.grad_traces(np.asarray(want_gradient_theta, dtype=np.float64), cols[0])
+            out["traces"] = self.gradient_traces(want_gradient_theta, cols[0])
         self.last = out
         return out
+
+    def gradient_traces(self, theta, b_dev):
+        """sum_ij (KV^-1 - b b^T)_ij dK_ij/dtheta_h for the default kernel at the hyperparameters of the last
+        evaluate(); inverts the factored matrix in place on first use."""
+        A = self._matrix()
+        if A.state == "factored":
+            A.invert()
+        return A.grad_traces(np.asarray(theta, dtype=np.float64), b_dev)
+
+    def solve(self, b):
+        """KV^-1 b for host right-hand sides (N,) or (N, r) against the factor of the last evaluate()."""
+        A = self._matrix()
+        assert A.state == "factored", "the factor was consumed by the inverse; evaluate() again"
+        b2 = np.asarray(b, dtype=np.float64).reshape(self.n, -1)
+        out = np.stack([A.solve(self.ops.upload(np.ascontiguousarray(b2[:, c]))).cpu().numpy()
+                        for c in range(b2.shape[1])], axis=1)
+        return out.reshape(np.shape(b))

@@ -108,7 +108,10 @@ int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int
 
 /* calculate_Chol_solve (gp_lin_alg.py:289-328): solve (L L^T) X = B in place.  d_B holds
  * nrhs right-hand sides, each contiguous with stride ldb (i.e. B^T in C order).
- * d_work: 2*n doubles. */
+ * d_work: fvgp_potrs_work_len(n) doubles.  Up to 4 right-hand sides run as blocked substitutions whose
+ * off-diagonal panels are matrix-vector products (HBM-read bound: the factor is read once per direction);
+ * more go through the tensor-core TRSM recursion. */
+int64_t fvgp_potrs_work_len(int64_t n);
 int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B, int nrhs,
                      int64_t ldb, double* d_work, void* stream);
 
@@ -166,16 +169,21 @@ int fvgp_dot(const double* d_a, const double* d_b, int64_t n, double* d_scratch1
  * the caller's choice for the final matrix; the kernels use int64 offsets); pass 2 fills
  * sorted column indices (same geometry pass) and then the values (lane-dense kernel over the stored
  * entries, reference operation order).  Pattern is bit-exact w.r.t. the reference predicate.
+ * Work is cut into (32-row tile, column chunk) units, at most 32 chunks; d_chunk (fvgp_wendland_chunk_len
+ * int32) carries the per-(chunk, row) counts from the count pass to the fill pass and must not be touched
+ * in between.
  * d_stats (may be NULL): one int64 the count pass ADDS the number of 32x32 tile pairs it tested to
  * (pair tests = 1024 x that; reported next to nnz as the cull efficiency). */
 int64_t fvgp_wendland_aabb_len(int64_t n, int dim); /* doubles per point set for tile bounding boxes */
 int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, void* stream);
+int64_t fvgp_wendland_chunk_len(int64_t n1, int64_t n2); /* int32 scratch shared by count and fill */
 int fvgp_wendland_csr_count(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                             const double* d_aabb2, int dim, const double* h_theta, int64_t* d_rowcount,
-                            int64_t* d_stats, void* stream);
+                            int32_t* d_chunk, int64_t* d_stats, void* stream);
 int fvgp_wendland_csr_fill(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                            const double* d_aabb2, int dim, const double* h_theta, const int64_t* d_indptr,
-                           const double* d_noise_diag, int32_t* d_indices, double* d_data, void* stream);
+                           const int32_t* d_chunk, const double* d_noise_diag, int32_t* d_indices, double* d_data,
+                           void* stream);
 /* exclusive scan of n counts into n+1 offsets (d_indptr[0] = 0); *h_total = nnz. */
 int fvgp_exclusive_scan_i64(const int64_t* d_counts, int64_t n, int64_t* d_indptr, int64_t* d_scratch,
                             int64_t* h_total, void* stream);

@@ -5,7 +5,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fvgp_b200 import _lib as L, ops
 
-for n in [int(a) for a in sys.argv[1:]] or [30000, 50000]:
+hog = []
+if "--hog" in sys.argv:                      # occupy HBM first (does placement of the output matter?)
+    gb = int(sys.argv[sys.argv.index("--hog") + 1])
+    hog = [torch.empty(int(1e9), dtype=torch.float64, device="cuda").fill_(1.0) for _ in range(gb // 8)]
+    print("hogging", 8 * len(hog), "GB")
+if "--after-gemm" in sys.argv:               # heat the chip with ~8 s of DMMA first (do clocks matter?)
+    a = torch.randn(16384, 16384, dtype=torch.float64, device="cuda")
+    c = torch.zeros_like(a)
+    for _ in range(30):
+        ops.dgemm_nt(a, a, c)
+    torch.cuda.synchronize()
+    del a, c
+    print("after 30 DGEMMs of 16384^3")
+sizes = [int(a) for a in sys.argv[1:] if a.isdigit() and (sys.argv[sys.argv.index(a) - 1] != "--hog")]
+for n in sizes or [30000, 50000]:
     rng = np.random.default_rng(0)
     x = L.to_dev(rng.random((n, 3)))
     noise = L.to_dev(np.full(n, 1e-2))
