@@ -27,6 +27,7 @@
 #include "../../include/fvgp_b200.h"
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace fvgp {
 
@@ -366,43 +367,65 @@ struct KrylovScalars {
   unsigned counter[4];
 };
 
-// One warp per row, four 32-entry strips of the row in flight at once: the (val, idx) loads of all strips
-// are issued before the first dependent gather of x, so a ~100-entry gp2Scale row costs three dependent
-// memory latencies (indptr -> val/idx -> x) instead of seven.
-__device__ __forceinline__ double csr_row_dot(const long long* __restrict__ indptr, const int* __restrict__ idx,
-                                              const double* __restrict__ val, const double* __restrict__ x,
-                                              long long row, int lane) {
-  const long long b = indptr[row], e = indptr[row + 1];
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for (long long k = b + lane; k < e; k += 128) {
-    const bool p1 = k + 32 < e, p2 = k + 64 < e, p3 = k + 96 < e;
-    const double v0 = val[k];
-    const int i0 = idx[k];
-    const double v1 = p1 ? val[k + 32] : 0.0;
-    const int i1 = p1 ? idx[k + 32] : 0;
-    const double v2 = p2 ? val[k + 64] : 0.0;
-    const int i2 = p2 ? idx[k + 64] : 0;
-    const double v3 = p3 ? val[k + 96] : 0.0;
-    const int i3 = p3 ? idx[k + 96] : 0;
-    const double x0 = x[i0];
-    const double x1 = p1 ? x[i1] : 0.0, x2 = p2 ? x[i2] : 0.0, x3 = p3 ? x[i3] : 0.0;  // no gather for absent strips
-    s0 = fma(v0, x0, s0);
-    s1 = fma(v1, x1, s1);
-    s2 = fma(v2, x2, s2);
-    s3 = fma(v3, x3, s3);
+// LPR lanes per row (32 / LPR rows per warp), U strips of LPR entries of every row in flight at once: the
+// (val, idx) loads of all strips are issued before the first dependent gather of x.  SpMV on the gp2Scale
+// matrix (~100 entries per row) is latency bound, not HBM bound, until enough bytes are in flight (ncu: 72 % of
+// the warp cycles are long-scoreboard stalls): what counts is rows-in-flight x occupancy, so the variants are
+// register-capped.  Returns the row sum in all LPR lanes of the group; groups with row >= n return 0.
+template <int LPR, int U>
+__device__ __forceinline__ double csr_group_dot(const long long* __restrict__ indptr, const int* __restrict__ idx,
+                                                const double* __restrict__ val, const double* __restrict__ x,
+                                                long long row, long long n, int sub) {
+  const bool valid = row < n;
+  const long long b = valid ? indptr[row] : 0, e = valid ? indptr[row + 1] : 0;
+  double acc[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) acc[u] = 0.0;
+  for (long long k = b + sub; k < e; k += LPR * U) {
+    double v[U];
+    int j[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool on = k + u * LPR < e;
+      v[u] = on ? val[k + u * LPR] : 0.0;
+      j[u] = on ? idx[k + u * LPR] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double xv = j[u] >= 0 ? x[j[u]] : 0.0;
+      acc[u] = fma(v[u], xv, acc[u]);
+    }
   }
-  return warp_sum((s0 + s1) + (s2 + s3));
+  double s = acc[0];
+#pragma unroll
+  for (int u = 1; u < U; ++u) s += acc[u];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
 }
 
-__global__ void __launch_bounds__(KR_THREADS) spmv_kernel(long long n, const long long* __restrict__ indptr,
-                                                          const int* __restrict__ idx, const double* __restrict__ val,
-                                                          const double* __restrict__ x, double* __restrict__ y) {
-  const int lane = threadIdx.x & 31;
+// Row loop shared by the three kernels that multiply by the matrix: f(row, sum) runs in the group's lane 0.
+template <int LPR, int U, typename F>
+__device__ __forceinline__ void spmv_rows(long long n, const long long* __restrict__ indptr,
+                                          const int* __restrict__ idx, const double* __restrict__ val,
+                                          const double* __restrict__ x, F f) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, grp = lane / LPR, sub = lane % LPR;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
-    const double s = csr_row_dot(indptr, idx, val, x, row, lane);
-    if (lane == 0) y[row] = s;
+  for (long long base = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; base < n;
+       base += warps * RPW) {
+    const long long row = base + grp;
+    const double s = csr_group_dot<LPR, U>(indptr, idx, val, x, row, n, sub);
+    if (sub == 0 && row < n) f(row, s);
   }
+}
+
+template <int LPR, int U, int MINB>
+__global__ void __launch_bounds__(KR_THREADS, MINB) spmv_kernel(long long n, const long long* __restrict__ indptr,
+                                                                const int* __restrict__ idx,
+                                                                const double* __restrict__ val,
+                                                                const double* __restrict__ x, double* __restrict__ y) {
+  spmv_rows<LPR, U>(n, indptr, idx, val, x, [&](long long row, double s) { y[row] = s; });
 }
 
 // Deterministic grid-wide sums: every CTA publishes its partial, the last CTA to arrive adds
@@ -436,24 +459,20 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double* partials, unsi
 }
 
 // r = b - A x ; bnorm2 = b.b ; sets the absolute tolerance.
-__global__ void __launch_bounds__(KR_THREADS) pcg_init_kernel(long long n, const long long* __restrict__ indptr,
-                                                              const int* __restrict__ idx,
-                                                              const double* __restrict__ val,
-                                                              const double* __restrict__ b, const double* __restrict__ x,
-                                                              double* __restrict__ r, double rtol, KrylovScalars* sc,
-                                                              double* partials) {
-  const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+template <int LPR, int U, int MINB>
+__global__ void __launch_bounds__(KR_THREADS, MINB) pcg_init_kernel(long long n, const long long* __restrict__ indptr,
+                                                                    const int* __restrict__ idx,
+                                                                    const double* __restrict__ val,
+                                                                    const double* __restrict__ b,
+                                                                    const double* __restrict__ x, double* __restrict__ r,
+                                                                    double rtol, KrylovScalars* sc, double* partials) {
   double v[2] = {0.0, 0.0};
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
-    const double ax = csr_row_dot(indptr, idx, val, x, row, lane);
-    if (lane == 0) {
-      const double bi = b[row], ri = bi - ax;
-      r[row] = ri;
-      v[0] += bi * bi;
-      v[1] += ri * ri;
-    }
-  }
+  spmv_rows<LPR, U>(n, indptr, idx, val, x, [&](long long row, double ax) {
+    const double bi = b[row], ri = bi - ax;
+    r[row] = ri;
+    v[0] += bi * bi;
+    v[1] += ri * ri;
+  });
   double tot[2];
   if (grid_sum<2>(v, partials, &sc->counter[0], tot) && threadIdx.x == 0) {
     sc->bnorm2 = tot[0];
@@ -527,22 +546,18 @@ __global__ void __launch_bounds__(KR_THREADS) pcg_update_p_kernel(long long n, c
 }
 
 // q = A p ; pq = p.q ; alpha = rho / pq
-__global__ void __launch_bounds__(KR_THREADS) pcg_spmv_kernel(long long n, const long long* __restrict__ indptr,
-                                                              const int* __restrict__ idx,
-                                                              const double* __restrict__ val,
-                                                              const double* __restrict__ p, double* __restrict__ q,
-                                                              KrylovScalars* sc, double* partials) {
+template <int LPR, int U, int MINB>
+__global__ void __launch_bounds__(KR_THREADS, MINB) pcg_spmv_kernel(long long n, const long long* __restrict__ indptr,
+                                                                    const int* __restrict__ idx,
+                                                                    const double* __restrict__ val,
+                                                                    const double* __restrict__ p, double* __restrict__ q,
+                                                                    KrylovScalars* sc, double* partials) {
   if (sc->done) return;
-  const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   double v[1] = {0.0};
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
-    const double s = csr_row_dot(indptr, idx, val, p, row, lane);
-    if (lane == 0) {
-      q[row] = s;
-      v[0] += s * p[row];
-    }
-  }
+  spmv_rows<LPR, U>(n, indptr, idx, val, p, [&](long long row, double s) {
+    q[row] = s;
+    v[0] += s * p[row];
+  });
   double tot[1];
   if (grid_sum<1>(v, partials, &sc->counter[2], tot) && threadIdx.x == 0) {
     sc->pq = tot[0];
@@ -772,6 +787,29 @@ __global__ void __launch_bounds__(KR_THREADS) lanczos_axpy_kernel(long long n, c
 
 static inline unsigned krylov_grid() { return (unsigned)sm_count() * 8u; }  // 8 x 256 threads = full occupancy
 
+// SpMV variant (lanes per row, strips in flight, minimum resident CTAs per SM = register cap):
+//   0: 32 / 1 / 8   one row per warp, the classic CSR-vector loop
+//   1:  8 / 4 / 8   four rows per warp, <= 32 registers
+//   2:  8 / 8 / 5   four rows per warp, deeper prefetch, 48 registers
+//   3: 16 / 4 / 8   two rows per warp
+// FVGP_SPMV_VARIANT overrides the default (chosen from the B200 A/B in profiles/).
+static int spmv_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FVGP_SPMV_VARIANT");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 3) v = 1;
+  }
+  return v;
+}
+#define FVGP_SPMV_DISPATCH(KERNEL, ...)                                         \
+  switch (spmv_variant()) {                                                     \
+    case 0: launch(KERNEL<32, 1, 8>, __VA_ARGS__); break;                       \
+    case 2: launch(KERNEL<8, 8, 5>, __VA_ARGS__); break;                        \
+    case 3: launch(KERNEL<16, 4, 8>, __VA_ARGS__); break;                       \
+    default: launch(KERNEL<8, 4, 8>, __VA_ARGS__); break;                       \
+  }
+
 // Column super tiles are cut into at most 32 chunks of a multiple of 32 super tiles each.
 static void wendland_chunking(int64_t n2, long long& supers_per_chunk, int& n_chunks) {
   const long long tiles2 = (n2 + WT - 1) / WT, super2 = (tiles2 + WS - 1) / WS;
@@ -922,10 +960,10 @@ int fvgp_exclusive_scan_i64(const int64_t* d_counts, int64_t n, int64_t* d_indpt
 int fvgp_csr_spmv(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
                   const double* d_x, double* d_y, void* stream) {
   if (n <= 0) return 0;
-  const long long want = (n * 32 + KR_THREADS - 1) / KR_THREADS;
+  const long long want = (n * 8 + KR_THREADS - 1) / KR_THREADS;
   const unsigned grid = (unsigned)(want < (long long)krylov_grid() ? want : (long long)krylov_grid());
-  launch(spmv_kernel, grid, KR_THREADS, 0, (cudaStream_t)stream, n, (const long long*)d_indptr, d_indices, d_data, d_x,
-                                                             d_y);
+  FVGP_SPMV_DISPATCH(spmv_kernel, grid, KR_THREADS, 0, (cudaStream_t)stream, (long long)n, (const long long*)d_indptr,
+                     d_indices, d_data, d_x, d_y);
   FVGP_LAUNCH_OK();
   return 0;
 }
@@ -960,7 +998,8 @@ int fvgp_pcg(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const
   const long long* ip = (const long long*)d_indptr;
   FVGP_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(KrylovScalars), st));
   FVGP_CUDA_OK(cudaMemsetAsync(p, 0, 2 * n * sizeof(double), st));  // p and q
-  launch(pcg_init_kernel, grid, KR_THREADS, 0, st, n, ip, d_indices, d_data, d_b, d_x, r, rtol, sc, partials);
+  FVGP_SPMV_DISPATCH(pcg_init_kernel, grid, KR_THREADS, 0, st, (long long)n, ip, d_indices, d_data, d_b,
+                     (const double*)d_x, r, rtol, sc, partials);
   FVGP_LAUNCH_OK();
   KrylovScalars h;
   const int batch = 16;
@@ -974,7 +1013,8 @@ int fvgp_pcg(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const
     for (int k = 0; k < batch; ++k) {
       launch(pcg_head_kernel, grid, KR_THREADS, 0, st, n, d_precond, p, q, d_x, r, z, sc, partials, maxiter);
       launch(pcg_update_p_kernel, grid, KR_THREADS, 0, st, n, z, p, sc);
-      launch(pcg_spmv_kernel, grid, KR_THREADS, 0, st, n, ip, d_indices, d_data, p, q, sc, partials);
+      FVGP_SPMV_DISPATCH(pcg_spmv_kernel, grid, KR_THREADS, 0, st, (long long)n, ip, d_indices, d_data,
+                         (const double*)p, q, sc, partials);
     }
     FVGP_LAUNCH_OK();
   }

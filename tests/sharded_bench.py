@@ -1,7 +1,7 @@
 """Timing harness of the block-cyclic dense path (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 \
-        tests/sharded_bench.py --n 60000 [--nb 2048] [--grad] [--check]
+        tests/sharded_bench.py --size 60000 [--nb 2048] [--grad] [--check]
 
 Prints one JSON line on rank 0: seconds per phase (CUDA events, max over ranks), TFLOP/s per GPU on the
 algorithmic N^3/3 (+ 2N^3/3 with --grad), bytes received per rank."""
@@ -21,7 +21,8 @@ import torch.distributed as dist  # noqa: E402
 from fvgp_b200 import parallel, sharded  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=40000)
+ap.add_argument("--size", dest="n", type=int, default=40000,
+                help="matrix order N (not --n: torchrun's own parser treats a bare --n as an ambiguous abbreviation)")
 ap.add_argument("--nb", type=int, default=0)
 ap.add_argument("--dim", type=int, default=3)
 ap.add_argument("--grad", action="store_true")
