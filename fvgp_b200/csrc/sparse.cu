@@ -753,6 +753,61 @@ __global__ void __launch_bounds__(KR_THREADS) lanczos_spmm_kernel(long long n, c
     sc->alpha[threadIdx.x] = tot[threadIdx.x];
 }
 
+// Same step with LANES = COLUMNS (NB >= 4): a group of NB lanes owns one row (32 / NB rows per warp), lane c
+// accumulates probe c.  The group streams the row NB entries at a time (lane u loads entry k + u, coalesced),
+// broadcasts (value, column) with shuffles and gathers u[column * NB + c] -- NB contiguous doubles per entry
+// across the group.  No cross-lane reduction, ~36 registers (full occupancy) and 32 / NB rows x NB gathers in
+// flight per warp; the per-lane-entry variant above needs NB accumulators + NB gathered doubles per lane
+// (64 registers at NB = 8, half occupancy) and was latency bound (ncu: 17 % issue-active, 13 % DRAM).
+template <int NB>
+__global__ void __launch_bounds__(KR_THREADS, (NB <= 4 ? 6 : NB == 8 ? 4 : 3)) lanczos_spmm_cols_kernel(
+    long long n, const long long* __restrict__ indptr, const int* __restrict__ idx, const double* __restrict__ val,
+    const double* __restrict__ u, const double* __restrict__ uprev, double* __restrict__ w, LanczosScalars* sc,
+    double* partials) {
+  __shared__ double tot[LZ_MAXB];
+  constexpr int RPW = 32 / NB;
+  const int lane = threadIdx.x & 31, grp = lane / NB, c = lane % NB;
+  const double s_cur = sc->s_cur[c], bs_prev = sc->beta[c] * sc->s_prev[c];
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double asum = 0.0;
+  for (long long base = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; base < n;
+       base += warps * RPW) {
+    const long long row = base + grp;
+    const bool valid = row < n;
+    const long long b = valid ? indptr[row] : 0, e = valid ? indptr[row + 1] : 0;
+    // every group of the warp runs the same number of rounds (shuffles need all lanes)
+    long long len = e - b;
+#pragma unroll
+    for (int o = NB; o < 32; o <<= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    double acc0 = 0.0, acc1 = 0.0;
+    for (long long k0 = 0; k0 < len; k0 += NB) {
+      const long long ka = b + k0 + c;
+      const double va = ka < e ? val[ka] : 0.0;
+      const int ja = ka < e ? idx[ka] : -1;
+      double xa[NB];
+#pragma unroll
+      for (int t = 0; t < NB; ++t) {  // all NB gathers of the round are issued before the first use
+        const int j1 = __shfl_sync(0xffffffffu, ja, grp * NB + t);
+        xa[t] = j1 >= 0 ? u[(long long)j1 * NB + c] : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < NB; t += 2) {
+        acc0 = fma(__shfl_sync(0xffffffffu, va, grp * NB + t), xa[t], acc0);
+        acc1 = fma(__shfl_sync(0xffffffffu, va, grp * NB + t + 1), xa[t + 1], acc1);
+      }
+    }
+    if (valid) {
+      const double wi = s_cur * (acc0 + acc1) - bs_prev * uprev[row * NB + c];
+      w[row * NB + c] = wi;
+      asum = fma(wi, s_cur * u[row * NB + c], asum);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= NB; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+  if (grid_sum_columns<NB>(asum, lane < NB, lane % NB, partials, &sc->counter[0], tot) && threadIdx.x < NB)
+    sc->alpha[threadIdx.x] = tot[threadIdx.x];
+}
+
 // w -= alpha v ; beta_next = ||w|| per column; rotates the scale factors and records (alpha_j, beta_{j+1}).
 template <int NB>
 __global__ void __launch_bounds__(KR_THREADS) lanczos_axpy_kernel(long long n, const double* __restrict__ u,
@@ -1030,6 +1085,16 @@ int64_t fvgp_lanczos_work_len(int64_t n, int degree) {
 
 }  // extern "C"
 
+// FVGP_LANCZOS_COLS=0 selects the per-lane-entry SpMM for batches of >= 4 probes (A/B on the GPU box).
+static int lanczos_cols_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FVGP_LANCZOS_COLS");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v;
+}
+
 template <int NB>
 static int lanczos_batch(int64_t n, const long long* ip, const int32_t* d_indices, const double* d_data, int degree,
                          int probe0, uint64_t seed, double* d_work, double* h_alpha, double* h_beta, cudaStream_t st) {
@@ -1045,8 +1110,17 @@ static int lanczos_batch(int64_t n, const long long* ip, const int32_t* d_indice
   launch(lanczos_start_kernel<NB>, grid, KR_THREADS, 0, st, (long long)n, (unsigned long long)seed,
          (unsigned long long)probe0, u, uprev, sc);
   for (int j = 0; j < degree; ++j) {
-    launch(lanczos_spmm_kernel<NB>, grid, KR_THREADS, 0, st, (long long)n, ip, d_indices, d_data, u, uprev, w, sc,
-           partials);
+    if constexpr (NB >= 4) {
+      if (lanczos_cols_variant())
+        launch(lanczos_spmm_cols_kernel<NB>, grid, KR_THREADS, 0, st, (long long)n, ip, d_indices, d_data, u, uprev, w, sc,
+               partials);
+      else
+        launch(lanczos_spmm_kernel<NB>, grid, KR_THREADS, 0, st, (long long)n, ip, d_indices, d_data, u, uprev, w, sc,
+               partials);
+    } else {
+      launch(lanczos_spmm_kernel<NB>, grid, KR_THREADS, 0, st, (long long)n, ip, d_indices, d_data, u, uprev, w, sc,
+             partials);
+    }
     launch(lanczos_axpy_kernel<NB>, grid, KR_THREADS, 0, st, (long long)n, u, w, sc, partials, d_alpha + (size_t)j * NB,
            d_beta + (size_t)j * NB);
     double* t = uprev;

@@ -268,8 +268,8 @@ def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None, stats=None
     L.check(lib.fvgp_exclusive_scan_i64(L.ptr(counts), n1, L.ptr(indptr), L.ptr(scratch), ctypes.byref(total), st),
             "fvgp_exclusive_scan_i64")
     nnz = total.value
-    indices = torch.empty(nnz, dtype=torch.int32, device="cuda")
-    data = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    indices = L.dev_empty_rounded(nnz, torch.int32)
+    data = L.dev_empty_rounded(nnz, torch.float64)
     if nnz:
         L.check(lib.fvgp_wendland_csr_fill(L.ptr(x1), n1, L.ptr(boxes1), L.ptr(x2), n2, L.ptr(boxes2), dim, th,
                                            L.ptr(indptr), L.ptr(chunk), L.ptr(noise), L.ptr(indices), L.ptr(data), st),
