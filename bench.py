@@ -265,7 +265,10 @@ def run_c4(args):
                                "pcg_bjacobi": t_cg, "pcg_bjacobi_iters": res[2], "pcg_plain": t_cg0,
                                "pcg_plain_iters": res0[2], "slq_10x20": t_slq},
             "roofline": {"bound": "hbm", "kernel": "spmv_kernel (CSR-vector), the inner kernel of PCG and SLQ",
-                         "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s", "frac": spmv_gbs / hbm, "traffic": None,
+                         "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s", "frac": spmv_gbs / hbm,
+                         # dram read + write of one launch on this matrix (ncu --set full,
+                         # profiles/r01/ncu_spmv.v6.summary.txt): 1.216 + 0.011 GB
+                         "traffic": 1.227e9 if n == 1000000 else None,
                          "algorithmic_bytes": 12.0 * nnz + 16.0 * n},
             "roofline_fill": {"bound": "hbm", "kernel": "wendland_csr_kernel count + fill (output-sensitive bytes)",
                               "achieved": fill_bytes / t_fill / 1e9, "peak": hbm, "unit": "GB/s",
@@ -363,7 +366,10 @@ def main():
     t_tensor = (phases.get("potrf", 0.0) + phases.get("potri", 0.0)) / args.steps
     achieved = n ** 3 / t_tensor / 1e12
     roofline = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri", "achieved": achieved,
-                "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value, "traffic": None,
+                "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
+                # thousands of GEMM launches of different shapes per step: no single per-launch DRAM figure; one
+                # 8192^3 launch moves 7.1 GB (profiles/r01/ncu_gemm.v1.summary.txt), 2.7 % of DRAM throughput
+                "traffic": None,
                 "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
                 "algorithmic_flops_per_step": float(n) ** 3,
                 "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
@@ -389,7 +395,10 @@ def main():
     kfill_gbs = 8.0 * n * n / best / 1e9
     roofline_kfill = {"bound": "hbm", "kernel": "kfill_kernel<MATERN32,3> symmetric (full square + noise diagonal)",
                       "achieved": kfill_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": kfill_gbs / hbm_peak,
-                      "traffic": None, "peak_source": hbm_src, "algorithmic_bytes": 8.0 * n * n}
+                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N = 50 000
+                      # (ncu --set full, profiles/r01/ncu_kfill.v6.summary.txt): 0.081 + 19.941 GB
+                      "traffic": 20.022e9 if n == 50000 else None, "peak_source": hbm_src,
+                      "algorithmic_bytes": 8.0 * n * n}
     del out_buf
 
     cpu = None

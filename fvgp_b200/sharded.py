@@ -188,6 +188,35 @@ class CudaLocalOps:
 GEMM_LOWER, GEMM_KB_FROM_M, GEMM_KB_FROM_N, GEMM_KE_FROM_M = 1, 2, 4, 8
 
 
+class _Overlap:
+    """Two-stream choreography helper: a high-priority side stream next to torch's current stream on CUDA,
+    plain sequential execution for LocalOps without streams (the CPU ops of the gloo tests)."""
+
+    def __init__(self, ops):
+        self.on = getattr(ops, "device", "cpu") == "cuda"
+        if self.on:
+            self.torch = ops.torch
+            self.main = self.torch.cuda.current_stream()
+            self.side_stream = self.torch.cuda.Stream(priority=-1)
+
+    def side(self):
+        import contextlib
+        return self.torch.cuda.stream(self.side_stream) if self.on else contextlib.nullcontext()
+
+    def _fence(self, src, dst):
+        ev = self.torch.cuda.Event()
+        ev.record(src)
+        dst.wait_event(ev)
+
+    def fence_main_to_side(self):
+        if self.on:
+            self._fence(self.main, self.side_stream)
+
+    def fence_side_to_main(self):
+        if self.on:
+            self._fence(self.side_stream, self.main)
+
+
 # --------------------------------------------------------------------------------------------------
 # communication: torch.distributed (NCCL over NVLink on the GPUs, gloo in the CPU tests)
 # --------------------------------------------------------------------------------------------------
@@ -299,10 +328,11 @@ class ShardedSPD:
         self.state = "filled"
 
     # ---- Cholesky -------------------------------------------------------------------------------
-    def _exchange_block_column(self, k):
+    def _exchange_block_column(self, k, panel=None):
         """After the owners of block column k have finished their pieces: every rank receives all of them.
         panel[pp][:m_pp] = rows of process row pp with blocks > k, in pp's local order."""
         lay, comm = self.lay, self.comm
+        panel = self.panel if panel is None else panel
         qk = k % lay.Q
         sizes = []
         for pp in range(lay.P):
@@ -310,57 +340,91 @@ class ShardedSPD:
             sizes.append(m_pp)
             if m_pp <= 0:
                 continue
-            buf = self.panel[pp][:m_pp]
+            buf = panel[pp][:m_pp]
             if lay.p == pp and lay.q == qk:
                 view, _ = self.block_rows(k, k + 1)
                 buf.copy_(view)
             comm.broadcast(buf, pp * lay.Q + qk)
         return sizes
 
+    def _panel_path(self, k, panel):
+        """The latency-bound part of step k: factor the diagonal block, replicate it, solve the block column
+        against it and replicate the block column into `panel`.  Returns the local failing pivot (0 = none)."""
+        lay, ops, comm = self.lay, self.ops, self.comm
+        nb = lay.nb
+        bk = lay.bsize(k)
+        pk, qk = k % lay.P, k % lay.Q
+        owner = pk * lay.Q + qk
+        D, T = self.diag[k], self.diag_tinv[k]
+        info = 0
+        if comm.rank == owner:
+            blk = self.block(k, k)
+            D[:bk, :bk].copy_(blk)
+            st = ops.potrf(D, bk, T)
+            if st > 0:
+                info = k * nb + st
+            blk.copy_(D[:bk, :bk])
+        comm.broadcast(D, owner)
+        comm.broadcast(T, owner)
+        if lay.q == qk:
+            view, m = self.block_rows(k, k + 1)
+            if m > 0:
+                ops.trsm_rlt(view, m, D, bk, T)
+        if k < lay.nblk - 1:
+            self._exchange_block_column(k, panel)
+        return info
+
+    def _trailing_update(self, k, panel, cols):
+        """A_IJ -= L_Ik L_Jk^T on my blocks of the block columns `cols` (all > k): one DMMA GEMM per column."""
+        lay, ops = self.lay, self.ops
+        bk = lay.bsize(k)
+        r0 = lay.rows_from(k + 1)
+        for J in cols:
+            bJ = lay.bsize(J)
+            C, m = self.block_rows(J, J)
+            if m <= 0:
+                continue
+            a_off = lay.rows_from(J) - r0
+            pj = J % lay.P
+            b_off = lay.lrow(J) - lay.rows_from(k + 1, pj)
+            Aop = panel[lay.p][a_off:a_off + m]
+            Bop = panel[pj][b_off:b_off + bJ]
+            ops.gemm(0, 0, Aop, Bop, C, m, bJ, bk, -1.0, 1.0, 0)
+
     def factor(self):
-        """In-place lower Cholesky.  Returns 0 or the 1-based global index of the first bad pivot."""
+        """In-place lower Cholesky, right-looking with ONE STEP OF LOOK-AHEAD.  Returns 0 or the 1-based global
+        index of the first bad pivot.
+
+        Step k's trailing update runs on the main stream; as soon as block column k+1 has received its update the
+        panel path of step k+1 (diagonal POTRF, broadcasts, TRSM, block-column exchange over NCCL) starts on a
+        high-priority side stream and overlaps the rest of the update.  The received block columns are double
+        buffered.  On CPU (gloo tests) the same order runs sequentially."""
         assert self.state == "filled"
         lay, ops, comm = self.lay, self.ops, self.comm
         nb, nblk = lay.nb, lay.nblk
         tl = ops.tileinv_len(nb)
         self.diag = ops.zeros(nblk, nb, nb)
         self.diag_tinv = ops.zeros(nblk, tl)
+        if getattr(self, "panel_b", None) is None:
+            self.panel_b = [ops.empty(*t.shape) for t in self.panel]
+        bufs = (self.panel, self.panel_b)
+        ov = _Overlap(ops)
         info_local = 0
-        for k in range(nblk):
-            bk = lay.bsize(k)
-            pk, qk = k % lay.P, k % lay.Q
-            owner = pk * lay.Q + qk
-            D, T = self.diag[k], self.diag_tinv[k]
-            if comm.rank == owner:
-                blk = self.block(k, k)
-                D[:bk, :bk].copy_(blk)
-                st = ops.potrf(D, bk, T)
-                if st > 0 and info_local == 0:
-                    info_local = k * nb + st
-                blk.copy_(D[:bk, :bk])
-            comm.broadcast(D, owner)
-            comm.broadcast(T, owner)
-            if lay.q == qk:
-                view, m = self.block_rows(k, k + 1)
-                if m > 0:
-                    ops.trsm_rlt(view, m, D, bk, T)
-            if k == nblk - 1:
-                break
-            self._exchange_block_column(k)
-            r0 = lay.rows_from(k + 1)
-            for J in self.my_cols:
-                if J <= k:
-                    continue
-                bJ = lay.bsize(J)
-                C, m = self.block_rows(J, J)
-                if m <= 0:
-                    continue
-                a_off = lay.rows_from(J) - r0
-                pj = J % lay.P
-                b_off = lay.lrow(J) - lay.rows_from(k + 1, pj)
-                Aop = self.panel[lay.p][a_off:a_off + m]
-                Bop = self.panel[pj][b_off:b_off + bJ]
-                ops.gemm(0, 0, Aop, Bop, C, m, bJ, bk, -1.0, 1.0, 0)
+        ov.fence_main_to_side()
+        with ov.side():
+            info_local = self._panel_path(0, bufs[0]) or info_local
+        ov.fence_side_to_main()
+        for k in range(nblk - 1):
+            cur, nxt = bufs[k % 2], bufs[(k + 1) % 2]
+            mine = [J for J in self.my_cols if J > k]
+            self._trailing_update(k, cur, [J for J in mine if J == k + 1])      # block column k+1 first ...
+            ov.fence_main_to_side()
+            self._trailing_update(k, cur, [J for J in mine if J > k + 1])       # ... the rest is queued before the
+            with ov.side():                                                     # host blocks in the next POTRF
+                st = self._panel_path(k + 1, nxt)
+            if st and not info_local:
+                info_local = st
+            ov.fence_side_to_main()
         flag = ops.zeros(1)
         flag[0] = float(info_local) if info_local else float("inf")
         if comm.world > 1:

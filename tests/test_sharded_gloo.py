@@ -65,7 +65,8 @@ def _reference(n):
 
 
 @pytest.mark.parametrize("grid,n,nb", [((1, 1), 700, 256), ((1, 2), 700, 128), ((2, 1), 650, 128),
-                                       ((2, 2), 1000, 128), ((2, 2), 512, 128), ((1, 2), 100, 128)])
+                                       ((2, 2), 1000, 128), ((2, 2), 512, 128), ((1, 2), 100, 128),
+                                       ((2, 4), 1100, 128)])
 def test_block_cyclic_lml_and_gradient(grid, n, nb):
     res = _run(grid, n, nb)
     lml_ref, grad_ref = _reference(n)
