@@ -279,6 +279,79 @@ def run_c4(args):
     print(json.dumps(line), flush=True)
 
 
+def synthetic_c5(n, seed=5):
+    """2-D inputs, smooth signal + noise."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, 2))
+    y = np.sin(4 * x[:, 0]) * np.cos(3 * x[:, 1]) + 0.1 * rng.standard_normal(n)
+    return x, y, np.full(n, 1e-2)
+
+
+def run_c5(args):
+    """Secondary workload: exact dense GP whose KV is sharded 2-D block-cyclically over all ranks (C5: N = 200 000 =
+    320 GB at 8 GPUs; smaller N by default on fewer GPUs so that a step stays within a minute).  One step = one
+    log_likelihood (+ gradient with --grad) through the public GP API with args["dense_sharded"] = True; every rank
+    calls collectively.  The reference has no multi-GPU dense path and cannot hold this matrix."""
+    import torch
+    from fvgp_b200 import GP, parallel
+    from fvgp_b200 import _lib as L
+    rank, local_rank, world = parallel.init()
+    lib = L.load()
+    n = args.n
+    x, y, noise = synthetic_c5(n)
+    th0 = np.array([1.0, .2, .2])
+    t0 = time.perf_counter()
+    gp = GP(x, y, init_hyperparameters=th0, noise_variances=noise, args={"dense_sharded": True})
+    t_ctor = time.perf_counter() - t0
+
+    def step(k):
+        th = th0 * (1.0 + 0.02 * ((k + 1) % 10))
+        lml = gp.log_likelihood(th)
+        grad = gp.neg_log_likelihood_gradient(th) if args.grad else None
+        return lml, grad
+    for k in range(args.warmup):
+        step(k)
+    parallel.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.fvgp_launch_count()
+    E = gp.kv._sharded_eval
+    E.comm.bytes_received = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        lml, grad = step(args.warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    if rank != 0:
+        return
+    import ctypes
+    scratch = L.dev_empty((148 * 8 * 256,))
+    pk = ctypes.c_double()
+    lib.fvgp_bench_fp64_peak(0, 2, 20000, L.ptr(scratch), ctypes.byref(pk), L.stream_ptr())
+    flops = float(n) ** 3 / 3.0 * (3.0 if args.grad else 1.0)
+    per_gpu = flops * args.steps / t_dev / world / 1e12
+    what = "LML + gradient" if args.grad else "LML"
+    line = {"metric": f"dense {what} evals/s, KV 2-D block-cyclic over the GPUs (N={n})", "value": args.steps / t_dev,
+            "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong within a run (one matrix over all GPUs); default N grows with the GPU count",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5-type: exact dense GP, 2-D input, N={n} ({8e-9 * n * n:.0f} GB KV), block-cyclic "
+                                   f"Cholesky{' + inverse + gradient traces' if args.grad else ''} over NCCL",
+                       "n": n, "grid": list(E.grid), "block": E.nb, "local_GB": E._matrix().local_bytes() / 1e9},
+            "gpu_launches": int(lib.fvgp_launch_count() - launches0), "constructor_seconds": t_ctor, "last_lml": lml,
+            "last_grad": None if grad is None else [float(g) for g in grad],
+            "recv_GB_per_rank_per_step": E.comm.bytes_received / 1e9 / args.steps,
+            "roofline": {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4), per GPU", "achieved": per_gpu,
+                         "peak": pk.value, "unit": "TFLOP/s", "frac": per_gpu / pk.value, "traffic": None,
+                         "algorithmic_flops_per_step": flops,
+                         "note": "whole step (fill, factor, solves, logdet" + (", inverse, traces" if args.grad else "")
+                                 + ") over the algorithmic flops, max over ranks"}}
+    print(json.dumps(line), flush=True)
+
+
 def workload_config(args):
     return {"workload": f"C2: single-task GP, 3-D input, N={args.n}, anisotropic Matern-3/2 (default kernel), dense FP64 "
                         f"Cholesky, LML + hyperparameter gradient per step",
@@ -296,13 +369,20 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-host", default="", help="c4 only: write a cProfile of one evaluation to this file")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
-                    help="c2 (default, the headline): dense N=50k LML+gradient; c4: gp2Scale N=1M LML")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 (default, the headline): dense N=50k LML+gradient; c4: gp2Scale N=1M LML; "
+                         "c5: dense LML with KV block-cyclic over all GPUs")
+    ap.add_argument("--grad", action="store_true", help="c5 only: add the gradient to every step")
     args = ap.parse_args()
     if args.workload == "c4":
         if args.n == 50000:
             args.n = 1000000
         return run_c4(args)
+    if args.workload == "c5":
+        if args.n == 50000:
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            args.n = {1: 60000, 2: 100000, 4: 140000}.get(world, 200000)
+        return run_c5(args)
     if args.impl == "reference":
         return run_reference(args)
 
