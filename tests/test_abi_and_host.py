@@ -31,6 +31,27 @@ def test_library_exports_every_declared_symbol():
     assert lib.fvgp_chol_workspace_len(130) == 2 * 128 * 128
     assert lib.fvgp_wendland_aabb_len(100, 3) == (4 + 1) * 6
     assert lib.fvgp_bjacobi_len(33) == 2 * 1024
+    assert lib.fvgp_potrs_work_len(1000) >= 2 * 1000 + 8 * 1000
+    # gp2Scale work units: at most 32 column chunks, each a multiple of 32 super tiles (1024 tiles, 32768 points)
+    assert lib.fvgp_wendland_chunk_len(10, 5000) == 10                      # one chunk
+    assert lib.fvgp_wendland_chunk_len(7, 1_000_000) == 31 * 7             # 977 super tiles -> 31 chunks of 32
+    assert lib.fvgp_wendland_chunk_len(1, 40_000_000) <= 32
+    assert lib.fvgp_wendland_chunk_len(0, 100) == 1
+    assert lib.fvgp_lanczos_work_len(1000, 20) >= 3 * 16 * 1000 + 2 * 20 * 16
+
+
+def test_rounded_allocation_sizes_are_stable():
+    """nnz-sized buffers are rounded so that a few per cent of drift maps to the same allocator block."""
+    def cap(count):
+        step = max(1 << 18, (1 << max(int(count), 1).bit_length() - 1) >> 3)
+        return (int(count) + step - 1) // step * step
+    assert cap(94_124_622) == cap(95_900_000) == cap(99_000_000)
+    assert cap(94_124_622) <= 1.13 * 94_124_622
+    assert all(cap(c) >= c for c in (0, 1, 3806, 2 ** 31 + 5))
+    import inspect
+    from fvgp_b200 import _lib
+    src = inspect.getsource(_lib.dev_empty_rounded)
+    assert "bit_length" in src and "1 << 18" in src                          # the helper above mirrors the product code
 
 
 def test_no_cpu_fallback():
