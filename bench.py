@@ -365,7 +365,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=50000)
+    ap.add_argument("--size", "--n", dest="n", type=int, default=50000,
+                    help="problem size N (use --size under torchrun: its own parser rejects a bare --n as ambiguous)")
     ap.add_argument("--cpu-sample-n", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-host", default="", help="c4 only: write a cProfile of one evaluation to this file")

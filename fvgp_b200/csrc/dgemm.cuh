@@ -10,22 +10,34 @@
 //     <MN,MN> LAUUM                                           (P = M^T M)
 // Math: mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- the only FP64 tensor shape
 // sm_100a has; the wider PTX shapes lower to sequences of it, tcgen05 has no f64 kind).
-// CTA tile 128x128x16, 8 warps (2x4) with 64x32 warp tiles, 4-stage cp.async pipeline.
+// CTA tile 128x128x16 (or 64x64x16 for small products), 8 warps (2x4) with 64x32 (32x16) warp tiles, 4-stage
+// cp.async pipeline.
 // Shared-memory rows are padded (+4 doubles) so the 8-byte fragment loads of a
 // half-warp hit 16 distinct bank pairs for both layouts.
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace fvgp {
 
+// BM is the algorithmic block of the factorisation (splits, triangular-operand alignment).  The GEMM CTA tile is
+// TB x TB with TB = 128 (large products: 1 CTA / SM, 64 accumulators per thread) or TB = 64 (products whose
+// 128-tile grid would leave most SMs idle -- the latency-bound diagonal chain of POTRF / TRTRI / LAUUM, where
+// a 128 x 128 x 128 product used to run on ONE SM for ~17 us: four times the CTAs, a quarter of the work each,
+// 2 CTAs / SM).
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 256;
 constexpr int KMAJ_STRIDE = BK + 4;                 // 20 doubles
-constexpr int MNMAJ_STRIDE = BM + 4;                // 132 doubles
-constexpr int OPERAND_DOUBLES = BM * KMAJ_STRIDE;   // 2560 (>= BK * MNMAJ_STRIDE = 2112)
-constexpr int STAGE_DOUBLES = 2 * OPERAND_DOUBLES;
-constexpr size_t GEMM_SMEM_BYTES = size_t(GEMM_STAGES) * STAGE_DOUBLES * sizeof(double);  // 163840
+template <int TB> struct GemmTile {
+  static constexpr int MNMAJ_STRIDE = TB + 4;                // 132 / 68 doubles
+  static constexpr int OPERAND_DOUBLES = TB * KMAJ_STRIDE;   // >= BK * MNMAJ_STRIDE
+  static constexpr int STAGE_DOUBLES = 2 * OPERAND_DOUBLES;
+  static constexpr size_t SMEM_BYTES = size_t(GEMM_STAGES) * STAGE_DOUBLES * sizeof(double);  // 163840 / 81920
+  static constexpr int MFR = TB / 16;   // 8x8 fragments per warp along m (warp grid 2 x 4)
+  static constexpr int NFR = TB / 32;   // ... along n
+  static constexpr int QN = TB / 32;    // 16-byte copies per thread, operand and stage
+};
 
 enum GemmFlags : int {
   GEMM_LOWER = 1,       // square tile grid, tiles strictly above the diagonal are skipped
@@ -101,11 +113,11 @@ __device__ __forceinline__ void map_tile(int id, int tiles_m, int tiles_n, bool 
 }
 
 // Stage one 128 x 16 operand tile.  `rows` is the operand's extent along m (or n).
-template <bool MN_MAJOR>
+template <bool MN_MAJOR, int TB>
 __device__ __forceinline__ void load_operand(double* s, const double* __restrict__ g, long long ld, int row0,
                                              int rows, int k0, int kend, int tid) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < GemmTile<TB>::QN; ++q) {
     const int c = tid + GEMM_THREADS * q;
     if (!MN_MAJOR) {
       const int r = c >> 3, kc = (c & 7) * 2;
@@ -114,46 +126,49 @@ __device__ __forceinline__ void load_operand(double* s, const double* __restrict
       const double* src = valid ? g + (long long)gr * ld + gk : g;
       cp_async16(s + r * KMAJ_STRIDE + kc, src, valid * 8);
     } else {
-      const int kk = c >> 6, mc = (c & 63) * 2;
+      const int kk = c / (TB / 2), mc = (c % (TB / 2)) * 2;
       const int gk = k0 + kk, gm = row0 + mc;
       int valid = (gk < kend) ? min(max(rows - gm, 0), 2) : 0;
       const double* src = valid ? g + (long long)gk * ld + gm : g;
-      cp_async16(s + kk * MNMAJ_STRIDE + mc, src, valid * 8);
+      cp_async16(s + kk * GemmTile<TB>::MNMAJ_STRIDE + mc, src, valid * 8);
     }
   }
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmArgs p) {
+template <bool A_MN, bool B_MN, int TB>
+__global__ void __launch_bounds__(GEMM_THREADS, (TB == 128 ? 1 : 2)) dgemm_mma_kernel(const GemmArgs p) {
+  using T = GemmTile<TB>;
+  constexpr int MFR = T::MFR, NFR = T::NFR, QN = T::QN;
+  constexpr int MNMAJ_STRIDE = T::MNMAJ_STRIDE, OPERAND_DOUBLES = T::OPERAND_DOUBLES, STAGE_DOUBLES = T::STAGE_DOUBLES;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wm0 = (warp >> 2) * (TB / 2), wn0 = (warp & 3) * (TB / 4);
 
   int tm, tn;
   map_tile(blockIdx.x, p.tiles_m, p.tiles_n, (p.flags & GEMM_LOWER) != 0, tm, tn);
-  const int m0 = tm * BM, n0 = tn * BN;
+  const int m0 = tm * TB, n0 = tn * TB;
 
   int kb = 0, ke = p.K;
   if (p.flags & GEMM_KB_FROM_M) kb = max(kb, m0);
   if (p.flags & GEMM_KB_FROM_N) kb = max(kb, n0);
-  if (p.flags & GEMM_KE_FROM_M) ke = min(ke, m0 + BM);
+  if (p.flags & GEMM_KE_FROM_M) ke = min(ke, m0 + TB);
   const int kt_total = ke > kb ? (ke - kb + BK - 1) / BK : 0;
 
-  double acc[8][4][2];
+  double acc[MFR][NFR][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MFR; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NFR; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // Per-thread copy descriptors, computed once: every k-tile except a ragged last one is a pure
   // pointer bump (the generic path costs ~150 integer instructions per k-tile and sat between the
   // barrier and the first DMMA of every warp).
-  const double* a_src[4];
-  const double* b_src[4];
-  int a_bytes[4], b_bytes[4], a_off[4], b_off[4];
+  const double* a_src[QN];
+  const double* b_src[QN];
+  int a_bytes[QN], b_bytes[QN], a_off[QN], b_off[QN];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < QN; ++q) {
     const int c = tid + GEMM_THREADS * q;
     if (!A_MN) {
       const int r = c >> 3, kc = (c & 7) * 2;
@@ -161,7 +176,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
       a_bytes[q] = (m0 + r < p.M) ? 16 : 0;
       a_src[q] = a_bytes[q] ? p.A + (long long)(m0 + r) * p.lda + kb + kc : p.A;
     } else {
-      const int kk = c >> 6, mc = (c & 63) * 2;
+      const int kk = c / (TB / 2), mc = (c % (TB / 2)) * 2;
       a_off[q] = kk * MNMAJ_STRIDE + mc;
       a_bytes[q] = 8 * min(max(p.M - (m0 + mc), 0), 2);
       a_src[q] = a_bytes[q] ? p.A + (long long)(kb + kk) * p.lda + m0 + mc : p.A;
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
       b_bytes[q] = (n0 + r < p.N) ? 16 : 0;
       b_src[q] = b_bytes[q] ? p.B + (long long)(n0 + r) * p.ldb + kb + kc : p.B;
     } else {
-      const int kk = c >> 6, nc = (c & 63) * 2;
+      const int kk = c / (TB / 2), nc = (c % (TB / 2)) * 2;
       b_off[q] = kk * MNMAJ_STRIDE + nc;
       b_bytes[q] = 8 * min(max(p.N - (n0 + nc), 0), 2);
       b_src[q] = b_bytes[q] ? p.B + (long long)(kb + kk) * p.ldb + n0 + nc : p.B;
@@ -186,13 +201,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
     const int k0 = kb + kt * BK;
     if (k0 + BK <= ke) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < QN; ++q) {
         cp_async16(st + a_off[q], a_src[q] + (a_bytes[q] ? kt * a_step : 0), a_bytes[q]);
         cp_async16(st + OPERAND_DOUBLES + b_off[q], b_src[q] + (b_bytes[q] ? kt * b_step : 0), b_bytes[q]);
       }
     } else {
-      load_operand<A_MN>(st, p.A, p.lda, m0, p.M, k0, ke, tid);
-      load_operand<B_MN>(st + OPERAND_DOUBLES, p.B, p.ldb, n0, p.N, k0, ke, tid);
+      load_operand<A_MN, TB>(st, p.A, p.lda, m0, p.M, k0, ke, tid);
+      load_operand<B_MN, TB>(st + OPERAND_DOUBLES, p.B, p.ldb, n0, p.N, k0, ke, tid);
     }
   };
 
@@ -210,17 +225,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
     const double* Bs = As + OPERAND_DOUBLES;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[8], b[4];
+      double a[MFR], b[NFR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MFR; ++i)
         a[i] = A_MN ? As[(4 * kk + t) * MNMAJ_STRIDE + wm0 + 8 * i + g] : As[(wm0 + 8 * i + g) * KMAJ_STRIDE + 4 * kk + t];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NFR; ++j)
         b[j] = B_MN ? Bs[(4 * kk + t) * MNMAJ_STRIDE + wn0 + 8 * j + g] : Bs[(wn0 + 8 * j + g) * KMAJ_STRIDE + 4 * kk + t];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MFR; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NFR; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       if (kk == 0) {
         // refill the stage freed by the barrier above only after this warp has fed the tensor pipe
         if (kt + GEMM_STAGES - 1 < kt_total) issue(kt + GEMM_STAGES - 1);
@@ -233,12 +248,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
   // Epilogue: each lane owns two adjacent columns -> 16-byte accesses, 64 B per row per quad.
   const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MFR; ++i) {
     const int row = m0 + wm0 + 8 * i + g;
     if (row >= p.M) continue;
     double* crow = p.C + (long long)row * p.ldc;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NFR; ++j) {
       const int col = n0 + wn0 + 8 * j + 2 * t;
       if (col + 1 < p.N) {
         double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
@@ -259,33 +274,55 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_mma_kernel(const GemmAr
 
 // Host launcher.  Requirements (checked): even leading dimensions and 16-byte aligned
 // bases (cp.async 16 B and double2 epilogue).
+// FVGP_GEMM_SMALL_TILES=0 disables the 64 x 64 tile variant (A/B on the GPU box).
+inline bool gemm_small_tiles_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FVGP_GEMM_SMALL_TILES");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+template <bool A_MN, bool B_MN, int TB>
+inline int launch_gemm_tile(cudaStream_t st, GemmArgs p) {
+  static bool configured = false;
+  if (!configured) {
+    FVGP_CUDA_OK(cudaFuncSetAttribute(dgemm_mma_kernel<A_MN, B_MN, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)GemmTile<TB>::SMEM_BYTES));
+    configured = true;
+  }
+  p.tiles_m = (p.M + TB - 1) / TB;
+  p.tiles_n = (p.N + TB - 1) / TB;
+  long long tiles;
+  if (p.flags & GEMM_LOWER) {
+    FVGP_REQUIRE(p.tiles_m == p.tiles_n);
+    tiles = (long long)p.tiles_m * (p.tiles_m + 1) / 2;
+  } else {
+    tiles = (long long)p.tiles_m * p.tiles_n;
+  }
+  launch(dgemm_mma_kernel<A_MN, B_MN, TB>, (unsigned)tiles, GEMM_THREADS, GemmTile<TB>::SMEM_BYTES, st, p);
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+// Host launcher.  Requirements (checked): even leading dimensions and 16-byte aligned
+// bases (cp.async 16 B and double2 epilogue).
 template <bool A_MN, bool B_MN>
 inline int launch_gemm(cudaStream_t st, const double* A, long long lda, const double* B, long long ldb, double* C,
                        long long ldc, int M, int N, int K, double alpha, double beta, int flags) {
   if (M <= 0 || N <= 0) return 0;
   FVGP_REQUIRE((lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0));
   FVGP_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0));
-  static bool configured = false;
-  if (!configured) {
-    FVGP_CUDA_OK(cudaFuncSetAttribute(dgemm_mma_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)GEMM_SMEM_BYTES));
-    configured = true;
-  }
   GemmArgs p;
   p.A = A, p.B = B, p.C = C, p.M = M, p.N = N, p.K = K;
   p.lda = lda, p.ldb = ldb, p.ldc = ldc, p.alpha = alpha, p.beta = beta, p.flags = flags;
-  p.tiles_m = (M + BM - 1) / BM;
-  p.tiles_n = (N + BN - 1) / BN;
-  long long tiles;
-  if (flags & GEMM_LOWER) {
-    FVGP_REQUIRE(p.tiles_m == p.tiles_n);
-    tiles = (long long)p.tiles_m * (p.tiles_m + 1) / 2;
-  } else {
-    tiles = (long long)p.tiles_m * p.tiles_n;
-  }
-  launch(dgemm_mma_kernel<A_MN, B_MN>, (unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, st, p);
-  FVGP_LAUNCH_OK();
-  return 0;
+  p.tiles_m = p.tiles_n = 0;
+  // 128-tiles when they fill at least half the SMs; otherwise the problem is latency bound and more, smaller CTAs win
+  const long long tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
+  const long long tiles128 = (flags & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn;
+  if (tiles128 * 2 < sm_count() && gemm_small_tiles_enabled()) return launch_gemm_tile<A_MN, B_MN, 64>(st, p);
+  return launch_gemm_tile<A_MN, B_MN, 128>(st, p);
 }
 
 }  // namespace fvgp

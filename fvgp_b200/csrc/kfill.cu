@@ -369,59 +369,123 @@ struct TraceParams {
   int dim;
 };
 
-template <int DIM>
-__global__ void __launch_bounds__(FILL_THREADS) kgrad_trace_kernel(const TraceParams p) {
-  __shared__ double red[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One 64x64 tile of the trace, same thread layout as fill_tile: warp w owns rows 8w..8w+7, lane l the adjacent
+// columns 2l, 2l+1 (one 16-byte load of W per lane and row), rows two at a time -> four independent sqrt / exp
+// chains per thread.  Row coordinates (already divided by the length scales) and b are staged per warp in shared
+// memory.  INTERIOR tiles (strictly below the diagonal, fully inside the matrix) carry no masks: weight 2.
+template <int DIM, bool INTERIOR>
+__device__ __forceinline__ void trace_tile(const TraceParams& p, long long ti, long long tj, double* sRow,
+                                           const double (&inv)[DIM > 0 ? DIM : kMaxDim], double (&acc)[(DIM > 0 ? DIM : kMaxDim) + 1],
+                                           int lane, int warp) {
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
-  const int dim = p.dim;
+  constexpr int DP = D + 1;  // staged per row: D scaled coordinates + b
+  const int dim = DIM > 0 ? DIM : p.dim;
   const double sqrt3 = 1.7320508075688772;
+  const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
+  const long long ca = c0 + 2 * lane, cb = ca + 1;
+  double xa[D], xb[D];
+  const bool oka = INTERIOR || ca < p.n, okb = INTERIOR || cb < p.n;
+  const double ba = oka ? p.b[ca] : 0.0, bb = okb ? p.b[cb] : 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const bool on = DIM > 0 || i < dim;
+    xa[i] = (oka && on) ? p.x[ca * dim + i] * inv[i] : 0.0;
+    xb[i] = (okb && on) ? p.x[cb * dim + i] * inv[i] : 0.0;
+  }
+  __syncwarp();  // the previous tile's reads of sRow are done
+  for (int idx = lane; idx < 8 * (dim + 1); idx += 32) {
+    const int rr = idx / (dim + 1), i = idx - rr * (dim + 1);
+    const long long r = r0 + rr;
+    double v = 0.0;
+    if (INTERIOR || r < p.n) v = (i < dim) ? p.x[r * dim + i] * p.inv_len[i] : p.b[r];
+    sRow[rr * DP + (i < dim ? i : D)] = v;
+  }
+  __syncwarp();
+  const bool vec = (p.ld % 2 == 0);
+#pragma unroll 1
+  for (int rr = 0; rr < 8; rr += 2) {
+    const long long ra = r0 + rr, rb = ra + 1;
+    if (!INTERIOR && ra >= p.n) break;
+    const bool okr = INTERIOR || rb < p.n;
+    const double* wrow = p.Kinv + ra * p.ld + ca;
+    double w00, w01, w10 = 0.0, w11 = 0.0;
+    if (INTERIOR && vec) {
+      const double2 u = *reinterpret_cast<const double2*>(wrow);
+      const double2 v = *reinterpret_cast<const double2*>(wrow + p.ld);
+      w00 = u.x, w01 = u.y, w10 = v.x, w11 = v.y;
+    } else {
+      w00 = (oka && ca <= ra) ? wrow[0] : 0.0;
+      w01 = (okb && cb <= ra) ? wrow[1] : 0.0;
+      if (okr) {
+        w10 = (oka && ca <= rb) ? wrow[p.ld] : 0.0;
+        w11 = (okb && cb <= rb) ? wrow[p.ld + 1] : 0.0;
+      }
+    }
+    const double b0 = sRow[rr * DP + D], b1 = sRow[(rr + 1) * DP + D];
+    double f00 = 2.0, f01 = 2.0, f10 = 2.0, f11 = 2.0;
+    if (!INTERIOR) {  // lower triangle only, diagonal once, nothing outside the matrix
+      f00 = (!oka || ca > ra) ? 0.0 : (ca == ra ? 1.0 : 2.0);
+      f01 = (!okb || cb > ra) ? 0.0 : (cb == ra ? 1.0 : 2.0);
+      f10 = (!okr || !oka || ca > rb) ? 0.0 : (ca == rb ? 1.0 : 2.0);
+      f11 = (!okr || !okb || cb > rb) ? 0.0 : (cb == rb ? 1.0 : 2.0);
+    }
+    w00 = (w00 - b0 * ba) * f00, w01 = (w01 - b0 * bb) * f01;
+    w10 = (w10 - b1 * ba) * f10, w11 = (w11 - b1 * bb) * f11;
+    double q00[D], q01[D], q10[D], q11[D];
+    double s00 = 1e-300, s01 = 1e-300, s10 = 1e-300, s11 = 1e-300;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (DIM > 0 || i < dim) {
+        const double x0 = sRow[rr * DP + i], x1 = sRow[(rr + 1) * DP + i];
+        const double t00 = x0 - xa[i], t01 = x0 - xb[i], t10 = x1 - xa[i], t11 = x1 - xb[i];
+        q00[i] = t00 * t00, q01[i] = t01 * t01, q10[i] = t10 * t10, q11[i] = t11 * t11;
+        s00 += q00[i], s01 += q01[i], s10 += q10[i], s11 += q11[i];
+      } else {
+        q00[i] = q01[i] = q10[i] = q11[i] = 0.0;
+      }
+    }
+    const double a00 = sqrt3 * sqrt_pos(s00), a01 = sqrt3 * sqrt_pos(s01);
+    const double a10 = sqrt3 * sqrt_pos(s10), a11 = sqrt3 * sqrt_pos(s11);
+    const double e00 = w00 * exp_neg(fmin(a00, 1.0e9)), e01 = w01 * exp_neg(fmin(a01, 1.0e9));
+    const double e10 = w10 * exp_neg(fmin(a10, 1.0e9)), e11 = w11 * exp_neg(fmin(a11, 1.0e9));
+    acc[0] = fma(e00, 1.0 + a00, acc[0]);
+    acc[0] = fma(e01, 1.0 + a01, acc[0]);
+    acc[0] = fma(e10, 1.0 + a10, acc[0]);
+    acc[0] = fma(e11, 1.0 + a11, acc[0]);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      acc[1 + i] = fma(e00, q00[i], acc[1 + i]);
+      acc[1 + i] = fma(e01, q01[i], acc[1 + i]);
+      acc[1 + i] = fma(e10, q10[i], acc[1 + i]);
+      acc[1 + i] = fma(e11, q11[i], acc[1 + i]);
+    }
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(FILL_THREADS, 2) kgrad_trace_kernel(const TraceParams p) {
+  __shared__ double red[32];
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  __shared__ double sRowAll[8][8 * (D + 1)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dim = p.dim;
   double inv[D], acc[D + 1];
 #pragma unroll
   for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < dim) ? p.inv_len[i] : 0.0;
 #pragma unroll
   for (int i = 0; i <= D; ++i) acc[i] = 0.0;
 
-  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    long long ti, tj;
-    tri_index(tile, ti, tj);  // tj <= ti
-    const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
-    const long long cc[2] = {c0 + lane, c0 + lane + 32};
-    double xc[2][D], bc[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const bool ok = cc[q] < p.n;
-      bc[q] = ok ? p.b[cc[q]] : 0.0;
-#pragma unroll
-      for (int i = 0; i < D; ++i) xc[q][i] = (ok && (DIM > 0 || i < dim)) ? p.x[cc[q] * dim + i] : 0.0;
-    }
-    for (int rr = 0; rr < 8; ++rr) {
-      const long long r = r0 + rr;
-      if (r >= p.n) break;
-      const double br = p.b[r];
-      double xr[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? p.x[r * dim + i] : 0.0;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const long long c = cc[q];
-        if (c > r || c >= p.n) continue;  // lower triangle only
-        const double w = (p.Kinv[r * p.ld + c] - br * bc[q]) * ((c == r) ? 1.0 : 2.0);
-        double t2[D], s = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          const double t = (xr[i] - xc[q][i]) * inv[i];
-          t2[i] = t * t;
-          s += t2[i];
-        }
-        const double a = sqrt3 * sqrt_pos(fmax(s, 1e-300));
-        const double ea = exp_nonpos(-a);
-        const double wea = w * ea;
-        acc[0] = fma(wea, 1.0 + a, acc[0]);
-#pragma unroll
-        for (int i = 0; i < D; ++i) acc[1 + i] = fma(wea, t2[i], acc[1 + i]);
-      }
-    }
+  // contiguous tile ranges per CTA, decoded once and advanced incrementally (row-major over the lower triangle)
+  const long long per_cta = (p.ntiles + gridDim.x - 1) / gridDim.x;
+  long long tile = blockIdx.x * per_cta;
+  const long long tile_end = min(p.ntiles, tile + per_cta);
+  long long ti = 0, tj = 0;
+  if (tile < tile_end) tri_index(tile, ti, tj);  // tj <= ti
+  for (; tile < tile_end; ++tile) {
+    const bool interior = tj < ti && (ti + 1) * FT <= p.n;
+    if (interior) trace_tile<DIM, true>(p, ti, tj, sRowAll[warp], inv, acc, lane, warp);
+    else trace_tile<DIM, false>(p, ti, tj, sRowAll[warp], inv, acc, lane, warp);
+    if (++tj > ti) tj = 0, ++ti;
   }
 #pragma unroll
   for (int i = 0; i <= D; ++i) {
@@ -702,7 +766,7 @@ int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, doubl
 
 static inline long long trace_grid(int64_t n) {
   const long long t = (n + FT - 1) / FT, ntiles = t * (t + 1) / 2;
-  const long long cap = (long long)sm_count() * 4;
+  const long long cap = (long long)sm_count() * 2;  // 126 registers: two resident CTAs per SM, one wave
   return ntiles < cap ? ntiles : cap;
 }
 
