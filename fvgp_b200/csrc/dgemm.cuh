@@ -321,7 +321,11 @@ inline int launch_gemm(cudaStream_t st, const double* A, long long lda, const do
   // 128-tiles when they fill at least half the SMs; otherwise the problem is latency bound and more, smaller CTAs win
   const long long tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
   const long long tiles128 = (flags & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn;
-  if (tiles128 * 2 < sm_count() && gemm_small_tiles_enabled()) return launch_gemm_tile<A_MN, B_MN, 64>(st, p);
+  // In-place products (C aliases an operand: the TRSM / LAUUM leaves, N <= 128) rely on ONE CTA owning complete rows
+  // of the output -- it has consumed its operand rows before the epilogue writes them; 64-wide tiles would let a
+  // neighbouring CTA overwrite columns that are still being read.
+  const bool in_place = (const double*)C == A || (const double*)C == B;
+  if (!in_place && tiles128 * 2 < sm_count() && gemm_small_tiles_enabled()) return launch_gemm_tile<A_MN, B_MN, 64>(st, p);
   return launch_gemm_tile<A_MN, B_MN, 128>(st, p);
 }
 
