@@ -122,12 +122,13 @@ class GP:
         return self.trainer.hyperparameters
 
     def update_gp_data(self, x_new, y_new, noise_variances_new=None, append=True, gp_rank_n_update=None):
-        """gp.py:689-749.  The covariance is regenerated on the device (a full refill of an
-        N x N matrix costs milliseconds), so no host-side rank-n bookkeeping is needed."""
+        """gp.py:689-749.  append=True extends the resident Cholesky factor by a bordered update on the device
+        (GPkv._append_refresh, O(N^2 m)); otherwise the covariance is regenerated and refactored."""
+        n_old = len(self.data.x_data)
         self.data.update(x_new, y_new, noise_variances_new, append=append)
         self.prior.update_state_data()
         self.likelihood.update_state()
-        self.kv.update_state()
+        self.kv.update_state(appended_from=n_old if append else None)
 
     def _get_default_hyperparameter_bounds(self):
         """gp.py:754-775."""

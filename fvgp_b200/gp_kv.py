@@ -302,8 +302,74 @@ class GPkv:
         self.KVinvY = ev.KVinvY
         self.logdet_KV = ev.logdet
 
-    def update_state(self):
+    def update_state(self, appended_from=None):
+        """Refresh after a hyperparameter or data change.  appended_from = the previous number of points when rows
+        were APPENDED (update_gp_data(append=True), gp.py:689-749): the stored Cholesky factor is then extended by a
+        bordered update instead of being recomputed (the reference does N sequential rank-1 updates,
+        gp_lin_alg.py:1310-1477, gp_kv.py:462-508)."""
+        if appended_from is not None and self._append_refresh(int(appended_from)):
+            return
         self._refresh()
+
+    def _append_refresh(self, n_old):
+        """Bordered Cholesky: with a = n_old rounded down to the 128-row tile grid,
+              rows [a, n) of K+V are (re)filled,  L21 = K21 L11^-T  (tensor-core TRSM),
+              S = K22 - L21 L21^T (SYRK),  L22 = chol(S)  (POTRF with tile index offset a / 128),
+        O(N^2 m) flops instead of O(N^3).  Returns False when the fast path does not apply."""
+        from . import kernels as K
+        ev0 = self.state
+        x = self.data.x_data
+        n = len(x)
+        V = self.likelihood.V
+        a = (n_old // 128) * 128
+        if (self.gp2Scale or self.mode != "Chol" or ev0 is None or ev0.factor is None or ev0.factor.inverted
+                or ev0.factor.n != n_old or a < 128 or n <= n_old or V is None or np.ndim(V) != 1 or len(V) != n
+                or not self.data.Euclidean):
+            return False
+        hps = np.asarray(self.prior.hyperparameters, dtype=np.float64)
+        res = self.prior._call_kernel(x, x, hps)
+        if not (isinstance(res, K.Radial) and res.dist.x1 is x and res.dist.x2 is x):
+            return False
+        lib, torch = L.load(), L._torch()
+        old = ev0.factor
+        new, ld = L.dev_matrix(n, n)
+        new[:a, :a].copy_(old.buf[:a, :a])
+        tileinv = L.dev_empty((int(lib.fvgp_chol_workspace_len(n)),))
+        tiles_a = a // 128
+        tileinv[:tiles_a * 128 * 128].copy_(old.tileinv[:tiles_a * 128 * 128])
+        xd = self.data.x_device()
+        Vd = L.to_dev(V)
+        bounds = res.dist.bounds()
+        m2 = n - a
+        # rows [a, n): off-diagonal block against the kept columns, then the diagonal block with the noise
+        ops.kfill(res.kind, xd[a:], xd[:a], res.amp, res.dist.inv_scale, res.length, mode=L.FILL_FULL,
+                  out=(new[a:, :a], ld), bounds=bounds)
+        ops.kfill(res.kind, xd[a:], xd[a:], res.amp, res.dist.inv_scale, res.length, noise=Vd[a:], mode=L.FILL_LOWER,
+                  out=(new[a:, a:], ld), bounds=bounds)
+        st = L.stream_ptr()
+        L.check(lib.fvgp_trsm_right_lower_t(L.ptr(new[a:, :a]), ld, m2, L.ptr(new), ld, a, L.ptr(tileinv), st),
+                "fvgp_trsm_right_lower_t")
+        L.check(lib.fvgp_dgemm(0, 0, L.ptr(new[a:, :a]), ld, L.ptr(new[a:, :a]), ld, L.ptr(new[a:, a:]), ld, m2, m2, a,
+                               -1.0, 1.0, 1, st), "fvgp_dgemm")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        status = L.check(lib.fvgp_potrf_lower(L.ptr(new[a:, a:]), m2, ld, L.ptr(tileinv[tiles_a * 128 * 128:]),
+                                              L.ptr(info), st), "fvgp_potrf_lower")
+        if status > 0:
+            raise L.NonPositiveDefiniteError(a + status, n)
+        ev = Evaluation()
+        ev.mode = "Chol"
+        ev.factor = ops.CholFactor(new, ld, n, tileinv)
+        y_mean = self.data.y_data - self.prior.m[:, None]
+        rhs = L.to_dev(np.ascontiguousarray(y_mean.T))
+        ops.potrs(ev.factor, rhs)
+        ev.alpha_dev = rhs
+        ev.KVinvY = rhs.cpu().numpy().T.copy()
+        ev.logdet = ops.chol_logdet(ev.factor)
+        ev.info["appended_rows"] = n - n_old
+        self._memo = None
+        self._KVinv_host = None
+        self.state, self.KVinvY, self.logdet_KV = ev, ev.KVinvY, ev.logdet
+        return True
 
     def solve(self, b, x0=None):
         """KV^-1 b with the stored factorisation (gp_kv.py:671-700); b is (N,) or (N, r) on the host."""

@@ -116,8 +116,16 @@ def test_set_hyperparameters_update_data_and_pickle(fv, golden):
     g = golden("dense_lml_c2")
     x, y, nz = g["x"], g["y"], g["noise"]
     gp = GP(x[:400], y[:400], init_hyperparameters=g["h0"], noise_variances=nz[:400])
-    gp.update_gp_data(x[400:], y[400:], noise_variances_new=nz[400:], append=True)
+    gp.update_gp_data(x[400:437], y[400:437], noise_variances_new=nz[400:437], append=True)   # bordered Cholesky update
+    assert gp.kv.state.info.get("appended_rows") == 37
+    gp.update_gp_data(x[437:], y[437:], noise_variances_new=nz[437:], append=True)
+    assert gp.kv.state.info.get("appended_rows") == len(x) - 437
     assert abs(gp.log_likelihood() / g["lml_h0"] - 1) <= 1e-8
+    fresh = GP(x, y, init_hyperparameters=g["h0"], noise_variances=nz)
+    assert abs(gp.kv.logdet_KV / fresh.kv.logdet_KV - 1) <= 1e-12
+    assert rel(gp.kv.KVinvY, fresh.kv.KVinvY) <= 1e-7
+    assert np.max(np.abs(np.tril(gp.kv.Chol_factor) - np.tril(fresh.kv.Chol_factor))) <= 1e-11
+    assert np.allclose(gp.posterior_covariance(g["x_pred"])["v(x)"], g["post_var"], rtol=1e-6, atol=1e-9)
     gp.set_hyperparameters(g["h1"])
     assert abs(gp.log_likelihood() / g["lml_h1"] - 1) <= 1e-8
     K0, m0 = gp.K.copy(), gp.posterior_mean(g["x_pred"])["m(x)"]
