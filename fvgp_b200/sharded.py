@@ -432,11 +432,15 @@ class ShardedSPD:
         v = float(flag.item())
         self.info = 0 if math.isinf(v) else int(v)
         self.state = "factored"
+        self._logdet = None
         return self.info
 
     def logdet(self):
         lay = self.lay
-        return float(sum(self.ops.logdet(self.diag[k], lay.bsize(k)) for k in range(lay.nblk)))
+        if self.state != "factored":                                 # the inverse reuses self.diag
+            return self._logdet
+        self._logdet = float(sum(self.ops.logdet(self.diag[k], lay.bsize(k)) for k in range(lay.nblk)))
+        return self._logdet
 
     # ---- solves -----------------------------------------------------------------------------------
     def solve(self, b_dev):
@@ -522,33 +526,42 @@ class ShardedSPD:
         assert self.state == "factored"
         lay, ops, comm = self.lay, self.ops, self.comm
         nb, nblk = lay.nb, lay.nblk
-        D = ops.zeros(nb, nb)
-        # -------- TRTRI, right-looking: after step k block column k and block row k hold their final /
-        # partially accumulated parts of M = L^-1.
+        # -------- TRTRI, right-looking.  Two parts of every step do not depend on the steps before it and are hoisted
+        # out of the loop, where they left most ranks idle: (A) M_kk = L_kk^-1 of every diagonal block (replicated in
+        # self.diag, which holds the inverses from here on), (B) the column panels C <- -C M_kk (block column k below
+        # the diagonal is still the original L there: steps j < k only touch columns J < j) -- one local GEMM per
+        # owned block column, all ranks busy.  The loop keeps what is truly sequential: row-panel gather, panel
+        # broadcast along the process row, accumulation into the columns to the left, M_kk times the block row.
         for k in range(nblk):
             bk = lay.bsize(k)
-            pk, qk = k % lay.P, k % lay.Q
-            owner = pk * lay.Q + qk
+            owner = (k % lay.P) * lay.Q + (k % lay.Q)
+            Dk = self.diag[k]
             if comm.rank == owner:
-                D.zero_()
-                D[:bk, :bk].copy_(self.diag[k][:bk, :bk])
-                ops.trtri(D, bk, self.diag_tinv[k])
-                D.tril_()
-                self.block(k, k).copy_(D[:bk, :bk])
-            comm.broadcast(D, owner)
-            # column panel: C <- -C * M_kk
-            if lay.q == qk:
-                view, m = self.block_rows(k, k + 1)
-                if m > 0:
-                    tmp = self.panel[lay.p][:m]
-                    ops.gemm(0, 1, view, D, tmp, m, bk, bk, -1.0, 0.0, GEMM_KB_FROM_N)
-                    view[:, :bk].copy_(tmp[:, :bk])
-            rowp = self._gather_row_panel(k, everyone=False) if k > 0 else {}
-            if k < nblk - 1 and k > 0:
-                # my process row's piece of the new column panel (A operand of the update)
+                ops.trtri(Dk, bk, self.diag_tinv[k])
+                Dk.tril_()
+                self.block(k, k).copy_(Dk[:bk, :bk])
+            comm.broadcast(Dk, owner)
+        self.state = "inverting"                                     # self.diag no longer holds the factor
+        for J in self.my_cols:
+            bJ = lay.bsize(J)
+            view, m = self.block_rows(J, J + 1)
+            if m > 0:
+                tmp = self.panel[lay.p][:m]
+                ops.gemm(0, 1, view, self.diag[J], tmp, m, bJ, bJ, -1.0, 0.0, GEMM_KB_FROM_N)
+                view[:, :bJ].copy_(tmp[:, :bJ])
+        for k in range(1, nblk):
+            bk = lay.bsize(k)
+            pk, qk = k % lay.P, k % lay.Q
+            D = self.diag[k]
+            rowp = self._gather_row_panel(k, everyone=False)
+            if k < nblk - 1:
+                # my process row's piece of column panel k (A operand of the update), from its owner column
                 m_p = self.mloc - lay.rows_from(k + 1)
                 if m_p > 0:
                     buf = self.panel[lay.p][:m_p]
+                    if lay.q == qk:
+                        view, _ = self.block_rows(k, k + 1)
+                        buf.copy_(view)
                     comm.row_broadcast(buf, lay.p * lay.Q + qk)
                     if lay.q in rowp:
                         rbuf, cols_q = rowp[lay.q]
@@ -561,6 +574,7 @@ class ShardedSPD:
                 rbuf, cols_q = rowp[lay.q]
                 for i, J in enumerate(cols_q):
                     ops.gemm(0, 1, D, rbuf[i], self.block(k, J), bk, lay.bsize(J), bk, 1.0, 0.0, GEMM_KE_FROM_M)
+        D = ops.zeros(nb, nb)
         # -------- LAUUM: lower(M^T M), block row by block row
         arow = ops.zeros(nb, (max(self.mloc, 2) + 15) // 16 * 16)
         for k in range(nblk):

@@ -16,7 +16,7 @@ python bench.py --workload c4 --steps 3 --warmup 2 > gpurun_out/bench_c4_1m.json
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo ref rc=$?; cut -c1-300 gpurun_out/bench_ref.json
 timeout 600 python bench.py --impl reference --workload c4 --steps 1 --warmup 0 > gpurun_out/bench_ref_c4.json 2> gpurun_out/bench_ref_c4.err; echo ref c4 rc=$?; cut -c1-600 gpurun_out/bench_ref_c4.json
 if [ "$1" = "ncu" ]; then
-  # constructor (LML only) + one warm-up evaluation are skipped; the list covers the timed evaluation (LML + gradient)
-  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip $2 --launch-count $3 --csv --log-file /tmp/launches_c2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo ncu rc=$?
-  python tools/launch_summary.py /tmp/launches_c2.csv "python bench.py --steps 1 --warmup 1 --no-cpu-baseline (N=50000), --launch-skip $2 --launch-count $3: the kernels of the timed evaluation (LML + gradient)" > gpurun_out/launches_bench_n50k.txt; head -24 gpurun_out/launches_bench_n50k.txt
+  # only the kernels inside bench.py's NVTX range "timed" (one LML + gradient evaluation) are profiled
+  timeout 1500 ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file /tmp/launches_c2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo ncu rc=$?
+  python tools/launch_summary.py /tmp/launches_c2.csv "python bench.py --steps 1 --warmup 1 --no-cpu-baseline (N=50000), NVTX range 'timed': every kernel of ONE timed evaluation (LML + gradient)" > gpurun_out/launches_bench_n50k.txt; head -24 gpurun_out/launches_bench_n50k.txt
 fi
