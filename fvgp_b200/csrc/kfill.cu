@@ -373,14 +373,33 @@ struct TraceParams {
 // columns 2l, 2l+1 (one 16-byte load of W per lane and row), rows two at a time -> four independent sqrt / exp
 // chains per thread.  Row coordinates (already divided by the length scales) and b are staged per warp in shared
 // memory.  INTERIOR tiles (strictly below the diagonal, fully inside the matrix) carry no masks: weight 2.
-template <int DIM, bool INTERIOR>
+// KIND selects the radial family; the coordinates arrive scaled by inv_scale_i * c_KIND / length so that the sum of
+// squared differences is a^2 (Matern-3/2: a = sqrt(3) u, Matern-5/2: sqrt(5) u, exponential: u) or u^2 / 2
+// (squared exponential), u = r / length.  Accumulated per entry, with W = (KV^-1 - b b^T) weighted 2 / 1 / 0:
+//   acc[0]   += W f(u)                 -> trace against dK/d(amp) (times amp^0)
+//   acc[1+i] += W h(u) q_i             -> -s_i / amp times the trace against dK/d(inv_scale_i)
+// with q_i the squared scaled difference along axis i and h = -g q-scaling (see fvgp_kgrad_trace_radial).
+template <int KIND>
+__device__ __forceinline__ void radial_trace_factors(double s, double& f, double& h) {
+  if (KIND == FVGP_K_SQEXP) {
+    const double e = exp_neg(fmin(s, 1.0e9));
+    f = e, h = 2.0 * e;
+    return;
+  }
+  const double a = sqrt_pos(s);
+  const double e = exp_neg(fmin(a, 1.0e9));
+  if (KIND == FVGP_K_MATERN32) f = (1.0 + a) * e, h = e;
+  else if (KIND == FVGP_K_MATERN52) f = fma(s, 1.0 / 3.0, 1.0 + a) * e, h = (1.0 + a) * e * (1.0 / 3.0);
+  else f = e, h = e / a;  // exponential; s >= 1e-300 keeps a > 0 and q_i = 0 for coincident points
+}
+
+template <int KIND, int DIM, bool INTERIOR>
 __device__ __forceinline__ void trace_tile(const TraceParams& p, long long ti, long long tj, double* sRow,
                                            const double (&inv)[DIM > 0 ? DIM : kMaxDim], double (&acc)[(DIM > 0 ? DIM : kMaxDim) + 1],
                                            int lane, int warp) {
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
   constexpr int DP = D + 1;  // staged per row: D scaled coordinates + b
   const int dim = DIM > 0 ? DIM : p.dim;
-  const double sqrt3 = 1.7320508075688772;
   const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
   const long long ca = c0 + 2 * lane, cb = ca + 1;
   double xa[D], xb[D];
@@ -444,14 +463,16 @@ __device__ __forceinline__ void trace_tile(const TraceParams& p, long long ti, l
         q00[i] = q01[i] = q10[i] = q11[i] = 0.0;
       }
     }
-    const double a00 = sqrt3 * sqrt_pos(s00), a01 = sqrt3 * sqrt_pos(s01);
-    const double a10 = sqrt3 * sqrt_pos(s10), a11 = sqrt3 * sqrt_pos(s11);
-    const double e00 = w00 * exp_neg(fmin(a00, 1.0e9)), e01 = w01 * exp_neg(fmin(a01, 1.0e9));
-    const double e10 = w10 * exp_neg(fmin(a10, 1.0e9)), e11 = w11 * exp_neg(fmin(a11, 1.0e9));
-    acc[0] = fma(e00, 1.0 + a00, acc[0]);
-    acc[0] = fma(e01, 1.0 + a01, acc[0]);
-    acc[0] = fma(e10, 1.0 + a10, acc[0]);
-    acc[0] = fma(e11, 1.0 + a11, acc[0]);
+    double v00, v01, v10, v11, e00, e01, e10, e11;
+    radial_trace_factors<KIND>(s00, v00, e00);
+    radial_trace_factors<KIND>(s01, v01, e01);
+    radial_trace_factors<KIND>(s10, v10, e10);
+    radial_trace_factors<KIND>(s11, v11, e11);
+    acc[0] = fma(w00, v00, acc[0]);
+    acc[0] = fma(w01, v01, acc[0]);
+    acc[0] = fma(w10, v10, acc[0]);
+    acc[0] = fma(w11, v11, acc[0]);
+    e00 *= w00, e01 *= w01, e10 *= w10, e11 *= w11;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       acc[1 + i] = fma(e00, q00[i], acc[1 + i]);
@@ -462,7 +483,7 @@ __device__ __forceinline__ void trace_tile(const TraceParams& p, long long ti, l
   }
 }
 
-template <int DIM>
+template <int KIND, int DIM>
 __global__ void __launch_bounds__(FILL_THREADS, 2) kgrad_trace_kernel(const TraceParams p) {
   __shared__ double red[32];
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
@@ -483,8 +504,8 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) kgrad_trace_kernel(const Trac
   if (tile < tile_end) tri_index(tile, ti, tj);  // tj <= ti
   for (; tile < tile_end; ++tile) {
     const bool interior = tj < ti && (ti + 1) * FT <= p.n;
-    if (interior) trace_tile<DIM, true>(p, ti, tj, sRowAll[warp], inv, acc, lane, warp);
-    else trace_tile<DIM, false>(p, ti, tj, sRowAll[warp], inv, acc, lane, warp);
+    if (interior) trace_tile<KIND, DIM, true>(p, ti, tj, sRowAll[warp], inv, acc, lane, warp);
+    else trace_tile<KIND, DIM, false>(p, ti, tj, sRowAll[warp], inv, acc, lane, warp);
     if (++tj > ti) tj = 0, ++ti;
   }
 #pragma unroll
@@ -495,14 +516,13 @@ __global__ void __launch_bounds__(FILL_THREADS, 2) kgrad_trace_kernel(const Trac
 }
 
 // out[h] = scale[h] * sum_cta partials[cta][h]; fixed order -> deterministic.
-__global__ void trace_reduce_kernel(const double* partials, int nctas, int H, double amp, const double* inv_len_dev,
-                                    double* out) {
+__global__ void trace_reduce_kernel(const double* partials, int nctas, int H, const double* scale_dev, double* out) {
   __shared__ double red[32];
   for (int h = 0; h < H; ++h) {
     double s = 0.0;
     for (int i = threadIdx.x; i < nctas; i += blockDim.x) s += partials[(long long)i * H + h];
     s = block_sum(s, red);
-    if (threadIdx.x == 0) out[h] = (h == 0) ? s : s * 3.0 * amp * inv_len_dev[h - 1];
+    if (threadIdx.x == 0) out[h] = s * scale_dev[h];
     __syncthreads();
   }
 }
@@ -772,33 +792,92 @@ static inline long long trace_grid(int64_t n) {
 
 int64_t fvgp_kgrad_partials_len(int64_t n, int dim) { return (trace_grid(n) + 2) * (dim + 1) + kMaxDim; }
 
-int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const double* h_theta, const double* d_Kinv,
-                              int64_t ld, const double* d_b, double* d_partials, double* h_out, void* stream) {
+}  // extern "C"
+
+template <int KIND>
+static void launch_trace_kind(const TraceParams& p, unsigned grid, cudaStream_t st) {
+  switch (p.dim) {
+    case 1: launch(kgrad_trace_kernel<KIND, 1>, grid, FILL_THREADS, 0, st, p); break;
+    case 2: launch(kgrad_trace_kernel<KIND, 2>, grid, FILL_THREADS, 0, st, p); break;
+    case 3: launch(kgrad_trace_kernel<KIND, 3>, grid, FILL_THREADS, 0, st, p); break;
+    case 4: launch(kgrad_trace_kernel<KIND, 4>, grid, FILL_THREADS, 0, st, p); break;
+    default: launch(kgrad_trace_kernel<KIND, 0>, grid, FILL_THREADS, 0, st, p); break;
+  }
+}
+
+// Shared driver: coordinates scaled by h_coord_scale[i]; h_out[h] = h_out_scale[h] * (raw sum h).
+static int trace_radial_impl(int kind, const double* d_x, int64_t n, int dim, const double* h_coord_scale,
+                             const double* h_out_scale, const double* d_Kinv, int64_t ld, const double* d_b,
+                             double* d_partials, double* h_out, cudaStream_t st) {
   FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n > 0);
-  cudaStream_t st = (cudaStream_t)stream;
   TraceParams p;
   p.x = d_x, p.Kinv = d_Kinv, p.b = d_b, p.partials = d_partials, p.n = n, p.ld = ld, p.dim = dim;
   const long long t = (n + FT - 1) / FT;
   p.ntiles = t * (t + 1) / 2;
-  double inv_len[kMaxDim];
-  for (int i = 0; i < kMaxDim; ++i) inv_len[i] = p.inv_len[i] = i < dim ? 1.0 / h_theta[1 + i] : 0.0;
+  for (int i = 0; i < kMaxDim; ++i) p.inv_len[i] = i < dim ? h_coord_scale[i] : 0.0;
   const unsigned grid = (unsigned)trace_grid(n);
-  switch (dim) {
-    case 1: launch(kgrad_trace_kernel<1>, grid, FILL_THREADS, 0, st, p); break;
-    case 2: launch(kgrad_trace_kernel<2>, grid, FILL_THREADS, 0, st, p); break;
-    case 3: launch(kgrad_trace_kernel<3>, grid, FILL_THREADS, 0, st, p); break;
-    case 4: launch(kgrad_trace_kernel<4>, grid, FILL_THREADS, 0, st, p); break;
-    default: launch(kgrad_trace_kernel<0>, grid, FILL_THREADS, 0, st, p); break;
+  switch (kind) {
+    case FVGP_K_MATERN32: launch_trace_kind<FVGP_K_MATERN32>(p, grid, st); break;
+    case FVGP_K_MATERN52: launch_trace_kind<FVGP_K_MATERN52>(p, grid, st); break;
+    case FVGP_K_SQEXP: launch_trace_kind<FVGP_K_SQEXP>(p, grid, st); break;
+    case FVGP_K_EXP: launch_trace_kind<FVGP_K_EXP>(p, grid, st); break;
+    default: FVGP_REQUIRE(!"gradient traces exist for the Matern-3/2, Matern-5/2, squared-exponential and exponential kinds");
   }
   FVGP_LAUNCH_OK();
   const int H = dim + 1;
   double* d_out = d_partials + (long long)grid * H;
-  double* d_invlen = d_out + H;
-  FVGP_CUDA_OK(cudaMemcpyAsync(d_invlen, inv_len, dim * sizeof(double), cudaMemcpyHostToDevice, st));
-  launch(trace_reduce_kernel, 1, 256, 0, st, d_partials, (int)grid, H, h_theta[0], d_invlen, d_out);
+  double* d_scale = d_out + H;
+  FVGP_CUDA_OK(cudaMemcpyAsync(d_scale, h_out_scale, H * sizeof(double), cudaMemcpyHostToDevice, st));
+  launch(trace_reduce_kernel, 1, 256, 0, st, d_partials, (int)grid, H, d_scale, d_out);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_out, H * sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" {
+
+int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const double* h_theta, const double* d_Kinv,
+                              int64_t ld, const double* d_b, double* d_partials, double* h_out, void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim);
+  // default kernel, theta = (amp, l_1..l_dim): dK/dl_i = amp * 3 t_i^2 e^-a / l_i with t_i = dx_i / l_i; the kernel
+  // accumulates e^-a * (sqrt(3) t_i)^2, hence the factor amp / l_i
+  double coord[kMaxDim], scale[kMaxDim + 1];
+  scale[0] = 1.0;
+  for (int i = 0; i < dim; ++i) {
+    coord[i] = sqrt(3.0) / h_theta[1 + i];
+    scale[1 + i] = h_theta[0] / h_theta[1 + i];
+  }
+  return trace_radial_impl(FVGP_K_MATERN32, d_x, n, dim, coord, scale, d_Kinv, ld, d_b, d_partials, h_out,
+                           (cudaStream_t)stream);
+}
+
+int fvgp_kgrad_trace_radial(int kind, const double* d_x, int64_t n, int dim, double amp, const double* h_inv_scale,
+                            double length, const double* d_Kinv, int64_t ld, const double* d_b, double* d_partials,
+                            double* h_out, void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && length > 0.0);
+  double fold = 1.0;
+  switch (kind) {
+    case FVGP_K_MATERN32: fold = sqrt(3.0) / length; break;
+    case FVGP_K_MATERN52: fold = sqrt(5.0) / length; break;
+    case FVGP_K_SQEXP: fold = sqrt(0.5) / length; break;
+    case FVGP_K_EXP: fold = 1.0 / length; break;
+    default: FVGP_REQUIRE(!"gradient traces exist for the Matern-3/2, Matern-5/2, squared-exponential and exponential kinds");
+  }
+  // raw sums R_0 = sum W f, R_i = sum W h q_i  ->  h_out = (T_amp, T_s1..T_sD, T_length):
+  //   T_amp = R_0,  T_si = -(amp / s_i) R_i,  T_length = (amp / length) sum_i R_i
+  double coord[kMaxDim], scale[kMaxDim + 1], raw[kMaxDim + 1];
+  scale[0] = 1.0;
+  for (int i = 0; i < dim; ++i) coord[i] = h_inv_scale[i] * fold, scale[1 + i] = 1.0;
+  int r = trace_radial_impl(kind, d_x, n, dim, coord, scale, d_Kinv, ld, d_b, d_partials, raw, (cudaStream_t)stream);
+  if (r != 0) return r;
+  double sum = 0.0;
+  h_out[0] = raw[0];
+  for (int i = 0; i < dim; ++i) {
+    sum += raw[1 + i];
+    h_out[1 + i] = h_inv_scale[i] != 0.0 ? -(amp / h_inv_scale[i]) * raw[1 + i] : 0.0;
+  }
+  h_out[dim + 1] = (amp / length) * sum;
   return 0;
 }
 

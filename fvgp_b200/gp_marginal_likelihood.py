@@ -80,6 +80,9 @@ class GPMarginalLikelihood:
         fused = self.prior.default_kernel and self.prior.kernel_grad is None
         if fused:
             traces = ops.kgrad_trace_matern32(self.data.x_device(), hps, ev.factor.buf, ev.factor.ld, b_dev)
+        elif self.prior.kernel_grad is None:
+            traces = self._fused_user_kernel_traces(hps, ev, b_dev)
+            fused = traces is not None
         dV = self.likelihood.calculate_V_grad(x, hps)
         have_dV = np.any(dV != 0.0)
         if have_dV:
@@ -102,6 +105,44 @@ class GPMarginalLikelihood:
             grad[i] += gm
         self._dk_cache = None
         return grad
+
+    def _descriptor(self, hps):
+        """(kind, [amp, inv_scale_1..D, length]) of a user kernel that folds into one fused radial expression of
+        the fvgp.kernels names on (x_data, x_data); None otherwise."""
+        from . import kernels as K
+        x = self.data.x_data
+        if not self.data.Euclidean:
+            return None
+        res = self.prior._call_kernel(x, x, np.asarray(hps, dtype=np.float64))
+        if not (isinstance(res, K.Radial) and res.dist.x1 is x and res.dist.x2 is x and res.kind in ops.TRACE_KINDS):
+            return None
+        inv = np.broadcast_to(np.asarray(res.dist.inv_scale, dtype=np.float64), (x.shape[1],))
+        return res.kind, np.concatenate([[res.amp], inv, [res.length]])
+
+    def _fused_user_kernel_traces(self, hps, ev, b_dev):
+        """tr-terms sum_ij (KV^-1 - b b^T)_ij dK_ij/dtheta_h for a user kernel composed of fvgp.kernels names, without
+        materialising dK (the reference forms it by finite differences, gp_prior.py:438-447: H dense N x N arrays).
+        The kernel evaluates the traces against the descriptor's parameters p = (amp, inv_scale, length); dp/dtheta
+        comes from central differences of the DESCRIPTOR (evaluating the lazy expression costs nothing)."""
+        d0 = self._descriptor(hps)
+        if d0 is None:
+            return None
+        kind, p0 = d0
+        H = len(hps)
+        J = np.zeros((len(p0), H))
+        for h in range(H):
+            step = 1e-6 * max(abs(hps[h]), 1e-3)
+            hp, hm = np.array(hps, dtype=np.float64), np.array(hps, dtype=np.float64)
+            hp[h] += step
+            hm[h] -= step
+            dp, dm = self._descriptor(hp), self._descriptor(hm)
+            if dp is None or dm is None or dp[0] != kind or dm[0] != kind:
+                return None
+            J[:, h] = (dp[1] - dm[1]) / (2.0 * step)
+        dim = self.data.x_data.shape[1]
+        T = ops.kgrad_trace_radial(kind, self.data.x_device(), p0[0], p0[1:1 + dim], p0[-1], ev.factor.buf, ev.factor.ld,
+                                   b_dev)
+        return T @ J
 
     def _gradient_sharded(self, hps, ev, component):
         """Block-cyclic multi-GPU path (fvgp_b200/sharded.py): distributed TRTRI + LAUUM, block traces, one

@@ -111,6 +111,23 @@ def kgrad_trace_matern32(x, theta, kinv_buf, ld, b):
     return np.array(out[:], dtype=np.float64)
 
 
+TRACE_KINDS = (L.K_MATERN32, L.K_MATERN52, L.K_SQEXP, L.K_EXP)
+
+
+def kgrad_trace_radial(kind, x, amp, inv_scale, length, kinv_buf, ld, b):
+    """sum_ij (Kinv - b b^T)_ij dK_ij/dp for p in (amp, inv_scale_1..D, length) of a fused radial kernel;
+    returns ndarray (dim + 2,)."""
+    lib = L.load()
+    n, dim = x.shape
+    partials = L.dev_empty((int(lib.fvgp_kgrad_partials_len(n, dim)),))
+    _, inv_p = L.dvec(inv_scale)
+    out = (c_double * (dim + 2))()
+    with _Phase("kgrad_trace"):
+        L.check(lib.fvgp_kgrad_trace_radial(int(kind), L.ptr(x), n, dim, float(amp), inv_p, float(length), L.ptr(kinv_buf),
+                                            ld, L.ptr(b), L.ptr(partials), out, L.stream_ptr()), "fvgp_kgrad_trace_radial")
+    return np.array(out[:], dtype=np.float64)
+
+
 def trace_sym_product(kinv_buf, ld, b, dK):
     """sum_ij (Kinv - b b^T)_ij dK_ij for a materialised symmetric dK (device, row-major 2-D tensor)."""
     lib = L.load()

@@ -581,11 +581,7 @@ class ShardedSPD:
             bk = lay.bsize(k)
             pk, qk = k % lay.P, k % lay.Q
             owner = pk * lay.Q + qk
-            if comm.rank == owner:
-                D.zero_()
-                D[:bk, :bk].copy_(self.block(k, k))
-                D[:bk, :bk].tril_()
-            comm.broadcast(D, owner)
+            D.copy_(self.diag[k])                                    # M_kk is already replicated (TRTRI pass A)
             rowp = self._gather_row_panel(k, everyone=True) if k > 0 else {}
             if k > 0:
                 # A operand: blocks (k, i) for MY row blocks i < k, laid out in my local row order

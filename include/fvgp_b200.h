@@ -76,6 +76,19 @@ int64_t fvgp_kgrad_partials_len(int64_t n, int dim);
 int fvgp_kgrad_trace_matern32(const double* d_x, int64_t n, int dim, const double* h_theta, const double* d_Kinv,
                               int64_t ld, const double* d_b, double* d_partials, double* h_out, void* stream);
 
+/* The same traces for every radial family with a fused form (Matern-3/2, Matern-5/2, squared exponential,
+ * exponential; kernels.py:16-188) and K = amp * f(||(x1 - x2) * inv_scale|| / length), with respect to the
+ * descriptor's own parameters:
+ *   h_out[0]       = sum_ij W_ij dK_ij/d(amp)
+ *   h_out[1 + i]   = sum_ij W_ij dK_ij/d(inv_scale_i)     (i < dim)
+ *   h_out[dim + 1] = sum_ij W_ij dK_ij/d(length)
+ * A user kernel composed from the fvgp.kernels names maps its hyperparameters to (amp, inv_scale, length); the
+ * host applies the chain rule (replaces the finite-difference dK of gp_prior.py:438-447, which materialises
+ * H dense N x N arrays).  d_partials: fvgp_kgrad_partials_len(n, dim) doubles. */
+int fvgp_kgrad_trace_radial(int kind, const double* d_x, int64_t n, int dim, double amp, const double* h_inv_scale,
+                            double length, const double* d_Kinv, int64_t ld, const double* d_b, double* d_partials,
+                            double* h_out, void* stream);
+
 /* One m x n block of the same trace for the block-cyclic multi-GPU layout: rows belong to (x1, b1), columns to
  * (x2, b2); the first diag_rows rows are a diagonal block aligned with the columns (lower triangle only, diagonal
  * weighted once), all other entries are weighted twice.  d_accum[h] (dim+1 doubles, device) += the block's

@@ -377,3 +377,54 @@ def test_potrf_lookahead_ragged_size(fv):
     with pytest.raises(L.NonPositiveDefiniteError) as ei:
         ops.potrf(bad, ld, n)
     assert ei.value.pivot == 5001
+
+
+def test_fused_gradient_for_named_user_kernels(fv):
+    """User kernels composed of the fvgp.kernels names get the fused gradient traces (no dK materialised); checked
+    against grad(-LML)_h = -1/2 (b^T dK_h b - tr(KV^-1 dK_h)) formed on the host with numpy and finite-difference dK."""
+    from scipy.spatial.distance import cdist
+    from fvgp_b200 import GP
+    from fvgp_b200.kernels import (exponential_kernel, get_anisotropic_distance_matrix, get_distance_matrix,
+                                   matern_kernel_diff1, matern_kernel_diff2, squared_exponential_kernel)
+    rng = np.random.default_rng(17)
+    n = 400
+    x = rng.random((n, 2))
+    y = np.sin(4 * x[:, 0]) + np.cos(3 * x[:, 1]) + 0.05 * rng.standard_normal(n)
+    nz = np.full(n, 2e-2)
+
+    def np_kernel(name, x1, x2, h):
+        if name == "se_iso":
+            return h[0] * np.exp(-cdist(x1, x2) ** 2 / (2 * h[1] ** 2))
+        if name == "m52_aniso":
+            d = cdist(x1 / h[1:3], x2 / h[1:3])
+            return h[0] ** 2 * (1 + np.sqrt(5) * d + 5 * d ** 2 / 3) * np.exp(-np.sqrt(5) * d)
+        if name == "exp_iso":
+            return h[0] * np.exp(-cdist(x1, x2) / h[1])
+        d = cdist(x1 / h[1:3], x2 / h[1:3])                                   # m32 with a length parameter on top
+        return h[0] * (1 + np.sqrt(3) * d / h[3]) * np.exp(-np.sqrt(3) * d / h[3])
+
+    kernels = {
+        "se_iso": (lambda a, b, h: h[0] * squared_exponential_kernel(get_distance_matrix(a, b), h[1]), np.array([1.3, 0.4])),
+        "m52_aniso": (lambda a, b, h: h[0] ** 2 * matern_kernel_diff2(get_anisotropic_distance_matrix(a, b, h[1:3]), 1.0),
+                      np.array([1.1, 0.35, 0.6])),
+        "exp_iso": (lambda a, b, h: h[0] * exponential_kernel(get_distance_matrix(a, b), h[1]), np.array([0.9, 0.7])),
+        "m32_len": (lambda a, b, h: h[0] * matern_kernel_diff1(get_anisotropic_distance_matrix(a, b, h[1:3]), h[3]),
+                    np.array([1.2, 0.5, 0.8, 0.9])),
+    }
+    for name, (kern, h) in kernels.items():
+        gp = GP(x, y, init_hyperparameters=h, noise_variances=nz, kernel_function=kern)
+        assert gp.marginal_likelihood._descriptor(h) is not None, name       # the fused path is taken
+        grad = gp.neg_log_likelihood_gradient(h)
+        KV = np_kernel(name, x, x, h) + np.diag(nz)
+        assert abs(gp.log_likelihood(h) / (-0.5 * ((y - y.mean()) @ np.linalg.solve(KV, y - y.mean())
+                                                    + np.linalg.slogdet(KV)[1] + n * np.log(2 * np.pi))) - 1) <= 1e-9, name
+        b = np.linalg.solve(KV, y - y.mean())
+        Kinv = np.linalg.inv(KV)
+        ref = np.zeros(len(h))
+        for i in range(len(h)):
+            hp, hm = h.copy(), h.copy()
+            hp[i] += 1e-6
+            hm[i] -= 1e-6
+            dK = (np_kernel(name, x, x, hp) - np_kernel(name, x, x, hm)) / 2e-6
+            ref[i] = -0.5 * (b @ dK @ b - np.sum(Kinv * dK))
+        assert np.max(np.abs(grad - ref) / np.abs(ref)) <= 2e-6, (name, grad, ref)
