@@ -69,6 +69,10 @@ _SIGNATURES = {
     "fvgp_lanczos_work_len": (c_int64, [c_int64, c_int]),
     "fvgp_lanczos_tridiag": (c_int, [c_int64, _P, _P, _P, c_int, c_int, c_int, c_uint64, _P, POINTER(c_double),
                                      POINTER(c_double), _P]),
+    "fvgp_population_slot_len": (c_int64, [c_int64, c_int, c_int]),
+    "fvgp_lml_population": (c_int, [c_int, _P, c_int64, c_int, c_int, POINTER(c_double), POINTER(c_double),
+                                    POINTER(c_double), POINTER(c_double), _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
+                                    _P, POINTER(c_double), POINTER(c_double), POINTER(c_double), POINTER(c_int), _P]),
     "fvgp_bench_fp64_peak": (c_int, [c_int, c_int, c_int, _P, POINTER(c_double), _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -148,6 +148,183 @@ __global__ void __launch_bounds__(512) potrf_tile_kernel(double* A, long long ld
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Second generation of the tile kernel (same contract, same outputs).  The first one spends ~3600 cycles in each of
+// its 128 column steps (two CTA barriers, a one-thread-per-row scaling pass and a 4-threads-per-row rank-1 update
+// that re-reads the whole trailing tile from shared memory every column): 150-240 us per tile, which is the
+// critical path of every evaluation at N ~ 1e3 (8 tiles = half of a 3 ms LML) and of the panel path at large N.
+// Here the factorisation is blocked by panels of 16 columns:
+//   * inside a panel the columns stay UNSCALED (column j's rank-1 update carries the factor 1/d_j), so one column
+//     step is: read the pivot, rsqrt, update the <= 15 remaining panel columns, ONE barrier;
+//   * after the 16 columns, one pass scales the panel and also stores it k-major in a 16 x 128 staging array;
+//   * the rank-16 update of the trailing tile runs from registers: each thread owns one 4 x 4 micro-tile of the
+//     lower triangle (<= 406 micro-tiles), reads its 2 x 4 panel values per k with 16-byte loads from the staging
+//     array and touches the trailing tile once per panel instead of once per column.
+// The inverse of the factor (steps 2 and 3 of the first kernel) is unchanged.
+// ----------------------------------------------------------------------------------------------
+constexpr int PW = 16;  // panel width
+constexpr size_t POTRF_TILE2_SMEM = POTRF_TILE_SMEM + size_t(PW) * TS * sizeof(double);  // ~214 KB
+
+__global__ void __launch_bounds__(512) potrf_tile2_kernel(double* A, long long ld, int nt, double* dinv, int* info,
+                                                          int global_row0) {
+  extern __shared__ __align__(16) double tile_smem[];
+  double(*T)[TP] = reinterpret_cast<double(*)[TP]>(tile_smem);
+  double(*InvA)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP);
+  double(*InvD)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP + (TS / 2) * HP);
+  double* Dg = tile_smem + TS * TP + 2 * (TS / 2) * HP;
+  double* RDg = Dg + TS;  // reciprocals of the diagonal
+  // staging array of the current panel, k-major; offset rounded so that its rows are 16-byte aligned
+  constexpr int P_OFF = ((TS * TP + 2 * (TS / 2) * HP + 2 * TS) + 1) / 2 * 2;
+  double(*P)[TS] = reinterpret_cast<double(*)[TS]>(tile_smem + P_OFF);
+  constexpr int H = TS / 2;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TS * TS; idx += 512) {
+    const int r = idx / TS, c = idx % TS;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < nt && c <= r) v = A[(long long)r * ld + c];
+    T[r][c] = v;
+  }
+  // micro-tile of the trailing update owned by this thread: index tid in the row-major enumeration of the lower
+  // triangle of a grid of 4 x 4 micro-tiles (the same for every panel; fewer of them are active as panels advance)
+  int ma = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+  while ((ma + 1) * (ma + 2) / 2 <= tid) ++ma;
+  while (ma * (ma + 1) / 2 > tid) --ma;
+  const int mb = tid - ma * (ma + 1) / 2;
+  const int row = tid & (TS - 1), cg = tid >> 7;  // column-step / scaling mapping: one row, 4 column groups
+  __syncthreads();
+  for (int p0 = 0; p0 < TS; p0 += PW) {
+    const int pend = p0 + PW;
+    for (int j = p0; j < pend; ++j) {
+      const double d = T[j][j];
+      if (!(d > 0.0) && tid == 0) atomicCAS(info, 0, global_row0 + j + 1);
+      double y;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const double e = fma(-(d * y), y, 1.0);
+        y = fma(0.5 * y, e, y);
+      }
+      if (tid == 0) {
+        double sq = d * y;
+        sq = fma(fma(-sq, sq, d), 0.5 * y, sq);
+        Dg[j] = sq, RDg[j] = y;
+      }
+      if (row > j) {  // T[row][k] -= T[row][j] T[k][j] / d for the panel columns k > j, rows >= k
+        const double lij = T[row][j] * (y * y);
+#pragma unroll
+        for (int q = 0; q < PW / 4; ++q) {
+          const int k = j + 1 + cg + 4 * q;
+          if (k < pend && k <= row) T[row][k] = fma(-lij, T[k][j], T[row][k]);
+        }
+      }
+      __syncthreads();
+    }
+    // scale the panel: L[r][j] = T[r][j] / sqrt(d_j); k-major copy for the register-tiled trailing update
+#pragma unroll
+    for (int q = 0; q < PW / 4; ++q) {
+      const int j = p0 + cg + 4 * q;
+      if (row > j) {
+        const double v = T[row][j] * RDg[j];
+        T[row][j] = v;
+        P[j - p0][row] = v;
+      }
+    }
+    __syncthreads();
+    const int off = pend, mt = (TS - off) / 4;
+    if (tid < mt * (mt + 1) / 2) {
+      const int r0 = off + 4 * ma, c0 = off + 4 * mb;
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+#pragma unroll
+      for (int k = 0; k < PW; ++k) {
+        const double2 ra = *reinterpret_cast<const double2*>(&P[k][r0]);
+        const double2 rb = *reinterpret_cast<const double2*>(&P[k][r0 + 2]);
+        const double2 ca = *reinterpret_cast<const double2*>(&P[k][c0]);
+        const double2 cb = *reinterpret_cast<const double2*>(&P[k][c0 + 2]);
+        const double rv[4] = {ra.x, ra.y, rb.x, rb.y};
+        const double cv[4] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(rv[i], cv[jj], acc[i][jj]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) T[r0 + i][c0 + jj] -= acc[i][jj];
+    }
+    __syncthreads();
+  }
+  const int part = tid & 3;
+  {  // inverses of the diagonal blocks: column (tid>>2) of block (tid>>8)
+    const int c = (tid >> 2) & (H - 1), base = (tid >> 8) * H;
+    double(*Inv)[HP] = (tid >> 8) ? InvD : InvA;
+    for (int i = 0; i < H; ++i) {
+      double acc0 = 0.0, acc1 = 0.0;
+      if (i > c) {
+        int k = c + part;
+        for (; k + 4 < i; k += 8) {
+          acc0 = fma(T[base + i][base + k], Inv[k][c], acc0);
+          acc1 = fma(T[base + i][base + k + 4], Inv[k + 4][c], acc1);
+        }
+        for (; k < i; k += 4) acc0 = fma(T[base + i][base + k], Inv[k][c], acc0);
+      }
+      double acc = acc0 + acc1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) Inv[i][c] = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - acc) * RDg[base + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  {  // E = C A^-1 into T[0..63][64..127]  (C = T[64+i][k])
+    const int i = tid >> 3, j0 = (tid & 7) * 8;
+    double e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = 0.0;
+    for (int k = 0; k < H; ++k) {
+      const double cik = T[H + i][k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) e[u] = fma(cik, InvA[k][j0 + u], e[u]);   // InvA[k][j] = 0 for k < j
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) T[i][H + j0 + u] = e[u];
+  }
+  __syncthreads();
+  {  // F = -D^-1 E  -> dinv[64+i][j]
+    const int i = tid >> 3, j0 = (tid & 7) * 8;
+    double f[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] = 0.0;
+    for (int k = 0; k <= i; ++k) {
+      const double dik = InvD[i][k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = fma(dik, T[k][H + j0 + u], f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dinv[(H + i) * TS + j0 + u] = -f[u];
+  }
+  for (int idx = tid; idx < TS * TS; idx += 512) {
+    const int r = idx / TS, c = idx % TS;
+    if (r < H) dinv[idx] = (c < H) ? InvA[r][c] : 0.0;
+    else if (c >= H) dinv[idx] = InvD[r - H][c - H];
+    if (r < nt && c < nt) A[(long long)r * ld + c] = (c < r) ? T[r][c] : ((c == r) ? Dg[r] : 0.0);
+  }
+}
+
+// FVGP_POTRF_TILE=1 selects the first-generation tile kernel (A/B on the GPU box).
+static bool use_tile_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FVGP_POTRF_TILE");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // dst (rows x cols, ldd) <- src (lds)
 __global__ void copy2d_kernel(double* dst, long long ldd, const double* src, long long lds, int rows, int cols) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,8 +548,9 @@ static int trsm_rn_rec(Ctx& c, double* B, long long ldb, int m, const double* L,
 
 static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
   if (n <= TS) {
-    launch(potrf_tile_kernel, 1, 512, POTRF_TILE_SMEM, c.st, A, ld, n, c.dinv + (long long)(row0 / TS) * TS * TS, c.info,
-                                                          row0);
+    double* tile_inv = c.dinv + (long long)(row0 / TS) * TS * TS;
+    if (use_tile_v1()) launch(potrf_tile_kernel, 1, 512, POTRF_TILE_SMEM, c.st, A, ld, n, tile_inv, c.info, row0);
+    else launch(potrf_tile2_kernel, 1, 512, POTRF_TILE2_SMEM, c.st, A, ld, n, tile_inv, c.info, row0);
     FVGP_LAUNCH_OK();
     return 0;
   }
@@ -514,6 +692,13 @@ static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
 
 using namespace fvgp;
 
+// kfill.cu: gradient traces without host synchronisation (result in d_out on the device)
+int trace_radial_enqueue(int kind, const double* d_x, int64_t n, int dim, const double* h_coord_scale,
+                         const double* h_out_scale, const double* d_Kinv, int64_t ld, const double* d_b,
+                         double* d_partials, double* d_out, cudaStream_t st);
+
+static inline int64_t round_up16(int64_t v) { return (v + 15) / 16 * 16; }
+
 extern "C" {
 
 int fvgp_version(void) { return 100; }
@@ -537,6 +722,8 @@ int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int
   if (!configured) {
     FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)POTRF_TILE_SMEM));
+    FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)POTRF_TILE2_SMEM));
     configured = true;
   }
   FVGP_CUDA_OK(cudaMemsetAsync(d_info, 0, sizeof(int), st));
@@ -549,21 +736,12 @@ int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int
   return info;
 }
 
-int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B, int nrhs,
-                     int64_t ldb, double* d_work, void* stream) {
-  FVGP_REQUIRE(n > 0 && nrhs >= 0 && ldb >= n && lda % 2 == 0);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (nrhs > 4) {
-    FVGP_REQUIRE(ldb % 2 == 0);
-    Ctx c{st, const_cast<double*>(d_tileinv), nullptr, nullptr, 0};
-    int r = trsm_rt_rec(c, d_B, ldb, nrhs, d_L, lda, (int)n, 0);   // rows of B <- rows * L^-T  (L y = b)
-    if (r != 0) return r;
-    return trsm_rn_rec(c, d_B, ldb, nrhs, d_L, lda, (int)n, 0);    // rows <- rows * L^-1      (L^T x = y)
-  }
-  // Few right-hand sides: HBM-read bound (the lower triangle is read once per direction).  Blocks of VBLK
-  // columns: inside a block the 64-wide leaf steps (tile inverse + rank-64 update of the block's own rows),
-  // then ONE matrix-vector product with the whole panel below (forward) / left of (backward) the block, which
-  // streams >95 % of the factor at GEMV speed instead of in 782 latency-bound slivers.
+// Few right-hand sides: HBM-read bound (the lower triangle is read once per direction).  Blocks of VBLK
+// columns: inside a block the 64-wide leaf steps (tile inverse + rank-64 update of the block's own rows),
+// then ONE matrix-vector product with the whole panel below (forward) / left of (backward) the block, which
+// streams >95 % of the factor at GEMV speed instead of in 782 latency-bound slivers.  Enqueue only.
+static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B,
+                     int nrhs, int64_t ldb, double* d_work) {
   double* w = d_work;
   double* z = d_work + n;
   double* gemv_work = d_work + 2 * n;
@@ -607,6 +785,20 @@ int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_
     FVGP_LAUNCH_OK();
   }
   return 0;
+}
+
+int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B, int nrhs,
+                     int64_t ldb, double* d_work, void* stream) {
+  FVGP_REQUIRE(n > 0 && nrhs >= 0 && ldb >= n && lda % 2 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nrhs > 4) {
+    FVGP_REQUIRE(ldb % 2 == 0);
+    Ctx c{st, const_cast<double*>(d_tileinv), nullptr, nullptr, 0};
+    int r = trsm_rt_rec(c, d_B, ldb, nrhs, d_L, lda, (int)n, 0);   // rows of B <- rows * L^-T  (L y = b)
+    if (r != 0) return r;
+    return trsm_rn_rec(c, d_B, ldb, nrhs, d_L, lda, (int)n, 0);    // rows <- rows * L^-1      (L^T x = y)
+  }
+  return potrs_few(st, d_L, n, lda, d_tileinv, d_B, nrhs, ldb, d_work);
 }
 
 int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratch1, double* h_out, void* stream) {
@@ -727,6 +919,136 @@ int fvgp_gemv(int transpose, const double* d_A, int64_t lda, int m, int n, doubl
   }
   FVGP_LAUNCH_OK();
   return 0;
+}
+
+/* ---- population evaluation: many hyperparameter proposals on concurrent streams ---- */
+
+int64_t fvgp_population_slot_len(int64_t n, int dim, int want_grad) {
+  int64_t len = round_up16(n * round_up16(n)) + round_up16(fvgp_chol_workspace_len(n)) + round_up16(fvgp_potrs_work_len(n));
+  if (want_grad) len += round_up16(fvgp_potri_workspace_len(n)) + round_up16(fvgp_kgrad_partials_len(n, dim));
+  return len;
+}
+
+int fvgp_lml_population(int kind, const double* d_x, int64_t n, int dim, int batch, const double* h_amp,
+                        const double* h_inv_scale, const double* h_length, const double* h_centre,
+                        const double* d_noise, const double* d_rhs, int nrhs, int want_grad, int grad_component,
+                        int slots, double* d_work, double* d_alpha, double* d_res, int* d_info, double* h_alpha,
+                        double* h_logdet, double* h_traces, int* h_info, void* stream) {
+  FVGP_REQUIRE(n > 0 && n < (1ll << 31) && dim >= 1 && dim <= kMaxDim && batch >= 1 && slots >= 1);
+  FVGP_REQUIRE(nrhs >= 1 && nrhs <= 4 && grad_component >= 0 && grad_component < nrhs);
+  cudaStream_t S = (cudaStream_t)stream;
+  const int64_t ld = round_up16(n);
+  const int H = dim + 1;                       // raw trace sums per proposal
+  const int res_stride = 1 + H;                // [logdet, raw traces]
+  const int64_t slot_len = fvgp_population_slot_len(n, dim, want_grad);
+  if (slots > batch) slots = batch;
+  static bool configured = false;
+  if (!configured) {
+    FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)POTRF_TILE_SMEM));
+    FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)POTRF_TILE2_SMEM));
+    configured = true;
+  }
+  std::vector<cudaStream_t> st(slots);
+  cudaEvent_t ev_start;
+  FVGP_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  FVGP_CUDA_OK(cudaEventRecord(ev_start, S));
+  for (int s = 0; s < slots; ++s) {
+    FVGP_CUDA_OK(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+    FVGP_CUDA_OK(cudaStreamWaitEvent(st[s], ev_start, 0));
+  }
+  FVGP_CUDA_OK(cudaMemsetAsync(d_info, 0, sizeof(int) * batch, S));
+  FVGP_CUDA_OK(cudaEventRecord(ev_start, S));  // re-recorded after the memset: the slots wait for it below
+  for (int s = 0; s < slots; ++s) FVGP_CUDA_OK(cudaStreamWaitEvent(st[s], ev_start, 0));
+  int rc = 0;
+  const int nb = potrf_block_width((int)n);
+  for (int b = 0; b < batch && rc == 0; ++b) {
+    const int s = b % slots;
+    cudaStream_t q = st[s];
+    double* A = d_work + (int64_t)s * slot_len;
+    double* tileinv = A + round_up16(n * ld);
+    double* swork = tileinv + round_up16(fvgp_chol_workspace_len(n));
+    double* pwork = swork + round_up16(fvgp_potrs_work_len(n));
+    double* partials = pwork + round_up16(fvgp_potri_workspace_len(n));
+    double* alpha = d_alpha + (int64_t)b * nrhs * n;
+    double* res = d_res + (int64_t)b * res_stride;
+    const double* inv = h_inv_scale + (int64_t)b * dim;
+    // K(theta_b) + diag(V), lower triangle
+    rc = fvgp_kfill_dense(kind, FVGP_FILL_LOWER, d_x, n, d_x, n, dim, h_amp[b], inv, h_centre, h_length[b], d_noise, A,
+                          ld, q);
+    if (rc != 0) break;
+    Ctx c{q, tileinv, d_info + b, pwork, 0};
+    rc = nb > 0 ? potrf_lookahead(c, A, ld, (int)n, nb) : potrf_rec(c, A, ld, (int)n, 0);
+    if (rc != 0) break;
+    // alpha_b = KV^-1 (y - m), one row per right-hand side
+    if (cudaMemcpyAsync(alpha, d_rhs, sizeof(double) * nrhs * n, cudaMemcpyDeviceToDevice, q) != cudaSuccess) {
+      rc = FVGP_ERR_CUDA;
+      break;
+    }
+    rc = potrs_few(q, A, n, ld, tileinv, alpha, nrhs, n, swork);
+    if (rc != 0) break;
+    launch(logdet_kernel, 1, 1024, 0, q, A, ld, (int)n, res);
+    if (want_grad) {
+      // lower(A) <- lower(KV^-1); raw sums R_0 = sum W f, R_i = sum W h q_i with W = KV^-1 - b b^T
+      launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, q, A, ld, (int)n);
+      rc = trtri_rec(c, A, ld, (int)n, 0);
+      if (rc == 0) rc = lauum_rec(c, A, ld, (int)n);
+      if (rc != 0) break;
+      double fold = 1.0;
+      switch (kind) {
+        case FVGP_K_MATERN32: fold = sqrt(3.0) / h_length[b]; break;
+        case FVGP_K_MATERN52: fold = sqrt(5.0) / h_length[b]; break;
+        case FVGP_K_SQEXP: fold = sqrt(0.5) / h_length[b]; break;
+        case FVGP_K_EXP: fold = 1.0 / h_length[b]; break;
+        default: rc = FVGP_ERR_ARG; break;
+      }
+      if (rc != 0) break;
+      double coord[kMaxDim], scale[kMaxDim + 1];
+      scale[0] = 1.0;
+      for (int i = 0; i < dim; ++i) coord[i] = inv[i] * fold, scale[1 + i] = 1.0;
+      rc = trace_radial_enqueue(kind, d_x, n, dim, coord, scale, A, ld, alpha + (int64_t)grad_component * n, partials,
+                                res + 1, q);
+      if (rc != 0) break;
+    }
+  }
+  if (cudaGetLastError() != cudaSuccess && rc == 0) rc = FVGP_ERR_CUDA;
+  // join: the caller's stream continues after every slot
+  for (int s = 0; s < slots; ++s) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) {
+      cudaEventRecord(e, st[s]);
+      cudaStreamWaitEvent(S, e, 0);
+      cudaEventDestroy(e);
+    }
+  }
+  if (rc == 0) {
+    std::vector<double> res_h((size_t)batch * res_stride);
+    FVGP_CUDA_OK(cudaMemcpyAsync(h_alpha, d_alpha, sizeof(double) * batch * nrhs * n, cudaMemcpyDeviceToHost, S));
+    FVGP_CUDA_OK(cudaMemcpyAsync(res_h.data(), d_res, sizeof(double) * batch * res_stride, cudaMemcpyDeviceToHost, S));
+    FVGP_CUDA_OK(cudaMemcpyAsync(h_info, d_info, sizeof(int) * batch, cudaMemcpyDeviceToHost, S));
+    FVGP_CUDA_OK(cudaStreamSynchronize(S));
+    for (int b = 0; b < batch; ++b) {
+      h_logdet[b] = res_h[(size_t)b * res_stride];
+      if (want_grad) {  // descriptor traces (T_amp, T_s1..T_sD, T_length), as fvgp_kgrad_trace_radial
+        const double* raw = &res_h[(size_t)b * res_stride + 1];
+        double* out = h_traces + (size_t)b * (dim + 2);
+        double sum = 0.0;
+        out[0] = raw[0];
+        for (int i = 0; i < dim; ++i) {
+          const double si = h_inv_scale[(size_t)b * dim + i];
+          sum += raw[1 + i];
+          out[1 + i] = si != 0.0 ? -(h_amp[b] / si) * raw[1 + i] : 0.0;
+        }
+        out[dim + 1] = (h_amp[b] / h_length[b]) * sum;
+      }
+    }
+  } else {
+    cudaStreamSynchronize(S);
+  }
+  for (int s = 0; s < slots; ++s) cudaStreamDestroy(st[s]);
+  cudaEventDestroy(ev_start);
+  return rc;
 }
 
 }  // extern "C"

@@ -805,10 +805,12 @@ static void launch_trace_kind(const TraceParams& p, unsigned grid, cudaStream_t 
   }
 }
 
-// Shared driver: coordinates scaled by h_coord_scale[i]; h_out[h] = h_out_scale[h] * (raw sum h).
-static int trace_radial_impl(int kind, const double* d_x, int64_t n, int dim, const double* h_coord_scale,
-                             const double* h_out_scale, const double* d_Kinv, int64_t ld, const double* d_b,
-                             double* d_partials, double* h_out, cudaStream_t st) {
+// Shared driver: coordinates scaled by h_coord_scale[i]; out[h] = h_out_scale[h] * (raw sum h).  Enqueue only:
+// the H results land in d_out (device; nullptr = the tail of d_partials) with no host synchronisation, so that
+// the population evaluator (dense_linalg.cu) can run many of these on concurrent streams.
+int trace_radial_enqueue(int kind, const double* d_x, int64_t n, int dim, const double* h_coord_scale,
+                         const double* h_out_scale, const double* d_Kinv, int64_t ld, const double* d_b,
+                         double* d_partials, double* d_out, cudaStream_t st) {
   FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n > 0);
   TraceParams p;
   p.x = d_x, p.Kinv = d_Kinv, p.b = d_b, p.partials = d_partials, p.n = n, p.ld = ld, p.dim = dim;
@@ -825,11 +827,22 @@ static int trace_radial_impl(int kind, const double* d_x, int64_t n, int dim, co
   }
   FVGP_LAUNCH_OK();
   const int H = dim + 1;
-  double* d_out = d_partials + (long long)grid * H;
-  double* d_scale = d_out + H;
+  double* d_tail = d_partials + (long long)grid * H;
+  double* d_scale = d_tail + H;
+  if (d_out == nullptr) d_out = d_tail;
   FVGP_CUDA_OK(cudaMemcpyAsync(d_scale, h_out_scale, H * sizeof(double), cudaMemcpyHostToDevice, st));
   launch(trace_reduce_kernel, 1, 256, 0, st, d_partials, (int)grid, H, d_scale, d_out);
   FVGP_LAUNCH_OK();
+  return 0;
+}
+
+static int trace_radial_impl(int kind, const double* d_x, int64_t n, int dim, const double* h_coord_scale,
+                             const double* h_out_scale, const double* d_Kinv, int64_t ld, const double* d_b,
+                             double* d_partials, double* h_out, cudaStream_t st) {
+  int r = trace_radial_enqueue(kind, d_x, n, dim, h_coord_scale, h_out_scale, d_Kinv, ld, d_b, d_partials, nullptr, st);
+  if (r != 0) return r;
+  const int H = dim + 1;
+  const double* d_out = d_partials + (long long)trace_grid(n) * H;
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_out, H * sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
   return 0;

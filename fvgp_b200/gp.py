@@ -178,7 +178,11 @@ class GP:
             objective_function_hessian = self.marginal_likelihood.neg_log_likelihood_hessian
         before_hps = np.array(self.hyperparameters)
         before = self.marginal_likelihood.log_likelihood() if accept_only_if_improved and not user_obj else None
+        population_objective = None
+        if not user_obj and method == "global" and self.marginal_likelihood.population_supported():
+            population_objective = lambda T: -self.marginal_likelihood.log_likelihood_population(T)   # noqa: E731
         hps = self.trainer.train(objective_function=objective_function,
+                                 population_objective=population_objective,
                                  objective_function_gradient=objective_function_gradient,
                                  objective_function_hessian=objective_function_hessian,
                                  hyperparameter_bounds=hyperparameter_bounds,
@@ -205,6 +209,15 @@ class GP:
 
     def neg_log_likelihood_hessian(self, hyperparameters=None):
         return self.marginal_likelihood.neg_log_likelihood_hessian(hyperparameters=hyperparameters)
+
+    # ---- population entry points (beyond the reference API; what train(method="global") uses) -----
+    def log_likelihood_population(self, hyperparameters):
+        """LML for every row of `hyperparameters` (B, H) -> (B,): the proposals run on concurrent streams."""
+        return self.marginal_likelihood.log_likelihood_population(hyperparameters)
+
+    def neg_log_likelihood_gradient_population(self, hyperparameters, component=0):
+        """grad(-LML) for every row of `hyperparameters` (B, H) -> (B, H)."""
+        return self.marginal_likelihood.neg_log_likelihood_gradient_population(hyperparameters, component=component)
 
     def test_log_likelihood_gradient(self, hyperparameters, epsilon=1e-6):
         return self.marginal_likelihood.test_log_likelihood_gradient(hyperparameters, epsilon=epsilon)

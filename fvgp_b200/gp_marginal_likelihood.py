@@ -119,17 +119,24 @@ class GPMarginalLikelihood:
         inv = np.broadcast_to(np.asarray(res.dist.inv_scale, dtype=np.float64), (x.shape[1],))
         return res.kind, np.concatenate([[res.amp], inv, [res.length]])
 
-    def _fused_user_kernel_traces(self, hps, ev, b_dev):
-        """tr-terms sum_ij (KV^-1 - b b^T)_ij dK_ij/dtheta_h for a user kernel composed of fvgp.kernels names, without
-        materialising dK (the reference forms it by finite differences, gp_prior.py:438-447: H dense N x N arrays).
-        The kernel evaluates the traces against the descriptor's parameters p = (amp, inv_scale, length); dp/dtheta
-        comes from central differences of the DESCRIPTOR (evaluating the lazy expression costs nothing)."""
+    def _descriptor_jacobian(self, hps):
+        """(kind, p0, J): descriptor parameters p = (amp, inv_scale_1..D, length) at hps and J = dp/dtheta
+        (len(p) x H).  Exact for the default kernel (amp = theta_0, inv_scale_i = 1 / theta_{1+i}); central differences
+        of the DESCRIPTOR for user kernels composed of the fvgp.kernels names (evaluating the lazy expression costs
+        nothing).  None when the kernel does not fold into one fused radial expression."""
+        hps = np.asarray(hps, dtype=np.float64)
         d0 = self._descriptor(hps)
         if d0 is None:
             return None
         kind, p0 = d0
         H = len(hps)
         J = np.zeros((len(p0), H))
+        dim = self.data.x_data.shape[1]
+        if self.prior.default_kernel:
+            J[0, 0] = 1.0
+            for i in range(dim):
+                J[1 + i, 1 + i] = -1.0 / hps[1 + i] ** 2
+            return kind, p0, J
         for h in range(H):
             step = 1e-6 * max(abs(hps[h]), 1e-3)
             hp, hm = np.array(hps, dtype=np.float64), np.array(hps, dtype=np.float64)
@@ -139,10 +146,105 @@ class GPMarginalLikelihood:
             if dp is None or dm is None or dp[0] != kind or dm[0] != kind:
                 return None
             J[:, h] = (dp[1] - dm[1]) / (2.0 * step)
+        return kind, p0, J
+
+    def _fused_user_kernel_traces(self, hps, ev, b_dev):
+        """tr-terms sum_ij (KV^-1 - b b^T)_ij dK_ij/dtheta_h for a user kernel composed of fvgp.kernels names, without
+        materialising dK (the reference forms it by finite differences, gp_prior.py:438-447: H dense N x N arrays).
+        The kernel evaluates the traces against the descriptor's parameters p = (amp, inv_scale, length); the chain
+        rule with dp/dtheta (_descriptor_jacobian) gives the traces against theta."""
+        dj = self._descriptor_jacobian(hps)
+        if dj is None:
+            return None
+        kind, p0, J = dj
         dim = self.data.x_data.shape[1]
         T = ops.kgrad_trace_radial(kind, self.data.x_device(), p0[0], p0[1:1 + dim], p0[-1], ev.factor.buf, ev.factor.ld,
                                    b_dev)
         return T @ J
+
+    # ------------------------------------------------------------------------------------------
+    # Population evaluation (SURVEY 8f-3): what the optimisers actually do is evaluate MANY proposals --
+    # differential-evolution generations (gp_training.py:60-80), multi-start / hgdl walkers, the H+1 gradients of the
+    # finite-difference Hessian (:312-336).  One proposal at N ~ 1e3 is a latency-bound chain of ~70 small launches;
+    # the population entry point overlaps the chains on concurrent streams with one host synchronisation.
+    def population_supported(self, want_grad=False):
+        """True when a set of proposals can go through ops.lml_population: dense Cholesky mode on one GPU, a kernel
+        that folds into one fused radial expression, and noise / prior mean that do not depend on theta."""
+        kv = self.kv
+        if self.data.gp2Scale or kv.mode != "Chol" or not self.data.Euclidean:
+            return False
+        if self.likelihood.noise_function is not None or self.prior.mean_function is not None:
+            return False
+        V = self.likelihood.V
+        if V is None or np.ndim(V) != 1 or self.data.y_data.shape[1] > 4 or kv._use_sharded(kv.mode, V):
+            return False
+        d = self._descriptor(self.trainer.hyperparameters) if want_grad else self._fill_descriptor(
+            self.trainer.hyperparameters)
+        return d is not None and (not want_grad or self.prior.kernel_grad is None)
+
+    def _fill_descriptor(self, hps):
+        """Like _descriptor, for every kind the fused K-fill knows (no gradient-trace requirement)."""
+        from . import kernels as K
+        x = self.data.x_data
+        res = self.prior._call_kernel(x, x, np.asarray(hps, dtype=np.float64))
+        if not (isinstance(res, K.Radial) and res.dist.x1 is x and res.dist.x2 is x):
+            return None
+        inv = np.broadcast_to(np.asarray(res.dist.inv_scale, dtype=np.float64), (x.shape[1],))
+        return res.kind, np.concatenate([[res.amp], inv, [res.length]])
+
+    def evaluate_population(self, thetas, with_gradient=False, component=0):
+        """LML (and grad(-LML)) for every row of `thetas` (B, H).  Returns (lml (B,), grad (B, H) or None).
+        Falls back to one-at-a-time evaluation when the population path does not apply."""
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        B, H = thetas.shape
+        plan = None
+        if B > 1 and self.population_supported(want_grad=with_gradient):
+            plan = []
+            for t in thetas:
+                dj = self._descriptor_jacobian(t) if with_gradient else self._fill_descriptor(t)
+                if dj is None or dj[0] != (plan[0][0] if plan else dj[0]):
+                    plan = None
+                    break
+                plan.append(dj)
+        if plan is None:
+            lml = np.array([self.log_likelihood(t) for t in thetas])
+            grad = np.array([self.neg_log_likelihood_gradient(t, component=component) for t in thetas]) \
+                if with_gradient else None
+            return lml, grad
+        x = self.data.x_data
+        n, dim = x.shape
+        y = self.data.y_data
+        m = self.prior.compute_mean(x, thetas[0])
+        y_mean = y - m[:, None]
+        P = np.array([pl[1] for pl in plan])
+        from . import kernels as K
+        try:
+            alpha, logdet, traces, info = ops.lml_population(
+                plan[0][0], self.data.x_device(), P[:, 0], P[:, 1:1 + dim], P[:, -1], L.to_dev(self.likelihood.V),
+                L.to_dev(np.ascontiguousarray(y_mean.T)), want_grad=with_gradient, component=component,
+                bounds=K.point_bounds(x))
+        except L.NativeLibraryError:
+            raise
+        bad = np.nonzero(info)[0]
+        if bad.size:
+            b = int(bad[0])
+            raise Exception(f"Linear algebra failed for hyperparameters {thetas[b]}: "
+                            f"{L.NonPositiveDefiniteError(int(info[b]), n)}")
+        lml = np.empty(B)
+        for b in range(B):
+            KVinvY = alpha[b].T.copy()
+            l1 = np.sum(y_mean * KVinvY) / y_mean.shape[1]
+            lml[b] = -0.5 * (l1 + logdet[b] + n * np.log(2.0 * np.pi))
+        grad = None
+        if with_gradient:
+            grad = np.array([0.5 * (traces[b] @ plan[b][2]) for b in range(B)])
+        return lml, grad
+
+    def log_likelihood_population(self, thetas):
+        return self.evaluate_population(thetas, with_gradient=False)[0]
+
+    def neg_log_likelihood_gradient_population(self, thetas, component=0):
+        return self.evaluate_population(thetas, with_gradient=True, component=component)[1]
 
     def _gradient_sharded(self, hps, ev, component):
         """Block-cyclic multi-GPU path (fvgp_b200/sharded.py): distributed TRTRI + LAUUM, block traces, one
@@ -194,15 +296,19 @@ class GPMarginalLikelihood:
 
     # ------------------------------------------------------------------------------------------
     def neg_log_likelihood_hessian(self, hyperparameters=None):
-        """Forward finite difference of the gradient, eps = 1e-6 (:312-336)."""
+        """Forward finite difference of the gradient, eps = 1e-6 (:312-336); the H + 1 gradients are one population."""
         hps = np.asarray(self.trainer.hyperparameters if hyperparameters is None else hyperparameters, dtype=float)
         H = len(hps)
         out = np.zeros((H, H))
-        g0 = self.neg_log_likelihood_gradient(hyperparameters=hps)
+        pts = np.tile(hps, (H + 1, 1))
         for i in range(H):
-            hp = np.array(hps)
-            hp[i] += 1e-6
-            out[i, i:] = ((self.neg_log_likelihood_gradient(hyperparameters=hp) - g0) / 1e-6)[i:]
+            pts[1 + i, i] += 1e-6
+        if self.population_supported(want_grad=True):
+            g = self.neg_log_likelihood_gradient_population(pts)
+        else:
+            g = np.array([self.neg_log_likelihood_gradient(hyperparameters=p) for p in pts])
+        for i in range(H):
+            out[i, i:] = ((g[1 + i] - g[0]) / 1e-6)[i:]
         return out + out.T - np.diag(np.diag(out))
 
     def test_log_likelihood_gradient(self, hyperparameters, epsilon=1e-6):

@@ -23,10 +23,20 @@ class GPtraining:
     def train(self, objective_function=None, objective_function_gradient=None, objective_function_hessian=None,
               hyperparameter_bounds=None, init_hyperparameters=None, method="global", pop_size=20, tolerance=0.0001,
               max_iter=120, local_optimizer="L-BFGS-B", global_optimizer="genetic", constraints=(), mcmc_prior=None,
-              mcmc_prop_distrs="normal", mcmc_args={}, bo_args=None, dask_client=None, info=False):
+              mcmc_prop_distrs="normal", mcmc_args={}, bo_args=None, dask_client=None, info=False,
+              population_objective=None):
         if not self._in_bounds(init_hyperparameters, hyperparameter_bounds):
             raise Exception("Starting positions outside of optimization bounds.", init_hyperparameters,
                             hyperparameter_bounds)
+        if method == "global" and population_objective is not None:
+            # A whole generation per call: scipy hands the trial population over as (H, S) and the S proposals run
+            # on concurrent streams (GPMarginalLikelihood.evaluate_population).  `vectorized` implies deferred
+            # updating (the best member is refreshed once per generation, not after every individual).
+            res = differential_evolution(lambda X: population_objective(np.atleast_2d(X.T)), hyperparameter_bounds,
+                                         maxiter=max_iter, popsize=pop_size, tol=tolerance, disp=info, polish=False,
+                                         x0=init_hyperparameters.reshape(1, -1)[0], constraints=constraints,
+                                         vectorized=True, updating="deferred")
+            return np.array(res["x"])
         if method == "global":
             res = differential_evolution(objective_function, hyperparameter_bounds, maxiter=max_iter, popsize=pop_size,
                                          tol=tolerance, disp=info, polish=False,

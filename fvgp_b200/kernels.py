@@ -39,6 +39,10 @@ def _device_points(x):
     return L.to_dev(x)
 
 
+def _is_scalar(s):
+    return np.isscalar(s) or (isinstance(s, np.ndarray) and s.ndim == 0)
+
+
 class _Lazy:
     """Base of the lazy covariance expressions."""
     ndim = 2
@@ -55,7 +59,30 @@ class _Lazy:
         buf, _ = self.materialize()
         return buf[:, :self.shape[1]]
 
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """numpy scalars / arrays on the LEFT of an operator (`hps[0] * squared_exponential_kernel(...)`: hps[0] is
+        an np.float64) reach numpy's ufunc machinery first; without this hook numpy would convert the lazy
+        expression through __array__ and the product would silently leave the fused path.  Scalar multiples of a
+        radial expression stay lazy; everything else materialises and applies the ufunc."""
+        if method == "__call__" and not kwargs and len(inputs) == 2:
+            a, b = inputs
+            if ufunc is np.multiply:
+                if isinstance(a, Radial) and _is_scalar(b):
+                    return a * b
+                if isinstance(b, Radial) and _is_scalar(a):
+                    return b * a
+            if ufunc is np.true_divide and isinstance(a, Radial) and _is_scalar(b):
+                return a / b
+        arrs = [np.asarray(i) if isinstance(i, _Lazy) else i for i in inputs]
+        return getattr(ufunc, method)(*arrs, **kwargs)
+
     # numpy-style fallbacks: any arithmetic we cannot fold materialises on the host
+    def __neg__(self):
+        return -np.asarray(self)
+
+    def __rtruediv__(self, other):
+        return np.asarray(other) / np.asarray(self)
+
     def __add__(self, other):
         return np.asarray(self) + np.asarray(other)
 
@@ -123,14 +150,14 @@ class Radial(_Lazy):
         self.shape = dist.shape
 
     def __mul__(self, s):
-        if np.isscalar(s) or (isinstance(s, np.ndarray) and s.ndim == 0):
+        if _is_scalar(s):
             return Radial(self.dist, self.kind, self.length, self.amp * float(s))
         return np.asarray(self) * np.asarray(s)
 
     __rmul__ = __mul__
 
     def __truediv__(self, s):
-        if np.isscalar(s):
+        if _is_scalar(s):
             return Radial(self.dist, self.kind, self.length, self.amp / float(s))
         return np.asarray(self) / np.asarray(s)
 

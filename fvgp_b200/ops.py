@@ -208,6 +208,63 @@ def potri(factor):
     return factor
 
 
+def population_slots(n, dim, want_grad, batch):
+    """Concurrent evaluation slots for a population of `batch` proposals: enough chains in flight to fill the SMs at
+    small N, bounded by 1/4 of the free HBM and by the streams the hardware keeps independent."""
+    lib = L.load()
+    torch = L._torch()
+    slot_bytes = 8 * int(lib.fvgp_population_slot_len(n, dim, int(want_grad)))
+    free, _total = torch.cuda.mem_get_info()
+    by_mem = max(1, int(0.25 * free) // max(slot_bytes, 1))
+    by_size = 32 if n <= 2048 else (16 if n <= 4096 else (8 if n <= 8192 else (4 if n <= 16384 else 2)))
+    return int(max(1, min(batch, by_mem, by_size)))
+
+
+def lml_population(kind, x, amps, inv_scales, lengths, noise, rhs_t, want_grad=False, component=0, bounds=None,
+                   slots=None):
+    """K-fill -> POTRF -> POTRS -> logdet (-> POTRI -> fused gradient traces) for B proposals of one radial family on
+    concurrent streams, ONE host synchronisation (include/fvgp_b200.h: fvgp_lml_population).
+
+    x (n, dim) device; amps (B,), inv_scales (B, dim), lengths (B,) host; noise (n,) device or None; rhs_t (nrhs, n)
+    device = (y - m)^T.  Returns alpha (B, nrhs, n), logdet (B,), traces (B, dim + 2) or None, info (B,) int32."""
+    lib = L.load()
+    torch = L._torch()
+    n, dim = x.shape
+    amps = np.ascontiguousarray(amps, dtype=np.float64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.float64)
+    inv_scales = np.ascontiguousarray(inv_scales, dtype=np.float64).reshape(len(amps), dim)
+    B = len(amps)
+    nrhs = rhs_t.shape[0]
+    assert rhs_t.is_contiguous() and rhs_t.shape[1] == n and 1 <= nrhs <= 4
+    centre = None
+    if bounds is not None:                 # the centred fill must be safe for EVERY proposal
+        centre = fill_centre(kind, inv_scales.max(axis=0), float(lengths.min()), bounds)
+    if centre is not None:
+        _keep, centre_p = L.dvec(centre)
+    else:
+        centre_p = None
+    if slots is None:
+        slots = population_slots(n, dim, want_grad, B)
+    slots = int(max(1, min(slots, B)))
+    work = L.dev_empty((slots * int(lib.fvgp_population_slot_len(n, dim, int(want_grad))),))
+    alpha_d = L.dev_empty((B, nrhs, n))
+    res_d = L.dev_empty((B, dim + 2))
+    info_d = torch.empty(B, dtype=torch.int32, device="cuda")
+    alpha = np.empty((B, nrhs, n))
+    logdet = np.empty(B)
+    traces = np.zeros((B, dim + 2))
+    info = np.zeros(B, dtype=np.int32)
+    dp = ctypes.POINTER(c_double)
+    with _Phase("population"):
+        L.check(lib.fvgp_lml_population(int(kind), L.ptr(x), n, dim, B, amps.ctypes.data_as(dp),
+                                        inv_scales.ctypes.data_as(dp), lengths.ctypes.data_as(dp), centre_p,
+                                        L.ptr(noise), L.ptr(rhs_t), nrhs, int(bool(want_grad)), int(component), slots,
+                                        L.ptr(work), L.ptr(alpha_d), L.ptr(res_d), L.ptr(info_d), alpha.ctypes.data_as(dp),
+                                        logdet.ctypes.data_as(dp), traces.ctypes.data_as(dp),
+                                        info.ctypes.data_as(ctypes.POINTER(c_int)), L.stream_ptr()), "fvgp_lml_population")
+    return alpha, logdet, (traces if want_grad else None), info
+
+
 def dot(a, b):
     lib = L.load()
     scratch = L.dev_empty((1,))

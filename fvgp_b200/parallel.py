@@ -70,11 +70,24 @@ def gather_results(local, num, width):
 
 
 def evaluate_proposals(gp, thetas, with_gradient=True):
-    """Evaluate LML (+ gradient) for every row of `thetas`, sharded over the ranks."""
+    """Evaluate LML (+ gradient) for every row of `thetas`, sharded over the ranks; each rank pushes its share through
+    the population entry point (concurrent streams, one synchronisation) when the GP offers it."""
     rank, _, world = dist_env()
+    thetas = np.asarray(thetas, dtype=np.float64)
     H = thetas.shape[1]
+    mine = shard_proposals(len(thetas), rank, world)
     local = {}
-    for i in shard_proposals(len(thetas), rank, world):
+    ml = getattr(gp, "marginal_likelihood", None)
+    if mine and ml is not None and hasattr(ml, "evaluate_population"):
+        lml, grad = ml.evaluate_population(thetas[mine], with_gradient=with_gradient)
+        for k, i in enumerate(mine):
+            row = np.zeros(1 + H)
+            row[0] = lml[k]
+            if with_gradient:
+                row[1:] = grad[k]
+            local[i] = row
+        return gather_results(local, len(thetas), 1 + H)
+    for i in mine:
         row = np.zeros(1 + H)
         row[0] = gp.log_likelihood(thetas[i])
         if with_gradient:

@@ -135,6 +135,31 @@ int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratc
  * (gp_marginal_likelihood.py:273-274): lower triangle of d_L <- lower triangle of (L L^T)^-1. */
 int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_work, void* stream);
 
+/* ---- population evaluation: B hyperparameter proposals of one radial kernel family on the same points.
+ * Replaces the per-individual objective calls of the optimisers -- scipy differential_evolution generations
+ * (gp_training.py:60-80), hgdl / multi-start local walkers, the H+1 gradient calls of the finite-difference Hessian
+ * (gp_marginal_likelihood.py:312-336) -- each of which is one compute_new_KVlogdet_KVinvY (gp_kv.py:574-631) plus,
+ * with want_grad, one neg_log_likelihood_gradient (gp_marginal_likelihood.py:224-309).  At the sizes where training
+ * loops are hot (N ~ 1e3..1e4) one evaluation is a latency-bound chain of small launches that leaves the GPU nearly
+ * empty; here proposal b runs K-fill -> POTRF -> POTRS -> logdet (-> POTRI -> fused traces) on stream b % slots with
+ * its own workspace slot, so up to `slots` chains overlap, and the host synchronises ONCE for the whole population.
+ * The arithmetic of every proposal is exactly that of the one-at-a-time entry points (same kernels, same order).
+ *   kind, h_amp[b], h_inv_scale[b*dim + i], h_length[b]: K_b = amp_b * f(||(x - x') * inv_scale_b|| / length_b)
+ *   h_centre: dim doubles or NULL, as fvgp_kfill_dense (must be valid for every proposal)
+ *   d_noise:  n doubles or NULL, added to the diagonal;  d_rhs: nrhs x n (row = one right-hand side, y - m), nrhs <= 4
+ *   d_work:   slots * fvgp_population_slot_len(n, dim, want_grad) doubles
+ *   d_alpha:  batch * nrhs * n doubles (device), h_alpha the same on the host: KV_b^-1 rhs
+ *   d_res:    batch * (dim + 2) doubles, d_info: batch ints (device scratch)
+ *   h_logdet[b] = log|KV_b|;  h_info[b] = 0, or the 1-based failing pivot when KV_b is not positive definite (its other
+ *   outputs are then undefined);  h_traces[b*(dim+2) ..] (want_grad) = sums of (KV_b^-1 - a a^T) o dK/dp over
+ *   p = (amp, inv_scale_1..dim, length) with a = column grad_component of alpha_b, as fvgp_kgrad_trace_radial. */
+int64_t fvgp_population_slot_len(int64_t n, int dim, int want_grad);
+int fvgp_lml_population(int kind, const double* d_x, int64_t n, int dim, int batch, const double* h_amp,
+                        const double* h_inv_scale, const double* h_length, const double* h_centre,
+                        const double* d_noise, const double* d_rhs, int nrhs, int want_grad, int grad_component,
+                        int slots, double* d_work, double* d_alpha, double* d_res, int* d_info, double* h_alpha,
+                        double* h_logdet, double* h_traces, int* h_info, void* stream);
+
 /* ---- building blocks of the 2-D block-cyclic multi-GPU factorisation (fvgp_b200/sharded.py).
  * Each is the single-GPU piece of one step of the distributed POTRF / POTRS / POTRI that replaces
  * calculate_Chol_factor / calculate_Chol_solve / the gradient's KV^-1 when KV exceeds one HBM. */

@@ -102,6 +102,14 @@ def test_lazy_kernel_algebra():
     assert K.exponential_kernel(a, 1.0).kind == L.K_EXP
     w = K.wendland_anisotropic_gp2Scale_cpu(x, x, np.array([1.0, .1, .1]))
     assert isinstance(w, K.SparseWendland) and w.same
+    # hyperparameters arrive as numpy scalars (hps[0] of an ndarray): numpy's operators run first and must hand the
+    # product back to the lazy expression instead of converting it through __array__ (which would leave the fused path)
+    h = np.array([1.3, 0.4, 0.6])
+    r = h[0] * K.squared_exponential_kernel(d, h[1])
+    assert isinstance(r, K.Radial) and r.amp == 1.3 and r.length == 0.4
+    r = h[0] ** 2 * K.matern_kernel_diff2(K.get_anisotropic_distance_matrix(x, x, h[1:3]), 1.0) / np.float64(2.0)
+    assert isinstance(r, K.Radial) and r.amp == 1.3 ** 2 / 2.0 and np.allclose(r.dist.inv_scale, 1.0 / h[1:3])
+    assert isinstance(np.array(2.0) * r, K.Radial) and isinstance(np.multiply(r, h[0]), K.Radial)
 
 
 def test_gp2scale_mode_thresholds():

@@ -428,3 +428,84 @@ def test_fused_gradient_for_named_user_kernels(fv):
             dK = (np_kernel(name, x, x, hp) - np_kernel(name, x, x, hm)) / 2e-6
             ref[i] = -0.5 * (b @ dK @ b - np.sum(Kinv * dK))
         assert np.max(np.abs(grad - ref) / np.abs(ref)) <= 2e-6, (name, grad, ref)
+
+
+def _pop_problem(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, d))
+    y = np.sin(5 * x[:, 0]) + (np.cos(3 * x[:, 1]) if d > 1 else 0.0) + 0.1 * rng.standard_normal(n)
+    return x, y, np.full(n, 1e-2)
+
+
+def test_population_matches_one_at_a_time(fv):
+    """B proposals on concurrent streams (fvgp_lml_population) give, proposal by proposal, the LML of
+    GP.log_likelihood to the last bit (same kernels, same order, quadratic form summed on the host the same way) and
+    the gradient of GP.neg_log_likelihood_gradient; both are also pinned to the oracle (1e-8)."""
+    from fvgp_b200 import GP
+    from oracle import fvgp_oracle as orc
+    for n, d, B in ((700, 3, 9), (1000, 1, 40), (2500, 2, 5)):
+        x, y, nz = _pop_problem(n, d, 100 + n)
+        h0 = np.array([1.0] + [0.3] * d)
+        gp = GP(x, y, init_hyperparameters=h0, noise_variances=nz)
+        assert gp.marginal_likelihood.population_supported(want_grad=True)
+        rng = np.random.default_rng(n)
+        T = h0 * (0.7 + 0.6 * rng.random((B, d + 1)))
+        lml_pop, grad_pop = gp.marginal_likelihood.evaluate_population(T, with_gradient=True)
+        lml_only = gp.log_likelihood_population(T)
+        for b in range(B):
+            one = gp.log_likelihood(T[b])
+            assert lml_pop[b] == one and lml_only[b] == one, (n, b, lml_pop[b], lml_only[b], one)
+            g = gp.neg_log_likelihood_gradient(T[b])
+            assert rel(grad_pop[b], g) <= 1e-9, (n, b, grad_pop[b], g)
+        for b in (0, B - 1):
+            assert abs(lml_pop[b] / orc.dense_log_likelihood(x, y, T[b], nz) - 1) <= 1e-8
+            assert rel(grad_pop[b], orc.dense_neg_log_likelihood_gradient(x, y, T[b], nz, economical=True)) <= 1e-8
+
+
+def test_population_user_kernel_hessian_and_failures(fv):
+    from fvgp_b200 import GP
+    from fvgp_b200.kernels import get_anisotropic_distance_matrix, matern_kernel_diff2
+    x, y, nz = _pop_problem(600, 2, 7)
+    kern = lambda a, b, h: h[0] * matern_kernel_diff2(get_anisotropic_distance_matrix(a, b, h[1:3]), 1.0)   # noqa: E731
+    h = np.array([1.2, 0.4, 0.5])
+    gp = GP(x, y, init_hyperparameters=h, noise_variances=nz, kernel_function=kern)
+    ml = gp.marginal_likelihood
+    assert ml.population_supported(want_grad=True)
+    T = h * np.array([[1.0, 1.0, 1.0], [1.1, 0.9, 1.2], [0.8, 1.3, 0.7]])
+    lml, grad = ml.evaluate_population(T, with_gradient=True)
+    for b in range(3):
+        assert lml[b] == gp.log_likelihood(T[b])
+        assert rel(grad[b], gp.neg_log_likelihood_gradient(T[b])) <= 1e-8
+    # Hessian: H + 1 gradients as one population == the reference's forward differences of single gradients
+    Hm = gp.neg_log_likelihood_hessian(h)
+    g0 = gp.neg_log_likelihood_gradient(h)
+    for i in range(3):
+        hp = h.copy()
+        hp[i] += 1e-6
+        row = (gp.neg_log_likelihood_gradient(hp) - g0) / 1e-6
+        assert np.allclose(Hm[i, i:], row[i:], rtol=1e-4, atol=1e-4 * np.abs(Hm).max())
+    assert np.array_equal(Hm, Hm.T)
+    # a proposal whose matrix is not positive definite is reported like the one-at-a-time path (raises)
+    bad = np.array([[1.0, 0.4, 0.5], [-1.0, 0.4, 0.5]])                  # negative amplitude: first pivot < 0
+    with pytest.raises(Exception, match="Linear algebra failed"):
+        gp.log_likelihood_population(bad)
+    with pytest.raises(Exception, match="Linear algebra failed"):
+        gp.log_likelihood(bad[1])
+    assert lml[0] == gp.log_likelihood_population(T)[0]                   # the evaluator is usable afterwards
+    # kernels that do not fold into a fused radial expression fall back to one-at-a-time evaluation
+    gpa = GP(x, y, init_hyperparameters=h, noise_variances=nz,
+             kernel_function=lambda a, b, hh: np.asarray(kern(a, b, hh)) + 0.0)
+    assert not gpa.marginal_likelihood.population_supported()
+    assert rel(gpa.log_likelihood_population(T), lml) <= 1e-12
+
+
+def test_train_global_uses_the_population_path(fv):
+    from fvgp_b200 import GP, ops
+    x, y, nz = _pop_problem(500, 1, 3)
+    gp = GP(x, y, init_hyperparameters=np.array([1.0, 0.3]), noise_variances=nz)
+    ops.start_phase_timing()
+    before = gp.log_likelihood()
+    hps = gp.train(hyperparameter_bounds=np.array([[0.05, 10.0], [0.02, 5.0]]), method="global", max_iter=6, pop_size=8)
+    phases = ops.stop_phase_timing()
+    assert "population" in phases and gp.log_likelihood() >= before
+    assert np.all(hps >= [0.05, 0.02]) and np.all(hps <= [10.0, 5.0])
