@@ -446,6 +446,24 @@ def run_c1(args):
     print(json.dumps(line), flush=True)
 
 
+def gemm_dram_traffic(n):
+    """Bytes the DMMA GEMM launches of one N = 50 000 evaluation moved through DRAM, from the committed ncu launch list
+    (tools/launch_summary.py JSON); None when no capture exists for this size."""
+    import glob
+    if n != 50000:
+        return None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "launches_bench_n50k*.json")), reverse=True):
+        try:
+            with open(path) as fh:
+                d = json.load(fh)
+            tot = sum(v["dram_read"] + v["dram_write"] for k, v in d["kernels"].items() if "dgemm_mma_kernel" in k)
+            if tot > 0:
+                return float(tot)
+        except Exception:
+            continue
+    return None
+
+
 def workload_config(args):
     return {"workload": f"C2: single-task GP, 3-D input, N={args.n}, anisotropic Matern-3/2 (default kernel), dense FP64 "
                         f"Cholesky, LML + hyperparameter gradient per step",
@@ -549,9 +567,9 @@ def main():
     achieved = n ** 3 / t_tensor / 1e12
     roofline = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri", "achieved": achieved,
                 "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
-                # thousands of GEMM launches of different shapes per step: no single per-launch DRAM figure; one
-                # 8192^3 launch moves 7.1 GB (profiles/r01/ncu_gemm.v1.summary.txt), 2.7 % of DRAM throughput
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum summed over every dgemm_mma_kernel launch of ONE timed
+                # evaluation (ncu launch list of this command, profiles/r01/launches_bench_n50k.*.json)
+                "traffic": gemm_dram_traffic(n),
                 "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
                 "algorithmic_flops_per_step": float(n) ** 3,
                 "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}

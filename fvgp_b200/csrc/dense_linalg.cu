@@ -43,8 +43,9 @@ constexpr size_t POTRF_TILE_SMEM = (size_t(TS) * TP + 2 * (TS / 2) * HP + 2 * TS
 // so that every triangular solve against this tile is ONE tensor-core GEMM with K = 128.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) potrf_tile_kernel(double* A, long long ld, int nt, double* dinv,
-                                                         int* info, int global_row0) {
+                                                         int* info, int global_row0, long long bstride) {
   extern __shared__ __align__(16) double tile_smem[];
+  A += blockIdx.x * bstride, dinv += blockIdx.x * bstride, info += blockIdx.x;  // one CTA per problem of a batch
   double(*T)[TP] = reinterpret_cast<double(*)[TP]>(tile_smem);
   double(*InvA)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP);
   double(*InvD)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP + (TS / 2) * HP);
@@ -166,8 +167,9 @@ constexpr int PW = 16;  // panel width
 constexpr size_t POTRF_TILE2_SMEM = POTRF_TILE_SMEM + size_t(PW) * TS * sizeof(double);  // ~214 KB
 
 __global__ void __launch_bounds__(512) potrf_tile2_kernel(double* A, long long ld, int nt, double* dinv, int* info,
-                                                          int global_row0) {
+                                                          int global_row0, long long bstride) {
   extern __shared__ __align__(16) double tile_smem[];
+  A += blockIdx.x * bstride, dinv += blockIdx.x * bstride, info += blockIdx.x;  // one CTA per problem of a batch
   double(*T)[TP] = reinterpret_cast<double(*)[TP]>(tile_smem);
   double(*InvA)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP);
   double(*InvD)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP + (TS / 2) * HP);
@@ -326,7 +328,9 @@ static bool use_tile_v1() {
 }
 
 // dst (rows x cols, ldd) <- src (lds)
-__global__ void copy2d_kernel(double* dst, long long ldd, const double* src, long long lds, int rows, int cols) {
+__global__ void copy2d_kernel(double* dst, long long ldd, const double* src, long long lds, int rows, int cols,
+                              long long bstride) {
+  dst += blockIdx.z * bstride, src += blockIdx.z * bstride;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r0 = blockIdx.y * 16;
   if (c >= cols) return;
@@ -335,7 +339,8 @@ __global__ void copy2d_kernel(double* dst, long long ldd, const double* src, lon
 
 // Zero the strict upper part inside every 128x128 diagonal block (the GEMM k-trims assume
 // triangular operands carry explicit zeros there).
-__global__ void zero_upper_diag_blocks_kernel(double* A, long long ld, int n) {
+__global__ void zero_upper_diag_blocks_kernel(double* A, long long ld, int n, long long bstride) {
+  A += blockIdx.y * bstride;
   const int b0 = blockIdx.x * BM;
   for (int idx = threadIdx.x; idx < BM * BM; idx += blockDim.x) {
     const int r = idx / BM, c = idx % BM;
@@ -362,7 +367,9 @@ __device__ __forceinline__ void stage_inverse_block(const double* __restrict__ d
 }
 
 __global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict__ L, long long ld, int n, int j0,
-                                                       const double* __restrict__ dinv, double* w, double* z) {
+                                                       const double* __restrict__ dinv, double* w, double* z,
+                                                       long long bstride) {
+  L += blockIdx.y * bstride, dinv += blockIdx.y * bstride, w += blockIdx.y * bstride, z += blockIdx.y * bstride;
   __shared__ double S[VS][VSP];
   __shared__ double yj[VS], zj[VS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -395,7 +402,8 @@ __global__ void __launch_bounds__(256) fwd_step_kernel(const double* __restrict_
 
 __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict__ L, long long ld, int n, int j0,
                                                        const double* __restrict__ dinv, double* z, double* x,
-                                                       int c_begin) {
+                                                       int c_begin, long long bstride) {
+  L += blockIdx.y * bstride, dinv += blockIdx.y * bstride, z += blockIdx.y * bstride, x += blockIdx.y * bstride;
   __shared__ double S[VS][VSP];
   __shared__ double zj[VS], xj[VS];
   const int tid = threadIdx.x;
@@ -432,7 +440,9 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(1024) logdet_kernel(const double* __restrict__ L, long long ld, int n, double* out) {
+__global__ void __launch_bounds__(1024) logdet_kernel(const double* __restrict__ L, long long ld, int n, double* out,
+                                                      long long bstride) {
+  L += blockIdx.x * bstride, out += blockIdx.x * bstride;
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 1024) s += log(fabs(L[(long long)i * ld + i]));
@@ -456,7 +466,9 @@ __global__ void __launch_bounds__(1024) dot_kernel(const double* __restrict__ a,
 // ----------------------------------------------------------------------------------------------
 // y[i] += alpha * sum_j A[i][j] x[j]; one warp per row.
 __global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ A, long long lda, int m, int n,
-                                                     double alpha, const double* __restrict__ x, double* y) {
+                                                     double alpha, const double* __restrict__ x, double* y,
+                                                     long long bstride) {
+  A += blockIdx.y * bstride, x += blockIdx.y * bstride, y += blockIdx.y * bstride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long i = (long long)blockIdx.x * 8 + warp; i < m; i += (long long)gridDim.x * 8) {
     const double* row = A + i * lda;
@@ -470,7 +482,9 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ 
 // partial[chunk][j] = sum_{i in chunk} A[i][j] x[i]; thread = column, CTA = (column group, row chunk).
 constexpr int GEMVT_ROWS = 256;
 __global__ void __launch_bounds__(256) gemv_t_partial_kernel(const double* __restrict__ A, long long lda, int m, int n,
-                                                             const double* __restrict__ x, double* partial) {
+                                                             const double* __restrict__ x, double* partial,
+                                                             long long bstride) {
+  A += blockIdx.z * bstride, x += blockIdx.z * bstride, partial += blockIdx.z * bstride;
   __shared__ double xs[GEMVT_ROWS];
   const int j = blockIdx.x * 256 + threadIdx.x;
   const int i0 = blockIdx.y * GEMVT_ROWS, i1 = min(m, i0 + GEMVT_ROWS);
@@ -488,7 +502,8 @@ __global__ void __launch_bounds__(256) gemv_t_partial_kernel(const double* __res
 }
 
 __global__ void __launch_bounds__(256) gemv_t_reduce_kernel(const double* __restrict__ partial, int chunks, int n,
-                                                            double alpha, double* y) {
+                                                            double alpha, double* y, long long bstride) {
+  partial += blockIdx.y * bstride, y += blockIdx.y * bstride;
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= n) return;
   double s = 0.0;
@@ -505,6 +520,8 @@ struct Ctx {
   int* info;
   double* work;        // scratch panel for trtri / lauum
   int err;
+  int batch = 1;       // > 1: every launch covers `batch` problems of identical shape (population evaluation) whose
+  long long bstride = 0;  // buffers (matrix, tile inverses, scratch) sit `bstride` doubles apart; info is an int per problem
 };
 
 static inline int split(int n) {  // n > TS: first part is a multiple of 128, at least 128, less than n
@@ -525,11 +542,12 @@ static int trsm_rt_rec(Ctx& c, double* B, long long ldb, int m, const double* L,
   if (m <= 0) return 0;
   if (n <= TS) {
     const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
-    return launch_gemm<false, false>(c.st, B, ldb, tile, TS, B, ldb, m, n, n, 1.0, 0.0, 0);
+    return launch_gemm<false, false>(c.st, B, ldb, tile, TS, B, ldb, m, n, n, 1.0, 0.0, 0, c.batch, c.bstride);
   }
   const int n1 = split(n), n2 = n - n1;
   REC_OK(trsm_rt_rec(c, B, ldb, m, L, ld, n1, row0));
-  REC_OK((launch_gemm<false, false>(c.st, B, ldb, L + (long long)n1 * ld, ld, B + n1, ldb, m, n2, n1, -1.0, 1.0, 0)));
+  REC_OK((launch_gemm<false, false>(c.st, B, ldb, L + (long long)n1 * ld, ld, B + n1, ldb, m, n2, n1, -1.0, 1.0, 0, c.batch,
+                                    c.bstride)));
   return trsm_rt_rec(c, B + n1, ldb, m, L + (long long)n1 * ld + n1, ld, n2, row0 + n1);
 }
 
@@ -538,19 +556,22 @@ static int trsm_rn_rec(Ctx& c, double* B, long long ldb, int m, const double* L,
   if (m <= 0) return 0;
   if (n <= TS) {
     const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
-    return launch_gemm<false, true>(c.st, B, ldb, tile, TS, B, ldb, m, n, n, 1.0, 0.0, 0);
+    return launch_gemm<false, true>(c.st, B, ldb, tile, TS, B, ldb, m, n, n, 1.0, 0.0, 0, c.batch, c.bstride);
   }
   const int n1 = split(n), n2 = n - n1;
   REC_OK(trsm_rn_rec(c, B + n1, ldb, m, L + (long long)n1 * ld + n1, ld, n2, row0 + n1));
-  REC_OK((launch_gemm<false, true>(c.st, B + n1, ldb, L + (long long)n1 * ld, ld, B, ldb, m, n1, n2, -1.0, 1.0, 0)));
+  REC_OK((launch_gemm<false, true>(c.st, B + n1, ldb, L + (long long)n1 * ld, ld, B, ldb, m, n1, n2, -1.0, 1.0, 0, c.batch,
+                                   c.bstride)));
   return trsm_rn_rec(c, B, ldb, m, L, ld, n1, row0);
 }
 
 static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
   if (n <= TS) {
     double* tile_inv = c.dinv + (long long)(row0 / TS) * TS * TS;
-    if (use_tile_v1()) launch(potrf_tile_kernel, 1, 512, POTRF_TILE_SMEM, c.st, A, ld, n, tile_inv, c.info, row0);
-    else launch(potrf_tile2_kernel, 1, 512, POTRF_TILE2_SMEM, c.st, A, ld, n, tile_inv, c.info, row0);
+    if (use_tile_v1())
+      launch(potrf_tile_kernel, c.batch, 512, POTRF_TILE_SMEM, c.st, A, ld, n, tile_inv, c.info, row0, c.bstride);
+    else
+      launch(potrf_tile2_kernel, c.batch, 512, POTRF_TILE2_SMEM, c.st, A, ld, n, tile_inv, c.info, row0, c.bstride);
     FVGP_LAUNCH_OK();
     return 0;
   }
@@ -559,7 +580,7 @@ static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
   double* A22 = A21 + n1;
   REC_OK(potrf_rec(c, A, ld, n1, row0));
   REC_OK(trsm_rt_rec(c, A21, ld, n2, A, ld, n1, row0));
-  REC_OK((launch_gemm<false, false>(c.st, A21, ld, A21, ld, A22, ld, n2, n2, n1, -1.0, 1.0, GEMM_LOWER)));
+  REC_OK((launch_gemm<false, false>(c.st, A21, ld, A21, ld, A22, ld, n2, n2, n1, -1.0, 1.0, GEMM_LOWER, c.batch, c.bstride)));
   return potrf_rec(c, A22, ld, n2, row0 + n1);
 }
 
@@ -657,7 +678,7 @@ static int potrf_block_width(int n) {
 static int trtri_rec(Ctx& c, double* L, long long ld, int n, int row0) {
   if (n <= TS) {
     const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
-    launch(copy2d_kernel, dim3(1, (n + 15) / 16), 128, 0, c.st, L, ld, tile, TS, n, n);
+    launch(copy2d_kernel, dim3(1, (n + 15) / 16, c.batch), 128, 0, c.st, L, ld, tile, TS, n, n, c.bstride);
     FVGP_LAUNCH_OK();
     return 0;
   }
@@ -667,23 +688,23 @@ static int trtri_rec(Ctx& c, double* L, long long ld, int n, int row0) {
   REC_OK(trtri_rec(c, L, ld, n1, row0));
   REC_OK(trtri_rec(c, L22, ld, n2, row0 + n1));
   // W = L21 * M11   (M11 lower: k >= column)
-  REC_OK((launch_gemm<false, true>(c.st, L21, ld, L, ld, c.work, n1, n2, n1, n1, 1.0, 0.0, GEMM_KB_FROM_N)));
+  REC_OK((launch_gemm<false, true>(c.st, L21, ld, L, ld, c.work, n1, n2, n1, n1, 1.0, 0.0, GEMM_KB_FROM_N, c.batch, c.bstride)));
   // L21 = -M22 * W  (M22 lower: k <= row)
-  return launch_gemm<false, true>(c.st, L22, ld, c.work, n1, L21, ld, n2, n1, n2, -1.0, 0.0, GEMM_KE_FROM_M);
+  return launch_gemm<false, true>(c.st, L22, ld, c.work, n1, L21, ld, n2, n1, n2, -1.0, 0.0, GEMM_KE_FROM_M, c.batch, c.bstride);
 }
 
 // lower(M) <- lower(M^T M) in place.
 static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
-  if (n <= BM) return launch_gemm<true, true>(c.st, M, ld, M, ld, M, ld, n, n, n, 1.0, 0.0, 0);
+  if (n <= BM) return launch_gemm<true, true>(c.st, M, ld, M, ld, M, ld, n, n, n, 1.0, 0.0, 0, c.batch, c.bstride);
   const int n1 = split(n), n2 = n - n1;
   double* M21 = M + (long long)n1 * ld;
   double* M22 = M21 + n1;
   REC_OK(lauum_rec(c, M, ld, n1));
   // P11 += M21^T M21
-  REC_OK((launch_gemm<true, true>(c.st, M21, ld, M21, ld, M, ld, n1, n1, n2, 1.0, 1.0, GEMM_LOWER)));
+  REC_OK((launch_gemm<true, true>(c.st, M21, ld, M21, ld, M, ld, n1, n1, n2, 1.0, 1.0, GEMM_LOWER, c.batch, c.bstride)));
   // W = M22^T M21  (M22 lower: k >= row of the output)
-  REC_OK((launch_gemm<true, true>(c.st, M22, ld, M21, ld, c.work, n1, n2, n1, n2, 1.0, 0.0, GEMM_KB_FROM_M)));
-  launch(copy2d_kernel, dim3((n1 + 255) / 256, (n2 + 15) / 16), 256, 0, c.st, M21, ld, c.work, n1, n2, n1);
+  REC_OK((launch_gemm<true, true>(c.st, M22, ld, M21, ld, c.work, n1, n2, n1, n2, 1.0, 0.0, GEMM_KB_FROM_M, c.batch, c.bstride)));
+  launch(copy2d_kernel, dim3((n1 + 255) / 256, (n2 + 15) / 16, c.batch), 256, 0, c.st, M21, ld, c.work, n1, n2, n1, c.bstride);
   FVGP_LAUNCH_OK();
   return lauum_rec(c, M22, ld, n2);
 }
@@ -740,8 +761,11 @@ int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int
 // columns: inside a block the 64-wide leaf steps (tile inverse + rank-64 update of the block's own rows),
 // then ONE matrix-vector product with the whole panel below (forward) / left of (backward) the block, which
 // streams >95 % of the factor at GEMV speed instead of in 782 latency-bound slivers.  Enqueue only.
+// batch > 1: the same solve for `batch` problems; d_L, d_tileinv, d_B and d_work of problem b sit b * bstride doubles
+// further (all inside equally sized workspace slots).
 static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B,
-                     int nrhs, int64_t ldb, double* d_work) {
+                     int nrhs, int64_t ldb, double* d_work, int batch = 1, long long bstride = 0) {
+  const unsigned nb = (unsigned)batch;
   double* w = d_work;
   double* z = d_work + n;
   double* gemv_work = d_work + 2 * n;
@@ -751,18 +775,24 @@ static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda,
   const int nblocks = (int)((n + VBLK - 1) / VBLK);
   for (int r = 0; r < nrhs; ++r) {
     double* b = d_B + (int64_t)r * ldb;
-    FVGP_CUDA_OK(cudaMemcpyAsync(w, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (batch == 1) {
+      FVGP_CUDA_OK(cudaMemcpyAsync(w, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+      FVGP_CUDA_OK(cudaMemcpy2DAsync(w, bstride * sizeof(double), b, bstride * sizeof(double), n * sizeof(double), batch,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
     for (int blk = 0; blk < nblocks; ++blk) {  // L z = b
       const int b0 = blk * VBLK, b1 = (int)std::min<int64_t>(n, b0 + VBLK);
       for (int j0 = b0; j0 < b1; j0 += VS) {
         const int rest = b1 - (j0 + VS);
         const int grid = rest > 0 ? (rest + 63) / 64 : 1;
-        launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), w, z);
+        launch(fwd_step_kernel, dim3(grid, nb), 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), w, z, bstride);
       }
       if (b1 < n) {
         const int m = (int)n - b1;
         const int grid = (int)std::min<long long>(((long long)m + 7) / 8, (long long)sm_count() * 16);
-        launch(gemv_n_kernel, grid, 256, 0, st, d_L + (int64_t)b1 * lda + b0, lda, m, b1 - b0, -1.0, z + b0, w + b1);
+        launch(gemv_n_kernel, dim3(grid, nb), 256, 0, st, d_L + (int64_t)b1 * lda + b0, lda, m, b1 - b0, -1.0, z + b0,
+               w + b1, bstride);
       }
     }
     FVGP_LAUNCH_OK();
@@ -772,14 +802,14 @@ static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda,
       for (int j0 = last; j0 >= b0; j0 -= VS) {
         const int cols = j0 - b0;
         const int grid = cols > 0 ? (cols + 255) / 256 : 1;
-        launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), z, b, b0);
+        launch(bwd_step_kernel, dim3(grid, nb), 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), z, b, b0, bstride);
       }
       if (b0 > 0) {  // z[0:b0] -= L[b0:b1, 0:b0]^T x[b0:b1]
         const int m = b1 - b0;
         const int chunks = (m + GEMVT_ROWS - 1) / GEMVT_ROWS;
-        launch(gemv_t_partial_kernel, dim3((b0 + 255) / 256, chunks), 256, 0, st, d_L + (int64_t)b0 * lda, lda, m, b0,
-               b + b0, gemv_work);
-        launch(gemv_t_reduce_kernel, (b0 + 255) / 256, 256, 0, st, gemv_work, chunks, b0, -1.0, z);
+        launch(gemv_t_partial_kernel, dim3((b0 + 255) / 256, chunks, nb), 256, 0, st, d_L + (int64_t)b0 * lda, lda, m, b0,
+               b + b0, gemv_work, bstride);
+        launch(gemv_t_reduce_kernel, dim3((b0 + 255) / 256, nb), 256, 0, st, gemv_work, chunks, b0, -1.0, z, bstride);
       }
     }
     FVGP_LAUNCH_OK();
@@ -803,7 +833,7 @@ int fvgp_potrs_lower(const double* d_L, int64_t n, int64_t lda, const double* d_
 
 int fvgp_chol_logdet(const double* d_L, int64_t n, int64_t lda, double* d_scratch1, double* h_out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  launch(logdet_kernel, 1, 1024, 0, st, d_L, lda, (int)n, d_scratch1);
+  launch(logdet_kernel, 1, 1024, 0, st, d_L, lda, (int)n, d_scratch1, 0ll);
   FVGP_LAUNCH_OK();
   FVGP_CUDA_OK(cudaMemcpyAsync(h_out, d_scratch1, sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
@@ -823,7 +853,7 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
   FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   Ctx c{st, const_cast<double*>(d_tileinv), nullptr, d_work, 0};
-  launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, st, d_L, lda, (int)n);
+  launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, st, d_L, lda, (int)n, 0ll);
   FVGP_LAUNCH_OK();
   int r = trtri_rec(c, d_L, lda, (int)n, 0);
   if (r != 0) return r;
@@ -860,7 +890,7 @@ int fvgp_trtri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
   FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   Ctx c{st, const_cast<double*>(d_tileinv), nullptr, d_work, 0};
-  launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, st, d_L, lda, (int)n);
+  launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, st, d_L, lda, (int)n, 0ll);
   FVGP_LAUNCH_OK();
   return trtri_rec(c, d_L, lda, (int)n, 0);
 }
@@ -887,7 +917,7 @@ int fvgp_trsv_lower(const double* d_L, int64_t n, int64_t lda, const double* d_t
       const int j0 = t * VS;
       const int rest = (int)n - (j0 + VS);
       const int grid = rest > 0 ? (rest + 63) / 64 : 1;
-      launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), w, z);
+      launch(fwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), w, z, 0ll);
     }
     FVGP_LAUNCH_OK();
     FVGP_CUDA_OK(cudaMemcpyAsync(d_b, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -896,7 +926,7 @@ int fvgp_trsv_lower(const double* d_L, int64_t n, int64_t lda, const double* d_t
     for (int t = tiles - 1; t >= 0; --t) {
       const int j0 = t * VS;
       const int grid = j0 > 0 ? (j0 + 255) / 256 : 1;
-      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), z, d_b, 0);
+      launch(bwd_step_kernel, grid, 256, 0, st, d_L, lda, (int)n, j0, block_inv(t), z, d_b, 0, 0ll);
     }
     FVGP_LAUNCH_OK();
   }
@@ -911,23 +941,112 @@ int fvgp_gemv(int transpose, const double* d_A, int64_t lda, int m, int n, doubl
   cudaStream_t st = (cudaStream_t)stream;
   if (!transpose) {
     const int grid = (int)std::min<long long>(((long long)m + 7) / 8, (long long)sm_count() * 16);
-    launch(gemv_n_kernel, grid, 256, 0, st, d_A, lda, m, n, alpha, d_x, d_y);
+    launch(gemv_n_kernel, grid, 256, 0, st, d_A, lda, m, n, alpha, d_x, d_y, 0ll);
   } else {
     const int chunks = (m + GEMVT_ROWS - 1) / GEMVT_ROWS;
-    launch(gemv_t_partial_kernel, dim3((n + 255) / 256, chunks), 256, 0, st, d_A, lda, m, n, d_x, d_work);
-    launch(gemv_t_reduce_kernel, (n + 255) / 256, 256, 0, st, d_work, chunks, n, alpha, d_y);
+    launch(gemv_t_partial_kernel, dim3((n + 255) / 256, chunks), 256, 0, st, d_A, lda, m, n, d_x, d_work, 0ll);
+    launch(gemv_t_reduce_kernel, (n + 255) / 256, 256, 0, st, d_work, chunks, n, alpha, d_y, 0ll);
   }
   FVGP_LAUNCH_OK();
   return 0;
 }
 
-/* ---- population evaluation: many hyperparameter proposals on concurrent streams ---- */
+/* ---- population evaluation: many hyperparameter proposals per call ----
+ * Two schedules behind one entry point:
+ *   lock step (n < 6144, where one evaluation is a chain of ~70-700 launches that each fill a few SMs): the chain is
+ *     launched ONCE for a whole chunk of proposals -- every kernel of the factorisation / solve / inverse takes the
+ *     problem index from its grid (blockIdx.y / .z, the GEMM's BATCHED instantiation) and every buffer of problem b
+ *     sits b * slot_len doubles further, so the host issues ~70 launches per chunk instead of per proposal;
+ *   streams (larger n, where the look-ahead POTRF already fills the GPU): proposal b runs on stream b % slots. */
 
-int64_t fvgp_population_slot_len(int64_t n, int dim, int want_grad) {
-  int64_t len = round_up16(n * round_up16(n)) + round_up16(fvgp_chol_workspace_len(n)) + round_up16(fvgp_potrs_work_len(n));
-  if (want_grad) len += round_up16(fvgp_potri_workspace_len(n)) + round_up16(fvgp_kgrad_partials_len(n, dim));
-  return len;
+// slot layout (doubles): [A n*ld][tile inverses][potrs work][alpha 4n][res 16]( [potri work][trace partials] )
+struct SlotLayout {
+  int64_t ld, tileinv, swork, alpha, res, pwork, partials, len;
+};
+static SlotLayout slot_layout(int64_t n, int dim, int want_grad) {
+  SlotLayout L;
+  L.ld = round_up16(n);
+  L.tileinv = round_up16(n * L.ld);
+  L.swork = L.tileinv + round_up16(fvgp_chol_workspace_len(n));
+  L.alpha = L.swork + round_up16(fvgp_potrs_work_len(n));
+  L.res = L.alpha + round_up16(4 * n);
+  L.pwork = L.res + 16;
+  L.partials = L.pwork + (want_grad ? round_up16(fvgp_potri_workspace_len(n)) : 0);
+  L.len = L.partials + (want_grad ? round_up16(fvgp_kgrad_partials_len(n, dim)) : 0);
+  return L;
 }
+
+int64_t fvgp_population_slot_len(int64_t n, int dim, int want_grad) { return slot_layout(n, dim, want_grad).len; }
+
+}  // extern "C"
+
+namespace fvgp {
+__global__ void broadcast_rows_kernel(double* dst, const double* __restrict__ src, long long count, long long bstride) {
+  dst += blockIdx.y * bstride;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+}  // namespace fvgp
+
+static double trace_fold(int kind, double length) {
+  switch (kind) {
+    case FVGP_K_MATERN32: return sqrt(3.0) / length;
+    case FVGP_K_MATERN52: return sqrt(5.0) / length;
+    case FVGP_K_SQEXP: return sqrt(0.5) / length;
+    case FVGP_K_EXP: return 1.0 / length;
+    default: return 0.0;
+  }
+}
+
+// Lock-step schedule.  res_h: batch x (dim + 2) raw results [logdet, raw trace sums].
+static int population_lockstep(int kind, const double* d_x, int64_t n, int dim, int batch, const double* h_amp,
+                               const double* h_inv_scale, const double* h_length, const double* h_centre,
+                               const double* d_noise, const double* d_rhs, int nrhs, int want_grad, int grad_component,
+                               int slots, double* d_work, int* d_info, double* h_alpha, double* res_h, cudaStream_t S) {
+  const SlotLayout L = slot_layout(n, dim, want_grad);
+  const int res_stride = dim + 2;
+  for (int b0 = 0; b0 < batch; b0 += slots) {
+    const int nb = std::min(slots, batch - b0);
+    double* A0 = d_work;
+    for (int b = 0; b < nb; ++b) {
+      int rc = fvgp_kfill_dense(kind, FVGP_FILL_LOWER, d_x, n, d_x, n, dim, h_amp[b0 + b],
+                                h_inv_scale + (int64_t)(b0 + b) * dim, h_centre, h_length[b0 + b], d_noise,
+                                A0 + (int64_t)b * L.len, L.ld, S);
+      if (rc != 0) return rc;
+    }
+    Ctx c{S, A0 + L.tileinv, d_info + b0, A0 + L.pwork, 0};
+    c.batch = nb, c.bstride = L.len;
+    REC_OK(potrf_rec(c, A0, L.ld, (int)n, 0));
+    const long long cnt = (long long)nrhs * n;
+    launch(broadcast_rows_kernel, dim3((unsigned)std::min<long long>((cnt + 255) / 256, 64), (unsigned)nb), 256, 0, S,
+           A0 + L.alpha, d_rhs, cnt, (long long)L.len);
+    REC_OK(potrs_few(S, A0, n, L.ld, A0 + L.tileinv, A0 + L.alpha, nrhs, n, A0 + L.swork, nb, L.len));
+    launch(logdet_kernel, (unsigned)nb, 1024, 0, S, A0, L.ld, (int)n, A0 + L.res, (long long)L.len);
+    FVGP_LAUNCH_OK();
+    if (want_grad) {
+      launch(zero_upper_diag_blocks_kernel, dim3((unsigned)((n + BM - 1) / BM), (unsigned)nb), 256, 0, S, A0, L.ld, (int)n,
+             (long long)L.len);
+      REC_OK(trtri_rec(c, A0, L.ld, (int)n, 0));
+      REC_OK(lauum_rec(c, A0, L.ld, (int)n));
+      for (int b = 0; b < nb; ++b) {
+        const double fold = trace_fold(kind, h_length[b0 + b]);
+        FVGP_REQUIRE(fold > 0.0);
+        double coord[kMaxDim];
+        for (int i = 0; i < dim; ++i) coord[i] = h_inv_scale[(int64_t)(b0 + b) * dim + i] * fold;
+        double* slot = A0 + (int64_t)b * L.len;
+        REC_OK(trace_radial_enqueue(kind, d_x, n, dim, coord, nullptr, slot, L.ld, slot + L.alpha + (int64_t)grad_component * n,
+                                    slot + L.partials, slot + L.res + 1, S));
+      }
+    }
+    FVGP_CUDA_OK(cudaMemcpy2DAsync(h_alpha + (int64_t)b0 * cnt, cnt * sizeof(double), A0 + L.alpha, L.len * sizeof(double),
+                                   cnt * sizeof(double), nb, cudaMemcpyDeviceToHost, S));
+    FVGP_CUDA_OK(cudaMemcpy2DAsync(res_h + (int64_t)b0 * res_stride, res_stride * sizeof(double), A0 + L.res,
+                                   L.len * sizeof(double), res_stride * sizeof(double), nb, cudaMemcpyDeviceToHost, S));
+  }
+  return 0;
+}
+
+extern "C" {
 
 int fvgp_lml_population(int kind, const double* d_x, int64_t n, int dim, int batch, const double* h_amp,
                         const double* h_inv_scale, const double* h_length, const double* h_centre,
@@ -936,11 +1055,11 @@ int fvgp_lml_population(int kind, const double* d_x, int64_t n, int dim, int bat
                         double* h_logdet, double* h_traces, int* h_info, void* stream) {
   FVGP_REQUIRE(n > 0 && n < (1ll << 31) && dim >= 1 && dim <= kMaxDim && batch >= 1 && slots >= 1);
   FVGP_REQUIRE(nrhs >= 1 && nrhs <= 4 && grad_component >= 0 && grad_component < nrhs);
+  FVGP_REQUIRE(!want_grad || trace_fold(kind, 1.0) > 0.0);
   cudaStream_t S = (cudaStream_t)stream;
-  const int64_t ld = round_up16(n);
-  const int H = dim + 1;                       // raw trace sums per proposal
-  const int res_stride = 1 + H;                // [logdet, raw traces]
-  const int64_t slot_len = fvgp_population_slot_len(n, dim, want_grad);
+  const SlotLayout lay = slot_layout(n, dim, want_grad);
+  const int64_t ld = lay.ld;
+  const int res_stride = dim + 2;              // [logdet, raw trace sums R_0..R_dim]
   if (slots > batch) slots = batch;
   static bool configured = false;
   if (!configured) {
@@ -950,105 +1069,104 @@ int fvgp_lml_population(int kind, const double* d_x, int64_t n, int dim, int bat
                                       (int)POTRF_TILE2_SMEM));
     configured = true;
   }
-  std::vector<cudaStream_t> st(slots);
-  cudaEvent_t ev_start;
-  FVGP_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-  FVGP_CUDA_OK(cudaEventRecord(ev_start, S));
-  for (int s = 0; s < slots; ++s) {
-    FVGP_CUDA_OK(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
-    FVGP_CUDA_OK(cudaStreamWaitEvent(st[s], ev_start, 0));
-  }
+  std::vector<double> res_h((size_t)batch * res_stride, 0.0);
   FVGP_CUDA_OK(cudaMemsetAsync(d_info, 0, sizeof(int) * batch, S));
-  FVGP_CUDA_OK(cudaEventRecord(ev_start, S));  // re-recorded after the memset: the slots wait for it below
-  for (int s = 0; s < slots; ++s) FVGP_CUDA_OK(cudaStreamWaitEvent(st[s], ev_start, 0));
-  int rc = 0;
   const int nb = potrf_block_width((int)n);
-  for (int b = 0; b < batch && rc == 0; ++b) {
-    const int s = b % slots;
-    cudaStream_t q = st[s];
-    double* A = d_work + (int64_t)s * slot_len;
-    double* tileinv = A + round_up16(n * ld);
-    double* swork = tileinv + round_up16(fvgp_chol_workspace_len(n));
-    double* pwork = swork + round_up16(fvgp_potrs_work_len(n));
-    double* partials = pwork + round_up16(fvgp_potri_workspace_len(n));
-    double* alpha = d_alpha + (int64_t)b * nrhs * n;
-    double* res = d_res + (int64_t)b * res_stride;
-    const double* inv = h_inv_scale + (int64_t)b * dim;
-    // K(theta_b) + diag(V), lower triangle
-    rc = fvgp_kfill_dense(kind, FVGP_FILL_LOWER, d_x, n, d_x, n, dim, h_amp[b], inv, h_centre, h_length[b], d_noise, A,
-                          ld, q);
-    if (rc != 0) break;
-    Ctx c{q, tileinv, d_info + b, pwork, 0};
-    rc = nb > 0 ? potrf_lookahead(c, A, ld, (int)n, nb) : potrf_rec(c, A, ld, (int)n, 0);
-    if (rc != 0) break;
-    // alpha_b = KV^-1 (y - m), one row per right-hand side
-    if (cudaMemcpyAsync(alpha, d_rhs, sizeof(double) * nrhs * n, cudaMemcpyDeviceToDevice, q) != cudaSuccess) {
-      rc = FVGP_ERR_CUDA;
-      break;
-    }
-    rc = potrs_few(q, A, n, ld, tileinv, alpha, nrhs, n, swork);
-    if (rc != 0) break;
-    launch(logdet_kernel, 1, 1024, 0, q, A, ld, (int)n, res);
-    if (want_grad) {
-      // lower(A) <- lower(KV^-1); raw sums R_0 = sum W f, R_i = sum W h q_i with W = KV^-1 - b b^T
-      launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, q, A, ld, (int)n);
-      rc = trtri_rec(c, A, ld, (int)n, 0);
-      if (rc == 0) rc = lauum_rec(c, A, ld, (int)n);
-      if (rc != 0) break;
-      double fold = 1.0;
-      switch (kind) {
-        case FVGP_K_MATERN32: fold = sqrt(3.0) / h_length[b]; break;
-        case FVGP_K_MATERN52: fold = sqrt(5.0) / h_length[b]; break;
-        case FVGP_K_SQEXP: fold = sqrt(0.5) / h_length[b]; break;
-        case FVGP_K_EXP: fold = 1.0 / h_length[b]; break;
-        default: rc = FVGP_ERR_ARG; break;
-      }
-      if (rc != 0) break;
-      double coord[kMaxDim], scale[kMaxDim + 1];
-      scale[0] = 1.0;
-      for (int i = 0; i < dim; ++i) coord[i] = inv[i] * fold, scale[1 + i] = 1.0;
-      rc = trace_radial_enqueue(kind, d_x, n, dim, coord, scale, A, ld, alpha + (int64_t)grad_component * n, partials,
-                                res + 1, q);
-      if (rc != 0) break;
-    }
-  }
-  if (cudaGetLastError() != cudaSuccess && rc == 0) rc = FVGP_ERR_CUDA;
-  // join: the caller's stream continues after every slot
-  for (int s = 0; s < slots; ++s) {
-    cudaEvent_t e;
-    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) {
-      cudaEventRecord(e, st[s]);
-      cudaStreamWaitEvent(S, e, 0);
-      cudaEventDestroy(e);
-    }
-  }
-  if (rc == 0) {
-    std::vector<double> res_h((size_t)batch * res_stride);
-    FVGP_CUDA_OK(cudaMemcpyAsync(h_alpha, d_alpha, sizeof(double) * batch * nrhs * n, cudaMemcpyDeviceToHost, S));
-    FVGP_CUDA_OK(cudaMemcpyAsync(res_h.data(), d_res, sizeof(double) * batch * res_stride, cudaMemcpyDeviceToHost, S));
-    FVGP_CUDA_OK(cudaMemcpyAsync(h_info, d_info, sizeof(int) * batch, cudaMemcpyDeviceToHost, S));
-    FVGP_CUDA_OK(cudaStreamSynchronize(S));
-    for (int b = 0; b < batch; ++b) {
-      h_logdet[b] = res_h[(size_t)b * res_stride];
-      if (want_grad) {  // descriptor traces (T_amp, T_s1..T_sD, T_length), as fvgp_kgrad_trace_radial
-        const double* raw = &res_h[(size_t)b * res_stride + 1];
-        double* out = h_traces + (size_t)b * (dim + 2);
-        double sum = 0.0;
-        out[0] = raw[0];
-        for (int i = 0; i < dim; ++i) {
-          const double si = h_inv_scale[(size_t)b * dim + i];
-          sum += raw[1 + i];
-          out[1 + i] = si != 0.0 ? -(h_amp[b] / si) * raw[1 + i] : 0.0;
-        }
-        out[dim + 1] = (h_amp[b] / h_length[b]) * sum;
-      }
+  // FVGP_POPULATION_STREAMS=1: stream schedule at every size (A/B on the GPU box, tests); read on every call
+  const char* env_streams = getenv("FVGP_POPULATION_STREAMS");
+  const bool force_streams = env_streams != nullptr && atoi(env_streams) != 0;
+  int rc = 0;
+  if (nb == 0 && !force_streams) {
+    rc = population_lockstep(kind, d_x, n, dim, batch, h_amp, h_inv_scale, h_length, h_centre, d_noise, d_rhs, nrhs,
+                             want_grad, grad_component, slots, d_work, d_info, h_alpha, res_h.data(), S);
+    if (rc != 0) {
+      cudaStreamSynchronize(S);
+      return rc;
     }
   } else {
+    std::vector<cudaStream_t> st(slots);
+    cudaEvent_t ev_start;
+    FVGP_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    FVGP_CUDA_OK(cudaEventRecord(ev_start, S));  // after the memset and everything the caller queued before
+    for (int s = 0; s < slots; ++s) {
+      FVGP_CUDA_OK(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+      FVGP_CUDA_OK(cudaStreamWaitEvent(st[s], ev_start, 0));
+    }
+    for (int b = 0; b < batch && rc == 0; ++b) {
+      const int s = b % slots;
+      cudaStream_t q = st[s];
+      double* A = d_work + (int64_t)s * lay.len;
+      double* tileinv = A + lay.tileinv;
+      double* alpha = d_alpha + (int64_t)b * nrhs * n;
+      double* res = d_res + (int64_t)b * res_stride;
+      const double* inv = h_inv_scale + (int64_t)b * dim;
+      // K(theta_b) + diag(V), lower triangle
+      rc = fvgp_kfill_dense(kind, FVGP_FILL_LOWER, d_x, n, d_x, n, dim, h_amp[b], inv, h_centre, h_length[b], d_noise, A,
+                            ld, q);
+      if (rc != 0) break;
+      Ctx c{q, tileinv, d_info + b, A + lay.pwork, 0};
+      rc = nb > 0 ? potrf_lookahead(c, A, ld, (int)n, nb) : potrf_rec(c, A, ld, (int)n, 0);
+      if (rc != 0) break;
+      // alpha_b = KV^-1 (y - m), one row per right-hand side
+      if (cudaMemcpyAsync(alpha, d_rhs, sizeof(double) * nrhs * n, cudaMemcpyDeviceToDevice, q) != cudaSuccess) {
+        rc = FVGP_ERR_CUDA;
+        break;
+      }
+      rc = potrs_few(q, A, n, ld, tileinv, alpha, nrhs, n, A + lay.swork);
+      if (rc != 0) break;
+      launch(logdet_kernel, 1, 1024, 0, q, A, ld, (int)n, res, 0ll);
+      if (want_grad) {
+        // lower(A) <- lower(KV^-1); raw sums R_0 = sum W f, R_i = sum W h q_i with W = KV^-1 - b b^T
+        launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, q, A, ld, (int)n, 0ll);
+        rc = trtri_rec(c, A, ld, (int)n, 0);
+        if (rc == 0) rc = lauum_rec(c, A, ld, (int)n);
+        if (rc != 0) break;
+        const double fold = trace_fold(kind, h_length[b]);
+        double coord[kMaxDim];
+        for (int i = 0; i < dim; ++i) coord[i] = inv[i] * fold;
+        rc = trace_radial_enqueue(kind, d_x, n, dim, coord, nullptr, A, ld, alpha + (int64_t)grad_component * n,
+                                  A + lay.partials, res + 1, q);
+        if (rc != 0) break;
+      }
+    }
+    if (cudaGetLastError() != cudaSuccess && rc == 0) rc = FVGP_ERR_CUDA;
+    // join: the caller's stream continues after every slot
+    for (int s = 0; s < slots; ++s) {
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) {
+        cudaEventRecord(e, st[s]);
+        cudaStreamWaitEvent(S, e, 0);
+        cudaEventDestroy(e);
+      }
+    }
+    if (rc == 0) {
+      if (cudaMemcpyAsync(h_alpha, d_alpha, sizeof(double) * batch * nrhs * n, cudaMemcpyDeviceToHost, S) != cudaSuccess ||
+          cudaMemcpyAsync(res_h.data(), d_res, sizeof(double) * batch * res_stride, cudaMemcpyDeviceToHost, S) != cudaSuccess)
+        rc = FVGP_ERR_CUDA;
+    }
     cudaStreamSynchronize(S);
+    for (int s = 0; s < slots; ++s) cudaStreamDestroy(st[s]);
+    cudaEventDestroy(ev_start);
+    if (rc != 0) return rc;
   }
-  for (int s = 0; s < slots; ++s) cudaStreamDestroy(st[s]);
-  cudaEventDestroy(ev_start);
-  return rc;
+  FVGP_CUDA_OK(cudaMemcpyAsync(h_info, d_info, sizeof(int) * batch, cudaMemcpyDeviceToHost, S));
+  FVGP_CUDA_OK(cudaStreamSynchronize(S));
+  for (int b = 0; b < batch; ++b) {
+    h_logdet[b] = res_h[(size_t)b * res_stride];
+    if (want_grad) {  // descriptor traces (T_amp, T_s1..T_sD, T_length), as fvgp_kgrad_trace_radial
+      const double* raw = &res_h[(size_t)b * res_stride + 1];
+      double* out = h_traces + (size_t)b * (dim + 2);
+      double sum = 0.0;
+      out[0] = raw[0];
+      for (int i = 0; i < dim; ++i) {
+        const double si = h_inv_scale[(size_t)b * dim + i];
+        sum += raw[1 + i];
+        out[1 + i] = si != 0.0 ? -(h_amp[b] / si) * raw[1 + i] : 0.0;
+      }
+      out[dim + 1] = (h_amp[b] / h_length[b]) * sum;
+    }
+  }
+  return 0;
 }
 
 }  // extern "C"

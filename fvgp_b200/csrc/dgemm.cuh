@@ -55,6 +55,7 @@ struct GemmArgs {
   double alpha, beta;
   int flags;
   int tiles_m, tiles_n;
+  long long bstride;  // BATCHED kernels: blockIdx.y selects a problem, every pointer moves by blockIdx.y * bstride doubles
 };
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, int src_bytes) {
@@ -135,9 +136,15 @@ __device__ __forceinline__ void load_operand(double* s, const double* __restrict
   }
 }
 
-template <bool A_MN, bool B_MN, int TB>
+// BATCHED: gridDim.y independent problems of identical shape whose operands all live at the same offsets of
+// equally sized workspace slots (population evaluation, dense_linalg.cu); the plain instantiation is unchanged.
+template <bool A_MN, bool B_MN, int TB, bool BATCHED = false>
 __global__ void __launch_bounds__(GEMM_THREADS, (TB == 128 ? 1 : 2)) dgemm_mma_kernel(const GemmArgs p) {
   using T = GemmTile<TB>;
+  const long long boff = BATCHED ? (long long)blockIdx.y * p.bstride : 0ll;
+  const double* gA = p.A + boff;
+  const double* gB = p.B + boff;
+  double* gC = p.C + boff;
   constexpr int MFR = T::MFR, NFR = T::NFR, QN = T::QN;
   constexpr int MNMAJ_STRIDE = T::MNMAJ_STRIDE, OPERAND_DOUBLES = T::OPERAND_DOUBLES, STAGE_DOUBLES = T::STAGE_DOUBLES;
   extern __shared__ __align__(16) double smem[];
@@ -174,23 +181,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, (TB == 128 ? 1 : 2)) dgemm_mma_k
       const int r = c >> 3, kc = (c & 7) * 2;
       a_off[q] = r * KMAJ_STRIDE + kc;
       a_bytes[q] = (m0 + r < p.M) ? 16 : 0;
-      a_src[q] = a_bytes[q] ? p.A + (long long)(m0 + r) * p.lda + kb + kc : p.A;
+      a_src[q] = a_bytes[q] ? gA + (long long)(m0 + r) * p.lda + kb + kc : gA;
     } else {
       const int kk = c / (TB / 2), mc = (c % (TB / 2)) * 2;
       a_off[q] = kk * MNMAJ_STRIDE + mc;
       a_bytes[q] = 8 * min(max(p.M - (m0 + mc), 0), 2);
-      a_src[q] = a_bytes[q] ? p.A + (long long)(kb + kk) * p.lda + m0 + mc : p.A;
+      a_src[q] = a_bytes[q] ? gA + (long long)(kb + kk) * p.lda + m0 + mc : gA;
     }
     if (!B_MN) {
       const int r = c >> 3, kc = (c & 7) * 2;
       b_off[q] = r * KMAJ_STRIDE + kc;
       b_bytes[q] = (n0 + r < p.N) ? 16 : 0;
-      b_src[q] = b_bytes[q] ? p.B + (long long)(n0 + r) * p.ldb + kb + kc : p.B;
+      b_src[q] = b_bytes[q] ? gB + (long long)(n0 + r) * p.ldb + kb + kc : gB;
     } else {
       const int kk = c / (TB / 2), nc = (c % (TB / 2)) * 2;
       b_off[q] = kk * MNMAJ_STRIDE + nc;
       b_bytes[q] = 8 * min(max(p.N - (n0 + nc), 0), 2);
-      b_src[q] = b_bytes[q] ? p.B + (long long)(kb + kk) * p.ldb + n0 + nc : p.B;
+      b_src[q] = b_bytes[q] ? gB + (long long)(kb + kk) * p.ldb + n0 + nc : gB;
     }
   }
   const long long a_step = A_MN ? (long long)BK * p.lda : BK;
@@ -206,8 +213,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, (TB == 128 ? 1 : 2)) dgemm_mma_k
         cp_async16(st + OPERAND_DOUBLES + b_off[q], b_src[q] + (b_bytes[q] ? kt * b_step : 0), b_bytes[q]);
       }
     } else {
-      load_operand<A_MN, TB>(st, p.A, p.lda, m0, p.M, k0, ke, tid);
-      load_operand<B_MN, TB>(st + OPERAND_DOUBLES, p.B, p.ldb, n0, p.N, k0, ke, tid);
+      load_operand<A_MN, TB>(st, gA, p.lda, m0, p.M, k0, ke, tid);
+      load_operand<B_MN, TB>(st + OPERAND_DOUBLES, gB, p.ldb, n0, p.N, k0, ke, tid);
     }
   };
 
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, (TB == 128 ? 1 : 2)) dgemm_mma_k
   for (int i = 0; i < MFR; ++i) {
     const int row = m0 + wm0 + 8 * i + g;
     if (row >= p.M) continue;
-    double* crow = p.C + (long long)row * p.ldc;
+    double* crow = gC + (long long)row * p.ldc;
 #pragma unroll
     for (int j = 0; j < NFR; ++j) {
       const int col = n0 + wn0 + 8 * j + 2 * t;
@@ -284,12 +291,12 @@ inline bool gemm_small_tiles_enabled() {
   return v != 0;
 }
 
-template <bool A_MN, bool B_MN, int TB>
-inline int launch_gemm_tile(cudaStream_t st, GemmArgs p) {
+template <bool A_MN, bool B_MN, int TB, bool BATCHED = false>
+inline int launch_gemm_tile(cudaStream_t st, GemmArgs p, int batch = 1) {
   static bool configured = false;
   if (!configured) {
-    FVGP_CUDA_OK(cudaFuncSetAttribute(dgemm_mma_kernel<A_MN, B_MN, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)GemmTile<TB>::SMEM_BYTES));
+    FVGP_CUDA_OK(cudaFuncSetAttribute(dgemm_mma_kernel<A_MN, B_MN, TB, BATCHED>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmTile<TB>::SMEM_BYTES));
     configured = true;
   }
   p.tiles_m = (p.M + TB - 1) / TB;
@@ -301,31 +308,41 @@ inline int launch_gemm_tile(cudaStream_t st, GemmArgs p) {
   } else {
     tiles = (long long)p.tiles_m * p.tiles_n;
   }
-  launch(dgemm_mma_kernel<A_MN, B_MN, TB>, (unsigned)tiles, GEMM_THREADS, GemmTile<TB>::SMEM_BYTES, st, p);
+  launch(dgemm_mma_kernel<A_MN, B_MN, TB, BATCHED>, dim3((unsigned)tiles, (unsigned)batch), GEMM_THREADS,
+         GemmTile<TB>::SMEM_BYTES, st, p);
   FVGP_LAUNCH_OK();
   return 0;
 }
 
 // Host launcher.  Requirements (checked): even leading dimensions and 16-byte aligned
-// bases (cp.async 16 B and double2 epilogue).
+// bases (cp.async 16 B and double2 epilogue).  batch > 1: the same product for `batch` problems whose operands sit
+// `bstride` doubles apart (bstride even).
 template <bool A_MN, bool B_MN>
 inline int launch_gemm(cudaStream_t st, const double* A, long long lda, const double* B, long long ldb, double* C,
-                       long long ldc, int M, int N, int K, double alpha, double beta, int flags) {
+                       long long ldc, int M, int N, int K, double alpha, double beta, int flags, int batch = 1,
+                       long long bstride = 0) {
   if (M <= 0 || N <= 0) return 0;
   FVGP_REQUIRE((lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0));
   FVGP_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0));
+  FVGP_REQUIRE(batch >= 1 && batch <= 65535 && (batch == 1 || bstride % 2 == 0));
   GemmArgs p;
   p.A = A, p.B = B, p.C = C, p.M = M, p.N = N, p.K = K;
   p.lda = lda, p.ldb = ldb, p.ldc = ldc, p.alpha = alpha, p.beta = beta, p.flags = flags;
   p.tiles_m = p.tiles_n = 0;
+  p.bstride = batch > 1 ? bstride : 0;
   // 128-tiles when they fill at least half the SMs; otherwise the problem is latency bound and more, smaller CTAs win
   const long long tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
-  const long long tiles128 = (flags & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn;
+  const long long tiles128 = ((flags & GEMM_LOWER) ? tm * (tm + 1) / 2 : tm * tn) * batch;
   // In-place products (C aliases an operand: the TRSM / LAUUM leaves, N <= 128) rely on ONE CTA owning complete rows
   // of the output -- it has consumed its operand rows before the epilogue writes them; 64-wide tiles would let a
   // neighbouring CTA overwrite columns that are still being read.
   const bool in_place = (const double*)C == A || (const double*)C == B;
-  if (!in_place && tiles128 * 2 < sm_count() && gemm_small_tiles_enabled()) return launch_gemm_tile<A_MN, B_MN, 64>(st, p);
+  const bool small = !in_place && tiles128 * 2 < sm_count() && gemm_small_tiles_enabled();
+  if (batch > 1) {
+    if (small) return launch_gemm_tile<A_MN, B_MN, 64, true>(st, p, batch);
+    return launch_gemm_tile<A_MN, B_MN, 128, true>(st, p, batch);
+  }
+  if (small) return launch_gemm_tile<A_MN, B_MN, 64>(st, p);
   return launch_gemm_tile<A_MN, B_MN, 128>(st, p);
 }
 

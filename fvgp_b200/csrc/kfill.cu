@@ -522,7 +522,7 @@ __global__ void trace_reduce_kernel(const double* partials, int nctas, int H, co
     double s = 0.0;
     for (int i = threadIdx.x; i < nctas; i += blockDim.x) s += partials[(long long)i * H + h];
     s = block_sum(s, red);
-    if (threadIdx.x == 0) out[h] = s * scale_dev[h];
+    if (threadIdx.x == 0) out[h] = scale_dev != nullptr ? s * scale_dev[h] : s;
     __syncthreads();
   }
 }
@@ -830,7 +830,11 @@ int trace_radial_enqueue(int kind, const double* d_x, int64_t n, int dim, const 
   double* d_tail = d_partials + (long long)grid * H;
   double* d_scale = d_tail + H;
   if (d_out == nullptr) d_out = d_tail;
-  FVGP_CUDA_OK(cudaMemcpyAsync(d_scale, h_out_scale, H * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (h_out_scale != nullptr) {
+    FVGP_CUDA_OK(cudaMemcpyAsync(d_scale, h_out_scale, H * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    d_scale = nullptr;  // raw sums
+  }
   launch(trace_reduce_kernel, 1, 256, 0, st, d_partials, (int)grid, H, d_scale, d_out);
   FVGP_LAUNCH_OK();
   return 0;

@@ -209,14 +209,16 @@ def potri(factor):
 
 
 def population_slots(n, dim, want_grad, batch):
-    """Concurrent evaluation slots for a population of `batch` proposals: enough chains in flight to fill the SMs at
-    small N, bounded by 1/4 of the free HBM and by the streams the hardware keeps independent."""
+    """Workspace slots for a population of `batch` proposals (= proposals per lock-step chunk, or concurrent streams at
+    large N), bounded by 1/4 of the free HBM."""
     lib = L.load()
     torch = L._torch()
     slot_bytes = 8 * int(lib.fvgp_population_slot_len(n, dim, int(want_grad)))
     free, _total = torch.cuda.mem_get_info()
     by_mem = max(1, int(0.25 * free) // max(slot_bytes, 1))
-    by_size = 32 if n <= 2048 else (16 if n <= 4096 else (8 if n <= 8192 else (4 if n <= 16384 else 2)))
+    # n < 6144: lock-step schedule, a slot per proposal of a chunk (more proposals per launch = fewer launches);
+    # larger: one stream per slot, each evaluation already fills the GPU
+    by_size = 64 if n <= 2048 else (32 if n <= 4096 else (16 if n < 6144 else (4 if n <= 16384 else 2)))
     return int(max(1, min(batch, by_mem, by_size)))
 
 

@@ -452,6 +452,12 @@ def test_population_matches_one_at_a_time(fv):
         T = h0 * (0.7 + 0.6 * rng.random((B, d + 1)))
         lml_pop, grad_pop = gp.marginal_likelihood.evaluate_population(T, with_gradient=True)
         lml_only = gp.log_likelihood_population(T)
+        os.environ["FVGP_POPULATION_STREAMS"] = "1"               # the stream schedule (what n >= 6144 uses)
+        try:
+            lml_st, grad_st = gp.marginal_likelihood.evaluate_population(T, with_gradient=True)
+        finally:
+            os.environ.pop("FVGP_POPULATION_STREAMS")
+        assert np.array_equal(lml_st, lml_pop) and rel(grad_st, grad_pop) <= 1e-12
         for b in range(B):
             one = gp.log_likelihood(T[b])
             assert lml_pop[b] == one and lml_only[b] == one, (n, b, lml_pop[b], lml_only[b], one)
