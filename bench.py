@@ -385,12 +385,16 @@ def run_c1(args):
     torch.cuda.synchronize()
     sampler.start()
     launches0 = lib.fvgp_launch_count()
+    ops.start_phase_timing()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("timed")
     e0.record()
     for k in range(args.steps):
         lml = gp.log_likelihood_population(thetas(args.warmup + k))
     e1.record()
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
+    t_gpu = ops.stop_phase_timing().get("population", 0.0) / args.steps      # first to last kernel of the C-ABI call
     t_pop = e0.elapsed_time(e1) * 1e-3 / args.steps
     launches = (lib.fvgp_launch_count() - launches0) // args.steps
     clocks = sampler.summary()
@@ -435,6 +439,7 @@ def run_c1(args):
             "e2e": {"value": B / t_pop, "unit": "evals/s", "h2d_bytes_per_step": B * 4 * 8 + 2 * n * 8,
                     "d2h_bytes_per_step": B * (n + 2) * 8 + B * 4},
             "gpu_launches": int(launches),
+            "device_ms_per_step": t_gpu * 1e3,
             "one_at_a_time": {"value": B / t_seq, "unit": "evals/s", "ms_per_eval": t_seq / B * 1e3},
             "population_with_gradient": {"value": B / t_pop_grad, "unit": "evals/s"},
             "roofline": {"bound": "tensor", "kernel": "whole population (latency-bound chains of small launches)",

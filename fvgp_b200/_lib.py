@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfvgp_b200.so")
 
 # kernel kinds / fill modes (mirror include/fvgp_b200.h)
-K_MATERN32, K_MATERN52, K_SQEXP, K_EXP, K_WENDLAND, K_DISTANCE = range(6)
+K_MATERN32, K_MATERN52, K_SQEXP, K_EXP, K_WENDLAND, K_DISTANCE, K_MATERN52_ROBUST = range(7)
 FILL_FULL, FILL_SYMMETRIC, FILL_LOWER = range(3)
 
 _P = c_void_p

@@ -734,6 +734,10 @@ int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const d
       p.c_arg = sqrt(5.0) / length, fold = p.c_arg;
       p.c_aux = centred ? amp / 3.0 : amp * 5.0 / (3.0 * length * length);
       break;
+    case FVGP_K_MATERN52_ROBUST:  // same evaluation, quadratic coefficient 15 / length^2 (= 3 a^2 in scaled coordinates)
+      p.c_arg = sqrt(5.0) / length, fold = p.c_arg;
+      p.c_aux = centred ? amp * 3.0 : amp * 15.0 / (length * length);
+      break;
     case FVGP_K_SQEXP: p.c_arg = 1.0 / (2.0 * length * length); fold = sqrt(p.c_arg); break;
     case FVGP_K_EXP: p.c_arg = 1.0 / length; fold = p.c_arg; break;
     case FVGP_K_WENDLAND: p.c_arg = 1.0 / length; fold = p.c_arg; break;
@@ -747,7 +751,8 @@ int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const d
   cudaStream_t st = (cudaStream_t)stream;
   switch (kind) {
     case FVGP_K_MATERN32: return launch_fill_dim<FVGP_K_MATERN32>(p, centred, st);
-    case FVGP_K_MATERN52: return launch_fill_dim<FVGP_K_MATERN52>(p, centred, st);
+    case FVGP_K_MATERN52:
+    case FVGP_K_MATERN52_ROBUST: return launch_fill_dim<FVGP_K_MATERN52>(p, centred, st);
     case FVGP_K_SQEXP: return launch_fill_dim<FVGP_K_SQEXP>(p, centred, st);
     case FVGP_K_EXP: return launch_fill_dim<FVGP_K_EXP>(p, centred, st);
     case FVGP_K_WENDLAND: return launch_fill_dim<FVGP_K_WENDLAND>(p, centred, st);
@@ -768,6 +773,10 @@ int fvgp_radial_elementwise(int kind, const double* d_dist, int64_t count, doubl
     case FVGP_K_MATERN52:
       launch(radial_elementwise_kernel<FVGP_K_MATERN52>, grid, 256, 0, st, d_dist, count, amp, sqrt(5.0) / length,
                                                                         amp * 5.0 / (3.0 * length * length), d_out);
+      break;
+    case FVGP_K_MATERN52_ROBUST:
+      launch(radial_elementwise_kernel<FVGP_K_MATERN52>, grid, 256, 0, st, d_dist, count, amp, sqrt(5.0) / length,
+                                                                        amp * 15.0 / (length * length), d_out);
       break;
     case FVGP_K_SQEXP:
       launch(radial_elementwise_kernel<FVGP_K_SQEXP>, grid, 256, 0, st, d_dist, count, amp, 1.0 / (2.0 * length * length), 0.0, d_out);

@@ -198,7 +198,18 @@ class GPMarginalLikelihood:
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
         B, H = thetas.shape
         plan = None
-        if B > 1 and self.population_supported(want_grad=with_gradient):
+        if B > 1 and self.population_supported(want_grad=with_gradient) and self.prior.default_kernel:
+            # default kernel: amp = theta_0, inv_scale_i = 1 / theta_{1+i}, length = 1 -- no per-proposal kernel call
+            dim = self.data.x_data.shape[1]
+            plan = []
+            for t in thetas:
+                J = None
+                if with_gradient:
+                    J = np.zeros((dim + 2, H))
+                    J[0, 0] = 1.0
+                    J[np.arange(1, dim + 1), np.arange(1, dim + 1)] = -1.0 / t[1:1 + dim] ** 2
+                plan.append((L.K_MATERN32, np.concatenate([[t[0]], 1.0 / t[1:1 + dim], [1.0]]), J))
+        elif B > 1 and self.population_supported(want_grad=with_gradient):
             plan = []
             for t in thetas:
                 dj = self._descriptor_jacobian(t) if with_gradient else self._fill_descriptor(t)

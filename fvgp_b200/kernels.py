@@ -24,8 +24,12 @@ from . import _lib as L
 from . import ops
 
 __all__ = ["squared_exponential_kernel", "exponential_kernel", "matern_kernel_diff1", "matern_kernel_diff2",
+           "squared_exponential_kernel_robust", "exponential_kernel_robust", "matern_kernel_diff1_robust",
+           "matern_kernel_diff2_robust", "wendland_kernel",
            "get_distance_matrix", "get_anisotropic_distance_matrix", "wendland_anisotropic",
-           "wendland_anisotropic_gp2Scale_cpu", "wendland_anisotropic_gp2Scale_gpu", "matern_kernel_diff1_grad"]
+           "wendland_anisotropic_gp2Scale_cpu", "wendland_anisotropic_gp2Scale_gpu",
+           "wendland_anisotropic_gp2Scale_cpu_sparse", "wendland_anisotropic_gp2Scale_gpu_sparse",
+           "matern_kernel_diff1_grad"]
 
 
 def _device_points(x):
@@ -219,6 +223,40 @@ def matern_kernel_diff2(distance, length):
     return _radial(L.K_MATERN52, distance, length)
 
 
+def _inv_phi2(phi):
+    """length = 1 / phi**2 of the *_robust parametrisation (phi = 0: infinite length, kernel = 1)."""
+    phi2 = float(phi) ** 2
+    return np.inf if phi2 == 0.0 else 1.0 / phi2
+
+
+def squared_exponential_kernel_robust(distance, phi):
+    """exp(-d^2 phi^2) (kernels.py:36-53) = the squared exponential with 2 l^2 = 1 / phi^2."""
+    return _radial(L.K_SQEXP, distance, np.sqrt(0.5 * _inv_phi2(phi)))
+
+
+def exponential_kernel_robust(distance, phi):
+    """exp(-d phi^2) (kernels.py:77-95)."""
+    return _radial(L.K_EXP, distance, _inv_phi2(phi))
+
+
+def matern_kernel_diff1_robust(distance, phi):
+    """(1 + sqrt3 d phi^2) exp(-sqrt3 d phi^2) (kernels.py:144-163)."""
+    return _radial(L.K_MATERN32, distance, _inv_phi2(phi))
+
+
+def matern_kernel_diff2_robust(distance, phi):
+    """(1 + sqrt5 d phi^2 + 15 d^2 phi^4) exp(-sqrt5 d phi^2), the reference's own coefficients (kernels.py:191-213)."""
+    return _radial(L.K_MATERN52_ROBUST, distance, _inv_phi2(phi))
+
+
+def wendland_kernel(d):
+    """(1 - d)^8 (32 d^3 + 25 d^2 + 8 d + 1) with d clamped to 1 (kernels.py:336-352).  Like the reference, an ndarray
+    argument is clamped IN PLACE."""
+    if isinstance(d, np.ndarray):
+        d[d > 1.] = 1.
+    return _radial(L.K_WENDLAND, d, 1.0)
+
+
 def matern_kernel_diff1_grad(distance, dist_der):
     """kernels.py:121-141, host-side helper for user gradient functions (O(size) numpy)."""
     a = np.sqrt(3.0) * np.asarray(distance)
@@ -268,4 +306,16 @@ def wendland_anisotropic_gp2Scale_cpu(x1, x2, hps):
 
 def wendland_anisotropic_gp2Scale_gpu(x1, x2, hps, args=None):
     """kernels.py:539-591 computes this in float32 on torch/cupy; here it is the same FP64 kernel."""
+    return wendland_anisotropic_gp2Scale_cpu(x1, x2, hps)
+
+
+def wendland_anisotropic_gp2Scale_cpu_sparse(x1, x2, hps):
+    """Support-aware block kernel (kernels.py:724-738; KD-tree ball queries behind an AABB cull on the host).  Here the
+    cull and the pair test are the CSR kernels' own (two-level bounding boxes, exact support predicate), so this is the
+    same lazy object as wendland_anisotropic_gp2Scale_cpu; `.tocsr()` / `.toarray()` give the block to a direct caller."""
+    return wendland_anisotropic_gp2Scale_cpu(x1, x2, hps)
+
+
+def wendland_anisotropic_gp2Scale_gpu_sparse(x1, x2, hps, args=None):
+    """kernels.py:827-840."""
     return wendland_anisotropic_gp2Scale_cpu(x1, x2, hps)

@@ -46,7 +46,7 @@ def stop_phase_timing():
 
 # ------------------------------------------------------------------------------ dense K
 _FOLD = {L.K_MATERN32: np.sqrt(3.0), L.K_MATERN52: np.sqrt(5.0), L.K_SQEXP: np.sqrt(0.5), L.K_EXP: 1.0,
-         L.K_WENDLAND: 1.0, L.K_DISTANCE: 1.0}
+         L.K_WENDLAND: 1.0, L.K_DISTANCE: 1.0, L.K_MATERN52_ROBUST: np.sqrt(5.0)}
 CENTRED_LIMIT = 512.0          # bound on |x - centre| * inv_scale * c for the centred fill
 
 

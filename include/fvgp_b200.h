@@ -34,7 +34,9 @@ enum fvgp_kernel_kind {
   FVGP_K_SQEXP = 2,    /* kernels.py:16-33   squared_exponential_kernel */
   FVGP_K_EXP = 3,      /* kernels.py:56-74   exponential_kernel */
   FVGP_K_WENDLAND = 4, /* kernels.py:355-378 wendland_anisotropic (dense form) */
-  FVGP_K_DISTANCE = 5  /* kernels.py:440-481 get_(anisotropic_)distance_matrix: value = d */
+  FVGP_K_DISTANCE = 5, /* kernels.py:440-481 get_(anisotropic_)distance_matrix: value = d */
+  FVGP_K_MATERN52_ROBUST = 6 /* kernels.py:191-213 matern_kernel_diff2_robust with length = 1 / phi^2: the reference's
+                              * quadratic term is (5 d^2)(3 phi^4) = 15 (d / length)^2, not 5/3 -- reproduced as is */
 };
 
 enum fvgp_fill_mode {

@@ -68,6 +68,41 @@ def matern52(d, length):
 RADIAL = {"se": squared_exponential, "exp": exponential, "matern32": matern32, "matern52": matern52}
 
 
+def squared_exponential_robust(d, phi):
+    """kernels.py:36-53."""
+    return np.exp(-(d ** 2) * (phi ** 2))
+
+
+def exponential_robust(d, phi):
+    """kernels.py:77-95."""
+    return np.exp(-d * (phi ** 2))
+
+
+def matern32_robust(d, phi):
+    """kernels.py:144-163: 1/length -> phi**2."""
+    return (1.0 + ((SQRT3 * d) * (phi ** 2))) * np.exp(-(SQRT3 * d) * (phi ** 2))
+
+
+def matern52_robust(d, phi):
+    """kernels.py:191-213.  The reference's quadratic term is (5 d^2)(3 phi^4) = 15 d^2 phi^4 (not 5/3): restated as is."""
+    return (1.0 + ((SQRT5 * d) * (phi ** 2)) + ((5.0 * d ** 2) * (3.0 * phi ** 4))) * np.exp(-(SQRT5 * d) * (phi ** 2))
+
+
+RADIAL_ROBUST = {"se": squared_exponential_robust, "exp": exponential_robust, "matern32": matern32_robust,
+                 "matern52": matern52_robust}
+
+
+def wendland(d):
+    """kernels.py:336-352 on a copy (the reference clamps its argument in place)."""
+    d = np.minimum(d, 1.0)
+    return (1.0 - d) ** 8 * (32.0 * d ** 3 + 25.0 * d ** 2 + 8.0 * d + 1.0)
+
+
+def wendland_anisotropic(x1, x2, hps):
+    """kernels.py:355-378: dense anisotropic Wendland, hps = (amplitude, support radii)."""
+    return hps[0] * wendland(anisotropic_distance_matrix(x1, x2, hps[1:]))
+
+
 # --------------------------------------------------------------------------- a1
 def default_kernel(x1, x2, hps):
     """ARD Matern-3/2, gp_prior.py:376-400: hps[0] * matern32(aniso distance with hps[1:], 1)."""

@@ -175,8 +175,34 @@ def gp2scale():
         del gp
 
 
+def robust_kernels():
+    """SURVEY 8a rows a3 / a16 / a17 beyond the four basic radial names: the *_robust variants (kernels.py:36, :77,
+    :144, :191), wendland_kernel (:336), the dense wendland_anisotropic (:355) and the support-aware sparse block
+    kernel wendland_anisotropic_gp2Scale_cpu_sparse (:724)."""
+    rng = np.random.default_rng(202)
+    x1 = rng.random((41, 3)) * 1.5 - 0.25
+    x2 = rng.random((33, 3)) * 1.5 - 0.25
+    hps = np.array([1.4, 0.5, 0.7, 0.9])
+    phi = 1.35
+    out = dict(x1=x1, x2=x2, hps=hps, phi=np.array(phi))
+    d_iso = rk.get_distance_matrix(x1, x2)
+    d_ani = rk.get_anisotropic_distance_matrix(x1, x2, hps[1:])
+    for nm, f in (("se", rk.squared_exponential_kernel_robust), ("exp", rk.exponential_kernel_robust),
+                  ("matern32", rk.matern_kernel_diff1_robust), ("matern52", rk.matern_kernel_diff2_robust)):
+        out[nm + "_robust_iso"] = f(d_iso, phi)
+        out[nm + "_robust_ani"] = f(d_ani, phi)
+    out["wendland_kernel_ani"] = rk.wendland_kernel(np.array(d_ani, copy=True))
+    out["wendland_anisotropic_12"] = rk.wendland_anisotropic(x1, x2, hps)
+    out["wendland_anisotropic_11"] = rk.wendland_anisotropic(x1, x1, hps)
+    sp12 = rk.wendland_anisotropic_gp2Scale_cpu_sparse(x1, x2, hps)
+    out["wendland_sparse_12"] = np.asarray(sp12.toarray())
+    out["wendland_block_12"] = rk.wendland_anisotropic_gp2Scale_cpu(x1, x2, hps)
+    save("robust_kernels", **out)
+
+
 if __name__ == "__main__":
     dense_kernels()
     dense_lml()
     multitask()
     gp2scale()
+    robust_kernels()

@@ -515,3 +515,30 @@ def test_train_global_uses_the_population_path(fv):
     phases = ops.stop_phase_timing()
     assert "population" in phases and gp.log_likelihood() >= before
     assert np.all(hps >= [0.05, 0.02]) and np.all(hps <= [10.0, 5.0])
+
+
+def test_robust_and_wendland_kernel_names(fv, golden):
+    """the *_robust radial kernels, wendland_kernel, the dense wendland_anisotropic and
+    the support-aware sparse block kernel, against outputs of the unmodified reference (tests/golden/robust_kernels.npz)."""
+    from fvgp_b200 import kernels as K
+    g = golden("robust_kernels")
+    x1, x2, h, phi = g["x1"], g["x2"], g["hps"], float(g["phi"])
+    d_iso = np.asarray(K.get_distance_matrix(x1, x2))
+    d_ani = np.asarray(K.get_anisotropic_distance_matrix(x1, x2, h[1:]))
+    for nm, f in (("se", K.squared_exponential_kernel_robust), ("exp", K.exponential_kernel_robust),
+                  ("matern32", K.matern_kernel_diff1_robust), ("matern52", K.matern_kernel_diff2_robust)):
+        assert rel(np.asarray(f(K.get_distance_matrix(x1, x2), phi)), g[nm + "_robust_iso"]) <= 1e-12, nm      # fused
+        assert rel(np.asarray(f(K.get_anisotropic_distance_matrix(x1, x2, h[1:]), phi)), g[nm + "_robust_ani"]) <= 1e-12, nm
+        assert rel(f(d_iso, phi), g[nm + "_robust_iso"]) <= 1e-12, nm                                          # ndarray
+        assert rel(1.7 * np.asarray(f(K.get_distance_matrix(x1, x2), 0.0)), np.full(d_iso.shape, 1.7)) <= 1e-15
+    dd = np.array(d_ani, copy=True)
+    w = K.wendland_kernel(dd)
+    assert np.max(np.abs(w - g["wendland_kernel_ani"])) <= 1e-13 and dd.max() <= 1.0       # clamped in place, like the reference
+    assert np.max(np.abs(np.asarray(K.wendland_anisotropic(x1, x2, h)) - g["wendland_anisotropic_12"])) <= 1e-13
+    assert np.max(np.abs(np.asarray(K.wendland_anisotropic(x1, x1, h)) - g["wendland_anisotropic_11"])) <= 1e-13
+    for f in (K.wendland_anisotropic_gp2Scale_cpu, K.wendland_anisotropic_gp2Scale_cpu_sparse,
+              K.wendland_anisotropic_gp2Scale_gpu_sparse):
+        blk = f(x1, x2, h).toarray()
+        assert np.array_equal(blk != 0, g["wendland_block_12"] != 0)                     # pattern bit-exact
+        assert rel(blk[blk != 0], g["wendland_block_12"][blk != 0]) <= 1e-12              # values (K entries: 1e-12)
+        assert np.max(np.abs(blk - g["wendland_sparse_12"])) <= 1e-12                     # KD-tree variant (a17)

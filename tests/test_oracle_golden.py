@@ -25,6 +25,22 @@ def test_dense_kernels(golden):
     assert rel(orc.default_kernel(g["c1_x"], g["c1_x"], g["c1_hps"]), g["c1_K"]) <= 1e-15
 
 
+def test_robust_and_wendland_kernels(golden):
+    g = golden("robust_kernels")
+    x1, x2, h, phi = g["x1"], g["x2"], g["hps"], float(g["phi"])
+    d_iso, d_ani = orc.distance_matrix(x1, x2), orc.anisotropic_distance_matrix(x1, x2, h[1:])
+    for nm in ("se", "exp", "matern32", "matern52"):
+        assert rel(orc.RADIAL_ROBUST[nm](d_iso, phi), g[nm + "_robust_iso"]) <= 1e-15
+        assert rel(orc.RADIAL_ROBUST[nm](d_ani, phi), g[nm + "_robust_ani"]) <= 1e-15
+    assert np.array_equal(orc.wendland(d_ani), g["wendland_kernel_ani"])
+    assert np.array_equal(orc.wendland_anisotropic(x1, x2, h), g["wendland_anisotropic_12"])
+    assert np.array_equal(orc.wendland_anisotropic(x1, x1, h), g["wendland_anisotropic_11"])
+    # the block kernel of gp2Scale (a16) and the support-aware sparse variant (a17) against the dense Wendland
+    assert np.array_equal(orc.wendland_block(x1, x2, h), g["wendland_block_12"])
+    assert np.array_equal(g["wendland_block_12"] != 0, g["wendland_sparse_12"] != 0)
+    assert np.max(np.abs(g["wendland_sparse_12"] - g["wendland_block_12"])) <= 1e-12
+
+
 def test_dense_lml_and_gradient(golden):
     for tag in ("c1", "c2"):
         g = golden("dense_lml_" + tag)
