@@ -69,34 +69,64 @@ def theta_k(k, rank=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.  In-process NVML (the library nvidia-smi itself
+    reads; the recipe's clocks line: clocks.sm, clocks.max.sm, clocks_event_reasons.*): forking nvidia-smi from a
+    process with a CUDA context costs tens of milliseconds per sample and perturbs short timed regions (the C1
+    population step is ~4 ms).  Falls back to the nvidia-smi subprocess when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = self.handle = None
+        self.mode = os.environ.get("FVGP_BENCH_SAMPLER", "nvml")      # nvml | smi | none (A/B of the sampler's own cost)
+        try:
+            if self.mode != "nvml":
+                raise RuntimeError("NVML sampler disabled")
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        return [str(sm), str(mx), "0"] + ["Active" if (r & b) else "Not Active" for b in bits]
 
     def run(self):
-        while not self.stop_flag:
+        while not self.stop_flag and self.mode != "none":
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=2)
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        reasons = sorted({self.NAMES[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def use_all_host_threads():
@@ -389,8 +419,11 @@ def run_c1(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.nvtx.range_push("timed")
     e0.record()
+    per_step = []
     for k in range(args.steps):
-        lml = gp.log_likelihood_population(thetas(args.warmup + k))
+        t_s = time.perf_counter()
+        lml = gp.log_likelihood_population(thetas(args.warmup + k))        # synchronises internally (host LMLs out)
+        per_step.append(time.perf_counter() - t_s)
     e1.record()
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()
@@ -439,7 +472,8 @@ def run_c1(args):
             "e2e": {"value": B / t_pop, "unit": "evals/s", "h2d_bytes_per_step": B * 4 * 8 + 2 * n * 8,
                     "d2h_bytes_per_step": B * (n + 2) * 8 + B * 4},
             "gpu_launches": int(launches),
-            "device_ms_per_step": t_gpu * 1e3,
+            "device_ms_per_step": t_gpu * 1e3, "ms_per_step_median": float(np.median(per_step)) * 1e3,
+            "ms_per_step_max": float(np.max(per_step)) * 1e3,
             "one_at_a_time": {"value": B / t_seq, "unit": "evals/s", "ms_per_eval": t_seq / B * 1e3},
             "population_with_gradient": {"value": B / t_pop_grad, "unit": "evals/s"},
             "roofline": {"bound": "tensor", "kernel": "whole population (latency-bound chains of small launches)",
@@ -496,6 +530,8 @@ def main():
     if args.workload == "c1":
         if args.n == 50000:
             args.n = 1000
+        if args.steps == 3:
+            args.steps = 20            # a step is ~4 ms: more of them, so that one host hiccup does not decide the line
         return run_c1(args)
     if args.workload == "c4":
         if args.n == 50000:

@@ -214,12 +214,15 @@ def population_slots(n, dim, want_grad, batch):
     lib = L.load()
     torch = L._torch()
     slot_bytes = 8 * int(lib.fvgp_population_slot_len(n, dim, int(want_grad)))
-    free, _total = torch.cuda.mem_get_info()
-    by_mem = max(1, int(0.25 * free) // max(slot_bytes, 1))
     # n < 6144: lock-step schedule, a slot per proposal of a chunk (more proposals per launch = fewer launches);
     # larger: one stream per slot, each evaluation already fills the GPU
     by_size = 64 if n <= 2048 else (32 if n <= 4096 else (16 if n < 6144 else (4 if n <= 16384 else 2)))
-    return int(max(1, min(batch, by_mem, by_size)))
+    want = int(max(1, min(batch, by_size)))
+    if want * slot_bytes <= (4 << 30):          # small workspaces: no driver query on the hot path (cudaMemGetInfo
+        return want                              # costs up to milliseconds and this call sits inside optimiser loops)
+    free, _total = torch.cuda.mem_get_info()
+    by_mem = max(1, int(0.25 * free) // max(slot_bytes, 1))
+    return int(max(1, min(want, by_mem)))
 
 
 def lml_population(kind, x, amps, inv_scales, lengths, noise, rhs_t, want_grad=False, component=0, bounds=None,

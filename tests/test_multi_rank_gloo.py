@@ -23,8 +23,25 @@ def _worker(rank, world, port, q):
 
         def neg_log_likelihood_gradient(self, th):
             return 2.0 * th
+    class FakePopulationGP(FakeGP):   # a GP that offers the population entry point: each rank's share is ONE call
+        calls = []
+
+        class _ML:
+            def __init__(self, outer):
+                self.outer = outer
+
+            def evaluate_population(self, T, with_gradient=False, component=0):
+                self.outer.calls.append(len(T))
+                return T.sum(axis=1), (2.0 * T if with_gradient else None)
+
+        def __init__(self):
+            self.marginal_likelihood = self._ML(self)
     thetas = np.arange(15.0).reshape(5, 3)
     table = parallel.evaluate_proposals(FakeGP(), thetas)
+    pgp = FakePopulationGP()
+    table_pop = parallel.evaluate_proposals(pgp, thetas)
+    assert np.array_equal(table_pop, table) and pgp.calls == [len(parallel.shard_proposals(5, rank, world))]
+    assert np.array_equal(parallel.evaluate_proposals(pgp, thetas, with_gradient=False)[:, 0], table[:, 0])
     tmax = parallel.max_over_ranks(1.0 + rank)
     parallel.barrier()
     q.put((rank, parallel.shard_proposals(5, rank, world), table, tmax))
