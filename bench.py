@@ -486,21 +486,28 @@ def run_c1(args):
 
 
 def gemm_dram_traffic(n):
-    """Bytes the DMMA GEMM launches of one N = 50 000 evaluation moved through DRAM, from the committed ncu launch list
-    (tools/launch_summary.py JSON); None when no capture exists for this size."""
+    """(bytes, note): what the DMMA GEMM launches of one N = 50 000 evaluation moved through DRAM, from the committed
+    ncu launch list (tools/launch_summary.py JSON); (None, why) when no capture exists for this size."""
     import glob
     if n != 50000:
-        return None
+        return None, "no ncu capture at this size"
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "launches_bench_n50k*.json")), reverse=True):
         try:
             with open(path) as fh:
                 d = json.load(fh)
-            tot = sum(v["dram_read"] + v["dram_write"] for k, v in d["kernels"].items() if "dgemm_mma_kernel" in k)
+            gemm = {k: v for k, v in d["kernels"].items() if "dgemm_mma_kernel" in k}
+            tot = sum(v["dram_read"] + v["dram_write"] for v in gemm.values())
             if tot > 0:
-                return float(tot)
+                note = (f"dram__bytes_read.sum + dram__bytes_write.sum over {sum(v['launches'] for v in gemm.values())} "
+                        f"dgemm_mma_kernel launches ({sum(v['ms'] for v in gemm.values()):.0f} ms of kernel time) of one "
+                        f"evaluation, {os.path.relpath(path, ROOT)}")
+                if "partial" in os.path.basename(path):
+                    note += ("; PARTIAL: the capture covers POTRF and TRTRI completely and 106 of the 453 LAUUM launches "
+                             "(about 2/3 of the N^3 flop), ncu ran into its time limit")
+                return float(tot), note
         except Exception:
             continue
-    return None
+    return None, "no ncu capture committed"
 
 
 def workload_config(args):
@@ -610,7 +617,7 @@ def main():
                 "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
                 # dram__bytes_read.sum + dram__bytes_write.sum summed over every dgemm_mma_kernel launch of ONE timed
                 # evaluation (ncu launch list of this command, profiles/r01/launches_bench_n50k.*.json)
-                "traffic": gemm_dram_traffic(n),
+                "traffic": gemm_dram_traffic(n)[0], "traffic_note": gemm_dram_traffic(n)[1],
                 "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
                 "algorithmic_flops_per_step": float(n) ** 3,
                 "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
