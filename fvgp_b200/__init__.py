@@ -6,14 +6,7 @@
 Importing the package never touches the GPU; the first compute call loads
 `fvgp_b200/lib/libfvgp_b200.so` and fails loudly if it (or a CUDA device) is missing.
 """
-import os as _os
-
-# The population evaluator (ops.lml_population) overlaps up to 32 independent evaluation chains on separate streams;
-# the driver multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8), and chains that share
-# a queue serialise.  Only takes effect when set before the CUDA context exists; a user setting wins.
-_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
-from . import kernels  # noqa: E402
+from . import kernels
 from ._lib import NativeLibraryError, NonPositiveDefiniteError
 from .fvgp import fvGP
 from .gp import GP

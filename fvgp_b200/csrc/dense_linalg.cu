@@ -443,6 +443,113 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(const double* __restrict_
   }
 }
 
+// Both substitutions of one right-hand side in ONE launch for n <= TRSV_FUSED_MAX: a single CTA per problem walks
+// the 64-wide tiles itself (stage the inverse block, leaf product, rank-64 update of the remaining vector, barrier).
+// At these sizes the step-per-launch version is a chain of 2 n / 64 dependent ~10 us launches (32 of the 66 launches
+// of an N = 1000 evaluation, 20 % of a population step); the arithmetic per row / column is the step kernels' own,
+// in the same order (bitwise identical results).  w, z: n doubles of scratch each; x: right-hand side in, solution out.
+constexpr int TRSV_FUSED_MAX = 2048;
+constexpr int TRSV_FUSED_THREADS = 1024;
+
+__device__ __forceinline__ void stage_inverse_block_wide(const double* __restrict__ dinv, double (*S)[VSP], int tid) {
+#pragma unroll
+  for (int q = 0; q < (VS * VS / 2) / TRSV_FUSED_THREADS; ++q) {  // 2048 double2 / 1024 threads
+    const int e = tid + TRSV_FUSED_THREADS * q, r = e / (VS / 2), c2 = (e % (VS / 2)) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(dinv + r * TS + c2);
+    S[r][c2] = v.x;
+    S[r][c2 + 1] = v.y;
+  }
+}
+
+__global__ void __launch_bounds__(TRSV_FUSED_THREADS) trsv_fused_kernel(const double* __restrict__ L, long long ld, int n,
+                                                                        const double* __restrict__ dinv_base, double* w,
+                                                                        double* z, double* x, long long bstride) {
+  L += blockIdx.x * bstride, dinv_base += blockIdx.x * bstride;
+  w += blockIdx.x * bstride, z += blockIdx.x * bstride, x += blockIdx.x * bstride;
+  __shared__ double S[VS][VSP];
+  __shared__ double yj[VS], zj[VS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = TRSV_FUSED_THREADS / 32;
+  const int ntile = (n + VS - 1) / VS;
+  for (int i = tid; i < n; i += TRSV_FUSED_THREADS) w[i] = x[i];
+  __syncthreads();
+  for (int t = 0; t < ntile; ++t) {  // L z = b
+    const int j0 = t * VS, nt = min(VS, n - j0);
+    stage_inverse_block_wide(dinv_base + (long long)(t / 2) * TS * TS + (t % 2) * ((long long)VS * TS + VS), S, tid);
+    if (tid < VS) yj[tid] = tid < nt ? w[j0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < 4 * VS) {
+      const int r = tid >> 2, part = tid & 3;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int k = part; k <= r; k += 4) acc = fma(S[r][k], yj[k], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) {
+        zj[r] = acc;
+        if (r < nt) z[j0 + r] = acc;
+      }
+    }
+    __syncthreads();
+    const double z0 = zj[lane], z1 = zj[lane + 32];
+    for (int i0 = j0 + VS + warp * 4; i0 < n; i0 += NW * 4) {  // four rows per warp in flight
+      double a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = min(i0 + u, n - 1);
+        const double* row = L + (long long)i * ld + j0;
+        a[u] = row[lane] * z0 + row[lane + 32] * z1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double acc = warp_sum(a[u]);
+        if (lane == 0 && i0 + u < n) w[i0 + u] -= acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int t = ntile - 1; t >= 0; --t) {  // L^T x = z
+    const int j0 = t * VS, nt = min(VS, n - j0);
+    stage_inverse_block_wide(dinv_base + (long long)(t / 2) * TS * TS + (t % 2) * ((long long)VS * TS + VS), S, tid);
+    if (tid < VS) zj[tid] = tid < nt ? z[j0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < 4 * VS) {
+      const int c = tid >> 2, part = tid & 3;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int r = c + part; r < VS; r += 4) acc = fma(S[r][c], zj[r], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) {
+        yj[c] = acc;
+        if (c < nt) x[j0 + c] = acc;
+      }
+    }
+    __syncthreads();
+    for (int c = tid; c < j0; c += TRSV_FUSED_THREADS) {
+      const double* col = L + (long long)j0 * ld + c;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int r = 0;
+      for (; r + 8 <= nt; r += 8) {  // eight independent loads in flight; accumulation order of bwd_step_kernel
+        const double v0 = col[(long long)r * ld], v1 = col[(long long)(r + 1) * ld], v2 = col[(long long)(r + 2) * ld],
+                     v3 = col[(long long)(r + 3) * ld], v4 = col[(long long)(r + 4) * ld], v5 = col[(long long)(r + 5) * ld],
+                     v6 = col[(long long)(r + 6) * ld], v7 = col[(long long)(r + 7) * ld];
+        a0 = fma(v0, yj[r], a0), a1 = fma(v1, yj[r + 1], a1), a2 = fma(v2, yj[r + 2], a2), a3 = fma(v3, yj[r + 3], a3);
+        a0 = fma(v4, yj[r + 4], a0), a1 = fma(v5, yj[r + 5], a1), a2 = fma(v6, yj[r + 6], a2), a3 = fma(v7, yj[r + 7], a3);
+      }
+      for (; r + 4 <= nt; r += 4) {
+        a0 = fma(col[(long long)r * ld], yj[r], a0);
+        a1 = fma(col[(long long)(r + 1) * ld], yj[r + 1], a1);
+        a2 = fma(col[(long long)(r + 2) * ld], yj[r + 2], a2);
+        a3 = fma(col[(long long)(r + 3) * ld], yj[r + 3], a3);
+      }
+      for (; r < nt; ++r) a0 = fma(col[(long long)r * ld], yj[r], a0);
+      z[c] -= (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(1024) logdet_kernel(const double* __restrict__ L, long long ld, int n, double* out,
                                                       long long bstride) {
   L += blockIdx.x * bstride, out += blockIdx.x * bstride;
@@ -764,6 +871,12 @@ int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int
 // columns: inside a block the 64-wide leaf steps (tile inverse + rank-64 update of the block's own rows),
 // then ONE matrix-vector product with the whole panel below (forward) / left of (backward) the block, which
 // streams >95 % of the factor at GEMV speed instead of in 782 latency-bound slivers.  Enqueue only.
+// FVGP_TRSV_FUSED=0 keeps the step-per-launch substitutions at every size (A/B on the GPU box); read on every call.
+static bool trsv_fused_enabled() {
+  const char* e = getenv("FVGP_TRSV_FUSED");
+  return e == nullptr || atoi(e) != 0;
+}
+
 // batch > 1: the same solve for `batch` problems; d_L, d_tileinv, d_B and d_work of problem b sit b * bstride doubles
 // further (all inside equally sized workspace slots).
 static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda, const double* d_tileinv, double* d_B,
@@ -776,6 +889,13 @@ static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda,
     return d_tileinv + (int64_t)(t / 2) * TS * TS + (t % 2) * ((int64_t)VS * TS + VS);
   };
   const int nblocks = (int)((n + VBLK - 1) / VBLK);
+  if (n <= TRSV_FUSED_MAX && trsv_fused_enabled()) {
+    for (int r = 0; r < nrhs; ++r)
+      launch(trsv_fused_kernel, nb, TRSV_FUSED_THREADS, 0, st, d_L, lda, (int)n, d_tileinv, w, z, d_B + (int64_t)r * ldb,
+             bstride);
+    FVGP_LAUNCH_OK();
+    return 0;
+  }
   for (int r = 0; r < nrhs; ++r) {
     double* b = d_B + (int64_t)r * ldb;
     if (batch == 1) {

@@ -542,3 +542,36 @@ def test_robust_and_wendland_kernel_names(fv, golden):
         assert np.array_equal(blk != 0, g["wendland_block_12"] != 0)                     # pattern bit-exact
         assert rel(blk[blk != 0], g["wendland_block_12"][blk != 0]) <= 1e-12              # values (K entries: 1e-12)
         assert np.max(np.abs(blk - g["wendland_sparse_12"])) <= 1e-12                     # KD-tree variant (a17)
+
+
+def test_fused_substitution_and_two_column_targets(fv):
+    """The single-launch substitution kernel (n <= 2048) against the step-per-launch kernels it replaces (bitwise: same
+    arithmetic per row / column), for ragged sizes; and y_data with two columns (r = 2 right-hand sides, the quadratic
+    form averaged over columns, gp_marginal_likelihood.py:171-178) through the one-at-a-time and the population path."""
+    from fvgp_b200 import GP
+    from oracle import fvgp_oracle as orc
+    for n in (37, 64, 129, 700, 2048):
+        x, y, nz = _pop_problem(n, 2, 900 + n)
+        h = np.array([1.1, 0.35, 0.45])
+        gp = GP(x, y, init_hyperparameters=h, noise_variances=nz)
+        fused = gp.log_likelihood(h * 1.01), gp.kv.evaluate(h * 1.01, gp.likelihood.V, gp.prior.m).KVinvY.copy()
+        os.environ["FVGP_TRSV_FUSED"] = "0"
+        try:
+            gp.kv._memo = None
+            steps = gp.log_likelihood(h * 1.01), gp.kv.evaluate(h * 1.01, gp.likelihood.V, gp.prior.m).KVinvY.copy()
+        finally:
+            os.environ.pop("FVGP_TRSV_FUSED")
+            gp.kv._memo = None
+        assert fused[0] == steps[0] and np.array_equal(fused[1], steps[1]), n
+        assert abs(fused[0] / orc.dense_log_likelihood(x, y, h * 1.01, nz) - 1) <= 1e-8
+    x, y, nz = _pop_problem(900, 2, 5)
+    y2 = np.column_stack([y, np.cos(4 * x[:, 0]) - 0.3 * x[:, 1]])
+    h = np.array([1.0, 0.3, 0.4])
+    gp = GP(x, y2, init_hyperparameters=h, noise_variances=nz)
+    T = h * np.array([[1.0, 1.0, 1.0], [1.2, 0.9, 1.1], [0.9, 1.1, 0.8]])
+    lml, grad = gp.marginal_likelihood.evaluate_population(T, with_gradient=True, component=1)
+    for b in range(3):
+        assert lml[b] == gp.log_likelihood(T[b])
+        assert abs(lml[b] / orc.dense_log_likelihood(x, y2, T[b], nz) - 1) <= 1e-8
+        assert rel(grad[b], gp.neg_log_likelihood_gradient(T[b], component=1)) <= 1e-9
+        assert rel(grad[b], orc.dense_neg_log_likelihood_gradient(x, y2, T[b], nz, component=1, economical=True)) <= 1e-8
