@@ -828,6 +828,13 @@ int trace_radial_enqueue(int kind, const double* d_x, int64_t n, int dim, const 
                          const double* h_out_scale, const double* d_Kinv, int64_t ld, const double* d_b,
                          double* d_partials, double* d_out, cudaStream_t st);
 
+// kfill.cu: lower-triangle fills of a batch of proposals in one launch (theta scratch on the device)
+int64_t kfill_batch_theta_len(int batch);
+int kfill_lower_batch_enqueue(int kind, const double* d_x, int64_t n, int dim, int batch, const double* h_amp,
+                              const double* h_inv_scale, const double* h_length, const double* h_centre,
+                              const double* d_noise, double* d_K, int64_t ldk, int64_t kstride, double* d_thetas,
+                              cudaStream_t st);
+
 static inline int64_t round_up16(int64_t v) { return (v + 15) / 16 * 16; }
 
 extern "C" {
@@ -1125,17 +1132,23 @@ static double trace_fold(int kind, double length) {
 static int population_lockstep(int kind, const double* d_x, int64_t n, int dim, int batch, const double* h_amp,
                                const double* h_inv_scale, const double* h_length, const double* h_centre,
                                const double* d_noise, const double* d_rhs, int nrhs, int want_grad, int grad_component,
-                               int slots, double* d_work, int* d_info, double* h_alpha, double* res_h, cudaStream_t S) {
+                               int slots, double* d_work, double* d_scratch, int64_t scratch_len, int* d_info,
+                               double* h_alpha, double* res_h, cudaStream_t S) {
   const SlotLayout L = slot_layout(n, dim, want_grad);
   const int res_stride = dim + 2;
   for (int b0 = 0; b0 < batch; b0 += slots) {
     const int nb = std::min(slots, batch - b0);
     double* A0 = d_work;
-    for (int b = 0; b < nb; ++b) {
-      int rc = fvgp_kfill_dense(kind, FVGP_FILL_LOWER, d_x, n, d_x, n, dim, h_amp[b0 + b],
-                                h_inv_scale + (int64_t)(b0 + b) * dim, h_centre, h_length[b0 + b], d_noise,
-                                A0 + (int64_t)b * L.len, L.ld, S);
-      if (rc != 0) return rc;
+    if (kfill_batch_theta_len(nb) <= scratch_len) {  // one fill launch for the whole chunk
+      REC_OK(kfill_lower_batch_enqueue(kind, d_x, n, dim, nb, h_amp + b0, h_inv_scale + (int64_t)b0 * dim, h_length + b0,
+                                       h_centre, d_noise, A0, L.ld, L.len, d_scratch, S));
+    } else {
+      for (int b = 0; b < nb; ++b) {
+        int rc = fvgp_kfill_dense(kind, FVGP_FILL_LOWER, d_x, n, d_x, n, dim, h_amp[b0 + b],
+                                  h_inv_scale + (int64_t)(b0 + b) * dim, h_centre, h_length[b0 + b], d_noise,
+                                  A0 + (int64_t)b * L.len, L.ld, S);
+        if (rc != 0) return rc;
+      }
     }
     Ctx c{S, A0 + L.tileinv, d_info + b0, A0 + L.pwork, 0};
     c.batch = nb, c.bstride = L.len;
@@ -1201,7 +1214,8 @@ int fvgp_lml_population(int kind, const double* d_x, int64_t n, int dim, int bat
   int rc = 0;
   if (nb == 0 && !force_streams) {
     rc = population_lockstep(kind, d_x, n, dim, batch, h_amp, h_inv_scale, h_length, h_centre, d_noise, d_rhs, nrhs,
-                             want_grad, grad_component, slots, d_work, d_info, h_alpha, res_h.data(), S);
+                             want_grad, grad_component, slots, d_work, d_alpha, (int64_t)batch * nrhs * n, d_info, h_alpha,
+                             res_h.data(), S);
     if (rc != 0) {
       cudaStreamSynchronize(S);
       return rc;

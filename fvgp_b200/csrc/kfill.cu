@@ -17,7 +17,9 @@
 // relative entry accuracy once coordinates exceed ~40 length scales (hard part 3).
 #include "../../include/fvgp_b200.h"
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 namespace fvgp {
 
@@ -357,6 +359,90 @@ static int launch_fill_dim(const FillParams& p, bool centred, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Batched fill for the population evaluator (dense_linalg.cu, lock-step schedule): blockIdx.y selects a proposal,
+// whose (amp, c_arg, c_aux, inv_scale) come from a device array and whose matrix sits blockIdx.y * kstride doubles
+// after the first one.  Same tile routine (fill_tile) and constants as the single fill -> bitwise the same matrices.
+// FULL / LOWER modes only (the factorisation wants the lower triangle; no mirror staging).
+// ----------------------------------------------------------------------------------------------
+struct FillTheta {
+  double amp, c_arg, c_aux;
+  double inv_scale[kMaxDim];
+};
+
+template <int KIND, int DIM, bool CENTRED>
+__global__ void __launch_bounds__(FILL_THREADS, 3) kfill_batch_kernel(const FillParams base,
+                                                                      const FillTheta* __restrict__ thetas,
+                                                                      long long kstride) {
+  extern __shared__ __align__(128) double fill_smem[];
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  constexpr int DPAD = (D + 1) & ~1;
+  FillParams p = base;
+  {
+    const FillTheta* t = thetas + blockIdx.y;
+    p.amp = t->amp, p.c_arg = t->c_arg, p.c_aux = t->c_aux;
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) p.inv_scale[i] = t->inv_scale[i];
+    p.K = base.K + (long long)blockIdx.y * kstride;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* sRow = fill_smem + warp * 8 * DPAD;
+  const long long per_cta = (p.ntiles + gridDim.x - 1) / gridDim.x;
+  long long tile = blockIdx.x * per_cta;
+  const long long tile_end = min(p.ntiles, tile + per_cta);
+  long long ia = 0, ib = 0;
+  if (tile < tile_end) {
+    if (p.mode == FVGP_FILL_FULL) {
+      ia = tile / p.tiles_j;
+      ib = tile - ia * p.tiles_j;
+    } else {
+      tri_index(tile, ia, ib);
+    }
+  }
+  for (; tile < tile_end; ++tile) {
+    const long long ti = ia, tj = ib;
+    if (p.mode == FVGP_FILL_FULL) {
+      if (++ib == p.tiles_j) ib = 0, ++ia;
+    } else if (++ib > ia) {
+      ib = 0, ++ia;
+    }
+    const bool interior = (ti + 1) * FT <= p.n1 && (tj + 1) * FT <= p.n2 && (p.noise == nullptr || ti != tj);
+    if (interior) fill_tile<KIND, DIM, CENTRED, true>(p, ti, tj, false, fill_smem, sRow, lane, warp);
+    else fill_tile<KIND, DIM, CENTRED, false>(p, ti, tj, false, fill_smem, sRow, lane, warp);
+  }
+}
+
+template <int KIND, int DIM, bool CENTRED>
+static void launch_fill_batch_one(const FillParams& p, const FillTheta* d_thetas, long long kstride, int batch,
+                                  cudaStream_t st) {
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  constexpr int DPAD = (D + 1) & ~1;
+  const long long per_problem = std::max<long long>(1, ((long long)sm_count() * 3 + batch - 1) / batch);
+  const unsigned gx = (unsigned)std::min<long long>(p.ntiles, per_problem);
+  launch(kfill_batch_kernel<KIND, DIM, CENTRED>, dim3(gx, (unsigned)batch), FILL_THREADS, 8 * 8 * DPAD * sizeof(double), st,
+         p, d_thetas, kstride);
+}
+
+template <int KIND>
+static int launch_fill_batch_dim(const FillParams& p, bool centred, const FillTheta* d_thetas, long long kstride,
+                                 int batch, cudaStream_t st) {
+#define FVGP_FILL_BATCH_CASE(DIMV)                                                              \
+  {                                                                                             \
+    if (centred) launch_fill_batch_one<KIND, DIMV, true>(p, d_thetas, kstride, batch, st);      \
+    else launch_fill_batch_one<KIND, DIMV, false>(p, d_thetas, kstride, batch, st);             \
+  }
+  switch (p.dim) {
+    case 1: FVGP_FILL_BATCH_CASE(1) break;
+    case 2: FVGP_FILL_BATCH_CASE(2) break;
+    case 3: FVGP_FILL_BATCH_CASE(3) break;
+    case 4: FVGP_FILL_BATCH_CASE(4) break;
+    default: launch_fill_batch_one<KIND, 0, false>(p, d_thetas, kstride, batch, st); break;
+  }
+#undef FVGP_FILL_BATCH_CASE
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // Gradient traces for the default ARD Matern-3/2 kernel.
 // ----------------------------------------------------------------------------------------------
 struct TraceParams {
@@ -690,6 +776,72 @@ __global__ void kgrad_dense_kernel(const double* __restrict__ x1, long long n1, 
 
 using namespace fvgp;
 
+// Kind-specific constants of the fill (shared by the single and the batched entry points).
+static bool fill_constants(int kind, double amp, double length, bool centred, double& c_arg, double& c_aux, double& fold) {
+  c_arg = 0.0, c_aux = 0.0, fold = 1.0;
+  switch (kind) {
+    case FVGP_K_MATERN32: c_arg = sqrt(3.0) / length; fold = c_arg; break;
+    case FVGP_K_MATERN52:
+      c_arg = sqrt(5.0) / length, fold = c_arg;
+      c_aux = centred ? amp / 3.0 : amp * 5.0 / (3.0 * length * length);
+      break;
+    case FVGP_K_MATERN52_ROBUST:  // same evaluation, quadratic coefficient 15 / length^2 (= 3 a^2 in scaled coordinates)
+      c_arg = sqrt(5.0) / length, fold = c_arg;
+      c_aux = centred ? amp * 3.0 : amp * 15.0 / (length * length);
+      break;
+    case FVGP_K_SQEXP: c_arg = 1.0 / (2.0 * length * length); fold = sqrt(c_arg); break;
+    case FVGP_K_EXP: c_arg = 1.0 / length; fold = c_arg; break;
+    case FVGP_K_WENDLAND: c_arg = 1.0 / length; fold = c_arg; break;
+    case FVGP_K_DISTANCE: break;
+    default: return false;
+  }
+  return true;
+}
+
+// Lower-triangle fills of `batch` proposals in ONE launch (population evaluator).  d_thetas: device scratch of
+// kfill_batch_theta_len(batch) doubles; matrix b at d_K + b * kstride.  Enqueue only.
+int64_t kfill_batch_theta_len(int batch) { return (int64_t)batch * (int64_t)(sizeof(FillTheta) / sizeof(double)); }
+
+int kfill_lower_batch_enqueue(int kind, const double* d_x, int64_t n, int dim, int batch, const double* h_amp,
+                              const double* h_inv_scale, const double* h_length, const double* h_centre,
+                              const double* d_noise, double* d_K, int64_t ldk, int64_t kstride, double* d_thetas,
+                              cudaStream_t st) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n > 0 && ldk >= n && batch >= 1 && batch <= 65535);
+  FillParams p;
+  p.x1 = d_x, p.x2 = d_x, p.noise = d_noise, p.K = d_K;
+  p.n1 = n, p.n2 = n, p.ldk = ldk, p.amp = 0.0, p.dim = dim, p.mode = FVGP_FILL_LOWER;
+  p.tiles_i = (n + FT - 1) / FT;
+  p.tiles_j = p.tiles_i;
+  p.ntiles = p.tiles_i * (p.tiles_i + 1) / 2;
+  p.vec2 = (ldk % 2 == 0 && kstride % 2 == 0 && ((uintptr_t)d_K % 16 == 0)) ? 1 : 0;
+  p.bulk = 0, p.band = 0, p.c_arg = 0.0, p.c_aux = 0.0;
+  const bool centred = h_centre != nullptr && dim <= 4;
+  std::vector<FillTheta> th((size_t)batch);
+  for (int b = 0; b < batch; ++b) {
+    double fold = 1.0;
+    th[b].amp = h_amp[b];
+    FVGP_REQUIRE(fill_constants(kind, h_amp[b], h_length[b], centred, th[b].c_arg, th[b].c_aux, fold));
+    for (int i = 0; i < kMaxDim; ++i)
+      th[b].inv_scale[i] = i < dim ? h_inv_scale[(size_t)b * dim + i] * (centred ? fold : 1.0) : 0.0;
+  }
+  for (int i = 0; i < kMaxDim; ++i) {
+    p.inv_scale[i] = 0.0;
+    p.centre[i] = (centred && i < dim) ? h_centre[i] : 0.0;
+  }
+  // pageable source: the runtime stages the bytes before returning, so the vector may go out of scope
+  FVGP_CUDA_OK(cudaMemcpyAsync(d_thetas, th.data(), sizeof(FillTheta) * batch, cudaMemcpyHostToDevice, st));
+  const FillTheta* dth = reinterpret_cast<const FillTheta*>(d_thetas);
+  switch (kind) {
+    case FVGP_K_MATERN32: return launch_fill_batch_dim<FVGP_K_MATERN32>(p, centred, dth, kstride, batch, st);
+    case FVGP_K_MATERN52:
+    case FVGP_K_MATERN52_ROBUST: return launch_fill_batch_dim<FVGP_K_MATERN52>(p, centred, dth, kstride, batch, st);
+    case FVGP_K_SQEXP: return launch_fill_batch_dim<FVGP_K_SQEXP>(p, centred, dth, kstride, batch, st);
+    case FVGP_K_EXP: return launch_fill_batch_dim<FVGP_K_EXP>(p, centred, dth, kstride, batch, st);
+    case FVGP_K_WENDLAND: return launch_fill_batch_dim<FVGP_K_WENDLAND>(p, centred, dth, kstride, batch, st);
+    default: return launch_fill_batch_dim<FVGP_K_DISTANCE>(p, centred, dth, kstride, batch, st);
+  }
+}
+
 extern "C" {
 
 // test / profiling hook: 0 = plain coalesced stores for the mirror tile, 1 = TMA bulk stores
@@ -728,22 +880,7 @@ int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const d
   // for every point, which bounds the extra relative error of an entry by ~2e-13.
   const bool centred = h_centre != nullptr && dim <= 4;
   double fold = 1.0;
-  switch (kind) {
-    case FVGP_K_MATERN32: p.c_arg = sqrt(3.0) / length; fold = p.c_arg; break;
-    case FVGP_K_MATERN52:
-      p.c_arg = sqrt(5.0) / length, fold = p.c_arg;
-      p.c_aux = centred ? amp / 3.0 : amp * 5.0 / (3.0 * length * length);
-      break;
-    case FVGP_K_MATERN52_ROBUST:  // same evaluation, quadratic coefficient 15 / length^2 (= 3 a^2 in scaled coordinates)
-      p.c_arg = sqrt(5.0) / length, fold = p.c_arg;
-      p.c_aux = centred ? amp * 3.0 : amp * 15.0 / (length * length);
-      break;
-    case FVGP_K_SQEXP: p.c_arg = 1.0 / (2.0 * length * length); fold = sqrt(p.c_arg); break;
-    case FVGP_K_EXP: p.c_arg = 1.0 / length; fold = p.c_arg; break;
-    case FVGP_K_WENDLAND: p.c_arg = 1.0 / length; fold = p.c_arg; break;
-    case FVGP_K_DISTANCE: break;
-    default: FVGP_REQUIRE(!"unknown kernel kind");
-  }
+  FVGP_REQUIRE(fill_constants(kind, amp, length, centred, p.c_arg, p.c_aux, fold));
   for (int i = 0; i < kMaxDim; ++i) {
     p.inv_scale[i] = i < dim ? h_inv_scale[i] * (centred ? fold : 1.0) : 0.0;
     p.centre[i] = (centred && i < dim) ? h_centre[i] : 0.0;
