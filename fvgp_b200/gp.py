@@ -178,11 +178,14 @@ class GP:
             objective_function_hessian = self.marginal_likelihood.neg_log_likelihood_hessian
         before_hps = np.array(self.hyperparameters)
         before = self.marginal_likelihood.log_likelihood() if accept_only_if_improved and not user_obj else None
-        population_objective = None
+        population_objective = population_log_likelihood = None
         if not user_obj and method == "global" and self.marginal_likelihood.population_supported():
             population_objective = lambda T: -self.marginal_likelihood.log_likelihood_population(T)   # noqa: E731
+        if method == "mcmc" and self.marginal_likelihood.population_supported():
+            population_log_likelihood = self.marginal_likelihood.log_likelihood_population
         hps = self.trainer.train(objective_function=objective_function,
                                  population_objective=population_objective,
+                                 population_log_likelihood=population_log_likelihood,
                                  objective_function_gradient=objective_function_gradient,
                                  objective_function_hessian=objective_function_hessian,
                                  hyperparameter_bounds=hyperparameter_bounds,

@@ -24,7 +24,7 @@ class GPtraining:
               hyperparameter_bounds=None, init_hyperparameters=None, method="global", pop_size=20, tolerance=0.0001,
               max_iter=120, local_optimizer="L-BFGS-B", global_optimizer="genetic", constraints=(), mcmc_prior=None,
               mcmc_prop_distrs="normal", mcmc_args={}, bo_args=None, dask_client=None, info=False,
-              population_objective=None):
+              population_objective=None, population_log_likelihood=None):
         if not self._in_bounds(init_hyperparameters, hyperparameter_bounds):
             raise Exception("Starting positions outside of optimization bounds.", init_hyperparameters,
                             hyperparameter_bounds)
@@ -55,7 +55,8 @@ class GPtraining:
             return np.array(res["x"])
         if method == "mcmc":
             res = run_mcmc(objective_function, init_hyperparameters, hyperparameter_bounds, n_updates=max_iter,
-                           prior=mcmc_prior, info=info, seed=mcmc_args.get("seed", None) if mcmc_args else None)
+                           prior=mcmc_prior, info=info, seed=mcmc_args.get("seed", None) if mcmc_args else None,
+                           population_log_likelihood=population_log_likelihood)
             self.mcmc_info = res
             return res["median(x)"]
         if method == "adam":
@@ -67,8 +68,15 @@ class GPtraining:
                         "or a callable); hgdl / bo need the hgdl / gp_bo packages")
 
 
-def run_mcmc(log_likelihood, x0, bounds, n_updates=10000, prior=None, info=False, seed=None):
-    """Adaptive random-walk Metropolis-Hastings over the hyperparameters (cf. gp_mcmc.py:96-224)."""
+def run_mcmc(log_likelihood, x0, bounds, n_updates=10000, prior=None, info=False, seed=None,
+             population_log_likelihood=None, max_batch=16):
+    """Adaptive random-walk Metropolis-Hastings over the hyperparameters (cf. gp_mcmc.py:96-224).
+
+    population_log_likelihood(T (B, H)) -> (B,): speculative evaluation.  While the chain rejects it stays where it
+    is, so the next proposals are all drawn around the SAME state: a batch of them is evaluated in one population
+    call and consumed in order up to (and including) the first acceptance; the rest -- drawn around a state the
+    chain has left, never looked at -- is discarded.  Every step still uses fresh independent randomness and the
+    exact acceptance ratio, so this is the same Markov chain; with acceptance rate a it advances ~1/a steps per call."""
     rng = np.random.default_rng(seed)
     x = np.array(x0, dtype=float)
     span = bounds[:, 1] - bounds[:, 0]
@@ -81,28 +89,52 @@ def run_mcmc(log_likelihood, x0, bounds, n_updates=10000, prior=None, info=False
 
     f = log_likelihood(x) + log_prior(x)
     chain, fs, accepted = [x.copy()], [f], 0
-    for it in range(int(n_updates)):
-        prop = x + step * rng.standard_normal(len(x))
-        lp = log_prior(prop)
-        if np.isfinite(lp):
-            fp = log_likelihood(prop) + lp
-            if np.isnan(fp):
-                raise Exception("NaN log-likelihood encountered in MCMC")
-            if np.log(rng.random()) < fp - f:
-                x, f, accepted = prop, fp, accepted + 1
-        chain.append(x.copy())
-        fs.append(f)
-        if (it + 1) % 50 == 0:                                  # adapt towards ~25-45 % acceptance
-            rate = accepted / (it + 1)
-            step *= 1.25 if rate > 0.45 else (0.8 if rate < 0.2 else 1.0)
-        if info and (it + 1) % 100 == 0:
-            print(f"mcmc iteration {it + 1}: f(x)= {f}")
+    n_updates = int(n_updates)
+    it = 0
+    calls = 0
+    while it < n_updates:
+        # batch: never across an adaptation boundary (the step width changes there), sized to the acceptance rate
+        rate = accepted / it if it >= 20 else 0.3
+        want = 1 if population_log_likelihood is None else int(np.clip(np.ceil(1.5 / max(rate, 0.05)), 2, max_batch))
+        m = max(1, min(want, n_updates - it, 50 - it % 50))
+        props = x + step * rng.standard_normal((m, len(x)))
+        us = rng.random(m)
+        lps = np.array([log_prior(p) for p in props], dtype=float)
+        ok = np.isfinite(lps)
+        fps = np.full(m, -np.inf)
+        lazy = population_log_likelihood is None or ok.sum() <= 1
+        if not lazy:
+            try:
+                fps[ok] = np.asarray(population_log_likelihood(props[ok]), dtype=float) + lps[ok]
+                calls += 1
+            except Exception:
+                lazy = True           # e.g. a speculative proposal that is not positive definite: decide one by one
+        for i in range(m):
+            took = False
+            if ok[i]:
+                if lazy:
+                    fps[i] = log_likelihood(props[i]) + lps[i]
+                    calls += 1
+                if np.isnan(fps[i]):
+                    raise Exception("NaN log-likelihood encountered in MCMC")
+                if np.log(us[i]) < fps[i] - f:
+                    x, f, accepted, took = props[i].copy(), fps[i], accepted + 1, True
+            chain.append(x.copy())
+            fs.append(f)
+            it += 1
+            if it % 50 == 0:                                    # adapt towards ~25-45 % acceptance
+                r = accepted / it
+                step *= 1.25 if r > 0.45 else (0.8 if r < 0.2 else 1.0)
+            if info and it % 100 == 0:
+                print(f"mcmc iteration {it}: f(x)= {f}")
+            if took:
+                break                                           # the remaining proposals were drawn around the old state
     chain = np.array(chain)
     burn = chain[len(chain) // 5:]
     best = int(np.argmax(fs))
     return {"x": chain, "f(x)": np.array(fs), "median(x)": np.median(burn, axis=0), "mean(x)": np.mean(burn, axis=0),
             "var(x)": np.var(burn, axis=0), "max x": chain[best], "max f(x)": fs[best],
-            "acceptance rate": accepted / max(1, int(n_updates))}
+            "acceptance rate": accepted / max(1, n_updates), "likelihood calls": calls}
 
 
 def adam_optimize(objective, gradient, x0, bounds, max_iter=200, tolerance=1e-4, lr=0.02, b1=0.9, b2=0.999):

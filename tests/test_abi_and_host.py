@@ -174,3 +174,38 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_speculative_mcmc_samples_the_same_distribution():
+    """run_mcmc with a population evaluator (batches of proposals around the current state, consumed up to the first
+    acceptance) must sample the same target as the one-proposal-at-a-time chain, with far fewer likelihood calls."""
+    from fvgp_b200.gp_training import run_mcmc
+    mu, sd = np.array([0.4, 1.2]), np.array([0.1, 0.3])
+
+    def ll(t):
+        return float(-0.5 * np.sum(((t - mu) / sd) ** 2))
+
+    seen = []
+
+    def pop(T):
+        seen.append(len(T))
+        return np.array([ll(t) for t in T])
+
+    bounds = np.array([[-2.0, 3.0], [-2.0, 4.0]])
+    stats = {}
+    for name, fn in (("seq", None), ("pop", pop)):
+        means, sds, calls = [], [], []
+        for seed in range(4):
+            r = run_mcmc(ll, np.zeros(2), bounds, n_updates=3000, seed=seed, population_log_likelihood=fn)
+            assert len(r["x"]) == 3001 and len(r["f(x)"]) == 3001
+            means.append(r["mean(x)"]); sds.append(np.sqrt(r["var(x)"])); calls.append(r["likelihood calls"])
+        stats[name] = (np.mean(means, axis=0), np.mean(sds, axis=0), np.mean(calls))
+    for name in ("seq", "pop"):
+        assert np.allclose(stats[name][0], mu, atol=0.03) and np.allclose(stats[name][1], sd, rtol=0.15), stats[name]
+    assert stats["seq"][2] == 3000 and stats["pop"][2] < 0.6 * 3000 and max(seen) <= 16 and min(seen) >= 2
+
+    # a population call that fails (a speculative proposal that is not positive definite) falls back to one-by-one
+    def bad_pop(T):
+        raise RuntimeError("Linear algebra failed")
+    r = run_mcmc(ll, np.zeros(2), bounds, n_updates=300, seed=0, population_log_likelihood=bad_pop)
+    assert len(r["x"]) == 301 and r["likelihood calls"] >= 250

@@ -575,3 +575,20 @@ def test_fused_substitution_and_two_column_targets(fv):
         assert abs(lml[b] / orc.dense_log_likelihood(x, y2, T[b], nz) - 1) <= 1e-8
         assert rel(grad[b], gp.neg_log_likelihood_gradient(T[b], component=1)) <= 1e-9
         assert rel(grad[b], orc.dense_neg_log_likelihood_gradient(x, y2, T[b], nz, component=1, economical=True)) <= 1e-8
+
+
+def test_train_mcmc_speculates_through_the_population_path(fv):
+    """train(method="mcmc"), the reference's default: batches of proposals around the current state go through
+    fvgp_lml_population (gp_training.run_mcmc); the chain must still find the posterior mode of the hyperparameters."""
+    from fvgp_b200 import GP, ops
+    x, y, nz = _pop_problem(600, 1, 11)
+    gp = GP(x, y, init_hyperparameters=np.array([0.4, 0.9]), noise_variances=nz)
+    before = gp.log_likelihood()
+    ops.start_phase_timing()
+    hps = gp.train(hyperparameter_bounds=np.array([[0.05, 10.0], [0.02, 5.0]]), method="mcmc", max_iter=150,
+                   mcmc_args={"seed": 3})
+    phases = ops.stop_phase_timing()
+    info = gp.trainer.mcmc_info
+    assert "population" in phases and info["likelihood calls"] < 150 and len(info["x"]) == 151
+    assert gp.log_likelihood() >= before and np.all(hps > 0)
+    assert gp.log_likelihood(info["max x"]) == info["max f(x)"]          # population LMLs are the one-at-a-time LMLs
