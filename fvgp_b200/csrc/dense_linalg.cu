@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(512) potrf_tile_kernel(double* A, long long ld
 // critical path of every evaluation at N ~ 1e3 (8 tiles = half of a 3 ms LML) and of the panel path at large N.
 // Here the factorisation is blocked by panels of 16 columns:
 //   * inside a panel the columns stay UNSCALED (column j's rank-1 update carries the factor 1/d_j), so one column
-//     step is: read the pivot, rsqrt, update the <= 15 remaining panel columns, ONE barrier;
+//     step is: read the pivot, reciprocal, update the <= 15 remaining panel columns, ONE barrier;
 //   * after the 16 columns, one pass scales the panel and also stores it k-major in a 16 x 128 staging array;
 //   * the rank-16 update of the trailing tile runs from registers: each thread owns one 4 x 4 micro-tile of the
 //     lower triangle (<= 406 micro-tiles), reads its 2 x 4 panel values per k with 16-byte loads from the staging
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(512) potrf_tile2_kernel(double* A, long long l
   // staging array of the current panel, k-major; offset rounded so that its rows are 16-byte aligned
   constexpr int P_OFF = ((TS * TP + 2 * (TS / 2) * HP + 2 * TS) + 1) / 2 * 2;
   double(*P)[TS] = reinterpret_cast<double(*)[TS]>(tile_smem + P_OFF);
+  __shared__ double Pv[PW];  // pivots d_j of the current panel
   constexpr int H = TS / 2;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < TS * TS; idx += 512) {
@@ -197,22 +198,22 @@ __global__ void __launch_bounds__(512) potrf_tile2_kernel(double* A, long long l
   for (int p0 = 0; p0 < TS; p0 += PW) {
     const int pend = p0 + PW;
     for (int j = p0; j < pend; ++j) {
+      // Only 1 / d_j sits on the per-column critical path (reciprocal seed + two Newton steps: 4 dependent FMAs); the
+      // square root that the scaling pass needs is taken once per panel, four independent chains per thread.
       const double d = T[j][j];
-      if (!(d > 0.0) && tid == 0) atomicCAS(info, 0, global_row0 + j + 1);
-      double y;
-      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+      if (tid == 0) {
+        if (!(d > 0.0)) atomicCAS(info, 0, global_row0 + j + 1);
+        Pv[j - p0] = d;
+      }
+      double r;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
-        const double e = fma(-(d * y), y, 1.0);
-        y = fma(0.5 * y, e, y);
-      }
-      if (tid == 0) {
-        double sq = d * y;
-        sq = fma(fma(-sq, sq, d), 0.5 * y, sq);
-        Dg[j] = sq, RDg[j] = y;
+        const double e = fma(-d, r, 1.0);
+        r = fma(r, e, r);
       }
       if (row > j) {  // T[row][k] -= T[row][j] T[k][j] / d for the panel columns k > j, rows >= k
-        const double lij = T[row][j] * (y * y);
+        const double lij = T[row][j] * r;
 #pragma unroll
         for (int q = 0; q < PW / 4; ++q) {
           const int k = j + 1 + cg + 4 * q;
@@ -225,10 +226,24 @@ __global__ void __launch_bounds__(512) potrf_tile2_kernel(double* A, long long l
 #pragma unroll
     for (int q = 0; q < PW / 4; ++q) {
       const int j = p0 + cg + 4 * q;
-      if (row > j) {
-        const double v = T[row][j] * RDg[j];
-        T[row][j] = v;
-        P[j - p0][row] = v;
+      if (row >= j) {
+        const double d = Pv[j - p0];
+        double y;  // 1/sqrt(d) by MUFU.RSQ64H + two Newton steps
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const double e = fma(-(d * y), y, 1.0);
+          y = fma(0.5 * y, e, y);
+        }
+        if (row == j) {
+          double sq = d * y;
+          sq = fma(fma(-sq, sq, d), 0.5 * y, sq);
+          Dg[j] = sq, RDg[j] = y;
+        } else {
+          const double v = T[row][j] * y;
+          T[row][j] = v;
+          P[j - p0][row] = v;
+        }
       }
     }
     __syncthreads();
