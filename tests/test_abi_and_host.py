@@ -209,3 +209,24 @@ def test_speculative_mcmc_samples_the_same_distribution():
         raise RuntimeError("Linear algebra failed")
     r = run_mcmc(ll, np.zeros(2), bounds, n_updates=300, seed=0, population_log_likelihood=bad_pop)
     assert len(r["x"]) == 301 and r["likelihood calls"] >= 250
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype in include/fvgp_b200.h has as many parameters as its ctypes binding (guards ABI drift: a missing
+    or extra argument in _lib._SIGNATURES would silently shift every later pointer)."""
+    from fvgp_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "fvgp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = dict(re.findall(r"\b(fvgp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt))
+    assert set(protos) == set(_lib._SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib._SIGNATURES[name][1]), (name, n, len(_lib._SIGNATURES[name][1]))
+    # pointer-vs-scalar agreement for the population entry point (the widest signature)
+    import ctypes
+    sig = _lib._SIGNATURES["fvgp_lml_population"][1]
+    decl = [p.strip() for p in protos["fvgp_lml_population"].split(",")]
+    for ctype, d in zip(sig, decl):
+        is_ptr = "*" in d
+        assert is_ptr == (ctype is ctypes.c_void_p or hasattr(ctype, "contents") or ctype.__name__.startswith("LP_")), (d, ctype)
