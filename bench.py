@@ -11,16 +11,30 @@ theta_k (synthetic data of SURVEY.md section 8d, seeded).
 
   value        evals/s with x / y / noise resident in HBM, timed with CUDA events on the launching
                stream, barrier + synchronize on both sides, max over ranks.
-  e2e          same metric through the public API with HOST buffers: every step re-uploads x from
-               pinned host memory and reads LML and gradient back (copies inside the timed region).
+  e2e          same metric through the public API with HOST buffers: args["host_inputs_every_call"]
+               makes every call copy x from pinned host memory; y - m and the noise diagonal are
+               uploaded and LML / gradient read back by every call anyway (copies inside the timed region).
   roofline     dominant kernel = the DMMA GEMM behind POTRF + POTRI: algorithmic N^3 flop / (CUDA-event
                time of the potrf + potri phases); peak = DMMA issue rate measured live in this run
-               (MEASURED_PEAKS.json has no FP64 figure).  roofline_kfill: the K-assembly kernel against HBM.
-  cpu_baseline the numpy/scipy oracle port of the reference algorithm on the host cores, on a bounded
-               sample (smaller N), extrapolated with N^3 (the reference gradient needs (3H+3) 8 N^2 bytes
-               = 300 GB at N = 50k and cannot run); reported, not the target.
-N > 1: hyperparameter proposals are independent evaluations (MCMC / DE populations), so each rank
-evaluates its own theta sequence on a replica of the data -- no data-path collective ("weak").
+               (MEASURED_PEAKS.json has no FP64 figure).  roofline_kfill: the K-assembly kernel against
+               HBM, in the symmetric mode (full square written) and in the lower mode the LML path uses.
+  cpu_baseline the numpy/scipy oracle port of the reference algorithm on the host cores, bounded sample.
+  parity       (N = 1 only, after the timed regions) the GPU results at the BENCHMARKED sizes against the
+               oracle on the host: C2 LML at N = 50 000, gradient at N = 8 000 / 16 000, C4 sampled blocks
+               of the N = 1M pattern, gp2Scale sparseLU LML at N = 50 000, C3-shaped fvGP through the
+               sharded evaluator.  pass / fail per check, tolerances in the record.
+  c4 / c1      the other single-GPU workloads of BASELINE.json's metric, as extra keys of the same line.
+  sharded      (N > 1) the DATA-sharded paths measured in the same run: C3-size dense LML + gradient with KV
+               2-D block-cyclic over all ranks (+ agreement with one GPU at the same size), C5 at 8 GPUs,
+               gp2Scale with the CSR rows sharded over the ranks.
+N > 1 headline: hyperparameter proposals are independent evaluations (MCMC / DE populations), so each
+rank evaluates its own theta sequence on a replica of the data -- no data-path collective ("weak").
+
+--impl reference: the UNMODIFIED reference package (baseline/_ref, see baseline/install_ref.py) through
+its own GP.log_likelihood / neg_log_likelihood_gradient on the host cores; each step a bounded sample
+(N = --cpu-sample-n), plus one measurement per size of a ladder for the a N^2 + b N^3 fit that extrapolates
+to N = 50 000 (the reference's gradient needs ~300 GB there) and a SAME-N measured point (N = 8 000) that
+the GPU arm measures too (`same_n`).
 """
 import argparse
 import json
@@ -29,6 +43,8 @@ import subprocess
 import sys
 import threading
 import time
+
+T_START = time.time()
 
 if "reference" in sys.argv and "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
     # torchrun exports OMP_NUM_THREADS=1 when it starts more than one rank; the CPU arm (rank 0 only) is meant
@@ -40,12 +56,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+HOLD = {"line": None, "printed": False}      # what the watchdog prints if an optional section hangs
+SAME_N = 8000                      # size both arms measure directly (no extrapolation in that ratio)
+METRIC_C2 = "LML+gradient evals/s (dense, N=50k, 3D, ARD Matern-3/2)"
 
+
+# ------------------------------------------------------------------------------------------ synthetic data
 def synthetic_c2(n, seed=2):
     rng = np.random.default_rng(seed)
     x = rng.random((n, 3))
     y = np.sin(5 * x[:, 0]) * np.cos(3 * x[:, 1]) + x[:, 2] + 0.1 * rng.standard_normal(n)
     return x, y, np.full(n, 1e-2)
+
+
+def synthetic_c3(points=20000, tasks=5, seed=3):
+    """2-D inputs x 5 tasks -> (points * tasks)-row K on the 3-D index set."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((points, 2))
+    y = np.stack([np.sin((3 + t) * x[:, 0]) + np.cos(2 * x[:, 1]) + 0.1 * rng.standard_normal(points)
+                  for t in range(tasks)], axis=1)
+    return x, y, np.full((points, tasks), 1e-2)
+
+
+THETA_C3 = np.array([1.0, .3, .3, 2.0])
 
 
 def synthetic_c4(n, seed=4):
@@ -68,6 +101,22 @@ def theta_k(k, rank=0):
     return np.array([1.0, .3, .4, .5]) * (1.0 + 0.02 * ((k + 7 * rank) % 20))
 
 
+def synthetic_c5(n, seed=5):
+    """SURVEY 8d config C5: 2-D inputs, smooth signal + noise."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, 2))
+    y = np.sin(4 * x[:, 0]) * np.cos(3 * x[:, 1]) + 0.1 * rng.standard_normal(n)
+    return x, y, np.full(n, 1e-2)
+
+
+def synthetic_c1(n=1000, seed=1):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, 1))
+    y = np.sin(5 * x[:, 0]) + np.cos(10 * x[:, 0]) + 0.05 * rng.standard_normal(n)
+    return x, y, np.full(n, 1e-2)
+
+
+# ------------------------------------------------------------------------------------------ helpers
 class ClockSampler(threading.Thread):
     """SM clock / throttle reasons sampled DURING the timed region.  In-process NVML (the library nvidia-smi itself
     reads; the recipe's clocks line: clocks.sm, clocks.max.sm, clocks_event_reasons.*): forking nvidia-smi from a
@@ -139,207 +188,407 @@ def use_all_host_threads():
     return os.cpu_count()
 
 
-def cpu_baseline_step(x, y, noise, theta, orc):
-    """Reference algorithm (stacked LU solves of KV against dK/dtheta) on the host cores."""
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def event_timed(fn, reps=1):
+    """Best-of-reps CUDA-event time of fn() on torch's current stream (seconds), and its last result."""
+    import torch
+    best, out = 1e30, None
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    return best, out
+
+
+class Deadline:
+    """Sub-records are optional evidence: each one runs only while the run is inside its time budget, and the
+    decision is taken on rank 0 and broadcast so that collective sections are entered by all ranks or none."""
+
+    def __init__(self, seconds):
+        self.limit = float(seconds)
+
+    def left(self):
+        return self.limit - (time.time() - T_START)
+
+    def allows(self, need):
+        import torch
+        import torch.distributed as dist
+        ok = self.left() > need
+        if dist.is_available() and dist.is_initialized():
+            t = torch.tensor([1 if ok else 0], device="cuda")
+            dist.broadcast(t, 0)
+            ok = bool(t.item())
+        return ok
+
+
+def emit(line, rank):
+    if rank == 0 and not HOLD["printed"]:
+        HOLD["printed"] = True
+        print(json.dumps(line), flush=True)
+
+
+def start_watchdog(limit_s, rank):
+    """The headline is measured first; the optional sections after it (multi-rank collectives, host oracles) must
+    never be able to lose it.  Past the hard limit every rank leaves, rank 0 after printing what it has."""
+    def run():
+        while time.time() - T_START < limit_s:
+            time.sleep(1.0)
+        line = HOLD["line"]
+        if line is not None and not HOLD["printed"]:
+            line["watchdog"] = f"optional sections cut off after {limit_s:.0f} s"
+            emit(line, rank)
+        sys.stdout.flush()
+        os._exit(0 if line is not None else 3)
+    threading.Thread(target=run, daemon=True).start()
+
+
+def guarded(name, fn, sink):
+    """Run one optional section; a failure is recorded in the line instead of killing the headline."""
+    t0 = time.time()
+    try:
+        sink[name] = fn()
+    except Exception as e:                      # noqa: BLE001 -- evidence sections must never lose the headline
+        import traceback
+        sink[name] = {"error": f"{type(e).__name__}: {e}", "trace_tail": traceback.format_exc()[-600:]}
+    if isinstance(sink.get(name), dict):
+        sink[name]["section_seconds"] = round(time.time() - t0, 2)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_port_step(x, y, noise, theta, orc):
+    """Reference ALGORITHM (stacked LU solves of KV against dK/dtheta) from the oracle port."""
     lml = orc.dense_log_likelihood(x, y, theta, noise)
     grad = orc.dense_neg_log_likelihood_gradient(x, y, theta, noise, economical=False)
     return lml, grad
 
 
+def _reference_gp(n):
+    """The unmodified reference's GP on the C2 data of size n (None when baseline/_ref is absent)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import install_ref
+    fv = install_ref.import_reference()
+    x, y, noise = synthetic_c2(n)
+    import warnings
+    warnings.filterwarnings("ignore")
+    return fv.GP(x, y, init_hyperparameters=theta_k(0), noise_variances=noise)
+
+
+def fit_n2_n3(ns, ts):
+    """Non-negative least squares of t = a N^2 + b N^3 (relative residuals)."""
+    from scipy.optimize import nnls
+    ns, ts = np.asarray(ns, dtype=float), np.asarray(ts, dtype=float)
+    A = np.stack([ns ** 2, ns ** 3], axis=1) / ts[:, None]
+    coef, _ = nnls(A, np.ones(len(ts)))
+    return float(coef[0]), float(coef[1])
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (numpy/scipy oracle port; the reference itself is
-    pure Python and absent on the GPU box) timed on the host cores, bounded sample, N^3-extrapolated."""
+    """--impl reference: see the module docstring."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import fvgp_oracle as orc
-    use_all_host_threads()
+    cores = use_all_host_threads()
+    budget = float(os.environ.get("FVGP_REF_BUDGET_S", "330"))
     ns = args.cpu_sample_n
-    x, y, noise = synthetic_c2(ns)
-    for k in range(min(args.warmup, 1)):
-        cpu_baseline_step(x, y, noise, theta_k(k), orc)
+    kind = "reference"
+    try:
+        gp = _reference_gp(ns)
+
+        def step(g, k):
+            th = theta_k(k)
+            return g.log_likelihood(th), g.neg_log_likelihood_gradient(th)
+    except Exception as e:                                         # baseline/_ref missing: the oracle port
+        kind = "port"
+        why = f"{type(e).__name__}: {e}"
+        from oracle import fvgp_oracle as orc
+
+        class _Port:
+            def __init__(self, n):
+                self.x, self.y, self.noise = synthetic_c2(n)
+        gp = _Port(ns)
+
+        def step(g, k):
+            return cpu_port_step(g.x, g.y, g.noise, theta_k(k), orc)
+    for k in range(min(args.warmup, 2)):
+        step(gp, k)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        cpu_baseline_step(x, y, noise, theta_k(k), orc)
+        out = step(gp, k)
     per = (time.perf_counter() - t0) / args.steps
-    scale = (args.n / ns) ** 3
-    value = 1.0 / (per * scale)
-    cores = os.cpu_count()
-    sample = (f"oracle port of the reference algorithm (K-fill numpy, scipy cho_factor, H stacked LU solves) at N={ns}: "
-              f"{per:.2f} s per LML+gradient on {cores} host threads; extrapolated x(N/{ns})^3 to N={args.n} "
-              f"(the reference gradient needs ~{(3 * 4 + 3) * 8 * args.n ** 2 / 1e9:.0f} GB at N={args.n})")
-    line = {"impl": "reference", "metric": "LML+gradient evals/s (dense, N=50k, 3D, ARD Matern-3/2)",
+    measured = {ns: per}
+    # ladder for the fit: one evaluation per size while the budget lasts (cost grows ~8x per doubling)
+    make = _reference_gp if kind == "reference" else (lambda n: _Port(n))
+    for n2 in (1000, 4000, SAME_N, 16000):
+        if n2 in measured:
+            continue
+        ref_n = max(measured)
+        predict = measured[ref_n] * (n2 / ref_n) ** 3 * 1.3 + 2.0
+        if n2 > ref_n and (time.time() - T_START) + predict > budget:
+            continue
+        g2 = make(n2)
+        t0 = time.perf_counter()
+        step(g2, 1)
+        measured[n2] = time.perf_counter() - t0
+        del g2
+    sizes = sorted(measured)
+    a, b = fit_n2_n3(sizes, [measured[s] for s in sizes])
+    t_full = a * args.n ** 2 + b * args.n ** 3
+    value = 1.0 / t_full
+    sample = (f"{'UNMODIFIED reference (baseline/_ref) GP.log_likelihood + GP.neg_log_likelihood_gradient' if kind == 'reference' else 'oracle port (baseline/_ref missing: ' + why + ')'}"
+              f" on {cores} host threads; timed steps at N={ns}: {per:.2f} s each; one evaluation per size "
+              f"{ {s: round(measured[s], 2) for s in sizes} } s; fit t = a N^2 + b N^3 (a={a:.3e}, b={b:.3e}) extrapolated to "
+              f"N={args.n}: {t_full:.0f} s (the reference gradient needs ~{(3 * 4 + 3) * 8 * args.n ** 2 / 1e9:.0f} GB "
+              f"there and cannot run); `value` is that extrapolation, `ms_per_step` the measured step at N={ns}")
+    line = {"impl": "reference", "metric": METRIC_C2,
             "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": per * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "extrapolated": True, "measured_seconds_by_n": {str(s): measured[s] for s in sizes},
+            "fit": {"model": "t = a N^2 + b N^3", "a": a, "b": b, "extrapolated_seconds_at_n": t_full},
+            "same_n": {"n": SAME_N, "seconds": measured.get(SAME_N), "evals_per_s": (1.0 / measured[SAME_N]) if SAME_N in measured else None,
+                       "note": "measured, not extrapolated; the GPU arm reports the same size under `same_n`"},
+            "last_lml": float(out[0]),
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.with_c4 and (time.time() - T_START) < budget:
+        try:
+            line["c4"] = reference_c4(min(args.c4_cpu_n, 200000), 1000000)
+        except Exception as e:                                     # noqa: BLE001
+            line["c4"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
 
 
-def run_c4(args):
-    """Secondary workload (not the driver's headline line): gp2Scale LML evaluations per second, N = 1M,
-    3-D, anisotropic Wendland, K assembled straight to CSR on the device, block-Jacobi PCG + SLQ logdet.
-    There is no gradient under gp2Scale in the reference (gp_marginal_likelihood.py:240)."""
-    n = args.n
-    if args.impl == "reference":
-        if int(os.environ.get("RANK", "0")) != 0:
-            return
-        from oracle import fvgp_oracle as orc
-        import scipy.sparse.linalg as spla
-        use_all_host_threads()
-        ns = min(n, 20000)
+def reference_c4(ns, n_full):
+    """gp2Scale on the host, the reference's OWN fast path, called through the
+    reference's own entry points on a bounded sample of the C4 point set (N = ns, support radius scaled to keep
+    ~102 nnz/row):
+      fill   gp2Scale_covariance.distributed_covariance (gp2Scale_covariance.py:313-431; blockwise, B = 10 000, synchronous
+             stub client -- dask is not installable here) with kernels.wendland_anisotropic_gp2Scale_cpu_sparse
+             (kernels.py:724, KD-tree ball queries behind the AABB cull) + assemble_triplets
+      solve  gp_lin_alg.calculate_sparse_conj_grad (gp_lin_alg.py:1213-1291; scipy cg, no preconditioner: the default ILU
+             is impractical)
+    The stochastic log-determinant (imate) is not installed and NOT included, which favours the reference.  The
+    defining dense-block kernel (kernels.py:502-528) is timed on two 10k x 10k blocks as a labelled second number."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    x, y, noise = synthetic_c4(ns)
+    th = theta_c4(0, ns)
+    rhs = (y - y.mean())[:, None]
+    out = {"n_sample": ns, "cores": os.cpu_count()}
+    from oracle import fvgp_oracle as orc
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import install_ref
+        install_ref.import_reference()
+        import ref_stubs
+        from fvgp import gp2Scale_covariance as g2s
+        from fvgp import gp_lin_alg as rla
+        from fvgp import kernels as rk
+        client = ref_stubs.Client()
+        fut = client.scatter(x)
+        t0 = time.perf_counter()
+        K = g2s.distributed_covariance(client, rk.wendland_anisotropic_gp2Scale_cpu_sparse, th, fut, ns, fut, ns, 10000,
+                                       symmetric=True, distribution="blockwise", k_n_params=3, args={})
+        t_fill = time.perf_counter() - t0
+        KV = orc.add_kv(K.tocsr(), noise)
+        t0 = time.perf_counter()
+        sol = rla.calculate_sparse_conj_grad(KV, rhs, args={"sparse_cg_tol": 1e-5})
+        t_cg = time.perf_counter() - t0
+        out["kind"], iters = "reference", None
+    except Exception as e:                                         # noqa: BLE001 -- baseline/_ref missing: oracle port
+        out["kind"] = "port"
+        out["reference_error"] = f"{type(e).__name__}: {e}"[:300]
+        ns = min(ns, 20000)
         x, y, noise = synthetic_c4(ns)
         th = theta_c4(0, ns)
         t0 = time.perf_counter()
-        K = orc.gp2scale_covariance(x, x, th, batch=2000, symmetric=True)      # the DEFINING dense-block path
+        K = orc.gp2scale_covariance(x, x, th, batch=2000, symmetric=True)
         t_fill = time.perf_counter() - t0
         KV = orc.add_kv(K, noise)
         t0 = time.perf_counter()
-        sol, iters = orc.sparse_cg(KV, (y - y.mean())[:, None], rtol=1e-5)
+        sol, it = orc.sparse_cg(KV, (y - y.mean())[:, None], rtol=1e-5)
         t_cg = time.perf_counter() - t0
-        per = t_fill * (n / ns) ** 2 + t_cg * (n / ns)
-        line = {"impl": "reference", "metric": "gp2Scale LML evals/s (N=1M, 3D, Wendland)", "value": 1.0 / per,
-                "unit": "evals/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": per * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C4: gp2Scale N={n}", "n": n},
-                "cpu_baseline": {"value": 1.0 / per, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-                                 "sample": f"oracle port at N={ns}: dense-block fill {t_fill:.1f} s (x(N/{ns})^2), scipy cg "
-                                           f"{t_cg:.2f} s / {iters[0]} iterations (x N/{ns}); the stochastic logdet (imate) is "
-                                           f"not available and not included"},
-                "e2e": {"value": 1.0 / per, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
-        return
+        iters = int(it[0])
+        out["n_sample"] = ns
+    t0 = time.perf_counter()
+    nb = 0
+    for i0 in range(0, min(ns, 20000), 10000):
+        orc.wendland_block(x[i0:i0 + 10000], x[i0:i0 + 10000], th)
+        nb += 1
+    t_dense_block = (time.perf_counter() - t0) / max(nb, 1)
+    scale = n_full / ns
+    per = (t_fill + t_cg) * scale                                  # both phases are O(N) at fixed nnz/row
+    out.update({"nnz": int(K.nnz), "fill_seconds": t_fill, "cg_seconds": t_cg, "cg_iterations": iters,
+                "value": 1.0 / per, "unit": "evals/s", "extrapolated": True,
+                "sample": f"KD-tree block kernel + assemble_triplets at N={ns}: {t_fill:.1f} s; scipy cg (no preconditioner, rtol 1e-5): "
+                          f"{t_cg:.1f} s; scaled x{scale:.0f} (linear in N at fixed nnz/row) to N={n_full}; log-determinant not "
+                          f"included (imate absent) -- favours the reference",
+                "dense_block_seconds_per_10k_block": t_dense_block,
+                "dense_block_path_seconds_at_full_n": t_dense_block * (n_full / 10000) * (n_full / 10000 + 1) / 2})
+    return out
+
+
+# ------------------------------------------------------------------------------------------ C4 (gp2Scale)
+C4_ARGS = {"sparse_cg_tol": 1e-5, "random_logdet_lanczos_degree": 20, "random_logdet_min_num_samples": 10,
+           "random_logdet_max_num_samples": 10}
+
+
+def c4_record(n, steps, warmup, rank=0, world=1, phases=True, sharded=False):
+    """gp2Scale LML evaluations per second: K assembled straight to CSR on the device, block-Jacobi PCG + SLQ logdet.
+    There is no gradient under gp2Scale in the reference (gp_marginal_likelihood.py:240).  sharded=True: the CSR rows
+    and the SLQ probes are split over the ranks (fvgp_b200/sharded_sparse.py), one LML for the whole job per step;
+    otherwise every rank evaluates its own theta (replicas)."""
     import torch
     from fvgp_b200 import GP, ops, parallel
     from fvgp_b200 import _lib as L
-    rank, local_rank, world = parallel.init()
     lib = L.load()
     x, y, noise = synthetic_c4(n)
-    mode_args = {"sparse_cg_tol": 1e-5, "random_logdet_lanczos_degree": 20, "random_logdet_min_num_samples": 10,
-                 "random_logdet_max_num_samples": 10}
+    mode_args = dict(C4_ARGS)
+    if sharded:
+        mode_args["gp2Scale_sharded"] = True
     t0 = time.perf_counter()
     gp = GP(x, y, init_hyperparameters=theta_c4(0, n), noise_variances=noise, gp2Scale=True,
             linalg_mode="sparseCGpre", args=mode_args)
     t_ctor = time.perf_counter() - t0
-    for k in range(args.warmup):
-        gp.log_likelihood(theta_c4(k + 1, n, rank))
+    trank = 0 if sharded else rank
+    for k in range(warmup):
+        gp.log_likelihood(theta_c4(k + 1, n, trank))
     parallel.barrier()
     torch.cuda.synchronize()
     launches0 = lib.fvgp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
-        lml = gp.log_likelihood(theta_c4(args.warmup + k + 1, n, rank))
+    variances = []
+    for k in range(steps):
+        lml = gp.log_likelihood(theta_c4(warmup + k + 1, n, trank))
+        variances.append(gp.log_likelihood_variance())
     e1.record()
     torch.cuda.synchronize()
     t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     launches = lib.fvgp_launch_count() - launches0
-    if args.profile_host and rank == 0:                      # where does the host side of one evaluation go?
-        import cProfile
-        import pstats
-        pr = cProfile.Profile()
-        pr.enable()
-        gp.log_likelihood(theta_c4(args.warmup + args.steps + 2, n, rank))
-        torch.cuda.synchronize()
-        pr.disable()
-        with open(args.profile_host, "w") as fh:
-            pstats.Stats(pr, stream=fh).sort_stats("cumulative").print_stats(35)
-    # phase breakdown of one evaluation
+    evals = steps if sharded else world * steps
+    rec = {"metric": "gp2Scale LML evals/s (N=1M, 3D, Wendland, sparse assembly + PCG + SLQ logdet)",
+           "value": evals / t_dev, "unit": "evals/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": t_dev / steps * 1e3, "scaling": "strong (rows and probes sharded)" if sharded else "weak (replicas)",
+           "config": {"workload": f"C4: gp2Scale, 3-D input, N={n}, wendland_anisotropic, CSR assembly on device, "
+                                  f"block-Jacobi PCG rtol 1e-5, SLQ logdet (degree 20, 10 probes)", "n": n,
+                      "parallelism": ("CSR row slabs + SLQ probes over the ranks" if sharded else f"replicas x{world}")},
+           "gpu_launches": int(launches), "constructor_seconds": t_ctor, "last_lml": lml,
+           "log_likelihood_variance": variances[-1],
+           "log_likelihood_std": None if variances[-1] is None else float(np.sqrt(variances[-1])),
+           "cg": {k2: v for k2, v in gp.kv.state.info.items() if k2.startswith("cg_")} if gp.kv.state is not None else None}
+    if sharded:
+        rec["sharding"] = getattr(gp.kv, "last_sharded_sparse_info", None)
+    if not phases:
+        del gp
+        return rec
+    # phase breakdown of one evaluation (single-GPU kernels)
     xd = gp.data.x_device()
     th = theta_c4(1, n)
     nd = L.to_dev(noise)
-
-    def timed(fn, reps=3):
-        best = 1e30
-        for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            out = fn()
-            b.record()
-            torch.cuda.synchronize()
-            best = min(best, a.elapsed_time(b) * 1e-3)
-        return best, out
-    t_fill, KV = timed(lambda: ops.wendland_csr(xd, xd, th, noise=nd))
-    stats = torch.zeros(1, dtype=torch.int64, device="cuda")
+    t_fill, KV = event_timed(lambda: ops.wendland_csr(xd, xd, th, noise=nd), reps=3)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
     ops.wendland_csr(xd, xd, th, noise=nd, stats=stats)
-    tile_pairs = int(stats.item())
+    tile_pairs = int(stats[0].item())
     v = L.to_dev(y - y.mean())
     yv = L.dev_empty((n,))
-    t_spmv, _ = timed(lambda: ops.spmv(KV, v, yv), reps=10)
-    t_pre, M = timed(lambda: ops.bjacobi(KV))
-    t_cg, res = timed(lambda: ops.pcg(KV, v, rtol=1e-5, precond=M), reps=2)
-    t_cg0, res0 = timed(lambda: ops.pcg(KV, v, rtol=1e-5), reps=2)
-    t_slq, _ = timed(lambda: ops.slq_logdet(KV, degree=20, probes=10, seed=0), reps=1)
+    t_spmv, _ = event_timed(lambda: ops.spmv(KV, v, yv), reps=10)
+    t_pre, M = event_timed(lambda: ops.bjacobi(KV), reps=3)
+    t_cg, res = event_timed(lambda: ops.pcg(KV, v, rtol=1e-5, precond=M), reps=2)
+    t_cg0, res0 = event_timed(lambda: ops.pcg(KV, v, rtol=1e-5), reps=2)
+    t_slq, _ = event_timed(lambda: ops.slq_logdet(KV, degree=20, probes=10, seed=0), reps=1)
+    hbm = load_peaks().get("hbm_gbs", 6650.0)
+    nnz = KV.nnz
+    spmv_bytes = 12.0 * nnz + 16.0 * n
+    fill_bytes = 12.0 * nnz + 4.0 * (n + 1) + 8.0 * n * 3
+    pcg_iter_bytes = 12.0 * nnz + 5 * 8.0 * n
+    rec["config"].update({"nnz": nnz, "nnz_per_row": nnz / n, "l2_policy": f"CSR is {12 * nnz / 1e9:.2f} GB > L2"})
+    rec["phases_seconds"] = {"csr_count+scan+fill": t_fill, "spmv": t_spmv, "bjacobi_build": t_pre,
+                             "pcg_bjacobi": t_cg, "pcg_bjacobi_iters": res[2], "pcg_plain": t_cg0,
+                             "pcg_plain_iters": res0[2], "slq_10x20": t_slq,
+                             "pcg_iteration_over_spmv": (t_cg / max(res[2], 1)) / t_spmv}
+    rec["roofline"] = {"bound": "hbm", "kernel": "spmv_kernel (CSR-vector), the inner kernel of PCG and SLQ",
+                       "achieved": spmv_bytes / t_spmv / 1e9, "peak": hbm, "unit": "GB/s",
+                       "frac": spmv_bytes / t_spmv / 1e9 / hbm,
+                       # dram read + write of one launch on this matrix (ncu --set full,
+                       # profiles/r01/ncu_spmv.v6.summary.txt): 1.216 + 0.011 GB
+                       "traffic": 1.227e9 if n == 1000000 else None, "algorithmic_bytes": spmv_bytes}
+    rec["roofline_pcg"] = {"bound": "hbm", "kernel": "one PCG iteration (SpMV + vector updates + block-Jacobi apply)",
+                           "achieved": pcg_iter_bytes * res[2] / t_cg / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": pcg_iter_bytes * res[2] / t_cg / 1e9 / hbm,
+                           "algorithmic_bytes_per_iteration": pcg_iter_bytes}
+    rec["roofline_fill"] = {"bound": "hbm", "kernel": "wendland_csr_kernel count + fill (output-sensitive bytes)",
+                            "achieved": fill_bytes / t_fill / 1e9, "peak": hbm, "unit": "GB/s",
+                            "frac": fill_bytes / t_fill / 1e9 / hbm, "algorithmic_bytes": fill_bytes,
+                            "tile_pairs_tested": tile_pairs,
+                            "pair_tests_per_stored_entry": float(stats[1].item()) / nnz if int(stats[1].item()) else tile_pairs * 1024.0 / nnz,
+                            "note": "output-sensitive bytes; the geometry passes are FP64-issue bound, not HBM bound"}
+    del gp, KV
+    return rec
+
+
+def run_c4(args):
+    """--workload c4: the gp2Scale line on its own."""
+    n = args.n
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        use_all_host_threads()
+        rec = reference_c4(min(args.c4_cpu_n, n), n)
+        line = {"impl": "reference", "metric": "gp2Scale LML evals/s (N=1M, 3D, Wendland)", "value": rec["value"],
+                "unit": "evals/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 / rec["value"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4: gp2Scale N={n}", "n": n},
+                "cpu_baseline": {"value": rec["value"], "unit": "evals/s", "cores": os.cpu_count(), "kind": rec["kind"],
+                                 "sample": rec["sample"]},
+                "detail": rec,
+                "e2e": {"value": rec["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    from fvgp_b200 import parallel
+    rank, local_rank, world = parallel.init()
+    rec = c4_record(n, args.steps, args.warmup, rank, world, phases=True, sharded=args.sharded and world > 1)
     if rank != 0:
         return
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    nnz = KV.nnz
-    spmv_gbs = (12.0 * nnz + 16.0 * n) / t_spmv / 1e9
-    fill_bytes = 12.0 * nnz + 4.0 * (n + 1) + 8.0 * n * 3
-    line = {"metric": "gp2Scale LML evals/s (N=1M, 3D, Wendland, sparse assembly + PCG + SLQ logdet)",
-            "value": world * args.steps / t_dev, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C4: gp2Scale, 3-D input, N={n}, wendland_anisotropic, CSR assembly on device, "
-                                   f"block-Jacobi PCG rtol 1e-5, SLQ logdet (degree 20, 10 probes)", "n": n, "nnz": nnz,
-                       "nnz_per_row": nnz / n, "l2_policy": f"CSR is {12 * nnz / 1e9:.2f} GB > L2"},
-            "gpu_launches": int(launches), "constructor_seconds": t_ctor, "last_lml": lml,
-            "phases_seconds": {"csr_count+scan+fill": t_fill, "spmv": t_spmv, "bjacobi_build": t_pre,
-                               "pcg_bjacobi": t_cg, "pcg_bjacobi_iters": res[2], "pcg_plain": t_cg0,
-                               "pcg_plain_iters": res0[2], "slq_10x20": t_slq},
-            "roofline": {"bound": "hbm", "kernel": "spmv_kernel (CSR-vector), the inner kernel of PCG and SLQ",
-                         "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s", "frac": spmv_gbs / hbm,
-                         # dram read + write of one launch on this matrix (ncu --set full,
-                         # profiles/r01/ncu_spmv.v6.summary.txt): 1.216 + 0.011 GB
-                         "traffic": 1.227e9 if n == 1000000 else None,
-                         "algorithmic_bytes": 12.0 * nnz + 16.0 * n},
-            "roofline_fill": {"bound": "hbm", "kernel": "wendland_csr_kernel count + fill (output-sensitive bytes)",
-                              "achieved": fill_bytes / t_fill / 1e9, "peak": hbm, "unit": "GB/s",
-                              "frac": fill_bytes / t_fill / 1e9 / hbm, "algorithmic_bytes": fill_bytes,
-                              "tile_pairs_tested": tile_pairs, "pair_tests_per_stored_entry": tile_pairs * 1024.0 / nnz,
-                              "note": "output-sensitive bytes; the geometry passes are FP64-issue bound "
-                                      "(3 DP instructions per axis and candidate pair), not HBM bound"}}
-    print(json.dumps(line), flush=True)
+    rec.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic"})
+    print(json.dumps(rec), flush=True)
 
 
-def synthetic_c5(n, seed=5):
-    """SURVEY 8d config C5: 2-D inputs, smooth signal + noise."""
-    rng = np.random.default_rng(seed)
-    x = rng.random((n, 2))
-    y = np.sin(4 * x[:, 0]) * np.cos(3 * x[:, 1]) + 0.1 * rng.standard_normal(n)
-    return x, y, np.full(n, 1e-2)
-
-
-def run_c5(args):
-    """Secondary workload: exact dense GP whose KV is sharded 2-D block-cyclically over all ranks (C5: N = 200 000 =
-    320 GB at 8 GPUs; smaller N by default on fewer GPUs so that a step stays within a minute).  One step = one
-    log_likelihood (+ gradient with --grad) through the public GP API with args["dense_sharded"] = True; every rank
-    calls collectively.  The reference has no multi-GPU dense path and cannot hold this matrix."""
+# ------------------------------------------------------------------------------------------ C5 / sharded dense
+def sharded_dense_record(gp_factory, n, steps, warmup, with_grad, label):
+    """LML (+ gradient) with KV 2-D block-cyclic over ALL ranks through the public API (args["dense_sharded"]).
+    Every rank calls collectively with the same theta.  Returns the record (meaningful on rank 0)."""
+    import ctypes
     import torch
-    from fvgp_b200 import GP, parallel
+    from fvgp_b200 import parallel
     from fvgp_b200 import _lib as L
-    rank, local_rank, world = parallel.init()
     lib = L.load()
-    n = args.n
-    x, y, noise = synthetic_c5(n)
-    th0 = np.array([1.0, .2, .2])
+    rank, _, world = parallel.dist_env()
     t0 = time.perf_counter()
-    gp = GP(x, y, init_hyperparameters=th0, noise_variances=noise, args={"dense_sharded": True})
+    gp, th0 = gp_factory()
     t_ctor = time.perf_counter() - t0
 
     def step(k):
         th = th0 * (1.0 + 0.02 * ((k + 1) % 10))
         lml = gp.log_likelihood(th)
-        grad = gp.neg_log_likelihood_gradient(th) if args.grad else None
-        return lml, grad
-    for k in range(args.warmup):
+        grad = gp.neg_log_likelihood_gradient(th) if with_grad else None
+        return th, lml, grad
+    for k in range(warmup):
         step(k)
     parallel.barrier()
     torch.cuda.synchronize()
@@ -348,68 +597,158 @@ def run_c5(args):
     E.comm.bytes_received = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
-        lml, grad = step(args.warmup + k)
+    for k in range(steps):
+        th, lml, grad = step(warmup + k)
     e1.record()
     torch.cuda.synchronize()
     parallel.barrier()
     t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    if rank != 0:
-        return
-    import ctypes
     scratch = L.dev_empty((148 * 8 * 256,))
     pk = ctypes.c_double()
     lib.fvgp_bench_fp64_peak(0, 2, 20000, L.ptr(scratch), ctypes.byref(pk), L.stream_ptr())
-    flops = float(n) ** 3 / 3.0 * (3.0 if args.grad else 1.0)
-    per_gpu = flops * args.steps / t_dev / world / 1e12
+    flops = float(n) ** 3 / 3.0 * (3.0 if with_grad else 1.0)
+    per_gpu = flops * steps / t_dev / world / 1e12
+    rec = {"what": label, "n": n, "n_gpus": world, "grid": list(E.grid), "block": E.nb, "steps": steps, "warmup": warmup,
+           "seconds_per_step": t_dev / steps, "evals_per_s": steps / t_dev, "with_gradient": bool(with_grad),
+           "tflops_per_gpu": per_gpu, "frac_of_fp64_tensor_peak": per_gpu / pk.value, "peak_tflops": pk.value,
+           "algorithmic_flops_per_step": flops, "local_GB": E._matrix().local_bytes() / 1e9,
+           "recv_GB_per_rank_per_step": E.comm.bytes_received / 1e9 / steps,
+           "gpu_launches_per_step": int(lib.fvgp_launch_count() - launches0) // steps,
+           "constructor_seconds": t_ctor, "theta": [float(t) for t in th], "lml": lml,
+           "grad": None if grad is None else [float(g) for g in grad],
+           "phase_seconds_last_step": getattr(E, "phase_seconds", None)}
+    return rec, gp
+
+
+def release(gp):
+    """Drop the device buffers a GP holds (memoised evaluation, sharded matrix) before the next section."""
+    import gc
+    import torch
+    try:
+        gp.kv._memo = None
+        gp.kv.state = None
+        gp.kv._sharded_eval = None
+    except Exception:
+        pass
+    del gp
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def single_gpu_check(make_gp, th, with_grad=True):
+    """The same LML (+ gradient) on ONE GPU (rank 0 only): agreement flag and the strong-scaling baseline."""
+    import torch
+    gp = make_gp()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lml = gp.log_likelihood(th)
+    grad = gp.neg_log_likelihood_gradient(th) if with_grad else None
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    release(gp)
+    return lml, grad, dt
+
+
+def sharded_section(args, deadline, rank, world):
+    """N > 1: the data-sharded paths, measured in the same run as the replica headline."""
+    from fvgp_b200 import GP, fvGP, parallel
+    out = {}
+
+    # ---- C3: fvGP 20 000 points x 5 tasks -> N = 100 000 rows, default kernel on the 3-D index set, LML + gradient
+    def c3():
+        pts = args.c3_points
+        x, y, noise = synthetic_c3(pts)
+        n = pts * y.shape[1]
+
+        def factory():
+            return fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise, args={"dense_sharded": True}), THETA_C3
+        rec, gp = sharded_dense_record(factory, n, steps=max(3, min(args.steps, 3)), warmup=1, with_grad=True,
+                                       label=f"C3: fvGP {pts} points x {y.shape[1]} tasks, dense LML + gradient, KV block-cyclic")
+        th = np.array(rec["theta"])
+        release(gp)
+        parallel.barrier()
+        if 10.0 * n * n < 0.85 * 180e9 and deadline.allows(150):           # fits one GPU: agreement + strong-scaling baseline
+            if rank == 0:
+                l1, g1, dt = single_gpu_check(lambda: fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise,
+                                                           args={"dense_sharded": False}), th)
+                rec["single_gpu"] = {"seconds_per_step": dt, "lml": l1, "grad": [float(g) for g in g1],
+                                     "lml_rel_diff": abs(rec["lml"] / l1 - 1), "grad_rel_diff": relerr(rec["grad"], g1),
+                                     "agree_1e-8": bool(abs(rec["lml"] / l1 - 1) <= 1e-8 and relerr(rec["grad"], g1) <= 1e-8)}
+                rec["strong_scaling_efficiency"] = dt / (world * rec["seconds_per_step"])
+            parallel.barrier()
+        return rec
+    if deadline.allows(200):
+        guarded("c3_dense_block_cyclic", c3, out)
+
+    # ---- C5: N = 200 000 (320 GB) on 8 GPUs; smaller N on fewer GPUs so that KV fills a comparable share of HBM
+    def c5():
+        n = args.c5_n or {2: 100000, 4: 140000}.get(world, 200000)
+        x, y, noise = synthetic_c5(n)
+        th0 = np.array([1.0, .2, .2])
+
+        def factory():
+            return GP(x, y, init_hyperparameters=th0, noise_variances=noise, args={"dense_sharded": True}), th0
+        rec, gp = sharded_dense_record(factory, n, steps=2, warmup=0, with_grad=False,
+                                       label=f"C5: exact dense GP, 2-D input, N={n} ({8e-9 * n * n:.0f} GB KV), LML")
+        release(gp)
+        return rec
+    if world >= 4 and deadline.allows(240):
+        guarded("c5_dense_block_cyclic", c5, out)
+
+    # ---- C4 with the CSR rows and the SLQ probes sharded over the ranks
+    def c4s():
+        return c4_record(args.c4_n, steps=5, warmup=2, rank=rank, world=world, phases=False, sharded=True)
+    if deadline.allows(120):
+        guarded("c4_gp2scale_sharded", c4s, out)
+    return out
+
+
+def run_c5(args):
+    """--workload c5: the block-cyclic dense line on its own."""
+    from fvgp_b200 import GP, parallel
+    rank, local_rank, world = parallel.init()
+    n = args.n
+    x, y, noise = synthetic_c5(n)
+    th0 = np.array([1.0, .2, .2])
+
+    def factory():
+        return GP(x, y, init_hyperparameters=th0, noise_variances=noise, args={"dense_sharded": True}), th0
+    rec, gp = sharded_dense_record(factory, n, args.steps, args.warmup, args.grad, f"C5-type dense, N={n}")
+    if rank != 0:
+        return
     what = "LML + gradient" if args.grad else "LML"
-    line = {"metric": f"dense {what} evals/s, KV 2-D block-cyclic over the GPUs (N={n})", "value": args.steps / t_dev,
+    line = {"metric": f"dense {what} evals/s, KV 2-D block-cyclic over the GPUs (N={n})", "value": rec["evals_per_s"],
             "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+            "ms_per_step": rec["seconds_per_step"] * 1e3, "higher_is_better": True,
             "scaling": "strong within a run (one matrix over all GPUs); default N grows with the GPU count",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5-type: exact dense GP, 2-D input, N={n} ({8e-9 * n * n:.0f} GB KV), block-cyclic "
                                    f"Cholesky{' + inverse + gradient traces' if args.grad else ''} over NCCL",
-                       "n": n, "grid": list(E.grid), "block": E.nb, "local_GB": E._matrix().local_bytes() / 1e9},
-            "gpu_launches": int(lib.fvgp_launch_count() - launches0), "constructor_seconds": t_ctor, "last_lml": lml,
-            "last_grad": None if grad is None else [float(g) for g in grad],
-            "recv_GB_per_rank_per_step": E.comm.bytes_received / 1e9 / args.steps,
-            "roofline": {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4), per GPU", "achieved": per_gpu,
-                         "peak": pk.value, "unit": "TFLOP/s", "frac": per_gpu / pk.value, "traffic": None,
-                         "algorithmic_flops_per_step": flops,
-                         "note": "whole step (fill, factor, solves, logdet" + (", inverse, traces" if args.grad else "")
-                                 + ") over the algorithmic flops, max over ranks"}}
+                       "n": n, "grid": rec["grid"], "block": rec["block"], "local_GB": rec["local_GB"]},
+            "detail": rec,
+            "roofline": {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4), per GPU", "achieved": rec["tflops_per_gpu"],
+                         "peak": rec["peak_tflops"], "unit": "TFLOP/s", "frac": rec["frac_of_fp64_tensor_peak"], "traffic": None,
+                         "algorithmic_flops_per_step": rec["algorithmic_flops_per_step"]}}
     print(json.dumps(line), flush=True)
 
 
-def synthetic_c1(n=1000, seed=1):
-    rng = np.random.default_rng(seed)
-    x = rng.random((n, 1))
-    y = np.sin(5 * x[:, 0]) + np.cos(10 * x[:, 0]) + 0.05 * rng.standard_normal(n)
-    return x, y, np.full(n, 1e-2)
-
-
-def run_c1(args):
-    """Secondary workload (BASELINE config 1): what train() does at the reference's own CPU-runnable size
-    -- populations of hyperparameter proposals (a differential-evolution generation = pop_size x H = 40 individuals at
-    the defaults) on a 1-D, N = 1000 GP.  A step = one population of `--population` LML evaluations through
-    GP.log_likelihood_population (host thetas in, host LMLs out).  Reported next to the same proposals evaluated one at
-    a time through GP.log_likelihood and to the oracle port on the host cores."""
+# ------------------------------------------------------------------------------------------ C1
+def c1_record(n, B, steps, warmup, cpu=True):
+    """What train() does at the reference's own CPU-runnable size (BASELINE config 1): populations of
+    hyperparameter proposals on a 1-D, N = 1000 GP.  A step = one population of B LML evaluations through
+    GP.log_likelihood_population (host thetas in, host LMLs out)."""
     import torch
     from fvgp_b200 import GP, ops
     from fvgp_b200 import _lib as L
     lib = L.load()
-    n = args.n
-    B = args.population
     x, y, noise = synthetic_c1(n)
     h0 = np.array([1.0, 0.3])
     gp = GP(x, y, init_hyperparameters=h0, noise_variances=noise)
-    rng = np.random.default_rng(0)
 
     def thetas(k):
         return h0 * (0.6 + 0.8 * np.random.default_rng(k).random((B, 2)))
 
-    for k in range(args.warmup):
+    for k in range(warmup):
         gp.log_likelihood_population(thetas(k))
     sampler = ClockSampler(0)
     torch.cuda.synchronize()
@@ -417,30 +756,26 @@ def run_c1(args):
     launches0 = lib.fvgp_launch_count()
     ops.start_phase_timing()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.nvtx.range_push("timed")
     e0.record()
     per_step = []
-    for k in range(args.steps):
+    for k in range(steps):
         t_s = time.perf_counter()
-        lml = gp.log_likelihood_population(thetas(args.warmup + k))        # synchronises internally (host LMLs out)
+        lml = gp.log_likelihood_population(thetas(warmup + k))        # synchronises internally (host LMLs out)
         per_step.append(time.perf_counter() - t_s)
     e1.record()
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_pop()
-    t_gpu = ops.stop_phase_timing().get("population", 0.0) / args.steps      # first to last kernel of the C-ABI call
-    t_pop = e0.elapsed_time(e1) * 1e-3 / args.steps
-    launches = (lib.fvgp_launch_count() - launches0) // args.steps
+    t_gpu = ops.stop_phase_timing().get("population", 0.0) / steps      # first to last kernel of the C-ABI call
+    t_pop = e0.elapsed_time(e1) * 1e-3 / steps
+    launches = (lib.fvgp_launch_count() - launches0) // steps
     clocks = sampler.summary()
-    # with gradients (multi-start local optimisers, the finite-difference Hessian)
     gp.marginal_likelihood.evaluate_population(thetas(0), with_gradient=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        gp.marginal_likelihood.evaluate_population(thetas(args.warmup + k), with_gradient=True)
+    for k in range(steps):
+        gp.marginal_likelihood.evaluate_population(thetas(warmup + k), with_gradient=True)
     torch.cuda.synchronize()
-    t_pop_grad = (time.perf_counter() - t0) / args.steps
-    # the same proposals one at a time (what the optimisers did before; also the MCMC path)
-    T = thetas(args.warmup)
+    t_pop_grad = (time.perf_counter() - t0) / steps
+    T = thetas(warmup)
     for t in T[:3]:
         gp.log_likelihood(t)
     torch.cuda.synchronize()
@@ -448,23 +783,22 @@ def run_c1(args):
     one = np.array([gp.log_likelihood(t) for t in T])
     torch.cuda.synchronize()
     t_seq = time.perf_counter() - t0
-    assert np.array_equal(one, gp.log_likelihood_population(T)), "population and one-at-a-time LML differ"
-    cpu = None
-    if not args.no_cpu_baseline:
+    bitwise = bool(np.array_equal(one, gp.log_likelihood_population(T)))
+    cpu_rec, parity = None, None
+    if cpu:
         from oracle import fvgp_oracle as orc
         use_all_host_threads()
         orc.dense_log_likelihood(x, y, T[0], noise)
         t0 = time.perf_counter()
         ref = [orc.dense_log_likelihood(x, y, t, noise) for t in T[:10]]
         per = (time.perf_counter() - t0) / 10
-        assert max(abs(a / b - 1) for a, b in zip(one[:10], ref)) <= 1e-8
-        cpu = {"value": 1.0 / per, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"oracle port, 10 of the {B} proposals at N={n}, {per * 1e3:.1f} ms each on {os.cpu_count()} host "
-                         f"threads (parity of the GPU LMLs against these: <= 1e-8 checked in this run)"}
+        parity = {"lml_max_rel_vs_oracle": relerr(one[:10], ref), "tol": 1e-8, "pass": bool(relerr(one[:10], ref) <= 1e-8),
+                  "population_bitwise_equals_one_at_a_time": bitwise}
+        cpu_rec = {"value": 1.0 / per, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"oracle port, 10 of the {B} proposals at N={n}, {per * 1e3:.1f} ms each"}
     flops = B * (n ** 3 / 3.0 + 2.0 * n * n)
-    line = {"metric": f"LML evals/s (dense, N={n}, 1D, populations of {B} proposals)", "value": B / t_pop,
-            "unit": "evals/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_pop * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    return {"metric": f"LML evals/s (dense, N={n}, 1D, populations of {B} proposals)", "value": B / t_pop,
+            "unit": "evals/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": t_pop * 1e3,
             "config": {"workload": f"C1: single-task GP, 1-D input, N={n}, default kernel, dense Cholesky; one step = one "
                                    f"population of {B} LML evaluations (GP.log_likelihood_population)",
                        "n": n, "population": B, "l2_policy": "latency-bound workload: every proposal refills its own K"},
@@ -481,10 +815,166 @@ def run_c1(args):
                          "frac": flops / t_pop / 1e12 / 37.1, "traffic": None,
                          "note": "N^3/3 + 2N^2 flop per proposal; at this size the bound is launch latency and the "
                                  "serial 128-column tile factorisations, not the tensor pipe"},
-            "cpu_baseline": cpu, "last_lml": float(lml[-1])}
-    print(json.dumps(line), flush=True)
+            "cpu_baseline": cpu_rec, "parity": parity, "last_lml": float(lml[-1])}
 
 
+def run_c1(args):
+    rec = c1_record(args.n, args.population, args.steps, args.warmup, cpu=not args.no_cpu_baseline)
+    rec.update({"higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic"})
+    print(json.dumps(rec), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ parity at size
+def parity_c2(args, gp, deadline):
+    """GPU results at the BENCHMARKED sizes against the oracle on the host cores."""
+    from fvgp_b200 import GP
+    from oracle import fvgp_oracle as orc
+    use_all_host_threads()
+    out = {}
+    n = args.n
+    x, y, noise = synthetic_c2(n)
+    th = theta_k(3)
+    # gradient at N = 8 000 and 16 000 against the oracle (LAPACK dpotrf / dpotri on the host, blocked dK)
+    for ng in (8000, 16000):
+        if deadline.left() < (60 if ng == 8000 else 150):
+            out[f"c2_grad_n{ng}"] = {"skipped": "time budget"}
+            continue
+        xs, ys, vs = synthetic_c2(ng)
+        g = GP(xs, ys, init_hyperparameters=theta_k(0), noise_variances=vs)
+        lml, grad = g.log_likelihood(th), g.neg_log_likelihood_gradient(th)
+        release(g)
+        t0 = time.perf_counter()
+        lml_ref, grad_ref = orc.dense_neg_log_likelihood_gradient_blocked(xs, ys, th, vs)
+        out[f"c2_grad_n{ng}"] = {"n": ng, "lml_rel": abs(lml / lml_ref - 1), "grad_max_rel": relerr(grad, grad_ref), "tol": 1e-8,
+                                 "pass": bool(abs(lml / lml_ref - 1) <= 1e-8 and relerr(grad, grad_ref) <= 1e-8),
+                                 "oracle_seconds": time.perf_counter() - t0, "grad": [float(v) for v in grad],
+                                 "grad_oracle": [float(v) for v in grad_ref]}
+    # LML at the full benchmarked N (20 GB on the host; the oracle's gradient does not fit at this size)
+    need_ram = 8.0 * n * n * 1.15
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    if avail < need_ram:
+        out[f"c2_lml_n{n}"] = {"skipped": f"host RAM: need {need_ram / 1e9:.0f} GB, available {avail / 1e9:.0f} GB"}
+    elif deadline.left() < 120:
+        out[f"c2_lml_n{n}"] = {"skipped": "time budget"}
+    else:
+        lml = gp.log_likelihood(th)
+        t0 = time.perf_counter()
+        lml_ref = orc.dense_log_likelihood_blocked(x, y, th, noise)
+        out[f"c2_lml_n{n}"] = {"n": n, "ours": lml, "oracle": lml_ref, "rel": abs(lml / lml_ref - 1), "tol": 1e-8,
+                               "pass": bool(abs(lml / lml_ref - 1) <= 1e-8), "oracle_seconds": time.perf_counter() - t0,
+                               "host_cores": os.cpu_count()}
+    return out
+
+
+def parity_c4_blocks(x, th, K_host, blocks, batch=10000, threads=8):
+    """Seeded blocks of the assembled CSR against the DEFINING dense block kernel (kernels.py:502-528 through
+    oracle.wendland_block; pattern = np.nonzero, gp2Scale_covariance.py:147): pattern bit-exact, values <= 1e-12."""
+    import concurrent.futures as cf
+    from oracle import fvgp_oracle as orc
+
+    def one(ij):
+        i, j = ij
+        r0, r1, c0, c1 = i * batch, min((i + 1) * batch, len(x)), j * batch, min((j + 1) * batch, len(x))
+        ref = orc.wendland_block(x[r0:r1], x[c0:c1], th)
+        rr, cc = np.nonzero(ref)
+        sub = K_host[r0:r1].tocsc()[:, c0:c1].tocsr()
+        sub.sort_indices()
+        ro, co = sub.nonzero()
+        same = len(rr) == len(ro) and np.array_equal(rr, ro) and np.array_equal(cc, co)
+        vrel = 0.0
+        if same and len(rr):
+            vrel = relerr(np.asarray(sub[rr, cc]).ravel(), ref[rr, cc])
+        return same, vrel, len(rr)
+    with cf.ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(one, blocks))
+    return {"blocks": len(blocks), "pattern_bit_exact": bool(all(r[0] for r in res)),
+            "values_max_rel": float(max((r[1] for r in res), default=0.0)), "entries_compared": int(sum(r[2] for r in res)),
+            "nonempty_blocks": int(sum(1 for r in res if r[2] > 0))}
+
+
+def choose_blocks(K_host, n, count, batch=10000, seed=0):
+    """count seeded (row-block, column-block) pairs: 2/5 diagonal, 2/5 non-empty off-diagonal, 1/5 uniformly random."""
+    rng = np.random.default_rng(seed)
+    nb = (n + batch - 1) // batch
+    coo_r = np.repeat(np.arange(n) // batch, np.diff(K_host.indptr))
+    pairs = np.unique(np.stack([coo_r, K_host.indices // batch], axis=1), axis=0)
+    off = pairs[pairs[:, 0] != pairs[:, 1]]
+    out = [(int(i), int(i)) for i in rng.choice(nb, size=min(nb, 2 * count // 5), replace=False)]
+    if len(off):
+        out += [tuple(int(v) for v in off[k]) for k in rng.choice(len(off), size=min(len(off), 2 * count // 5), replace=False)]
+    while len(out) < count:
+        out.append((int(rng.integers(nb)), int(rng.integers(nb))))
+    return out
+
+
+def parity_c4(args, deadline, nblocks):
+    from fvgp_b200 import GP, ops
+    from fvgp_b200 import _lib as L
+    from oracle import fvgp_oracle as orc
+    out = {}
+    n = args.c4_n
+    if deadline.left() > 150:
+        x, y, noise = synthetic_c4(n)
+        th = theta_c4(0, n)
+        xd = L.to_dev(x)
+        K_host = ops.wendland_csr(xd, xd, th).to_scipy()
+        blocks = choose_blocks(K_host, n, nblocks)
+        t0 = time.perf_counter()
+        rec = parity_c4_blocks(x, th, K_host, blocks, threads=min(8, os.cpu_count()))
+        rec.update({"n": n, "nnz": int(K_host.nnz), "symmetric_pattern": bool((abs(K_host - K_host.T)).nnz == 0) if n <= 200000 else None,
+                    "oracle_seconds": time.perf_counter() - t0, "pass": bool(rec["pattern_bit_exact"] and rec["values_max_rel"] <= 1e-12),
+                    "tol": "pattern bit-exact, values 1e-12"})
+        out[f"c4_blocks_n{n}"] = rec
+        del K_host, xd
+    else:
+        out[f"c4_blocks_n{n}"] = {"skipped": "time budget"}
+    # N = 50 000 LML with the exact sparse LU (the reference's sparseLU mode) against the oracle
+    if deadline.left() > 120:
+        ns = 50000
+        x, y, noise = synthetic_c4(ns)
+        th = theta_c4(0, ns) * np.array([1.0, 0.6, 0.6, 0.6])          # ~22 nnz/row keeps SuperLU's fill-in in seconds
+        gp = GP(x, y, init_hyperparameters=th, noise_variances=noise, gp2Scale=True, linalg_mode="sparseLU")
+        lml = gp.log_likelihood(th)
+        K = gp.K
+        release(gp)
+        t0 = time.perf_counter()
+        Kref = orc.gp2scale_covariance(x, x, th, batch=2500, symmetric=True)
+        lml_ref = orc.log_likelihood_from(*_lu(orc, Kref, noise, y), (y - y.mean())[:, None])
+        out["c4_sparselu_n50000"] = {"n": ns, "nnz": int(K.nnz), "pattern_bit_exact": bool(np.array_equal(K.indptr, Kref.indptr) and np.array_equal(K.indices, Kref.indices)),
+                                     "ours": lml, "oracle": lml_ref, "rel": abs(lml / lml_ref - 1), "tol": 1e-8,
+                                     "pass": bool(abs(lml / lml_ref - 1) <= 1e-8 and np.array_equal(K.indices, Kref.indices)),
+                                     "oracle_seconds": time.perf_counter() - t0}
+    else:
+        out["c4_sparselu_n50000"] = {"skipped": "time budget"}
+    return out
+
+
+def _lu(orc, K, noise, y):
+    KV = orc.add_kv(K, noise)
+    alpha, logdet = orc.sparse_lu_solve_logdet(KV, (y - y.mean())[:, None])
+    return alpha.reshape(-1, 1), logdet
+
+
+def parity_c3(points=2000):
+    """C3 shape at 2000 points x 5 tasks through fvGP(..., dense_sharded) on this rank's grid vs the oracle."""
+    from fvgp_b200 import fvGP
+    from oracle import fvgp_oracle as orc
+    x, y, noise = synthetic_c3(points)
+    gp = fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise, args={"dense_sharded": True})
+    th = THETA_C3 * 1.03
+    lml, grad = gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
+    release(gp)
+    xi, yi, vi = orc.fvgp_transform(x, y, noise)
+    lml_ref, grad_ref = orc.dense_neg_log_likelihood_gradient_blocked(xi, yi, th, vi)
+    return {"n": len(xi), "lml_rel": abs(lml / lml_ref - 1), "grad_max_rel": relerr(grad, grad_ref), "tol": 1e-8,
+            "pass": bool(abs(lml / lml_ref - 1) <= 1e-8 and relerr(grad, grad_ref) <= 1e-8)}
+
+
+# ------------------------------------------------------------------------------------------ headline
 def gemm_dram_traffic(n):
     """(bytes, note): what the DMMA GEMM launches of one N = 50 000 evaluation moved through DRAM, from the committed
     ncu launch list (tools/launch_summary.py JSON); (None, why) when no capture exists for this size."""
@@ -517,6 +1007,40 @@ def workload_config(args):
             "l2_policy": f"inputs larger than L2: K is {8 * args.n ** 2 / 1e9:.1f} GB"}
 
 
+def kfill_rooflines(n, gp, x, noise):
+    """K-assembly against HBM: the symmetric mode (full square + noise diagonal, 8 N^2 bytes written) and FILL_LOWER,
+    the mode the LML path uses (tiles on / below the diagonal only: 4 N^2 + 256 N bytes)."""
+    import torch
+    from fvgp_b200 import ops
+    from fvgp_b200 import _lib as L
+    peaks = load_peaks()
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    out_buf = L.dev_matrix(n, n)
+    xd, nd = gp.data.x_device(), L.to_dev(noise)
+    th = theta_k(1)
+    bounds = (x.min(axis=0), x.max(axis=0))      # host reductions stay outside the event pair
+    recs = {}
+    for mode, name in ((L.FILL_SYMMETRIC, "symmetric"), (L.FILL_LOWER, "lower")):
+        best, _ = event_timed(lambda: ops.kfill(L.K_MATERN32, xd, xd, th[0], 1 / th[1:], 1.0, noise=nd, mode=mode,
+                                                out=out_buf, bounds=bounds), reps=5)
+        tiles = (n + 63) // 64
+        nbytes = 8.0 * n * n if mode == L.FILL_SYMMETRIC else 8.0 * 64 * 64 * tiles * (tiles + 1) / 2
+        recs[name] = {"seconds": best, "bytes": nbytes, "GB/s": nbytes / best / 1e9, "frac": nbytes / best / 1e9 / hbm_peak,
+                      "entries_evaluated_per_s": (n * (n + 64.0) / 2) / best}
+    del out_buf
+    torch.cuda.empty_cache()
+    sym = recs["symmetric"]
+    return {"bound": "hbm", "kernel": "kfill_kernel<MATERN32,3> symmetric (full square + noise diagonal)",
+            "achieved": sym["GB/s"], "peak": hbm_peak, "unit": "GB/s", "frac": sym["frac"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N = 50 000
+            # (ncu --set full, profiles/r01/ncu_kfill.v6.summary.txt): 0.081 + 19.941 GB
+            "traffic": 20.022e9 if n == 50000 else None, "peak_source": hbm_src, "algorithmic_bytes": 8.0 * n * n,
+            "lower_mode_on_the_lml_path": {"achieved": recs["lower"]["GB/s"], "frac": recs["lower"]["frac"],
+                                           "seconds": recs["lower"]["seconds"], "algorithmic_bytes": recs["lower"]["bytes"],
+                                           "note": "half the bytes, the same number of evaluated entries: FP64-issue bound"},
+            "symmetric_seconds": sym["seconds"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -525,14 +1049,25 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", "--n", dest="n", type=int, default=50000,
                     help="problem size N (use --size under torchrun: its own parser rejects a bare --n as ambiguous)")
-    ap.add_argument("--cpu-sample-n", type=int, default=3000)
+    ap.add_argument("--cpu-sample-n", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-host", default="", help="c4 only: write a cProfile of one evaluation to this file")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"],
-                    help="c2 (default, the headline): dense N=50k LML+gradient; c4: gp2Scale N=1M LML; "
-                         "c5: dense LML with KV block-cyclic over all GPUs; c1: populations of proposals at N=1000")
+                    help="c2 (default, the headline; carries c4 / c1 / parity / sharded sub-records): dense N=50k LML+gradient; "
+                         "c4: gp2Scale N=1M LML; c5: dense LML with KV block-cyclic over all GPUs; c1: populations at N=1000")
     ap.add_argument("--population", type=int, default=40, help="c1 only: proposals per step")
     ap.add_argument("--grad", action="store_true", help="c5 only: add the gradient to every step")
+    ap.add_argument("--sharded", action="store_true", help="c4 only: shard CSR rows and SLQ probes over the ranks")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip parity / c4 / c1 / sharded sub-records")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-blocks", type=int, default=12, help="C4 blocks compared with the oracle inside bench.py "
+                    "(the -m gpu suite compares 50)")
+    ap.add_argument("--c4-n", type=int, default=1000000)
+    ap.add_argument("--c4-cpu-n", type=int, default=200000)
+    ap.add_argument("--c3-points", type=int, default=20000)
+    ap.add_argument("--c5-n", type=int, default=0)
+    ap.add_argument("--with-c4", action="store_true", default=True)
+    ap.add_argument("--budget", type=float, default=float(os.environ.get("FVGP_BENCH_BUDGET_S", "780")),
+                    help="seconds after which optional sub-records are skipped")
     args = ap.parse_args()
     if args.workload == "c1":
         if args.n == 50000:
@@ -558,9 +1093,9 @@ def main():
     rank, local_rank, world = parallel.init()
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     lib = L.load()
+    deadline = Deadline(args.budget)
     n = args.n
     x, y, noise = synthetic_c2(n)
-    x_pinned = torch.from_numpy(x).pin_memory()
     gp = GP(x, y, init_hyperparameters=theta_k(0), noise_variances=noise)
     H = 4
 
@@ -591,87 +1126,121 @@ def main():
     clocks = sampler.summary()
     t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
-    # ---- end to end: host buffers in, host results out ---------------------------------------
+    # ---- end to end: host buffers in, host results out, through the public API -------------------
+    gp.args = dict(gp.args, host_inputs_every_call=True)           # every call copies x from pinned host memory
+    step(args.warmup + args.steps)                                  # pins the staging buffer (untimed)
     parallel.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        gp.data._x_dev = x_pinned.cuda(non_blocking=True)          # H2D of this step's inputs
-        lml, grad = step(args.warmup + args.steps + k)
+        lml, grad = step(args.warmup + args.steps + 1 + k)
         assert np.isfinite(lml) and np.all(np.isfinite(grad))
     torch.cuda.synchronize()
     t_e2e = parallel.max_over_ranks(time.perf_counter() - t0)
-    h2d = x.nbytes + 2 * n * 8                                      # x, y - m, noise diagonal
+    gp.args = {k: v for k, v in gp.args.items() if k != "host_inputs_every_call"}
+    h2d = 2 * x.nbytes + 2 * n * 8                                  # x (LML call and gradient call), y - m, noise diagonal
     d2h = n * 8 + 8 + 4 + H * 8                                     # KVinvY, logdet, potrf status, traces
 
-    if rank != 0:
-        return
-    # ---- roofline of the dominant kernel (DMMA GEMM inside potrf + potri) ----------------------
-    import ctypes
-    scratch = L.dev_empty((148 * 8 * 256,))
-    pk = ctypes.c_double()
-    lib.fvgp_bench_fp64_peak(0, 2, 20000, L.ptr(scratch), ctypes.byref(pk), L.stream_ptr())
-    t_tensor = (phases.get("potrf", 0.0) + phases.get("potri", 0.0)) / args.steps
-    achieved = n ** 3 / t_tensor / 1e12
-    roofline = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri", "achieved": achieved,
-                "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
-                # dram__bytes_read.sum + dram__bytes_write.sum summed over every dgemm_mma_kernel launch of ONE timed
-                # evaluation (ncu launch list of this command, profiles/r01/launches_bench_n50k.*.json)
-                "traffic": gemm_dram_traffic(n)[0], "traffic_note": gemm_dram_traffic(n)[1],
-                "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
-                "algorithmic_flops_per_step": float(n) ** 3,
-                "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
-    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    out_buf = L.dev_matrix(n, n)
-    xd, nd = gp.data.x_device(), L.to_dev(noise)
-    th = theta_k(1)
-    best = 1e30
-    bounds = (x.min(axis=0), x.max(axis=0))      # host reductions stay outside the event pair
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.kfill(L.K_MATERN32, xd, xd, th[0], 1 / th[1:], 1.0, noise=nd, mode=L.FILL_SYMMETRIC, out=out_buf, bounds=bounds)
-        b.record()
-        torch.cuda.synchronize()
-        best = min(best, a.elapsed_time(b) * 1e-3)
-    kfill_gbs = 8.0 * n * n / best / 1e9
-    roofline_kfill = {"bound": "hbm", "kernel": "kfill_kernel<MATERN32,3> symmetric (full square + noise diagonal)",
-                      "achieved": kfill_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": kfill_gbs / hbm_peak,
-                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N = 50 000
-                      # (ncu --set full, profiles/r01/ncu_kfill.v6.summary.txt): 0.081 + 19.941 GB
-                      "traffic": 20.022e9 if n == 50000 else None, "peak_source": hbm_src,
-                      "algorithmic_bytes": 8.0 * n * n}
-    del out_buf
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import fvgp_oracle as orc
-        use_all_host_threads()
-        ns = args.cpu_sample_n
-        xs, ys, vs = synthetic_c2(ns)
-        t0 = time.perf_counter()
-        cpu_baseline_step(xs, ys, vs, theta_k(1), orc)
-        per = time.perf_counter() - t0
-        cpu = {"value": 1.0 / (per * (n / ns) ** 3), "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"oracle port of the reference algorithm, one LML+gradient at N={ns} took {per:.2f} s on "
-                         f"{os.cpu_count()} host threads, extrapolated x(N/{ns})^3 to N={n}"}
-
-    line = {"metric": "LML+gradient evals/s (dense, N=50k, 3D, ARD Matern-3/2)",
+    line = {"metric": METRIC_C2,
             "value": world * args.steps / t_dev, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": world * args.steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline, "roofline_kfill": roofline_kfill,
-            "cpu_baseline": cpu, "last_lml": out[0]}
-    print(json.dumps(line), flush=True)
+            "gpu_launches": int(launches), "last_lml": out[0], "last_grad": [float(g) for g in out[1]]}
+    HOLD["line"] = line
+    start_watchdog(args.budget + 75.0, rank)
+
+    # ---- roofline of the dominant kernel (DMMA GEMM inside potrf + potri) ----------------------
+    if rank == 0:
+        import ctypes
+        scratch = L.dev_empty((148 * 8 * 256,))
+        pk = ctypes.c_double()
+        lib.fvgp_bench_fp64_peak(0, 2, 20000, L.ptr(scratch), ctypes.byref(pk), L.stream_ptr())
+        t_tensor = (phases.get("potrf", 0.0) + phases.get("potri", 0.0)) / args.steps
+        achieved = n ** 3 / t_tensor / 1e12
+        step_tflops = n ** 3 / (t_dev / args.steps) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri",
+                            "achieved": achieved, "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
+                            "whole_step": {"achieved": step_tflops, "frac": step_tflops / pk.value,
+                                           "note": "N^3 flop over ms_per_step (fill, solves, traces and host time included)"},
+                            # dram__bytes_read.sum + dram__bytes_write.sum summed over every dgemm_mma_kernel launch of ONE
+                            # timed evaluation (ncu launch list of this command, profiles/*/launches_bench_n50k.*.json)
+                            "traffic": gemm_dram_traffic(n)[0], "traffic_note": gemm_dram_traffic(n)[1],
+                            "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
+                            "algorithmic_flops_per_step": float(n) ** 3,
+                            "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
+        line["roofline_kfill"] = kfill_rooflines(n, gp, x, noise)
+
+        # the size both arms measure directly: ours through the public API with host buffers
+        xs, ys, vs = synthetic_c2(SAME_N)
+        g8 = GP(xs, ys, init_hyperparameters=theta_k(0), noise_variances=vs, args={"host_inputs_every_call": True})
+        for k in range(2):
+            g8.log_likelihood(theta_k(k + 1)), g8.neg_log_likelihood_gradient(theta_k(k + 1))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(5):
+            g8.log_likelihood(theta_k(k + 3)), g8.neg_log_likelihood_gradient(theta_k(k + 3))
+        torch.cuda.synchronize()
+        dt8 = (time.perf_counter() - t0) / 5
+        release(g8)
+        line["same_n"] = {"n": SAME_N, "seconds": dt8, "evals_per_s": 1.0 / dt8,
+                          "note": "LML + gradient through the public API, host buffers; the reference arm measures this size too"}
+
+        line["cpu_baseline"] = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import fvgp_oracle as orc
+            use_all_host_threads()
+            ns = 3000
+            xs, ys, vs = synthetic_c2(ns)
+            t0 = time.perf_counter()
+            cpu_port_step(xs, ys, vs, theta_k(1), orc)
+            per = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / (per * (n / ns) ** 3), "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"oracle port of the reference algorithm, one LML+gradient at N={ns} took {per:.2f} s on "
+                                              f"{os.cpu_count()} host threads, extrapolated x(N/{ns})^3 to N={n}; the reference arm "
+                                              f"(--impl reference) times the unmodified reference over a ladder of sizes instead"}
+
+    extras = not args.no_extras
+    # ---- parity at the benchmarked sizes (one GPU; the host needs its cores) ----------------------
+    if extras and world == 1 and not args.no_parity:
+        par = {}
+
+        def merge(name, fn):
+            tmp = {}
+            guarded(name, fn, tmp)
+            res = tmp[name]
+            if "error" in res:
+                par[name + "_error"] = res
+            else:
+                res.pop("section_seconds", None)
+                par.update(res)
+        merge("c2", lambda: parity_c2(args, gp, deadline))
+        release(gp)
+        gp = None
+        merge("c4", lambda: parity_c4(args, deadline, args.parity_blocks))
+        guarded("c3_n10000_fvgp_dense_sharded_1rank", parity_c3, par)
+        checks = [v for v in par.values() if isinstance(v, dict) and "skipped" not in v]
+        par["all_pass"] = bool(checks and all(v.get("pass", False) for v in checks))
+        line["parity"] = par
+        HOLD["line"] = line
+    if gp is not None:
+        release(gp)
+        gp = None
+
+    # ---- the other workloads of BASELINE.json's metric --------------------------------------------
+    if extras and world == 1:
+        if deadline.allows(60):
+            guarded("c4", lambda: c4_record(args.c4_n, steps=max(5, min(args.steps, 10)), warmup=3), line)
+        if deadline.allows(30):
+            guarded("c1", lambda: c1_record(1000, 40, 20, 3), line)
+    if extras and world > 1:
+        sh = sharded_section(args, deadline, rank, world)
+        line["sharded"] = sh
+    line["wall_seconds"] = round(time.time() - T_START, 1)
+    emit(line, rank)
+    parallel.barrier()
 
 
 if __name__ == "__main__":

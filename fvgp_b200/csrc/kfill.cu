@@ -749,26 +749,28 @@ __global__ void sum_partials_kernel(const double* partials, int count, double* o
 __global__ void kgrad_dense_kernel(const double* __restrict__ x1, long long n1, const double* __restrict__ x2,
                                    long long n2, int dim, double amp, const double* __restrict__ len, double* out) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long r = blockIdx.y;
-  if (c >= n2 || r >= n1) return;
+  if (c >= n2) return;
   const double sqrt3 = 1.7320508075688772;
-  double s = 0.0, dx2[kMaxDim];
-  for (int i = 0; i < dim; ++i) {
-    const double dx = fabs(x1[r * dim + i] - x2[c * dim + i]);
-    const double t = dx / len[i];
-    dx2[i] = dx * dx;
-    s += t * t;
-  }
-  const double d = sqrt(s), a = sqrt3 * d, ea = exp(-a);
-  const long long plane = n1 * n2, at = r * n2 + c;
-  out[at] = (1.0 + a) * ea;
-  for (int i = 0; i < dim; ++i) {
-    double v = 0.0;
-    if (d != 0.0) {
-      const double dadl = sqrt3 * (-dx2[i] / (len[i] * len[i] * len[i] * d));
-      v = amp * (dadl * ea - (1.0 + a) * dadl * ea);  // gp_prior.py:431-434, kernels.py:137-141
+  const long long plane = n1 * n2;
+  for (long long r = blockIdx.y; r < n1; r += gridDim.y) {  // grid.y is capped at 65535: rows are strided
+    double s = 0.0, dx2[kMaxDim];
+    for (int i = 0; i < dim; ++i) {
+      const double dx = fabs(x1[r * dim + i] - x2[c * dim + i]);
+      const double t = dx / len[i];
+      dx2[i] = dx * dx;
+      s += t * t;
     }
-    out[(1 + i) * plane + at] = v;
+    const double d = sqrt(s), a = sqrt3 * d, ea = exp(-a);
+    const long long at = r * n2 + c;
+    out[at] = (1.0 + a) * ea;
+    for (int i = 0; i < dim; ++i) {
+      double v = 0.0;
+      if (d != 0.0) {
+        const double dadl = sqrt3 * (-dx2[i] / (len[i] * len[i] * len[i] * d));
+        v = amp * (dadl * ea - (1.0 + a) * dadl * ea);  // gp_prior.py:431-434, kernels.py:137-141
+      }
+      out[(1 + i) * plane + at] = v;
+    }
   }
 }
 
@@ -1093,17 +1095,18 @@ int fvgp_trace_sym_product(const double* d_Kinv, int64_t ld, const double* d_b, 
 
 int fvgp_kgrad_dense_matern32(const double* d_x1, int64_t n1, const double* d_x2, int64_t n2, int dim,
                               const double* h_theta, double* d_out, void* stream) {
-  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n1 > 0 && n2 > 0 && n1 < 65536ll * 32768);
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && n1 > 0 && n2 > 0 && (n2 + 255) / 256 <= 0x7fffffffll);
   cudaStream_t st = (cudaStream_t)stream;
-  // length scales go through a tiny device buffer at the tail of the output's first row? no: use a managed copy
-  double* d_len = nullptr;
+  double* d_len = nullptr;  // the length scales travel through a small stream-ordered device buffer
   FVGP_CUDA_OK(cudaMallocAsync((void**)&d_len, kMaxDim * sizeof(double), st));
-  FVGP_CUDA_OK(cudaMemcpyAsync(d_len, h_theta + 1, dim * sizeof(double), cudaMemcpyHostToDevice, st));
-  dim3 grid((unsigned)((n2 + 255) / 256), (unsigned)n1);
-  FVGP_REQUIRE(n1 <= 65535);
-  launch(kgrad_dense_kernel, grid, 256, 0, st, d_x1, n1, d_x2, n2, dim, h_theta[0], d_len, d_out);
-  FVGP_LAUNCH_OK();
-  FVGP_CUDA_OK(cudaFreeAsync(d_len, st));
+  cudaError_t err = cudaMemcpyAsync(d_len, h_theta + 1, dim * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess) {
+    dim3 grid((unsigned)((n2 + 255) / 256), (unsigned)(n1 < 65535 ? n1 : 65535));
+    launch(kgrad_dense_kernel, grid, 256, 0, st, d_x1, n1, d_x2, n2, dim, h_theta[0], d_len, d_out);
+    err = cudaGetLastError();
+  }
+  cudaFreeAsync(d_len, st);  // released on every path
+  FVGP_CUDA_OK(err);
   return 0;
 }
 

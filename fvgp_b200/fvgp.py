@@ -10,7 +10,7 @@ from .gp import GP
 
 
 class fvGP(GP):
-    def __init__(self, x_data, y_data, init_hyperparameters=None, noise_variances=None, compute_device="gpu",
+    def __init__(self, x_data, y_data, init_hyperparameters=None, noise_variances=None, compute_device="cpu",
                  kernel_function=None, kernel_function_grad=None, noise_function=None, noise_function_grad=None,
                  prior_mean_function=None, prior_mean_function_grad=None, gp2Scale=False, dask_client=None,
                  gp2Scale_batch_size=10000, gp2Scale_distribution="blockwise", linalg_mode=None, ram_economy=False,

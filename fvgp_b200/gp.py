@@ -4,8 +4,9 @@ Constructor and method signatures are the reference's (gp.py:419-439, :781-801, 
 Inputs and outputs are host numpy arrays; everything between them on the training hot
 path -- covariance assembly, factorisation, solves, log-determinant, likelihood gradient --
 runs in the CUDA library behind `fvgp_b200._lib` and stays on the device.
-`compute_device` is accepted for compatibility; the B200 is always the compute device and
-there is no CPU fallback.  `dask_client` is accepted and ignored: the gp2Scale block loop
+`compute_device` (default "cpu", as in the reference signature) and args["GPU_engine"] (any value,
+"b200" included) are accepted for compatibility and do not select anything: the B200 is always
+the compute device and there is no CPU fallback.  `dask_client` is accepted and ignored: the gp2Scale block loop
 that needed it is a single pair of kernel launches here.
 """
 import warnings
@@ -26,7 +27,7 @@ def out_of_bounds(x, bounds):
 
 
 class GP:
-    def __init__(self, x_data, y_data, init_hyperparameters=None, noise_variances=None, compute_device="gpu",
+    def __init__(self, x_data, y_data, init_hyperparameters=None, noise_variances=None, compute_device="cpu",
                  kernel_function=None, kernel_function_grad=None, noise_function=None, noise_function_grad=None,
                  prior_mean_function=None, prior_mean_function_grad=None, gp2Scale=False, dask_client=None,
                  gp2Scale_batch_size=10000, gp2Scale_distribution="blockwise", linalg_mode=None, ram_economy=False,
@@ -109,6 +110,7 @@ class GP:
     @args.setter
     def args(self, value):
         self.data.args = value
+        self.kv._memo = None                    # a 4-argument kernel / the CG and SLQ keys read them
 
     # ---- state changes ---------------------------------------------------------------------------
     def set_hyperparameters(self, hps):

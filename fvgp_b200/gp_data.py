@@ -4,7 +4,7 @@ import numpy as np
 
 class GPdata:
     def __init__(self, x_data, y_data, args=None, noise_variances=None, ram_economy=False, gp2Scale=False,
-                 compute_device="gpu", dask_client=None):
+                 compute_device="cpu", dask_client=None):
         assert isinstance(x_data, (np.ndarray, list)), "wrong format in x_data"
         assert isinstance(y_data, np.ndarray) and np.ndim(y_data) in (1, 2), "wrong format in y_data"
         assert noise_variances is None or isinstance(noise_variances, np.ndarray), "wrong format in noise_variances"
@@ -31,15 +31,25 @@ class GPdata:
         self.compute_device = compute_device
         self.dask_client = dask_client
         self._x_dev = None
+        self.generation = 0                     # bumped by every data change; part of GPkv's memo key
 
     @property
     def point_number(self):
         return len(self.x_data)
 
     def x_device(self):
-        """x_data resident on the GPU (uploaded once, 8*N*D bytes)."""
+        """x_data on the GPU: uploaded once (8*N*D bytes) and kept resident.  args["host_inputs_every_call"] = True
+        makes every call copy x from (pinned) host memory again -- the reference-facing contract is host arrays in,
+        host results out, and this is the switch that lets an end-to-end measurement include that copy."""
+        from . import _lib as L
+        if self.args.get("host_inputs_every_call", False) and self.Euclidean:
+            torch = L._torch()
+            if getattr(self, "_x_pinned", None) is None or self._x_pinned_gen != self.generation:
+                self._x_pinned = torch.from_numpy(self.x_data).pin_memory()
+                self._x_pinned_gen = self.generation
+            self._x_dev = self._x_pinned.to(device="cuda", non_blocking=True)
+            return self._x_dev
         if self._x_dev is None:
-            from . import _lib as L
             self._x_dev = L.to_dev(self.x_data)
         return self._x_dev
 
@@ -59,9 +69,11 @@ class GPdata:
         if self.Euclidean:
             self.x_data = np.ascontiguousarray(self.x_data, dtype=np.float64)
         self._x_dev = None
+        self.generation += 1
 
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_x_dev"] = None
+        state["_x_pinned"] = None
         state["dask_client"] = None
         return state

@@ -119,7 +119,8 @@ class GPkv:
         # (gp_marginal_likelihood.py:158-165, :250-254); remember the last evaluation so that the
         # pair costs one K-fill + one Cholesky.
         key = (np.asarray(hps, dtype=np.float64).tobytes(), np.asarray(m).tobytes(),
-               np.asarray(V).tobytes() if isinstance(V, np.ndarray) else id(V), len(self.data.x_data))
+               np.asarray(V).tobytes() if isinstance(V, np.ndarray) else id(V), len(self.data.x_data),
+               self.data.generation, self._args_fingerprint())
         memo = getattr(self, "_memo", None)
         if memo is not None and memo[0] == key and x0 is None:
             old = memo[1]
@@ -134,6 +135,18 @@ class GPkv:
         ev = self._evaluate_uncached(hps, V, m, x0, want_logdet)
         self._memo = (key, ev)
         return ev
+
+    def _args_fingerprint(self):
+        """Cheap identity of `args` for the memo key: a 4-argument kernel reads them, and the CG / SLQ keys change
+        what an evaluation returns.  Scalars by value, everything else by object identity."""
+        a = self.data.args
+        if not a:
+            return ()
+        try:
+            return tuple((k, v if isinstance(v, (bool, int, float, str, type(None))) else id(v))
+                         for k, v in sorted(a.items(), key=lambda kv: str(kv[0])))
+        except Exception:
+            return (id(a),)
 
     def _evaluate_uncached(self, hps, V, m, x0, want_logdet):
         ev = Evaluation()
@@ -183,7 +196,7 @@ class GPkv:
             raise Exception(f"No mode: {mode}")
         rtol = float(self.args.get("sparse_cg_tol", self.args.get("cg_minres_tol", self.args.get("sparse_minres_tol", 1e-5))))
         maxiter = self.args.get("sparse_cg_maxiter", self.args.get("sparse_krylov_maxiter", None))
-        precond = ops.bjacobi(obj) if mode in _CGPRE else None
+        precond = self._preconditioner(obj) if mode in _CGPRE else None
         sol = np.empty_like(y_mean)
         cols = []
         for c in range(r):
@@ -199,6 +212,21 @@ class GPkv:
         if want_logdet:
             ev.logdet = self._random_logdet(obj, ev)
         return ev
+
+    _BJACOBI_NAMES = (None, "", "default", "block_jacobi", "blockjacobi", "bjacobi", "block-jacobi", "jacobi")
+
+    def _preconditioner(self, csr):
+        """Block-Jacobi (32 x 32 dense inverse blocks, built and applied on the device) is the ONE preconditioner of
+        this build; the reference's host-side ILU / IC / AMG / Schwarz family (gp_lin_alg.py:890-930) is out of scope
+        (DESIGN.md section 7).  Any other `sparse_preconditioner_type` is answered with a warning, not silently."""
+        want = self.args.get("sparse_preconditioner_type", None)
+        key = want.lower() if isinstance(want, str) else want
+        if key not in self._BJACOBI_NAMES and not getattr(self, "_warned_precond", False):
+            import warnings
+            warnings.warn(f"sparse_preconditioner_type={want!r} is not available on the B200 path; "
+                          "using the device block-Jacobi preconditioner")
+            self._warned_precond = True
+        return ops.bjacobi(csr)
 
     # ---- multi-GPU dense path (SURVEY 8e): KV block-cyclic over the ranks of torch.distributed ----------------
     def _use_sharded(self, mode, V):
@@ -218,7 +246,10 @@ class GPkv:
         except Exception:
             world = 1
         n = len(self.data.x_data)
-        return world > 1 and 10.0 * n * n > 0.9 * 180e9          # 8 N^2 matrix + 2 N^2 inverse scratch
+        if world <= 1:
+            return False
+        hbm = float(L._torch().cuda.get_device_properties(L._torch().cuda.current_device()).total_memory)
+        return 10.0 * n * n > 0.9 * hbm                          # 8 N^2 matrix + 2 N^2 inverse scratch
 
     def _evaluate_sharded(self, ev, hps, V, m, y_mean):
         from . import kernels as K
@@ -309,6 +340,7 @@ class GPkv:
         gp_lin_alg.py:1310-1477, gp_kv.py:462-508)."""
         if appended_from is not None and self._append_refresh(int(appended_from)):
             return
+        self._memo = None                       # never hand a previous data set's factor to the new state
         self._refresh()
 
     def _append_refresh(self, n_old):
@@ -395,7 +427,7 @@ class GPkv:
         if "lu" in ev.info:
             return ev.info["lu"].solve(b2).reshape(b.shape)
         rtol = float(self.args.get("sparse_cg_tol", self.args.get("cg_minres_tol", 1e-5)))
-        precond = ops.bjacobi(ev.csr) if self.mode in _CGPRE else None
+        precond = self._preconditioner(ev.csr) if self.mode in _CGPRE else None
         out = np.empty_like(b2)
         for c in range(b2.shape[1]):
             x, _, _, _ = ops.pcg(ev.csr, L.to_dev(np.ascontiguousarray(b2[:, c])), rtol=rtol, precond=precond)

@@ -39,16 +39,30 @@ class GPposterior:
         return np.column_stack([np.tile(x, (len(y), 1)), np.repeat(y, len(x))])
 
     def _cross(self, x_pred, hps):
-        """k(x_pred, x_data) on the device: ("dense", (n_pred, n) tensor) or ("sparse", DeviceCSR)."""
+        """k(x_pred, x_data) on the device: ("dense", (n_pred, n) tensor) or ("sparse", DeviceCSR).
+
+        The kernel is called as kernel(x_data, x_pred, hps) like the reference (gp_posterior.py:151).  The lazy result
+        is evaluated on the point sets the KERNEL chose (a user kernel may slice or warp its inputs); the resident
+        device copy of x_data is substituted only when the expression really is on (x_data, x_pred)."""
         x = self.data.x_data
         res = self.prior._call_kernel(x, x_pred, np.asarray(hps, dtype=np.float64))
-        xd = self.data.x_device()
         if isinstance(res, K.SparseWendland):
-            return "sparse", ops.wendland_csr(K._device_points(x_pred), xd, res.hps)
+            if res.x1 is x and res.x2 is x_pred:
+                return "sparse", ops.wendland_csr(K._device_points(x_pred), self.data.x_device(), res.hps)
+            kt = res.tocsr().T.tocsr()                    # (n_pred, n), canonical
+            kt.sort_indices()
+            torch = L._torch()
+            return "sparse", ops.DeviceCSR(L.to_dev(kt.indptr, torch.int64), L.to_dev(kt.indices, torch.int32),
+                                           L.to_dev(kt.data), kt.shape)
         if isinstance(res, K.Radial):                   # radial kernels are symmetric in their arguments
-            buf, _ = ops.kfill(res.kind, K._device_points(x_pred), xd, res.amp, res.dist.inv_scale, res.length,
-                               bounds=res.dist.bounds())
-            return "dense", buf[:, :len(x)]
+            if res.dist.x1 is x and res.dist.x2 is x_pred:
+                buf, _ = ops.kfill(res.kind, K._device_points(x_pred), self.data.x_device(), res.amp,
+                                   res.dist.inv_scale, res.length, bounds=res.dist.bounds())
+                return "dense", buf[:, :len(x)]
+            buf, _ = res.materialize()                    # (n, n_pred) on the kernel's own point sets
+            return "dense", buf[:, :res.shape[1]].t().contiguous()
+        if isinstance(res, K._Lazy):
+            return "dense", res.to_device().t().contiguous()
         if sp.issparse(res):
             res = res.toarray()
         return "dense", L.to_dev(np.asarray(res, dtype=np.float64)).t().contiguous()

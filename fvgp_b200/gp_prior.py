@@ -132,20 +132,6 @@ class GPprior:
             return res.to_host()
         return res
 
-    def device_cross_covariance(self, x_pred, hps):
-        """k(x_data, x_pred) on the device: dense (n, n_pred) tensor or DeviceCSR."""
-        res = self._call_kernel(self.x_data, x_pred, np.asarray(hps, dtype=np.float64))
-        if isinstance(res, K.SparseWendland):
-            return res.to_device_csr(x1_dev=self.data.x_device())
-        if isinstance(res, K.Radial):
-            buf, _ = res.materialize(x1_dev=self.data.x_device())
-            return buf[:, :res.shape[1]]
-        if isinstance(res, K._Lazy):
-            return res.to_device()
-        if sp.issparse(res):
-            return L.to_dev(res.toarray())
-        return L.to_dev(np.asarray(res, dtype=np.float64))
-
     def compute_prior_covariance_matrix(self, x, hps):
         """gp_prior.py:185-195."""
         return self.compute_covariances(x, x, hps)

@@ -108,18 +108,32 @@ class _Lazy:
 _BOUNDS_CACHE = {}
 
 
+def _fingerprint(x):
+    """First, middle and last rows: catches in-place edits of a cached array without an O(N) pass."""
+    n = len(x)
+    return x[0].tobytes() + x[n // 2].tobytes() + x[n - 1].tobytes()
+
+
 def point_bounds(x):
-    """Per-axis (lo, hi) of a host point set, cached per array (the training set is asked once per evaluation)."""
+    """Per-axis (lo, hi) of a host point set.  Cached per LIVE array object: the entry is dropped by a weakref
+    finaliser when the array dies, so a new array at a recycled address can never see stale bounds, and a cheap row
+    fingerprint guards against in-place mutation (the centred fill's safety decision depends on these extents)."""
+    import weakref
     if not isinstance(x, np.ndarray) or x.ndim != 2 or x.size == 0:
         return None
-    key = (id(x), x.shape, x.__array_interface__["data"][0])
+    key = id(x)
     hit = _BOUNDS_CACHE.get(key)
-    if hit is None:
-        if len(_BOUNDS_CACHE) > 16:
-            _BOUNDS_CACHE.clear()
-        hit = (x.min(axis=0), x.max(axis=0))
-        _BOUNDS_CACHE[key] = hit
-    return hit
+    fp = _fingerprint(x)
+    if hit is not None and hit[0] == x.shape and hit[1] == fp:
+        return hit[2]
+    bounds = (x.min(axis=0), x.max(axis=0))
+    try:
+        if hit is None:
+            weakref.finalize(x, _BOUNDS_CACHE.pop, key, None)
+        _BOUNDS_CACHE[key] = (x.shape, fp, bounds)
+    except TypeError:                                   # not weak-referenceable: do not cache
+        _BOUNDS_CACHE.pop(key, None)
+    return bounds
 
 
 class Distance(_Lazy):

@@ -65,6 +65,14 @@ def fill_centre(kind, inv_scale, length, bounds):
     return 0.5 * (lo + hi)
 
 
+def _require_len(values, need, what, at_least=False):
+    """The C side reads `need` doubles through a raw pointer: a short host array must fail here, like the shape
+    error the reference's numpy code would raise."""
+    have = int(np.size(values))
+    if have != need and not (at_least and have > need):
+        raise ValueError(f"{what}: expected {'at least ' if at_least else ''}{need} values, got {have}")
+
+
 def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL, out=None, bounds=None):
     """K = amp * f(||(x1-x2)*inv_scale|| / length) [+ diag(noise)].  Returns (buffer, ld);
     buffer[:, :n2] is the matrix (gp_prior.py:376-400, kernels.py:16-188, gp_kv.py:640-669).
@@ -75,6 +83,8 @@ def kfill(kind, x1, x2, amp, inv_scale, length=1.0, noise=None, mode=L.FILL_FULL
         buf, ld = L.dev_matrix(n1, n2)
     else:
         buf, ld = out
+    _require_len(inv_scale, dim, "inv_scale (one per input dimension; hyperparameters too short?)")
+    assert x2.shape[1] == dim, "x1 and x2 must have the same number of columns"
     _, inv_p = L.dvec(inv_scale)
     centre = fill_centre(kind, inv_scale, length, bounds)
     if centre is not None:
@@ -92,6 +102,7 @@ def kgrad_dense_matern32(x1, x2, theta):
     lib = L.load()
     n1, n2, dim = x1.shape[0], x2.shape[0], x1.shape[1]
     out = L.dev_empty((dim + 1, n1, n2))
+    _require_len(theta, dim + 1, "theta (signal variance + one length scale per dimension)", at_least=True)
     _, th = L.dvec(theta)
     L.check(lib.fvgp_kgrad_dense_matern32(L.ptr(x1), n1, L.ptr(x2), n2, dim, th, L.ptr(out), L.stream_ptr()),
             "fvgp_kgrad_dense_matern32")
@@ -103,6 +114,7 @@ def kgrad_trace_matern32(x, theta, kinv_buf, ld, b):
     lib = L.load()
     n, dim = x.shape
     partials = L.dev_empty((int(lib.fvgp_kgrad_partials_len(n, dim)),))
+    _require_len(theta, dim + 1, "theta (signal variance + one length scale per dimension)", at_least=True)
     _, th = L.dvec(theta)
     out = (c_double * (dim + 1))()
     with _Phase("kgrad_trace"):
@@ -120,6 +132,7 @@ def kgrad_trace_radial(kind, x, amp, inv_scale, length, kinv_buf, ld, b):
     lib = L.load()
     n, dim = x.shape
     partials = L.dev_empty((int(lib.fvgp_kgrad_partials_len(n, dim)),))
+    _require_len(inv_scale, dim, "inv_scale (one per input dimension)")
     _, inv_p = L.dvec(inv_scale)
     out = (c_double * (dim + 2))()
     with _Phase("kgrad_trace"):
@@ -237,6 +250,8 @@ def lml_population(kind, x, amps, inv_scales, lengths, noise, rhs_t, want_grad=F
     n, dim = x.shape
     amps = np.ascontiguousarray(amps, dtype=np.float64)
     lengths = np.ascontiguousarray(lengths, dtype=np.float64)
+    _require_len(inv_scales, len(amps) * dim, "inv_scales (B x dim)")
+    _require_len(lengths, len(amps), "lengths (one per proposal)")
     inv_scales = np.ascontiguousarray(inv_scales, dtype=np.float64).reshape(len(amps), dim)
     B = len(amps)
     nrhs = rhs_t.shape[0]

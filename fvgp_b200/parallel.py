@@ -3,8 +3,9 @@
 What shards on this path: hyperparameter proposals are independent evaluations of
 the same data (MCMC / differential-evolution / hgdl populations, gp_training.py:60-162), so N
 GPUs evaluate N proposals concurrently with NO data-path collective -- "replicas"; the only
-exchange is a gather of (H+1) doubles per proposal.  The dense factorisation itself is not
-sharded in this round ('what comes next')."""
+exchange is a gather of (H+1) doubles per proposal.  Paths whose DATA is sharded live elsewhere:
+the 2-D block-cyclic dense factorisation in `sharded.py`, the row-sharded gp2Scale assembly /
+probe-split log-determinant in `sharded_sparse.py`."""
 import os
 
 import numpy as np

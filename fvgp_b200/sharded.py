@@ -178,6 +178,7 @@ class CudaLocalOps:
 
     def trace_block(self, x1, x2, theta, W, m, n, b1, b2, diag_rows, accum):
         partials = self._work("_partials", self.lib.fvgp_kgrad_block_partials_len(x1.shape[1]))
+        assert np.size(theta) >= x1.shape[1] + 1, "theta needs a signal variance and one length scale per dimension"
         _, th = L.dvec(theta)
         L.check(self.lib.fvgp_kgrad_trace_block_matern32(L.ptr(x1), m, L.ptr(x2), n, x1.shape[1], th, L.ptr(W),
                                                          self._ld(W), L.ptr(b1), L.ptr(b2), int(diag_rows),

@@ -113,12 +113,12 @@ int fvgp_kgrad_dense_matern32(const double* d_x1, int64_t n1, const double* d_x2
                               const double* h_theta, double* d_out, void* stream);
 
 /* ---- dense FP64 factorisation (gp_lin_alg.py:237-360, :1558) */
-int64_t fvgp_chol_workspace_len(int64_t n);  /* doubles: per-64-tile inverses kept by potrf   */
+int64_t fvgp_chol_workspace_len(int64_t n);  /* doubles: per-128-tile inverses kept by potrf  */
 int64_t fvgp_potri_workspace_len(int64_t n); /* doubles: scratch panel of trtri / lauum       */
 
 /* calculate_Chol_factor (gp_lin_alg.py:237-269): in-place lower Cholesky of the lower
  * triangle of d_A.  d_tileinv (fvgp_chol_workspace_len doubles) receives the inverses of the
- * 64x64 diagonal tiles and must be passed unchanged to potrs / potri.  d_info: one int. */
+ * 128x128 diagonal tiles (tile t at offset t*128*128) and must be passed unchanged to potrs / potri.  d_info: one int. */
 int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream);
 
 /* calculate_Chol_solve (gp_lin_alg.py:289-328): solve (L L^T) X = B in place.  d_B holds

@@ -340,3 +340,75 @@ def posterior_mean_cov(x, y, hps, noise, x_pred, kernel=default_kernel):
     mean = k.T @ chol_solve(c, y - m0) + m0
     S = kernel(x_pred, x_pred, hps) - k.T @ chol_solve(c, k)
     return mean[:, 0], S
+
+
+# --------------------------------------------------------------------------- large-N variants (memory-lean)
+# Same arithmetic per entry as the functions above (they CALL default_kernel / default_kernel_gradient on row
+# blocks); only the storage differs: one N x N array, upper triangle, factorised / inverted in place by LAPACK, so
+# that the oracle reaches the benchmarked sizes on the GPU box's host (N = 50 000 LML: 20 GB; the literal
+# formulation needs (3H+3) N^2 doubles for the gradient).  Pinned against the plain functions in
+# tests/test_oracle_golden.py, which are pinned against the reference's outputs.
+def _fill_upper_blocked(x, hps, noise, block=1024, threads=None):
+    """C-ordered A with A[r, c>=r] = default_kernel(x, x, hps)[r, c] + noise on the diagonal (gp_prior.py:376-400,
+    gp_kv.py:640-669); the strict lower triangle is left uninitialised."""
+    import concurrent.futures as cf
+    import os
+    n = len(x)
+    A = np.empty((n, n))
+
+    def work(r0):
+        r1 = min(r0 + block, n)
+        A[r0:r1, r0:] = default_kernel(x[r0:r1], x[r0:], hps)
+        idx = np.arange(r0, r1)
+        A[idx, idx] += noise[r0:r1]
+    with cf.ThreadPoolExecutor(threads or os.cpu_count()) as ex:
+        list(ex.map(work, range(0, n, block)))
+    return A
+
+
+def dense_log_likelihood_blocked(x, y, hps, noise, block=1024, threads=None, return_factor=False):
+    """dense_log_likelihood for large N: blocked K-fill, in-place LAPACK dpotrf (what scipy cho_factor calls,
+    gp_lin_alg.py:237-269), dpotrs, 2 sum log diag (gp_lin_alg.py:289-360), LML (gp_marginal_likelihood.py:171-178)."""
+    from scipy.linalg import lapack
+    y = y.reshape(len(y), -1)
+    n = len(x)
+    A = _fill_upper_blocked(x, np.asarray(hps, dtype=float), noise, block, threads)
+    c, info = lapack.dpotrf(A.T, lower=1, overwrite_a=1, clean=0)        # A.T: Fortran view, lower triangle filled
+    if info != 0:
+        raise NonPositiveDefinite(f"dpotrf info = {info}")
+    assert np.shares_memory(c, A), "LAPACK copied the matrix"
+    m = np.full(n, np.mean(y))
+    ym = y - m[:, None]
+    alpha, info = lapack.dpotrs(c, ym, lower=1)
+    logdet = 2.0 * np.sum(np.log(np.abs(np.diagonal(c))))
+    lml = log_likelihood_from(alpha, logdet, ym)
+    return (lml, c, alpha) if return_factor else lml
+
+
+def dense_neg_log_likelihood_gradient_blocked(x, y, hps, noise, component=0, block=512, threads=None):
+    """dense_neg_log_likelihood_gradient(economical=True) for large N: KV^-1 by LAPACK dpotri in place, traces
+    sum(KV^-1 o dK_i) and b^T dK_i b accumulated over row blocks of the upper triangle (off-diagonal entries count
+    twice), dK from default_kernel_gradient (gp_prior.py:421-436).  Returns (lml, grad)."""
+    import concurrent.futures as cf
+    import os
+    from scipy.linalg import lapack
+    hps = np.asarray(hps, dtype=float)
+    n, H = len(x), len(hps)
+    lml, c, alpha = dense_log_likelihood_blocked(x, y, hps, noise, 1024, threads, return_factor=True)
+    b = alpha[:, component].copy()
+    inv, info = lapack.dpotri(c, lower=1, overwrite_c=1)
+    assert info == 0 and np.shares_memory(inv, c)
+    W = inv.T                                                            # C view: W[r, c>=r] = KV^-1[r, c]
+
+    def work(r0):
+        r1 = min(r0 + block, n)
+        dK = default_kernel_gradient(x[r0:r1], x[r0:], hps)             # (H, rows, n - r0)
+        w = np.full((r1 - r0, n - r0), 2.0)
+        k = np.arange(r1 - r0)
+        w[k, k] = 1.0
+        w[np.tril_indices(r1 - r0, -1)] = 0.0                            # inside the diagonal block: upper part only
+        core = w * (np.outer(b[r0:r1], b[r0:]) - W[r0:r1, r0:])          # (b b^T - KV^-1) o weights
+        return np.array([np.sum(core * dK[i]) for i in range(H)])
+    with cf.ThreadPoolExecutor(threads or os.cpu_count()) as ex:
+        parts = list(ex.map(work, range(0, n, block)))
+    return lml, -0.5 * np.sum(parts, axis=0)                             # -1/2 (b^T dK b - tr(KV^-1 dK))
