@@ -247,32 +247,44 @@ def chunk_ranges(n, batch):
     return [(s, min(s + batch, n)) for s in range(0, n, batch)]
 
 
-def gp2scale_covariance(x1, x2, hps, batch=10000, kernel=wendland_block, symmetric=None):
+def gp2scale_covariance(x1, x2, hps, batch=10000, kernel=wendland_block, symmetric=None, threads=1):
     """Blockwise sparse assembly, gp2Scale_covariance.py:136-170, 240-287, 313-431.
 
     Per block: dense kernel, np.nonzero pattern; symmetric diagonal blocks keep row<=col;
     off-diagonal entries are mirrored; COO -> canonical CSR (sorted int32 indices).
+    threads > 1 evaluates the independent blocks in a thread pool (the reference maps them over dask workers);
+    the triplets are concatenated in the same block order either way.
     """
     if symmetric is None:
         symmetric = x1 is x2
     n1, n2 = len(x1), len(x2)
-    rows, cols, vals = [], [], []
-    for (i0, i1) in chunk_ranges(n1, batch):
-        for (j0, j1) in chunk_ranges(n2, batch):
-            if symmetric and i0 > j0:
-                continue
-            blk = np.asarray(kernel(x1[i0:i1], x2[j0:j1], hps))
-            r, c = np.nonzero(blk)
-            v = blk[r, c]
-            if symmetric and i0 == j0:
-                keep = r <= c
-                r, c, v = r[keep], c[keep], v[keep]
-            r = r + i0
-            c = c + j0
-            rows.append(r), cols.append(c), vals.append(v)
-            if symmetric:
-                off = r != c
-                rows.append(c[off]), cols.append(r[off]), vals.append(v[off])
+
+    def block(ij):
+        (i0, i1), (j0, j1) = ij
+        blk = np.asarray(kernel(x1[i0:i1], x2[j0:j1], hps))
+        r, c = np.nonzero(blk)
+        v = blk[r, c]
+        if symmetric and i0 == j0:
+            keep = r <= c
+            r, c, v = r[keep], c[keep], v[keep]
+        r = r + i0
+        c = c + j0
+        out = [(r, c, v)]
+        if symmetric:
+            off = r != c
+            out.append((c[off], r[off], v[off]))
+        return out
+    todo = [(ri, cj) for ri in chunk_ranges(n1, batch) for cj in chunk_ranges(n2, batch)
+            if not (symmetric and ri[0] > cj[0])]
+    if threads > 1 and len(todo) > 1:
+        import concurrent.futures as cf
+        with cf.ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(block, todo))
+    else:
+        parts = [block(t) for t in todo]
+    rows = [t[0] for part in parts for t in part]
+    cols = [t[1] for part in parts for t in part]
+    vals = [t[2] for part in parts for t in part]
     if not rows:
         return sp.csr_matrix((n1, n2))
     idx = np.int32 if max(n1, n2) < 2 ** 31 else np.int64          # :107-114

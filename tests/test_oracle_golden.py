@@ -115,3 +115,22 @@ def test_gp2scale_lml(golden):
         sol, iters = orc.sparse_cg(KV, ym, rtol=1e-12)
         assert np.allclose(sol, g["KVinvY_h0"], rtol=1e-7, atol=1e-9) and iters[0] > 0
         assert sp.issparse(KV)
+
+
+def test_large_n_oracle_variants_equal_the_pinned_ones(golden):
+    """The memory-lean variants bench.py / the -m gpu suite use at N = 8 000 ... 50 000 (in-place LAPACK, blocked dK,
+    threaded block assembly) against the reference's own outputs and the plain oracle functions."""
+    for tag in ("c1", "c2"):
+        g = golden("dense_lml_" + tag)
+        x, y, nz = g["x"], g["y"], g["noise"]
+        for hk in ("h0", "h1"):
+            assert abs(orc.dense_log_likelihood_blocked(x, y, g[hk], nz, block=97) / g["lml_" + hk] - 1) <= 1e-11
+            lml, gr = orc.dense_neg_log_likelihood_gradient_blocked(x, y, g[hk], nz, block=53, threads=3)
+            assert abs(lml / g["lml_" + hk] - 1) <= 1e-11
+            assert rel(gr, g["grad_" + hk]) <= 1e-8, (tag, hk, gr, g["grad_" + hk])
+    rng = np.random.default_rng(7)
+    x = rng.random((900, 3))
+    th = np.array([1.3, .11, .12, .1])
+    a = orc.gp2scale_covariance(x, x, th, batch=128, symmetric=True)
+    b = orc.gp2scale_covariance(x, x, th, batch=128, symmetric=True, threads=4)
+    assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
