@@ -45,6 +45,15 @@ import threading
 import time
 
 T_START = time.time()
+import faulthandler
+
+faulthandler.enable()                 # a native crash must leave a Python traceback on stderr
+
+
+def log(msg):
+    """Progress marker on stderr (stdout carries the one JSON line only)."""
+    print(f"[bench {time.time() - T_START:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
 
 if "reference" in sys.argv and "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
     # torchrun exports OMP_NUM_THREADS=1 when it starts more than one rank; the CPU arm (rank 0 only) is meant
@@ -260,6 +269,7 @@ def start_watchdog(limit_s, rank):
 def guarded(name, fn, sink):
     """Run one optional section; a failure is recorded in the line instead of killing the headline."""
     t0 = time.time()
+    log(f"section {name} ...")
     try:
         sink[name] = fn()
     except Exception as e:                      # noqa: BLE001 -- evidence sections must never lose the headline
@@ -1126,6 +1136,7 @@ def main():
     clocks = sampler.summary()
     t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
+    log(f"device-timed region done: {t_dev / args.steps:.3f} s per step")
     # ---- end to end: host buffers in, host results out, through the public API -------------------
     gp.args = dict(gp.args, host_inputs_every_call=True)           # every call copies x from pinned host memory
     step(args.warmup + args.steps)                                  # pins the staging buffer (untimed)
@@ -1152,6 +1163,7 @@ def main():
     HOLD["line"] = line
     start_watchdog(args.budget + 75.0, rank)
 
+    log(f"e2e region done: {t_e2e / args.steps:.3f} s per step")
     # ---- roofline of the dominant kernel (DMMA GEMM inside potrf + potri) ----------------------
     if rank == 0:
         import ctypes
@@ -1171,7 +1183,9 @@ def main():
                             "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
                             "algorithmic_flops_per_step": float(n) ** 3,
                             "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
+        log("fp64 peak probe done; K-fill rooflines ...")
         line["roofline_kfill"] = kfill_rooflines(n, gp, x, noise)
+        log("same-N point ...")
 
         # the size both arms measure directly: ours through the public API with host buffers
         xs, ys, vs = synthetic_c2(SAME_N)
@@ -1188,6 +1202,7 @@ def main():
         line["same_n"] = {"n": SAME_N, "seconds": dt8, "evals_per_s": 1.0 / dt8,
                           "note": "LML + gradient through the public API, host buffers; the reference arm measures this size too"}
 
+        log("cpu baseline sample ...")
         line["cpu_baseline"] = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import fvgp_oracle as orc

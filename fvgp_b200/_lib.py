@@ -56,8 +56,8 @@ _SIGNATURES = {
     "fvgp_wendland_aabb": (c_int, [_P, c_int64, c_int, _P, _P]),
     "fvgp_wendland_chunk_len": (c_int64, [c_int64, c_int64]),
     "fvgp_wendland_csr_count": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
-    "fvgp_wendland_csr_fill": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P, _P, _P,
-                                       _P]),
+    "fvgp_wendland_csr_fill": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int, POINTER(c_double), _P, _P, _P, c_int64,
+                                       _P, _P, _P]),
     "fvgp_exclusive_scan_i64": (c_int, [_P, c_int64, _P, _P, POINTER(c_int64), _P]),
     "fvgp_scan_scratch_len": (c_int64, [c_int64]),
     "fvgp_csr_spmv": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
@@ -73,6 +73,16 @@ _SIGNATURES = {
     "fvgp_lml_population": (c_int, [c_int, _P, c_int64, c_int, c_int, POINTER(c_double), POINTER(c_double),
                                     POINTER(c_double), POINTER(c_double), _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
                                     _P, POINTER(c_double), POINTER(c_double), POINTER(c_double), POINTER(c_int), _P]),
+    "fvgp_nccl_attach": (c_int, [ctypes.c_char_p]),
+    "fvgp_comm_unique_id": (c_int, [_P]),
+    "fvgp_comm_create": (c_int, [_P, c_int, c_int, POINTER(c_void_p)]),
+    "fvgp_comm_adopt": (c_int, [_P, c_int, c_int, POINTER(c_void_p)]),
+    "fvgp_comm_destroy": (c_int, [_P]),
+    "fvgp_comm_allgatherv": (c_int, [_P, _P, POINTER(c_int64), _P]),
+    "fvgp_comm_allreduce_sum": (c_int, [_P, _P, c_int64, _P]),
+    "fvgp_pcg_sharded_work_len": (c_int64, [c_int64]),
+    "fvgp_pcg_sharded": (c_int, [_P, c_int64, POINTER(c_int64), _P, _P, _P, _P, _P, _P, c_double, c_int, _P,
+                                 POINTER(c_int), POINTER(c_double), _P]),
     "fvgp_bench_fp64_peak": (c_int, [c_int, c_int, c_int, _P, POINTER(c_double), _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

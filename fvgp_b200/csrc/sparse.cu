@@ -26,6 +26,7 @@
 // exclusive scan -> index pass (same geometry, writes column indices) -> value pass (lane-dense).
 #include "../../include/fvgp_b200.h"
 #include "common.cuh"
+#include "comm.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -50,6 +51,7 @@ struct WendlandParams {
   int* indices;
   double* data;
   long long n1, n2, tiles1, tiles2, super2;
+  long long row0;  // global index of row 0 of x1 inside x2's numbering (row slabs of a symmetric matrix); diagonal = row + row0
   double amp;
   double theta[kMaxDim];
   int dim;
@@ -171,8 +173,11 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
   const long long r_mine = tile * WT + lane;
   const int rows_here = (int)min((long long)WT, p.n1 - tile * WT);
   long long cur = 0;  // lane r: entries of row r found by this unit (count) / write cursor of row r (fill)
-  long long pairs = 0;
+  long long pairs = 0, row_tests = 0;
   bool staged = false;
+  double xrow[DIM];   // this lane's row point (valid once staged)
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) xrow[i] = 0.0;
 
   const double* tile_boxes = p.aabb2;
   const double* super_boxes = p.aabb2 + p.tiles2 * 2 * DIM;
@@ -192,7 +197,10 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
     unsigned smask = __ballot_sync(0xffffffffu, keep);
     if (smask != 0u && !staged) {  // first survivor: stage the row points, fetch the cursors
 #pragma unroll
-      for (int i = 0; i < DIM; ++i) xs[warp][lane][i] = r_mine < p.n1 ? p.x1[r_mine * DIM + i] : 0.0;
+      for (int i = 0; i < DIM; ++i) {
+        xrow[i] = r_mine < p.n1 ? p.x1[r_mine * DIM + i] : 0.0;
+        xs[warp][lane][i] = xrow[i];
+      }
       if (FILL && r_mine < p.n1) cur = p.indptr[r_mine] + p.chunk[(long long)chunk * p.n1 + r_mine];
       staged = true;
       __syncwarp();
@@ -215,46 +223,77 @@ __global__ void __launch_bounds__(W_WARPS * 32) wendland_csr_kernel(const Wendla
         const int tb = __ffs(tmask) - 1;
         tmask &= tmask - 1;
         const long long ct = (s0 + sb) * WS + tb;
+        // Per-ROW cull: lane r tests ITS row point against the column tile's box (broadcast loads of the box).  A
+        // row tile's box inflated by the support radius is ~3x the radius wide at C4, so roughly half of its rows
+        // are out of reach of any given surviving column tile; only the rows that pass enter the pair loop.
+        unsigned rmask;
+        {
+          const double* bx = tile_boxes + ct * 2 * DIM;
+          double gs = 0.0;
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) {
+            const double g = fmax(0.0, fmax(bx[i] - xrow[i], xrow[i] - bx[DIM + i]));
+            const double t = g * rinv[i];
+            gs = fma(t, t, gs);
+          }
+          rmask = __ballot_sync(0xffffffffu, lane < rows_here && gs < FVGP_CULL_LIMIT);
+        }
+        if (rmask == 0u) continue;
+        row_tests += __popc(rmask);
         const long long c = ct * WT + lane;
         const bool c_ok = c < p.n2;
         double xc[DIM];
 #pragma unroll
         for (int i = 0; i < DIM; ++i) xc[i] = c_ok ? p.x2[c * DIM + i] : 0.0;
-#pragma unroll 4
-        for (int rr = 0; rr < rows_here; ++rr) {
-          double xr[DIM];
+        while (rmask) {
+          // two rows per trip: two independent distance chains in flight
+          const int ra = __ffs(rmask) - 1;
+          rmask &= rmask - 1;
+          const int rb = rmask ? __ffs(rmask) - 1 : -1;
+          if (rb >= 0) rmask &= rmask - 1;
+          double xa[DIM], xb[DIM];
 #pragma unroll
-          for (int i = 0; i < DIM; ++i) xr[i] = xs[warp][rr][i];
-          double sa = 0.0;
+          for (int i = 0; i < DIM; ++i) xa[i] = xs[warp][ra][i], xb[i] = xs[warp][rb >= 0 ? rb : ra][i];
+          double sa = 0.0, sb2 = 0.0;
 #pragma unroll
           for (int i = 0; i < DIM; ++i) {
-            const double t = (xr[i] - xc[i]) * rinv[i];
-            sa = fma(t, t, sa);
+            const double ta = (xa[i] - xc[i]) * rinv[i], tb2 = (xb[i] - xc[i]) * rinv[i];
+            sa = fma(ta, ta, sa), sb2 = fma(tb2, tb2, sb2);
           }
-          bool hit = c_ok && sa < FVGP_SURE_LIMIT;
-          if (STRICT) {
-            hit = false;
-            if (c_ok && sa < FVGP_CULL_LIMIT) {
-              const double s = exact_s<DIM>(xr, xc, theta);
-              hit = s < 1.0 && wendland_value(s, p.amp) != 0.0;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int rr = half == 0 ? ra : rb;
+            if (rr < 0) break;  // warp-uniform
+            const double sv = half == 0 ? sa : sb2;
+            const double* xr = half == 0 ? xa : xb;
+            bool hit = c_ok && sv < FVGP_SURE_LIMIT;
+            if (STRICT) {
+              hit = false;
+              if (c_ok && sv < FVGP_CULL_LIMIT) {
+                const double s = exact_s<DIM>(xr, xc, theta);
+                hit = s < 1.0 && wendland_value(s, p.amp) != 0.0;
+              }
+            } else if (c_ok && !hit && sv < FVGP_CULL_LIMIT) {
+              hit = exact_s<DIM>(xr, xc, theta) < 1.0;  // the sliver: decided by the reference's sequence
             }
-          } else if (c_ok && !hit && sa < FVGP_CULL_LIMIT) {
-            hit = exact_s<DIM>(xr, xc, theta) < 1.0;  // the sliver: decided by the reference's sequence
+            const unsigned hmask = __ballot_sync(0xffffffffu, hit);
+            if (hmask == 0u) continue;
+            if (FILL) {
+              const long long base = __shfl_sync(0xffffffffu, cur, rr);
+              if (hit) p.indices[base + __popc(hmask & lt_mask)] = (int)c;
+            }
+            if (lane == rr) cur += __popc(hmask);
           }
-          const unsigned hmask = __ballot_sync(0xffffffffu, hit);
-          if (hmask == 0u) continue;
-          if (FILL) {
-            const long long base = __shfl_sync(0xffffffffu, cur, rr);
-            if (hit) p.indices[base + __popc(hmask & lt_mask)] = (int)c;
-          }
-          if (lane == rr) cur += __popc(hmask);
         }
       }
     }
   }
   if (!FILL) {
     if (r_mine < p.n1) p.chunk[(long long)chunk * p.n1 + r_mine] = (int)cur;
-    if (p.stats != nullptr && lane == 0 && pairs != 0) atomicAdd((unsigned long long*)p.stats, (unsigned long long)pairs);
+    if (p.stats != nullptr && lane == 0 && pairs != 0) {   // stats[0]: tile pairs that reached the pair loop's door,
+      atomicAdd((unsigned long long*)p.stats, (unsigned long long)pairs);            // stats[1]: candidate pairs tested
+      atomicAdd((unsigned long long*)p.stats + 1, (unsigned long long)row_tests * 32ull);
+    }
   }
 }
 
@@ -292,7 +331,7 @@ __global__ void __launch_bounds__(256) wendland_values_kernel(const WendlandPara
 #pragma unroll
       for (int i = 0; i < DIM; ++i) xc[i] = p.x2[c * DIM + i];
       double v = wendland_value(exact_s<DIM>(xr, xc, theta), p.amp);
-      if (p.noise != nullptr && c == row) v += p.noise[row];
+      if (p.noise != nullptr && c == row + p.row0) v += p.noise[row];
       p.data[k] = v;
     }
   }
@@ -563,6 +602,133 @@ __global__ void __launch_bounds__(KR_THREADS, MINB) pcg_spmv_kernel(long long n,
     sc->pq = tot[0];
     sc->alpha = sc->rho / tot[0];
   }
+}
+
+// ---------------------------------------------------------------------------- row-sharded PCG (multi-GPU)
+// Rank r owns rows [row0, row0 + nrows) of the matrix and of x, r, z, q; the search direction p is kept in full on
+// every rank (the slab SpMV gathers from all of it).  One iteration = the single-GPU iteration with three
+// collectives spliced in (fvgp_pcg_sharded): the local partial sums of (r.r, r.z) and of p.q are all-reduced in
+// place in sc->loc, p's slabs are all-gathered after the update.  The derived scalars (rho, alpha, beta, the
+// convergence flag) are computed redundantly on every rank from the same reduced values by a one-thread kernel, so
+// every rank takes the same branch and issues the same sequence of collectives.
+struct ShardScalars {
+  double loc[4];  // [0] r.r (b.b at init)  [1] r.z (r.r at init)  [2] p.q      -- all-reduced in place
+  double rho, rho_old, atol, alpha, beta, bnorm2, rr;
+  int done, iters, calls, pad;
+  unsigned counter[4];
+};
+
+template <int LPR, int U, int MINB>
+__global__ void __launch_bounds__(KR_THREADS, MINB) pcgs_init_kernel(long long nrows, const long long* __restrict__ indptr,
+                                                                     const int* __restrict__ idx,
+                                                                     const double* __restrict__ val,
+                                                                     const double* __restrict__ b_slab,
+                                                                     const double* __restrict__ x_full,
+                                                                     double* __restrict__ r, ShardScalars* sc,
+                                                                     double* partials) {
+  double v[2] = {0.0, 0.0};
+  spmv_rows<LPR, U>(nrows, indptr, idx, val, x_full, [&](long long row, double ax) {
+    const double bi = b_slab[row], ri = bi - ax;
+    r[row] = ri;
+    v[0] += bi * bi;
+    v[1] += ri * ri;
+  });
+  double tot[2];
+  if (grid_sum<2>(v, partials, &sc->counter[0], tot) && threadIdx.x == 0) sc->loc[0] = tot[0], sc->loc[1] = tot[1];
+}
+
+// which = 0 after the init reduction, 1 after the head reduction, 2 after the p.q reduction
+__global__ void pcgs_scalar_kernel(ShardScalars* sc, int which, double rtol, int maxiter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (which == 0) {
+    sc->bnorm2 = sc->loc[0];
+    sc->rr = sc->loc[1];
+    sc->atol = rtol * sqrt(sc->loc[0]);
+    sc->rho = 0.0, sc->rho_old = 0.0, sc->iters = 0, sc->calls = 0, sc->alpha = 0.0, sc->beta = 0.0;
+    sc->done = (sc->loc[0] == 0.0) ? 1 : 0;  // scipy returns at once for b = 0
+    return;
+  }
+  if (sc->done) return;
+  if (which == 1) {
+    sc->rr = sc->loc[0];
+    sc->iters = sc->calls;  // completed x / r updates
+    sc->calls += 1;
+    if (sqrt(sc->loc[0]) < sc->atol) sc->done = 1;
+    else if (sc->iters >= maxiter) sc->done = 2;
+    sc->rho_old = sc->rho;
+    sc->rho = sc->loc[1];
+    sc->beta = sc->iters > 0 ? sc->loc[1] / sc->rho_old : 0.0;
+  } else {
+    sc->alpha = sc->rho / sc->loc[2];
+  }
+}
+
+// x += alpha p ; r -= alpha q ; z = M r ; local sums of r.r and r.z   (all pointers are slab-local)
+__global__ void __launch_bounds__(KR_THREADS) pcgs_head_kernel(long long nrows, const double* __restrict__ blocks,
+                                                               const double* __restrict__ p, const double* __restrict__ q,
+                                                               double* __restrict__ x, double* __restrict__ r,
+                                                               double* __restrict__ z, ShardScalars* sc,
+                                                               double* partials) {
+  if (sc->done) return;
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nblk = (nrows + 31) / 32;
+  const double alpha = sc->alpha;
+  const bool update = sc->calls > 0;
+  double v[2] = {0.0, 0.0};
+  for (long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblk; blk += warps) {
+    const long long i = blk * 32 + lane;
+    double ri = 0.0;
+    if (i < nrows) {
+      ri = r[i];
+      if (update) {
+        x[i] = fma(alpha, p[i], x[i]);
+        ri = fma(-alpha, q[i], ri);
+        r[i] = ri;
+      }
+    }
+    double zi = ri;
+    if (blocks != nullptr) {
+      const double* B = blocks + blk * 1024;
+      zi = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) zi = fma(B[j * 32 + lane], __shfl_sync(0xffffffffu, ri, j), zi);
+    }
+    if (i < nrows) {
+      z[i] = zi;
+      v[0] += ri * ri;
+      v[1] += ri * zi;
+    }
+  }
+  double tot[2];
+  if (grid_sum<2>(v, partials, &sc->counter[1], tot) && threadIdx.x == 0) sc->loc[0] = tot[0], sc->loc[1] = tot[1];
+}
+
+__global__ void __launch_bounds__(KR_THREADS) pcgs_update_p_kernel(long long nrows, const double* __restrict__ z,
+                                                                   double* __restrict__ p_slab, const ShardScalars* sc) {
+  if (sc->done) return;
+  const double beta = sc->beta;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x)
+    p_slab[i] = z[i] + beta * p_slab[i];
+}
+
+// q = A_slab p ; local p.q
+template <int LPR, int U, int MINB>
+__global__ void __launch_bounds__(KR_THREADS, MINB) pcgs_spmv_kernel(long long nrows, const long long* __restrict__ indptr,
+                                                                     const int* __restrict__ idx,
+                                                                     const double* __restrict__ val,
+                                                                     const double* __restrict__ p_full,
+                                                                     const double* __restrict__ p_slab,
+                                                                     double* __restrict__ q, ShardScalars* sc,
+                                                                     double* partials) {
+  if (sc->done) return;
+  double v[1] = {0.0};
+  spmv_rows<LPR, U>(nrows, indptr, idx, val, p_full, [&](long long row, double s) {
+    q[row] = s;
+    v[0] += s * p_slab[row];
+  });
+  double tot[1];
+  if (grid_sum<1>(v, partials, &sc->counter[2], tot) && threadIdx.x == 0) sc->loc[2] = tot[0];
 }
 
 // Dense 32x32 diagonal blocks of the CSR matrix, inverted in shared memory (Gauss-Jordan, SPD).
@@ -922,6 +1088,7 @@ static int fill_wendland_params(WendlandParams& p, const double* d_x1, int64_t n
   p.tiles1 = (n1 + WT - 1) / WT, p.tiles2 = (n2 + WT - 1) / WT, p.super2 = (p.tiles2 + WS - 1) / WS;
   wendland_chunking(n2, p.supers_per_chunk, p.n_chunks);
   p.chunk = nullptr;
+  p.row0 = 0;
   for (int i = 0; i < kMaxDim; ++i) p.theta[i] = i < dim ? h_theta[1 + i] : 1.0;
   p.indptr = nullptr, p.noise = nullptr, p.rowcount = nullptr, p.stats = nullptr, p.indices = nullptr, p.data = nullptr;
   return 0;
@@ -976,12 +1143,13 @@ int fvgp_wendland_csr_count(const double* d_x1, int64_t n1, const double* d_aabb
 
 int fvgp_wendland_csr_fill(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                            const double* d_aabb2, int dim, const double* h_theta, const int64_t* d_indptr,
-                           const int32_t* d_chunk, const double* d_noise_diag, int32_t* d_indices, double* d_data,
-                           void* stream) {
+                           const int32_t* d_chunk, const double* d_noise_diag, int64_t row0, int32_t* d_indices,
+                           double* d_data, void* stream) {
   WendlandParams p;
   int r = fill_wendland_params(p, d_x1, n1, d_aabb1, d_x2, n2, d_aabb2, dim, h_theta);
   if (r != 0) return r;
   if (n1 == 0) return 0;
+  p.row0 = row0;
   p.indptr = (const long long*)d_indptr, p.noise = d_noise_diag, p.indices = d_indices, p.data = d_data;
   p.chunk = const_cast<int32_t*>(d_chunk);
   r = launch_wendland<true>(p, (cudaStream_t)stream);
@@ -1073,6 +1241,64 @@ int fvgp_pcg(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const
     }
     FVGP_LAUNCH_OK();
   }
+  if (h_iters) *h_iters = h.iters;
+  if (h_relres) *h_relres = h.bnorm2 > 0.0 ? sqrt(h.rr / h.bnorm2) : 0.0;
+  return h.done == 1 ? 0 : 1;
+}
+
+// work layout: p (n, full) | r | z | q (nrows each, padded to n) | partials (2*grid) | ShardScalars
+int64_t fvgp_pcg_sharded_work_len(int64_t n) { return 4 * n + 2 * (int64_t)krylov_grid() + 64; }
+
+int fvgp_pcg_sharded(void* comm, int64_t n, const int64_t* h_row_offsets, const int64_t* d_indptr_slab,
+                     const int32_t* d_indices, const double* d_data, const double* d_precond_slab, const double* d_b,
+                     double* d_x, double rtol, int maxiter, double* d_work, int* h_iters, double* h_relres,
+                     void* stream) {
+  FVGP_REQUIRE(comm != nullptr && n > 0 && maxiter > 0 && h_row_offsets != nullptr);
+  const Comm* c = (const Comm*)comm;
+  const long long row0 = h_row_offsets[c->rank], nrows = h_row_offsets[c->rank + 1] - row0;
+  FVGP_REQUIRE(h_row_offsets[0] == 0 && h_row_offsets[c->world] == n && nrows >= 0 && row0 % 32 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = krylov_grid();
+  double* p = d_work;  // full
+  double* r = p + n;
+  double* z = r + n;
+  double* q = z + n;
+  double* partials = q + n;
+  ShardScalars* sc = (ShardScalars*)(partials + 2 * grid);
+  const long long* ip = (const long long*)d_indptr_slab;
+  int64_t off[65];
+  FVGP_REQUIRE(c->world <= 64);
+  for (int k = 0; k <= c->world; ++k) off[k] = h_row_offsets[k] * (int64_t)sizeof(double);
+  FVGP_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(ShardScalars), st));
+  FVGP_CUDA_OK(cudaMemsetAsync(p, 0, 4 * n * sizeof(double), st));
+  FVGP_SPMV_DISPATCH(pcgs_init_kernel, grid, KR_THREADS, 0, st, nrows, ip, d_indices, d_data, d_b + row0,
+                     (const double*)d_x, r, sc, partials);
+  FVGP_LAUNCH_OK();
+  int rc = comm_allreduce_sum(c, sc->loc, 2, st);
+  if (rc != 0) return rc;
+  launch(pcgs_scalar_kernel, 1, 32, 0, st, sc, 0, rtol, maxiter);
+  ShardScalars h;
+  const int batch = 16;
+  for (long long launched = 0;; launched += batch) {
+    FVGP_CUDA_OK(cudaMemcpyAsync(&h, sc, sizeof(ShardScalars), cudaMemcpyDeviceToHost, st));
+    FVGP_CUDA_OK(cudaStreamSynchronize(st));
+    if (h.done || launched > (long long)maxiter + batch) break;  // identical on every rank: same reduced scalars
+    for (int k = 0; k < batch; ++k) {
+      launch(pcgs_head_kernel, grid, KR_THREADS, 0, st, nrows, d_precond_slab, (const double*)(p + row0), (const double*)q,
+             d_x + row0, r, z, sc, partials);
+      if ((rc = comm_allreduce_sum(c, sc->loc, 2, st)) != 0) return rc;
+      launch(pcgs_scalar_kernel, 1, 32, 0, st, sc, 1, rtol, maxiter);
+      launch(pcgs_update_p_kernel, grid, KR_THREADS, 0, st, nrows, (const double*)z, p + row0, (const ShardScalars*)sc);
+      if ((rc = comm_allgatherv_bytes(c, p, off, st)) != 0) return rc;
+      FVGP_SPMV_DISPATCH(pcgs_spmv_kernel, grid, KR_THREADS, 0, st, nrows, ip, d_indices, d_data, (const double*)p,
+                         (const double*)(p + row0), q, sc, partials);
+      if ((rc = comm_allreduce_sum(c, sc->loc + 2, 1, st)) != 0) return rc;
+      launch(pcgs_scalar_kernel, 1, 32, 0, st, sc, 2, rtol, maxiter);
+    }
+    FVGP_LAUNCH_OK();
+  }
+  if ((rc = comm_allgatherv_bytes(c, d_x, off, st)) != 0) return rc;  // every rank leaves with the whole solution
+  FVGP_CUDA_OK(cudaStreamSynchronize(st));
   if (h_iters) *h_iters = h.iters;
   if (h_relres) *h_relres = h.bnorm2 > 0.0 ? sqrt(h.rr / h.bnorm2) : 0.0;
   return h.done == 1 ? 0 : 1;

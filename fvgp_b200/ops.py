@@ -339,8 +339,8 @@ def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None, stats=None
     """k(x1, x2) for the compact-support Wendland kernel as canonical CSR (bit-exact pattern).
 
     Replaces the per-block dask tasks + host assembly (gp2Scale_covariance.py:136-287); `noise`
-    fuses K + diag(V) (gp_kv.py:655-661).  stats: optional int64 device tensor (1,), receives += the number
-    of 32x32 tile pairs the geometry pass tested."""
+    fuses K + diag(V) (gp_kv.py:655-661).  stats: optional int64 device tensor (2,), receives += the number
+    of 32x32 tile pairs that survived the box culls and the number of candidate point pairs tested."""
     lib = L.load()
     torch = L._torch()
     n1, dim = x1.shape
@@ -366,7 +366,7 @@ def wendland_csr(x1, x2, theta, noise=None, boxes1=None, boxes2=None, stats=None
     data = L.dev_empty_rounded(nnz, torch.float64)
     if nnz:
         L.check(lib.fvgp_wendland_csr_fill(L.ptr(x1), n1, L.ptr(boxes1), L.ptr(x2), n2, L.ptr(boxes2), dim, th,
-                                           L.ptr(indptr), L.ptr(chunk), L.ptr(noise), L.ptr(indices), L.ptr(data), st),
+                                           L.ptr(indptr), L.ptr(chunk), L.ptr(noise), 0, L.ptr(indices), L.ptr(data), st),
                 "fvgp_wendland_csr_fill")
     return DeviceCSR(indptr, indices, data, (n1, n2))
 

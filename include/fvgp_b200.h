@@ -212,8 +212,12 @@ int fvgp_dot(const double* d_a, const double* d_b, int64_t n, double* d_scratch1
  * Work is cut into (32-row tile, column chunk) units, at most 32 chunks; d_chunk (fvgp_wendland_chunk_len
  * int32) carries the per-(chunk, row) counts from the count pass to the fill pass and must not be touched
  * in between.
- * d_stats (may be NULL): one int64 the count pass ADDS the number of 32x32 tile pairs it tested to
- * (pair tests = 1024 x that; reported next to nnz as the cull efficiency). */
+ * d_stats (may be NULL): TWO int64 the count pass ADDS to: [0] the number of (row tile, column tile) pairs whose
+ * boxes survived both culls, [1] the number of candidate point pairs actually tested (a per-row cull against the
+ * column tile's box runs in front of the pair loop) -- reported next to nnz as the cull efficiency.
+ * Row slabs (multi-GPU row sharding; gp2Scale_covariance.py:381-396 rowwise tasks): x1 may be rows
+ * [row0, row0 + n1) of x2; d_indptr then points at the slab's n1 + 1 offsets (absolute positions inside d_indices /
+ * d_data), d_noise_diag at the slab's n1 noise values, and row0 tells the fill where the diagonal is. */
 int64_t fvgp_wendland_aabb_len(int64_t n, int dim); /* doubles per point set for tile bounding boxes */
 int fvgp_wendland_aabb(const double* d_x, int64_t n, int dim, double* d_aabb, void* stream);
 int64_t fvgp_wendland_chunk_len(int64_t n1, int64_t n2); /* int32 scratch shared by count and fill */
@@ -222,8 +226,8 @@ int fvgp_wendland_csr_count(const double* d_x1, int64_t n1, const double* d_aabb
                             int32_t* d_chunk, int64_t* d_stats, void* stream);
 int fvgp_wendland_csr_fill(const double* d_x1, int64_t n1, const double* d_aabb1, const double* d_x2, int64_t n2,
                            const double* d_aabb2, int dim, const double* h_theta, const int64_t* d_indptr,
-                           const int32_t* d_chunk, const double* d_noise_diag, int32_t* d_indices, double* d_data,
-                           void* stream);
+                           const int32_t* d_chunk, const double* d_noise_diag, int64_t row0, int32_t* d_indices,
+                           double* d_data, void* stream);
 /* exclusive scan of n counts into n+1 offsets (d_indptr[0] = 0); *h_total = nnz. */
 int fvgp_exclusive_scan_i64(const int64_t* d_counts, int64_t n, int64_t* d_indptr, int64_t* d_scratch,
                             int64_t* h_total, void* stream);
@@ -259,6 +263,36 @@ int64_t fvgp_lanczos_work_len(int64_t n, int degree);
 int fvgp_lanczos_tridiag(int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const double* d_data,
                          int degree, int probe0, int nprobes, uint64_t seed, double* d_work, double* h_alpha,
                          double* h_beta, void* stream);
+
+/* ---- multi-GPU (SURVEY 8b "multi-GPU variants take an ncclComm_t", 8e).  One process per GPU; the reference's
+ * counterpart is the dask cluster of gp2Scale (gp2Scale_covariance.py:313-431: blockwise / rowwise tasks, scatter of
+ * x, gp_prior.py:301-322) -- it has no multi-GPU solver.  The library does not link NCCL: fvgp_nccl_attach binds the
+ * NCCL the calling process already uses (path of the loaded libnccl.so.2, or NULL for the SONAME).
+ * A comm handle is either created here (rank 0 draws fvgp_comm_unique_id, the host distributes the 128 bytes -- e.g.
+ * through torch.distributed -- and every rank calls fvgp_comm_create) or adopts an ncclComm_t the caller owns.
+ * All collective entry points must be called by every rank of the communicator, in the same order. */
+int fvgp_nccl_attach(const char* libnccl_path);
+int fvgp_comm_unique_id(void* h_id128);
+int fvgp_comm_create(const void* h_id128, int rank, int world, void** comm_out);
+int fvgp_comm_adopt(void* nccl_comm, int rank, int world, void** comm_out);
+int fvgp_comm_destroy(void* comm);
+/* In-place all-gather of unequal parts: rank r owns bytes [h_offsets_bytes[r], h_offsets_bytes[r+1]) of d_buf
+ * (row slabs of the gp2Scale CSR: assemble_row_strips, gp2Scale_covariance.py:290-296).  One grouped NCCL launch. */
+int fvgp_comm_allgatherv(void* comm, void* d_buf, const int64_t* h_offsets_bytes, void* stream);
+int fvgp_comm_allreduce_sum(void* comm, double* d_buf, int64_t count, void* stream);
+
+/* Row-sharded preconditioned CG (calculate_sparse_conj_grad, gp_lin_alg.py:1213-1291, same stopping rule as
+ * fvgp_pcg): rank r owns rows [h_row_offsets[r], h_row_offsets[r+1]) (multiples of 32) of the matrix, of the
+ * block-Jacobi blocks and of x / r / z / q; the search direction lives in full on every rank.  d_indptr_slab: the
+ * slab's nrows + 1 offsets (absolute positions in d_indices / d_data), d_precond_slab: the slab's 32 x 32 blocks or
+ * NULL, d_b: full right-hand side, d_x: full vector (x0 in, the whole solution out on every rank).  Per iteration:
+ * slab SpMV + fused vector kernels + two scalar all-reduces + one all-gather of p, all enqueued on `stream`; the host
+ * polls the convergence flag every 16 iterations.  d_work: fvgp_pcg_sharded_work_len(n) doubles. */
+int64_t fvgp_pcg_sharded_work_len(int64_t n);
+int fvgp_pcg_sharded(void* comm, int64_t n, const int64_t* h_row_offsets, const int64_t* d_indptr_slab,
+                     const int32_t* d_indices, const double* d_data, const double* d_precond_slab, const double* d_b,
+                     double* d_x, double rtol, int maxiter, double* d_work, int* h_iters, double* h_relres,
+                     void* stream);
 
 /* ---- measurement only: register-resident FP64 issue-rate probes (which: 0 = DMMA.8x8x4,
  * 1 = DFMA) giving the FP64 roofline denominator of the box.  d_scratch: 148*8*256 doubles. */
