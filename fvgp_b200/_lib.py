@@ -32,6 +32,8 @@ _SIGNATURES = {
     "fvgp_kgrad_block_partials_len": (c_int64, [c_int]),
     "fvgp_kgrad_trace_block_matern32": (c_int, [_P, c_int64, _P, c_int64, c_int, POINTER(c_double), _P, c_int64, _P, _P,
                                                 c_int64, _P, _P, _P]),
+    "fvgp_kgrad_trace_block_radial": (c_int, [c_int, _P, c_int64, _P, c_int64, c_int, POINTER(c_double), c_double, _P,
+                                              c_int64, _P, _P, c_int64, _P, _P, _P]),
     "fvgp_trace_sym_product": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, POINTER(c_double), _P]),
     "fvgp_kgrad_dense_matern32": (c_int, [_P, c_int64, _P, c_int64, c_int, POINTER(c_double), _P, _P]),
     "fvgp_chol_workspace_len": (c_int64, [c_int64]),

@@ -703,6 +703,86 @@ __global__ void __launch_bounds__(FILL_THREADS) kgrad_trace_block_kernel(const T
   }
 }
 
+// The same block trace for every radial family of the fused fill (squared exponential, exponential, Matern-3/2,
+// Matern-5/2): coordinates arrive scaled by inv_scale_i * c_KIND / length (see radial_trace_factors), the raw sums
+//   acc[0] = sum W f(u),   acc[1+i] = sum W h(u) q_i
+// are converted to the traces against (amp, inv_scale_1..D, length) on the host after the all-reduce.
+template <int KIND, int DIM>
+__global__ void __launch_bounds__(FILL_THREADS) kgrad_trace_block_radial_kernel(const TraceBlockParams p) {
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int D = DIM > 0 ? DIM : kMaxDim;
+  const int dim = p.dim;
+  double inv[D], acc[D + 1];
+#pragma unroll
+  for (int i = 0; i < D; ++i) inv[i] = (DIM > 0 || i < dim) ? p.inv_len[i] : 0.0;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) acc[i] = 0.0;
+  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long ti = tile / p.tiles_j, tj = tile - ti * p.tiles_j;
+    const long long r0 = ti * FT + warp * 8, c0 = tj * FT;
+    if (r0 + 7 < p.diag_rows && c0 > r0 + 7) continue;  // strictly above the diagonal of the diagonal block
+    const long long cc[2] = {c0 + lane, c0 + lane + 32};
+    double xc[2][D], bc[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const bool ok = cc[q] < p.n;
+      bc[q] = ok ? p.b2[cc[q]] : 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) xc[q][i] = (ok && (DIM > 0 || i < dim)) ? p.x2[cc[q] * dim + i] * inv[i] : 0.0;
+    }
+    for (int rr = 0; rr < 8; ++rr) {
+      const long long r = r0 + rr;
+      if (r >= p.m) break;
+      const double br = p.b1[r];
+      double xr[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xr[i] = (DIM > 0 || i < dim) ? p.x1[r * dim + i] * inv[i] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const long long c = cc[q];
+        if (c >= p.n) continue;
+        double weight = 2.0;
+        if (r < p.diag_rows) {
+          if (c > r) continue;
+          if (c == r) weight = 1.0;
+        }
+        const double w = (p.W[r * p.ld + c] - br * bc[q]) * weight;
+        double t2[D], s = 1e-300;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const double t = xr[i] - xc[q][i];
+          t2[i] = t * t;
+          s += t2[i];
+        }
+        double f, h;
+        radial_trace_factors<KIND>(s, f, h);
+        acc[0] = fma(w, f, acc[0]);
+        const double wh = w * h;
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[1 + i] = fma(wh, t2[i], acc[1 + i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i <= D; ++i) {
+    const double v = block_sum(acc[i], red);
+    if (tid == 0 && (DIM > 0 || i <= dim)) p.partials[(long long)blockIdx.x * (dim + 1) + i] = v;
+  }
+}
+
+// accum[h] += sum_cta partials[cta][h]   (raw sums; the host applies the chain-rule factors)
+__global__ void trace_accumulate_raw_kernel(const double* partials, int nctas, int H, double* accum) {
+  __shared__ double red[32];
+  for (int h = 0; h < H; ++h) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nctas; i += blockDim.x) s += partials[(long long)i * H + h];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) accum[h] += s;
+    __syncthreads();
+  }
+}
+
 // accum[h] += scale[h] * sum_cta partials[cta][h]
 __global__ void trace_accumulate_kernel(const double* partials, int nctas, int H, double amp, const double* inv_len_dev,
                                         double* accum) {
@@ -1084,6 +1164,56 @@ int fvgp_kgrad_trace_block_matern32(const double* d_x1, int64_t m, const double*
   double* d_invlen = d_partials + (long long)(sm_count() * 4 + 2) * H;
   FVGP_CUDA_OK(cudaMemcpyAsync(d_invlen, inv_len, dim * sizeof(double), cudaMemcpyHostToDevice, st));
   launch(trace_accumulate_kernel, 1, 256, 0, st, d_partials, (int)grid, H, h_theta[0], d_invlen, d_accum);
+  FVGP_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C" (templates need C++ linkage)
+
+template <int KIND>
+static void launch_trace_block_radial(const TraceBlockParams& p, unsigned grid, cudaStream_t st) {
+  switch (p.dim) {
+    case 1: launch(kgrad_trace_block_radial_kernel<KIND, 1>, grid, FILL_THREADS, 0, st, p); break;
+    case 2: launch(kgrad_trace_block_radial_kernel<KIND, 2>, grid, FILL_THREADS, 0, st, p); break;
+    case 3: launch(kgrad_trace_block_radial_kernel<KIND, 3>, grid, FILL_THREADS, 0, st, p); break;
+    case 4: launch(kgrad_trace_block_radial_kernel<KIND, 4>, grid, FILL_THREADS, 0, st, p); break;
+    default: launch(kgrad_trace_block_radial_kernel<KIND, 0>, grid, FILL_THREADS, 0, st, p); break;
+  }
+}
+
+extern "C" {
+
+int fvgp_kgrad_trace_block_radial(int kind, const double* d_x1, int64_t m, const double* d_x2, int64_t n, int dim,
+                                  const double* h_inv_scale, double length, const double* d_W, int64_t ldw,
+                                  const double* d_b1, const double* d_b2, int64_t diag_rows, double* d_partials,
+                                  double* d_accum_raw, void* stream) {
+  FVGP_REQUIRE(dim >= 1 && dim <= kMaxDim && m >= 0 && n >= 0 && diag_rows >= 0 && diag_rows <= m && length > 0.0);
+  double fold = 1.0;
+  switch (kind) {
+    case FVGP_K_MATERN32: fold = sqrt(3.0) / length; break;
+    case FVGP_K_MATERN52: fold = sqrt(5.0) / length; break;
+    case FVGP_K_SQEXP: fold = sqrt(0.5) / length; break;
+    case FVGP_K_EXP: fold = 1.0 / length; break;
+    default: FVGP_REQUIRE(!"gradient traces exist for the Matern-3/2, Matern-5/2, squared-exponential and exponential kinds");
+  }
+  if (m == 0 || n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  TraceBlockParams p;
+  p.x1 = d_x1, p.x2 = d_x2, p.W = d_W, p.b1 = d_b1, p.b2 = d_b2, p.partials = d_partials;
+  p.m = m, p.n = n, p.ld = ldw, p.dim = dim, p.diag_rows = diag_rows;
+  p.tiles_j = (n + FT - 1) / FT;
+  p.ntiles = ((m + FT - 1) / FT) * p.tiles_j;
+  for (int i = 0; i < kMaxDim; ++i) p.inv_len[i] = i < dim ? h_inv_scale[i] * fold : 0.0;
+  const long long cap = (long long)sm_count() * 4;
+  const unsigned grid = (unsigned)(p.ntiles < cap ? p.ntiles : cap);
+  switch (kind) {
+    case FVGP_K_MATERN32: launch_trace_block_radial<FVGP_K_MATERN32>(p, grid, st); break;
+    case FVGP_K_MATERN52: launch_trace_block_radial<FVGP_K_MATERN52>(p, grid, st); break;
+    case FVGP_K_SQEXP: launch_trace_block_radial<FVGP_K_SQEXP>(p, grid, st); break;
+    default: launch_trace_block_radial<FVGP_K_EXP>(p, grid, st); break;
+  }
+  FVGP_LAUNCH_OK();
+  launch(trace_accumulate_raw_kernel, 1, 256, 0, st, (const double*)d_partials, (int)grid, dim + 1, d_accum_raw);
   FVGP_LAUNCH_OK();
   return 0;
 }

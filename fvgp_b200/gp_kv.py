@@ -61,6 +61,8 @@ class GPkv:
         self.KVinvY = None
         self.logdet_KV = None
         self._KVinv_host = None
+        self._sparse_eval = None
+        self.last_sharded_sparse_info = None
         self._refresh()
 
     # ---- properties mirroring the reference -----------------------------------------------------
@@ -164,7 +166,11 @@ class GPkv:
             done = self._evaluate_sharded(ev, hps, V, m, y_mean)
             if done is not None:
                 return done
-        kind, obj = self.prior.device_KV(hps, V)
+        shard = self._sparse_shard(hps, V)
+        if shard is not None:
+            kind, obj = "sparse", shard
+        else:
+            kind, obj = self.prior.device_KV(hps, V)
         if kind == "sparse":
             mode = self._set_gp2Scale_mode(obj.nnz) if self.gp2Scale else (mode or "sparseCG")
             if mode in _DENSE:
@@ -199,10 +205,11 @@ class GPkv:
         precond = self._preconditioner(obj) if mode in _CGPRE else None
         sol = np.empty_like(y_mean)
         cols = []
+        solver = self._sparse_eval.pcg if shard is not None else ops.pcg      # row-sharded PCG over NCCL | one GPU
         for c in range(r):
             x0c = None if x0 is None else L.to_dev(np.ascontiguousarray(x0[:, c]))
-            x, info, iters, relres = ops.pcg(obj, L.to_dev(np.ascontiguousarray(y_mean[:, c])), x0=x0c, rtol=rtol,
-                                             maxiter=maxiter, precond=precond)
+            x, info, iters, relres = solver(obj, L.to_dev(np.ascontiguousarray(y_mean[:, c])), x0=x0c, rtol=rtol,
+                                            maxiter=maxiter, precond=precond)
             ev.info.setdefault("cg_iters", []).append(iters)
             ev.info.setdefault("cg_relres", []).append(relres)
             cols.append(x)
@@ -210,8 +217,37 @@ class GPkv:
         ev.alpha_dev = cols
         ev.KVinvY = sol
         if want_logdet:
-            ev.logdet = self._random_logdet(obj, ev)
+            ev.logdet = self._random_logdet(obj, ev, sharded=shard is not None)
         return ev
+
+    # ---- multi-GPU gp2Scale: CSR row slabs + SLQ probes over the ranks of torch.distributed -----------
+    def _sparse_shard(self, hps, V):
+        """args["gp2Scale_sharded"] = True with more than one rank: assemble K + diag(V) with the rows sharded over
+        all ranks (fvgp_b200/sharded_sparse.py) and return the replicated DeviceCSR; None otherwise.  Every rank must
+        then call log_likelihood collectively with the same hyperparameters."""
+        if not (self.gp2Scale and self.args.get("gp2Scale_sharded", False)) or callable_mode(self.mode):
+            return None
+        if self.mode is not None and self.mode not in _CG + _CGPRE:
+            return None
+        from . import kernels as K
+        from . import sharded_sparse
+        try:
+            import torch.distributed as dist
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        except Exception:
+            world = 1
+        if world <= 1:
+            return None
+        x = self.data.x_data
+        res = self.prior._call_kernel(x, x, np.asarray(hps, dtype=np.float64))
+        if not (isinstance(res, K.SparseWendland) and res.x1 is x and res.x2 is x and V is not None and np.ndim(V) == 1):
+            raise Exception("gp2Scale_sharded needs the anisotropic Wendland gp2Scale kernel on (x_data, x_data) and "
+                            "vector noise")
+        if getattr(self, "_sparse_eval", None) is None:
+            self._sparse_eval = sharded_sparse.ShardedSparseEvaluator()
+        csr, _rows = self._sparse_eval.assemble(self.data.x_device(), res.hps, L.to_dev(V))
+        self.last_sharded_sparse_info = dict(self._sparse_eval.info)
+        return csr
 
     _BJACOBI_NAMES = (None, "", "default", "block_jacobi", "blockjacobi", "bjacobi", "block-jacobi", "jacobi")
 
@@ -276,8 +312,9 @@ class GPkv:
         """True while the evaluator's in-place matrix still belongs to evaluation `ev` and is un-inverted."""
         return ev.sharded is not None and ev.serial == self._sharded_serial and ev.sharded._matrix().state == "factored"
 
-    def _random_logdet(self, csr, ev=None):
-        """SLQ estimate with the reference's argument keys (gp_lin_alg.py:1103-1181)."""
+    def _random_logdet(self, csr, ev=None, sharded=False):
+        """SLQ estimate with the reference's argument keys (gp_lin_alg.py:1103-1181).  sharded: the probes are
+        split over the ranks (same probe stream, same estimate as on one GPU)."""
         a = self.args
         degree = int(a.get("random_logdet_lanczos_degree", 20))
         lo = int(a.get("random_logdet_min_num_samples", 10))
@@ -285,12 +322,17 @@ class GPkv:
         rtol = float(a.get("random_logdet_error_rtol", 0.01))
         seed = int(a.get("random_logdet_seed", 0))
         probes = lo
-        est, var, samples = ops.slq_logdet(csr, degree=degree, probes=probes, seed=seed)
+        if sharded:
+            def slq(csr, degree, probes, seed):
+                return self._sparse_eval.slq_logdet(csr, degree, probes, seed)
+        else:
+            slq = ops.slq_logdet
+        est, var, samples = slq(csr, degree=degree, probes=probes, seed=seed)
         # imate stops when the standard error falls under error_rtol * |estimate|; extend in one step
         if np.isfinite(var) and var > 0 and np.sqrt(var) > rtol * abs(est) and probes < hi:
             need = int(min(hi, np.ceil(samples.var(ddof=1) / (rtol * abs(est)) ** 2)))
             if need > probes:
-                est, var, samples = ops.slq_logdet(csr, degree=degree, probes=need, seed=seed)
+                est, var, samples = slq(csr, degree=degree, probes=need, seed=seed)
         self.last_logdet_variance = var
         self.last_logdet_info = {"variance": var, "num_samples_used": len(samples), "lanczos_degree": degree}
         return est
@@ -452,6 +494,7 @@ class GPkv:
         state["state"] = None                    # device buffers are rebuilt on first use after unpickling
         state["_memo"] = None
         state["_sharded_eval"] = state["_sharded_x"] = None
+        state["_sparse_eval"] = None
         return state
 
     def __setstate__(self, state):

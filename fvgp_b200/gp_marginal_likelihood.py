@@ -259,14 +259,27 @@ class GPMarginalLikelihood:
 
     def _gradient_sharded(self, hps, ev, component):
         """Block-cyclic multi-GPU path (fvgp_b200/sharded.py): distributed TRTRI + LAUUM, block traces, one
-        all-reduce of H doubles.  Same host-side switch on the mean gradient as the single-GPU path."""
+        all-reduce of H doubles.  Default kernel: analytic traces against theta.  User kernels composed of the
+        fvgp.kernels names: traces against the fused descriptor (amp, inv_scale, length) times its Jacobian, as on one
+        GPU (_fused_user_kernel_traces).  Same host-side switch on the mean gradient as the single-GPU path."""
         x = self.data.x_data
-        if not (self.prior.default_kernel and self.prior.kernel_grad is None):
-            raise Exception("the sharded dense gradient is implemented for the default kernel (analytic dK/dtheta)")
+        if self.prior.kernel_grad is not None:
+            raise Exception("the sharded dense gradient regenerates dK/dtheta on the device; a user kernel_function_grad "
+                            "is not supported on this path")
         if np.any(self.likelihood.calculate_V_grad(x, hps) != 0.0):
             raise Exception("noise-function gradients are not supported on the sharded dense path")
         b = ev.KVinvY[:, component]
-        traces = ev.sharded.gradient_traces(hps, ev.alpha_dev[component])
+        if self.prior.default_kernel:
+            traces = ev.sharded.gradient_traces(hps, ev.alpha_dev[component])
+        else:
+            dj = self._descriptor_jacobian(hps)
+            if dj is None:
+                raise Exception("the sharded dense gradient needs the default kernel or a kernel composed of the "
+                                "fvgp_b200.kernels radial functions (squared exponential, exponential, Matern)")
+            kind, p0, J = dj
+            dim = x.shape[1]
+            T = ev.sharded.gradient_traces(None, ev.alpha_dev[component], radial=(kind, p0[0], p0[1:1 + dim], p0[-1]))
+            traces = T @ J
         dm = self.prior.dm_dh(x, hps)
         grad = np.zeros(len(hps))
         for i in range(len(hps)):

@@ -186,6 +186,17 @@ class CudaLocalOps:
                 "fvgp_kgrad_trace_block_matern32")
 
 
+    def trace_block_radial(self, kind, x1, x2, inv_scale, length, W, m, n, b1, b2, diag_rows, accum):
+        """accum (dim + 1, device) += raw sums of the block trace for a fused radial family."""
+        partials = self._work("_partials", self.lib.fvgp_kgrad_block_partials_len(x1.shape[1]))
+        assert np.size(inv_scale) == x1.shape[1], "one inverse length scale per input dimension"
+        _, inv = L.dvec(inv_scale)
+        L.check(self.lib.fvgp_kgrad_trace_block_radial(int(kind), L.ptr(x1), m, L.ptr(x2), n, x1.shape[1], inv,
+                                                       float(length), L.ptr(W), self._ld(W), L.ptr(b1), L.ptr(b2),
+                                                       int(diag_rows), L.ptr(partials), L.ptr(accum), L.stream_ptr()),
+                "fvgp_kgrad_trace_block_radial")
+
+
 GEMM_LOWER, GEMM_KB_FROM_M, GEMM_KB_FROM_N, GEMM_KE_FROM_M = 1, 2, 4, 8
 
 
@@ -490,9 +501,10 @@ class ShardedSPD:
         lay = self.lay
         return [J for J in self.my_cols if J < k] if lay.p == k % lay.P else []
 
-    def _gather_row_panel(self, k, everyone):
+    def _gather_row_panel(self, k, everyone, slot=0):
         """rowbuf[q'][i] = block (k, j_i) for the i-th block column j_i < k of process column q'.
-        everyone=False: only my own process column's pieces are fetched (TRTRI); True: all (LAUUM)."""
+        everyone=False: only my own process column's pieces are fetched (TRTRI); True: all (LAUUM).
+        slot: which of the two receive-buffer sets to use (the look-ahead double-buffers them)."""
         lay, ops, comm = self.lay, self.ops, self.comm
         nb, bk, pk = lay.nb, lay.bsize(k), k % lay.P
         out = {}
@@ -502,7 +514,7 @@ class ShardedSPD:
                 continue
             if not everyone and qq != lay.q:
                 continue
-            buf = self._rowbuf(qq, len(cols_q))
+            buf = self._rowbuf(qq, len(cols_q), slot)
             if lay.p == pk and lay.q == qq:
                 for i, J in enumerate(cols_q):                      # J < k <= nblk-1, so block J is full width
                     buf[i, :bk].copy_(self.block(k, J))
@@ -513,20 +525,30 @@ class ShardedSPD:
             out[qq] = (buf, cols_q)
         return out
 
-    def _rowbuf(self, qq, count):
+    def _rowbuf(self, qq, count, slot=0):
         store = self.__dict__.setdefault("_rowbufs", {})
-        buf = store.get(qq)
+        buf = store.get((slot, qq))
         if buf is None or buf.shape[0] < count:
             cap = len(self.lay.col_blocks(qq))
             buf = self.ops.zeros(cap, self.lay.nb, self.lay.nb)
-            store[qq] = buf
+            store[(slot, qq)] = buf
         return buf[:count]
 
     def invert(self):
-        """Lower staircase <- lower staircase of (L L^T)^-1 (calculate_inv_from_chol, gp_lin_alg.py:1558)."""
+        """Lower staircase <- lower staircase of (L L^T)^-1 (calculate_inv_from_chol, gp_lin_alg.py:1558).
+
+        TRTRI then LAUUM, both right-looking over block rows with ONE STEP OF LOOK-AHEAD: every collective of step
+        k+1 (row-panel gather, column-panel broadcast) is issued on the high-priority side stream as soon as its
+        inputs exist and lands in the second set of receive buffers while the main stream runs step k's GEMMs.  In
+        TRTRI the inputs of step k+1 are block row k+1, which step k updates FIRST (split GEMMs); in LAUUM block row
+        k+1 still holds its TRTRI value until step k+1 overwrites it, so its gather has no producer to wait for."""
         assert self.state == "factored"
         lay, ops, comm = self.lay, self.ops, self.comm
         nb, nblk = lay.nb, lay.nblk
+        ov = _Overlap(ops)
+        if getattr(self, "panel_b", None) is None:
+            self.panel_b = [ops.empty(*t.shape) for t in self.panel]
+        colbufs = (self.panel[lay.p], self.panel_b[lay.p])
         # -------- TRTRI, right-looking.  Two parts of every step do not depend on the steps before it and are hoisted
         # out of the loop, where they left most ranks idle: (A) M_kk = L_kk^-1 of every diagonal block (replicated in
         # self.diag, which holds the inverses from here on), (B) the column panels C <- -C M_kk (block column k below
@@ -550,40 +572,83 @@ class ShardedSPD:
                 tmp = self.panel[lay.p][:m]
                 ops.gemm(0, 1, view, self.diag[J], tmp, m, bJ, bJ, -1.0, 0.0, GEMM_KB_FROM_N)
                 view[:, :bJ].copy_(tmp[:, :bJ])
-        for k in range(1, nblk):
-            bk = lay.bsize(k)
-            pk, qk = k % lay.P, k % lay.Q
-            D = self.diag[k]
-            rowp = self._gather_row_panel(k, everyone=False)
+
+        def fetch_trtri(k, slot):
+            """Collectives of TRTRI step k: my process column's piece of block row k, my process row's piece of
+            column panel k.  Returns (row pieces, column-panel buffer or None)."""
+            rowp = self._gather_row_panel(k, everyone=False, slot=slot)
+            buf = None
             if k < nblk - 1:
-                # my process row's piece of column panel k (A operand of the update), from its owner column
                 m_p = self.mloc - lay.rows_from(k + 1)
                 if m_p > 0:
-                    buf = self.panel[lay.p][:m_p]
-                    if lay.q == qk:
+                    buf = colbufs[slot][:m_p]
+                    if lay.q == k % lay.Q:
                         view, _ = self.block_rows(k, k + 1)
                         buf.copy_(view)
-                    comm.row_broadcast(buf, lay.p * lay.Q + qk)
-                    if lay.q in rowp:
-                        rbuf, cols_q = rowp[lay.q]
-                        for i, J in enumerate(cols_q):
-                            C, m = self.block_rows(J, k + 1)
-                            if m > 0:
-                                ops.gemm(0, 1, buf, rbuf[i], C, m, lay.bsize(J), bk, 1.0, 1.0, 0)
+                    comm.row_broadcast(buf, lay.p * lay.Q + k % lay.Q)
+            return rowp, buf
+
+        def trtri_update(k, rowp, buf, first_only):
+            """C_iJ += P_ik R_kJ for my rows i > k of my block columns J < k.  first_only: just the rows of block
+            k+1 (when they are mine) -- the producer of step k+1's row panel; otherwise everything after them."""
+            if buf is None or lay.q not in rowp:
+                return
+            head = lay.bsize(k + 1) if (k + 1) % lay.P == lay.p else 0
+            rbuf, cols_q = rowp[lay.q]
+            for i, J in enumerate(cols_q):
+                C, m = self.block_rows(J, k + 1)
+                if m <= 0:
+                    continue
+                lo, hi = (0, min(head, m)) if first_only else (min(head, m), m)
+                if hi > lo:
+                    ops.gemm(0, 1, buf[lo:hi], rbuf[i], C[lo:hi], hi - lo, lay.bsize(J), lay.bsize(k), 1.0, 1.0, 0)
+
+        cur = None
+        if nblk > 1:
+            ov.fence_main_to_side()
+            with ov.side():
+                cur = fetch_trtri(1, 1)
+        for k in range(1, nblk):
+            pk = k % lay.P
+            D = self.diag[k]
+            ov.fence_side_to_main()                                   # step k's panels have arrived
+            rowp, buf = cur
+            nxt = None
+            if k < nblk - 1:
+                trtri_update(k, rowp, buf, first_only=True)           # block row k+1 is final after this
+                ov.fence_main_to_side()
+                with ov.side():
+                    nxt = fetch_trtri(k + 1, (k + 1) % 2)
+                trtri_update(k, rowp, buf, first_only=False)
             # block row k: R <- M_kk * R
             if lay.p == pk and lay.q in rowp:
                 rbuf, cols_q = rowp[lay.q]
                 for i, J in enumerate(cols_q):
-                    ops.gemm(0, 1, D, rbuf[i], self.block(k, J), bk, lay.bsize(J), bk, 1.0, 0.0, GEMM_KE_FROM_M)
+                    ops.gemm(0, 1, D, rbuf[i], self.block(k, J), lay.bsize(k), lay.bsize(J), lay.bsize(k), 1.0, 0.0,
+                             GEMM_KE_FROM_M)
+            cur = nxt
+        ov.fence_side_to_main()
         D = ops.zeros(nb, nb)
         # -------- LAUUM: lower(M^T M), block row by block row
         arow = ops.zeros(nb, (max(self.mloc, 2) + 15) // 16 * 16)
+        cur = None
+        if nblk > 1:
+            ov.fence_main_to_side()
+            with ov.side():
+                cur = self._gather_row_panel(1, everyone=True, slot=1)
         for k in range(nblk):
             bk = lay.bsize(k)
             pk, qk = k % lay.P, k % lay.Q
             owner = pk * lay.Q + qk
             D.copy_(self.diag[k])                                    # M_kk is already replicated (TRTRI pass A)
-            rowp = self._gather_row_panel(k, everyone=True) if k > 0 else {}
+            rowp = {}
+            if k > 0:
+                ov.fence_side_to_main()
+                rowp = cur
+            if k + 1 < nblk:
+                ov.fence_main_to_side()                               # the other buffer set is free once step k-1 is queued
+                with ov.side():
+                    cur = self._gather_row_panel(k + 1, everyone=True, slot=(k + 1) % 2)
             if k > 0:
                 # A operand: blocks (k, i) for MY row blocks i < k, laid out in my local row order
                 my_rows_lt = [I for I in lay.row_blocks() if I < k]
@@ -608,11 +673,15 @@ class ShardedSPD:
             if comm.rank == owner:
                 ops.lauum(D, bk)
                 self.block(k, k).copy_(D[:bk, :bk])
+        ov.fence_side_to_main()
         self.state = "inverted"
 
     # ---- gradient traces ----------------------------------------------------------------------------
-    def grad_traces(self, theta, b_dev):
-        """sum_ij (KV^-1 - b b^T)_ij dK_ij/dtheta_h for the default kernel, all-reduced (H,) ndarray."""
+    def grad_traces(self, theta, b_dev, radial=None):
+        """sum_ij (KV^-1 - b b^T)_ij dK_ij/dtheta_h for the default kernel, all-reduced (H,) ndarray.
+        radial = (kind, amp, inv_scale, length): instead the traces against the descriptor parameters
+        (amp, inv_scale_1..D, length) of a fused radial kernel, (D + 2,) ndarray (the single-GPU counterpart is
+        fvgp_kgrad_trace_radial)."""
         assert self.state == "inverted"
         lay, ops, comm = self.lay, self.ops, self.comm
         H = self.x_dev.shape[1] + 1
@@ -626,10 +695,25 @@ class ShardedSPD:
                 continue
             r0 = self.col_r0[J]
             diag_rows = bJ if J % lay.P == lay.p else 0
-            ops.trace_block(self.x_rows[r0:], self.x_dev[J * lay.nb:J * lay.nb + bJ], theta, view, m, bJ,
-                            b_rows[r0:], b_dev[J * lay.nb:J * lay.nb + bJ], diag_rows, accum)
+            if radial is None:
+                ops.trace_block(self.x_rows[r0:], self.x_dev[J * lay.nb:J * lay.nb + bJ], theta, view, m, bJ,
+                                b_rows[r0:], b_dev[J * lay.nb:J * lay.nb + bJ], diag_rows, accum)
+            else:
+                ops.trace_block_radial(radial[0], self.x_rows[r0:], self.x_dev[J * lay.nb:J * lay.nb + bJ], radial[2],
+                                       radial[3], view, m, bJ, b_rows[r0:], b_dev[J * lay.nb:J * lay.nb + bJ],
+                                       diag_rows, accum)
         comm.all_reduce(accum)
-        return accum.cpu().numpy()
+        raw = accum.cpu().numpy()
+        if radial is None:
+            return raw
+        _kind, amp, inv_scale, length = radial
+        inv_scale = np.broadcast_to(np.asarray(inv_scale, dtype=np.float64), (H - 1,))
+        out = np.zeros(H + 1)
+        out[0] = raw[0]
+        for i in range(H - 1):
+            out[1 + i] = -(amp / inv_scale[i]) * raw[1 + i] if inv_scale[i] != 0.0 else 0.0
+        out[H] = (amp / length) * float(np.sum(raw[1:]))
+        return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -701,13 +785,14 @@ class ShardedDenseEvaluator:
         self.last = out
         return out
 
-    def gradient_traces(self, theta, b_dev):
+    def gradient_traces(self, theta, b_dev, radial=None):
         """sum_ij (KV^-1 - b b^T)_ij dK_ij/dtheta_h for the default kernel at the hyperparameters of the last
-        evaluate(); inverts the factored matrix in place on first use."""
+        evaluate() -- or, with radial = (kind, amp, inv_scale, length), the traces against that descriptor's
+        parameters; inverts the factored matrix in place on first use."""
         A = self._matrix()
         if A.state == "factored":
             A.invert()
-        return A.grad_traces(np.asarray(theta, dtype=np.float64), b_dev)
+        return A.grad_traces(None if theta is None else np.asarray(theta, dtype=np.float64), b_dev, radial=radial)
 
     def solve(self, b):
         """KV^-1 b for host right-hand sides (N,) or (N, r) against the factor of the last evaluate()."""

@@ -102,6 +102,16 @@ int fvgp_kgrad_trace_block_matern32(const double* d_x1, int64_t m, const double*
                                     const double* d_b2, int64_t diag_rows, double* d_partials, double* d_accum,
                                     void* stream);
 
+/* The same block trace for every radial family with fused gradient traces (kinds MATERN32, MATERN52, SQEXP, EXP),
+ * i.e. for user kernels composed of the fvgp.kernels names (kernels.py:16-188) on the sharded dense path.
+ * d_accum_raw (dim + 1 doubles, device) is INCREMENTED by the raw sums R_0 = sum W f, R_i = sum W h q_i; after the
+ * all-reduce the traces against (amp, inv_scale_1..D, length) are T_amp = R_0, T_si = -(amp / s_i) R_i,
+ * T_length = (amp / length) sum_i R_i -- the conversion fvgp_kgrad_trace_radial applies on one GPU. */
+int fvgp_kgrad_trace_block_radial(int kind, const double* d_x1, int64_t m, const double* d_x2, int64_t n, int dim,
+                                  const double* h_inv_scale, double length, const double* d_W, int64_t ldw,
+                                  const double* d_b1, const double* d_b2, int64_t diag_rows, double* d_partials,
+                                  double* d_accum_raw, void* stream);
+
 /* Same trace against a MATERIALISED symmetric dK (user kernel_function_grad, gp_prior.py:236-240):
  * *h_out = sum_ij (Kinv - b b^T)_ij dK_ij.  d_partials: 148*8 + 1 doubles. */
 int fvgp_trace_sym_product(const double* d_Kinv, int64_t ld, const double* d_b, const double* d_dK, int64_t lddk,

@@ -28,9 +28,13 @@ class CpuLocalOps:
         return 8
 
     def fill(self, kind, x1, x2, amp, inv_scale, length, noise, out, centre):
-        assert kind == K_MATERN32 and length == 1.0
-        hps = np.concatenate([[amp], 1.0 / np.asarray(inv_scale)])
-        k = orc.default_kernel(x1.numpy(), x2.numpy(), hps)
+        if kind == K_MATERN32 and length == 1.0:
+            hps = np.concatenate([[amp], 1.0 / np.asarray(inv_scale)])
+            k = orc.default_kernel(x1.numpy(), x2.numpy(), hps)
+        else:                                                             # the other radial families, oracle formulas
+            d = orc.anisotropic_distance_matrix(x1.numpy(), x2.numpy(), 1.0 / np.asarray(inv_scale))
+            name = {0: "matern32", 1: "matern52", 2: "se", 3: "exp"}[int(kind)]
+            k = amp * orc.RADIAL[name](d, length)
         if noise is not None:
             k[np.arange(len(noise)), np.arange(len(noise))] += noise.numpy()
         out[:x1.shape[0], :x2.shape[0]] = torch.from_numpy(k)
@@ -88,3 +92,30 @@ class CpuLocalOps:
             weight[:diag_rows] = np.where(c > r, 0.0, np.where(c == r, 1.0, 2.0))
         w = np.where(weight == 0.0, 0.0, w) * weight
         accum += torch.from_numpy(np.einsum("hij,ij->h", dK, w))
+
+    def trace_block_radial(self, kind, x1, x2, inv_scale, length, W, m, n, b1, b2, diag_rows, accum):
+        """Raw sums R_0 = sum W f(u), R_i = sum W h(u) q_i of the radial families (fvgp_kgrad_trace_block_radial):
+        q_i = squared difference along axis i in coordinates scaled by inv_scale_i * c_KIND / length."""
+        fold = {0: np.sqrt(3.0), 1: np.sqrt(5.0), 2: np.sqrt(0.5), 3: 1.0}[int(kind)] / float(length)
+        a1 = x1.numpy()[:m] * (np.asarray(inv_scale) * fold)
+        a2 = x2.numpy()[:n] * (np.asarray(inv_scale) * fold)
+        q = (a1[:, None, :] - a2[None, :, :]) ** 2                                           # (m, n, D)
+        s = q.sum(-1)
+        a = np.sqrt(np.maximum(s, 1e-300))
+        e = np.exp(-a)
+        if kind == 2:
+            f, h = np.exp(-s), 2.0 * np.exp(-s)
+        elif kind == 0:
+            f, h = (1 + a) * e, e
+        elif kind == 1:
+            f, h = (1 + a + s / 3.0) * e, (1 + a) * e / 3.0
+        else:
+            f, h = e, e / a
+        w = W[:m, :n].numpy() - np.outer(b1.numpy()[:m], b2.numpy()[:n])
+        weight = np.full((m, n), 2.0)
+        if diag_rows:
+            r, c = np.arange(diag_rows)[:, None], np.arange(n)[None, :]
+            weight[:diag_rows] = np.where(c > r, 0.0, np.where(c == r, 1.0, 2.0))
+        w = np.where(weight == 0.0, 0.0, w) * weight
+        raw = np.concatenate([[np.sum(w * f)], np.einsum("ij,ijd->d", w * h, q)])
+        accum[:len(raw)] += torch.from_numpy(raw)

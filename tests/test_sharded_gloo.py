@@ -100,3 +100,70 @@ def test_layout_arithmetic():
         assert lay.rows_from(lay.nblk) == lay.mloc()
     assert np.all(seen == 1)
     assert default_block(200_000, 8) == 2048 and default_block(4000, 2) % 128 == 0
+
+
+def _worker_radial(rank, world, port, grid, n, nb, kind, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    torch.set_num_threads(2)
+    if world > 1:
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    from cpu_local_ops import CpuLocalOps
+    from fvgp_b200 import sharded
+    x, y, noise, _ = _problem(n)
+    amp, inv, length = 1.2, np.array([2.5, 1.9, 2.2]), 0.8
+    ev = sharded.ShardedDenseEvaluator(x, y, noise, nb=nb, grid=grid, ops=CpuLocalOps())
+    out = ev.evaluate(kind, amp, inv, length, np.full(n, y.mean()))
+    T = ev.gradient_traces(None, out["alpha_dev"][0], radial=(kind, amp, inv, length))
+    q.put((rank, out["lml"], out["alpha"][:, 0], T))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("grid,kind", [((1, 2), 2), ((2, 2), 1), ((2, 1), 3), ((1, 1), 0)])
+def test_block_cyclic_traces_of_the_radial_families(grid, kind):
+    """Gradient traces against the fused descriptor (amp, inv_scale, length) of squared-exponential / Matern-5/2 /
+    exponential / Matern-3/2 kernels on the sharded matrix vs central differences of the dense kernel matrix."""
+    n, nb = 420, 128
+    world = grid[0] * grid[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 25100 + (os.getpid() * 11 + grid[0] * 37 + grid[1] * 53 + kind) % 2000
+    procs = [ctx.Process(target=_worker_radial, args=(r, world, port, grid, n, nb, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, noise, _ = _problem(n)
+    amp, inv, length = 1.2, np.array([2.5, 1.9, 2.2]), 0.8
+
+    def K(amp, inv, length):
+        d = np.sqrt((((x[:, None, :] - x[None, :, :]) * inv) ** 2).sum(-1))
+        u = d / length
+        if kind == 2:
+            return amp * np.exp(-u ** 2 / 2)
+        if kind == 0:
+            return amp * (1 + np.sqrt(3) * u) * np.exp(-np.sqrt(3) * u)
+        if kind == 1:
+            return amp * (1 + np.sqrt(5) * u + 5 * u ** 2 / 3) * np.exp(-np.sqrt(5) * u)
+        return amp * np.exp(-u)
+    KV = K(amp, inv, length) + np.diag(noise)
+    b = np.linalg.solve(KV, y - y.mean())
+    M = np.linalg.inv(KV) - np.outer(b, b)
+    eps = 1e-6
+    fd = [np.sum(M * (K(amp + eps, inv, length) - K(amp - eps, inv, length))) / (2 * eps)]
+    for i in range(3):
+        e = np.zeros(3)
+        e[i] = eps
+        fd.append(np.sum(M * (K(amp, inv + e, length) - K(amp, inv - e, length))) / (2 * eps))
+    fd.append(np.sum(M * (K(amp, inv, length + eps) - K(amp, inv, length - eps))) / (2 * eps))
+    for rank, lml, alpha, T in res:
+        assert np.max(np.abs(alpha - b)) <= 1e-8 * np.max(np.abs(b))
+        assert np.max(np.abs(T - np.array(fd)) / np.maximum(np.abs(fd), 1.0)) <= 2e-6, (T, fd)
