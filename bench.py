@@ -504,6 +504,10 @@ def c4_record(n, steps, warmup, rank=0, world=1, phases=True, sharded=False):
            "cg": {k2: v for k2, v in gp.kv.state.info.items() if k2.startswith("cg_")} if gp.kv.state is not None else None}
     if sharded:
         rec["sharding"] = getattr(gp.kv, "last_sharded_sparse_info", None)
+        ev_s = getattr(gp.kv, "_sparse_eval", None)
+        if ev_s is not None and ev_s.timing is not None:          # FVGP_SHARDED_TIMING=1 (diagnosis: marks synchronise)
+            calls = warmup + steps + 1
+            rec["phase_ms_per_evaluation"] = {k: 1e3 * v / calls for k, v in ev_s.timing.items()}
     if not phases:
         del gp
         return rec

@@ -335,6 +335,233 @@ __global__ void __launch_bounds__(512) potrf_tile2_kernel(double* A, long long l
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Third-generation tile kernel: 32-column panels, the 32 x 32 diagonal block of each panel factored by ONE WARP IN
+// REGISTERS.  The second-generation kernel pays one CTA-wide barrier and a dependent pivot chain per COLUMN (128 of
+// them, ~720 cycles each: 138 us per tile, ncu r01) -- the critical path of every evaluation below N ~ 16 000 and 3.4x
+// slower than cuSOLVER at N = 8192.  Here a tile is 4 panels x 3 barriers:
+//   (1) warp 0, lane r = row r of the 32 x 32 diagonal block (32 doubles in registers): right-looking Cholesky, the
+//       pivot travels by shuffle, the finished column through a 32-double shared buffer read back as broadcasts; no
+//       CTA barrier inside the block;
+//   (2) concurrently: warps 1-3 solve the rows BELOW the block against it (one row per thread in registers, forward
+//       substitution with broadcast reads of L), warp 0 inverts the block (one row of the inverse per lane) straight
+//       into the diagonal position of the 64 x 64 inverses the epilogue needs;
+//   (3) all warps: rank-32 update of the trailing tile from the k-major staged panel (4 x 4 register micro-tiles).
+// Epilogue: 32 -> 64 -> 128 assembly of the inverse of the factor by -D^-1 C A^-1 products.  Same outputs as before:
+// L in place (explicit zeros above the diagonal) and the full 128 x 128 inverse of L.
+// ----------------------------------------------------------------------------------------------
+constexpr int DB = 32;  // diagonal sub-block / panel width
+// T | InvA | InvD | Dg | RDg | P (32 x 96, k-major panel staging; reused as 2 x 32 x 33 scratch by the epilogue) | cb (2 x 32)
+constexpr int TILE3_P_OFF = ((TS * TP + 2 * (TS / 2) * HP + 2 * TS) + 1) / 2 * 2;
+constexpr int TILE3_CB_OFF = TILE3_P_OFF + DB * (TS - DB);
+constexpr size_t POTRF_TILE3_SMEM = size_t(TILE3_CB_OFF + 2 * DB) * sizeof(double);  // ~221 KB
+
+__device__ __forceinline__ double rsqrt_newton(double d) {  // 1 / sqrt(d), d > 0: MUFU.RSQ64H + two Newton steps
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-(d * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
+}
+
+__global__ void __launch_bounds__(512) potrf_tile3_kernel(double* A, long long ld, int nt, double* dinv, int* info,
+                                                          int global_row0, long long bstride) {
+  extern __shared__ __align__(16) double tile_smem[];
+  A += blockIdx.x * bstride, dinv += blockIdx.x * bstride, info += blockIdx.x;  // one CTA per problem of a batch
+  double(*T)[TP] = reinterpret_cast<double(*)[TP]>(tile_smem);
+  double(*InvA)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP);
+  double(*InvD)[HP] = reinterpret_cast<double(*)[HP]>(tile_smem + TS * TP + (TS / 2) * HP);
+  double* Dg = tile_smem + TS * TP + 2 * (TS / 2) * HP;
+  double* RDg = Dg + TS;  // reciprocals of the diagonal of L
+  double(*P)[TS - DB] = reinterpret_cast<double(*)[TS - DB]>(tile_smem + TILE3_P_OFF);
+  double(*cb)[DB] = reinterpret_cast<double(*)[DB]>(tile_smem + TILE3_CB_OFF);
+  constexpr int H = TS / 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < TS * TS; idx += 512) {
+    const int r = idx / TS, c = idx % TS;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < nt && c <= r) v = A[(long long)r * ld + c];
+    T[r][c] = v;
+  }
+  for (int idx = tid; idx < 2 * H * HP; idx += 512) (&InvA[0][0])[idx] = 0.0;  // InvA and InvD are contiguous
+  // micro-tile of the trailing update owned by this thread (row-major enumeration of the lower triangle of 4 x 4 tiles)
+  int ma = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+  while ((ma + 1) * (ma + 2) / 2 <= tid) ++ma;
+  while (ma * (ma + 1) / 2 > tid) --ma;
+  const int mb = tid - ma * (ma + 1) / 2;
+  __syncthreads();
+#pragma unroll 1
+  for (int p0 = 0; p0 < TS; p0 += DB) {
+    // ---- (1) diagonal block in registers, one warp
+    if (warp == 0) {
+      double a[DB];
+#pragma unroll
+      for (int c = 0; c < DB; ++c) a[c] = (c <= lane) ? T[p0 + lane][p0 + c] : 0.0;
+#pragma unroll
+      for (int j = 0; j < DB; ++j) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (lane == 0 && !(d > 0.0)) atomicCAS(info, 0, global_row0 + p0 + j + 1);
+        const double y = rsqrt_newton(d);
+        double l = 0.0;
+        if (lane > j) {
+          l = a[j] * y;
+        } else if (lane == j) {
+          double sq = d * y;
+          sq = fma(fma(-sq, sq, d), 0.5 * y, sq);
+          l = sq;
+          Dg[p0 + j] = sq, RDg[p0 + j] = y;
+        }
+        a[j] = l;
+        cb[j & 1][lane] = l;
+        __syncwarp();
+#pragma unroll
+        for (int k = j + 1; k < DB; ++k)
+          if (lane >= k) a[k] = fma(-l, cb[j & 1][k], a[k]);
+      }
+#pragma unroll
+      for (int c = 0; c < DB; ++c)
+        if (c <= lane) T[p0 + lane][p0 + c] = a[c];
+    }
+    __syncthreads();
+    // ---- (2) rows below the block (warps 1..3) | inverse of the block (warp 0)
+    if (warp == 0) {
+      double s[DB];
+#pragma unroll
+      for (int c = 0; c < DB; ++c) s[c] = (c == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int c = DB - 1; c >= 0; --c) {  // row `lane` of X with X L = I:  x_c = s_c / L_cc ; s_c' -= x_c L_cc'
+        const double x = s[c] * RDg[p0 + c];
+        s[c] = x;
+#pragma unroll
+        for (int c2 = 0; c2 < c; ++c2) s[c2] = fma(-x, T[p0 + c][p0 + c2], s[c2]);
+      }
+      double(*Inv)[HP] = (p0 < H) ? InvA : InvD;
+      const int q0 = p0 & (H - 1);
+#pragma unroll
+      for (int c = 0; c < DB; ++c) Inv[q0 + lane][q0 + c] = s[c];  // zeros above the diagonal included
+    } else {
+      const int r = p0 + DB + (tid - 32);
+      if (tid - 32 < TS - DB && r < TS) {
+        double b[DB];
+#pragma unroll
+        for (int c = 0; c < DB; ++c) b[c] = T[r][p0 + c];
+#pragma unroll
+        for (int c = 0; c < DB; ++c) {  // x L^T = b:  x_c = b_c / L_cc ; b_c' -= x_c L_c'c
+          const double x = b[c] * RDg[p0 + c];
+          b[c] = x;
+#pragma unroll
+          for (int c2 = c + 1; c2 < DB; ++c2) b[c2] = fma(-x, T[p0 + c2][p0 + c], b[c2]);
+        }
+#pragma unroll
+        for (int c = 0; c < DB; ++c) {
+          T[r][p0 + c] = b[c];
+          P[c][r - (p0 + DB)] = b[c];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (3) rank-32 update of the trailing tile
+    const int off = p0 + DB, mt = (TS - off) / 4;
+    if (tid < mt * (mt + 1) / 2) {
+      const int r0 = 4 * ma, c0 = 4 * mb;  // relative to `off`
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < DB; ++k) {
+        const double2 ra = *reinterpret_cast<const double2*>(&P[k][r0]);
+        const double2 rb = *reinterpret_cast<const double2*>(&P[k][r0 + 2]);
+        const double2 ca = *reinterpret_cast<const double2*>(&P[k][c0]);
+        const double2 cb2 = *reinterpret_cast<const double2*>(&P[k][c0 + 2]);
+        const double rv[4] = {ra.x, ra.y, rb.x, rb.y};
+        const double cv[4] = {ca.x, ca.y, cb2.x, cb2.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fma(rv[i], cv[jj], acc[i][jj]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) T[off + r0 + i][off + c0 + jj] -= acc[i][jj];
+    }
+    __syncthreads();
+  }
+  // ---- inverse of the factor, 32 -> 64: Inv[32+i][j] = -(Inv_hi C Inv_lo)[i][j] inside both 64 x 64 blocks
+  {
+    double(*E32)[DB][DB + 1] = reinterpret_cast<double(*)[DB][DB + 1]>(tile_smem + TILE3_P_OFF);  // 2 x 32 x 33
+    const int blk = tid >> 8, i = (tid >> 3) & 31, jc = tid & 7, base = blk * H;
+    double(*Inv)[HP] = blk ? InvD : InvA;
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < DB; ++k) {  // E = C Inv_lo   (Inv_lo[k][j] = 0 for k < j)
+      const double cik = T[base + DB + i][base + k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = fma(cik, Inv[k][jc + 8 * u], e[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) E32[blk][i][jc + 8 * u] = e[u];
+    __syncthreads();
+    double f[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k <= i; ++k) {  // F = Inv_hi E
+      const double dik = Inv[DB + i][DB + k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) f[u] = fma(dik, E32[blk][k][jc + 8 * u], f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Inv[DB + i][jc + 8 * u] = -f[u];
+  }
+  __syncthreads();
+  // ---- 64 -> 128 (as in the second-generation kernel): E = C A^-1 into T[0..63][64..127], F = -D^-1 E -> dinv
+  {
+    const int i = tid >> 3, jc = tid & 7;
+    double e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = 0.0;
+    for (int k = 0; k < H; ++k) {
+      const double cik = T[H + i][k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) e[u] = fma(cik, InvA[k][jc + 8 * u], e[u]);  // InvA[k][j] = 0 for k < j
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) T[i][H + jc + 8 * u] = e[u];
+  }
+  __syncthreads();
+  {
+    const int i = tid >> 3, jc = tid & 7;
+    double f[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] = 0.0;
+    for (int k = 0; k <= i; ++k) {
+      const double dik = InvD[i][k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = fma(dik, T[k][H + jc + 8 * u], f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dinv[(H + i) * TS + jc + 8 * u] = -f[u];
+  }
+  for (int idx = tid; idx < TS * TS; idx += 512) {
+    const int r = idx / TS, c = idx % TS;
+    if (r < H) dinv[idx] = (c < H) ? InvA[r][c] : 0.0;
+    else if (c >= H) dinv[idx] = InvD[r - H][c - H];
+    if (r < nt && c < nt) A[(long long)r * ld + c] = (c < r) ? T[r][c] : ((c == r) ? Dg[r] : 0.0);
+  }
+}
+
+// FVGP_POTRF_TILE=2 selects the second-generation tile kernel (A/B on the GPU box).
+static bool use_tile_v2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FVGP_POTRF_TILE");
+    v = (e && atoi(e) == 2) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // FVGP_POTRF_TILE=1 selects the first-generation tile kernel (A/B on the GPU box).
 static bool use_tile_v1() {
   static int v = -1;
@@ -695,8 +922,10 @@ static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
     double* tile_inv = c.dinv + (long long)(row0 / TS) * TS * TS;
     if (use_tile_v1())
       launch(potrf_tile_kernel, c.batch, 512, POTRF_TILE_SMEM, c.st, A, ld, n, tile_inv, c.info, row0, c.bstride);
-    else
+    else if (use_tile_v2())
       launch(potrf_tile2_kernel, c.batch, 512, POTRF_TILE2_SMEM, c.st, A, ld, n, tile_inv, c.info, row0, c.bstride);
+    else
+      launch(potrf_tile3_kernel, c.batch, 512, POTRF_TILE3_SMEM, c.st, A, ld, n, tile_inv, c.info, row0, c.bstride);
     FVGP_LAUNCH_OK();
     return 0;
   }
@@ -877,6 +1106,8 @@ int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int
                                       (int)POTRF_TILE_SMEM));
     FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)POTRF_TILE2_SMEM));
+    FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)POTRF_TILE3_SMEM));
     configured = true;
   }
   FVGP_CUDA_OK(cudaMemsetAsync(d_info, 0, sizeof(int), st));
@@ -1218,6 +1449,8 @@ int fvgp_lml_population(int kind, const double* d_x, int64_t n, int dim, int bat
                                       (int)POTRF_TILE_SMEM));
     FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)POTRF_TILE2_SMEM));
+    FVGP_CUDA_OK(cudaFuncSetAttribute(potrf_tile3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)POTRF_TILE3_SMEM));
     configured = true;
   }
   std::vector<double> res_h((size_t)batch * res_stride, 0.0);

@@ -25,6 +25,8 @@ Device work goes through a small ops object; `CudaSparseOps` is the product (eve
 choreography is tested on CPU with gloo by injecting a numpy/torch-CPU stand-in that lives in tests/ only.
 """
 import ctypes
+import os
+import time
 
 import numpy as np
 
@@ -236,18 +238,36 @@ class ShardedSparseEvaluator:
         self.rank, self.world = self.ops.rank, self.ops.world
         self.rows = None
         self.info = {}
+        # FVGP_SHARDED_TIMING=1: wall-clock per phase with a device synchronisation at every mark (diagnosis only;
+        # the marks serialise host and device)
+        self.timing = {} if os.environ.get("FVGP_SHARDED_TIMING") == "1" else None
+        self._t_last = None
+
+    def _mark(self, name):
+        if self.timing is None:
+            return
+        if getattr(self.ops, "device", "cpu") == "cuda":
+            self.ops.torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name is not None and self._t_last is not None:
+            self.timing[name] = self.timing.get(name, 0.0) + (now - self._t_last)
+        self._t_last = now
 
     def assemble(self, x_dev, theta, noise_dev):
         """K(x, x; theta) + diag(noise) as a replicated canonical CSR; returns (csr, row offsets)."""
         ops = self.ops
         n = int(x_dev.shape[0])
+        self._mark(None)
         boxes = ops.aabb(x_dev)
         rows = equal_slabs(n, self.world)
         counts = ops.zeros_i64(n)
         r0, r1 = rows[self.rank], rows[self.rank + 1]
         chunk = ops.count_slab(x_dev, boxes, r0, r1 - r0, theta, counts)
+        self._mark("count")
         ops.allgatherv(counts[:n], rows)
+        self._mark("gather_counts")
         indptr, nnz = ops.scan(counts, n)
+        self._mark("scan")
         recount = False
         if self.world > 1 and n >= 64 * self.world:
             at = ops.prefix_at(indptr, rows)
@@ -260,11 +280,14 @@ class ShardedSparseEvaluator:
             r0, r1 = rows[self.rank], rows[self.rank + 1]
             scratch = ops.zeros_i64(n)
             chunk = ops.count_slab(x_dev, boxes, r0, r1 - r0, theta, scratch)
+        self._mark("balance")
         indices, data = ops.alloc_csr(nnz)
         ops.fill_slab(x_dev, boxes, r0, r1 - r0, theta, indptr, chunk, noise_dev, indices, data)
+        self._mark("fill")
         at = ops.prefix_at(indptr, rows)
         ops.allgatherv(indices, at)
         ops.allgatherv(data, at)
+        self._mark("gather_csr")
         self.rows = rows
         self.info = {"rows": list(rows), "nnz": nnz, "nnz_per_rank": [at[r + 1] - at[r] for r in range(self.world)],
                      "rebalanced": bool(recount)}
@@ -272,13 +295,19 @@ class ShardedSparseEvaluator:
 
     def pcg(self, csr, b, x0=None, rtol=1e-5, maxiter=None, precond=None):
         """Same contract as ops.pcg (scipy cg semantics); every rank returns the whole solution."""
-        return self.ops.pcg(self.rows, csr, precond, b, x0, rtol, maxiter)
+        self._mark(None)
+        out = self.ops.pcg(self.rows, csr, precond, b, x0, rtol, maxiter)
+        self._mark("pcg")
+        return out
 
     def slq_logdet(self, csr, degree, probes, seed):
         """(estimate, variance of the mean, samples): the probes of the single-GPU stream, split over the ranks."""
         offs = split_probes(int(probes), self.world)
+        self._mark(None)
         mine = self.ops.slq_samples(csr, degree, offs[self.rank], offs[self.rank + 1] - offs[self.rank], seed)
+        self._mark("slq")
         samples = np.asarray(self.ops.gather_samples(mine, offs), dtype=np.float64)
+        self._mark("gather_samples")
         est = float(samples.mean())
         var = float(samples.var(ddof=1) / len(samples)) if len(samples) > 1 else float("nan")
         return est, var, samples

@@ -202,7 +202,7 @@ def test_sharded_sparse_two_ranks_nccl():
         assert p.exitcode == 0
     for rank, lml, lml1, same_pattern, same_values, dalpha, iters, iters1, info in res:
         assert same_pattern and same_values, info
-        assert dalpha <= 1e-7 and abs(iters[0] - iters1[0]) <= 2, (dalpha, iters, iters1)
+        assert dalpha <= 1e-7 and abs(iters[0] - iters1[0]) <= 0.01 * iters1[0] + 2, (dalpha, iters, iters1)
         assert abs(lml / lml1 - 1) <= 1e-9, (lml, lml1)
         assert sum(info["nnz_per_rank"]) == info["nnz"] and info["rows"][1] % 32 == 0
     assert res[0][1] == res[1][1]                                         # both ranks return the same LML
