@@ -34,8 +34,13 @@ constexpr int FT_STRIDE = FT + 2;  // even (16-byte rows for the bulk copy)
 __device__ __forceinline__ int stage_shift(int c) { return 2 * ((c >> 3) & 1); }
 constexpr int FILL_THREADS = 256;
 constexpr int STAGE_DOUBLES = FT * FT_STRIDE;
+// Per-warp mirror staging (bulk mode 2): every warp transposes its own 8 x 64 strip into a 64 x 8 block (row slot of
+// 10 doubles = 8 values + the 16-byte bank shift) and sends it with 64-byte bulk stores of its own -- no CTA-wide
+// barrier anywhere in the tile loop, the warps of a CTA drift apart and hide each other's sqrt / exp chains.
+constexpr int WSTRIDE = 10;
+constexpr int WSTAGE_DOUBLES = FT * WSTRIDE;  // per warp
 
-static int g_use_bulk_store = 1;
+static int g_use_bulk_store = 2;
 
 struct FillParams {
   const double* x1;
@@ -169,7 +174,7 @@ __device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc,
 // tile in shared memory (already centred and scaled in the CENTRED variant): the inner loop then has no global
 // loads and, per entry, D subtractions + D fused multiply-adds for the distance.
 // INTERIOR tiles carry no bounds checks and no noise test.
-template <int KIND, int DIM, bool CENTRED, bool INTERIOR>
+template <int KIND, int DIM, bool CENTRED, bool INTERIOR, bool WARP_STAGE = false>
 __device__ __forceinline__ void fill_tile(const FillParams& p, long long ti, long long tj, bool mirror, double* sT,
                                           double* sRow, int lane, int warp) {
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
@@ -201,7 +206,8 @@ __device__ __forceinline__ void fill_tile(const FillParams& p, long long ti, lon
   }
   __syncwarp();
   double* krow = p.K + r0 * p.ldk + ca;
-  double* srow = sT + (2 * lane) * FT_STRIDE + stage_shift(2 * lane) + warp * 8;
+  constexpr int SSTR = WARP_STAGE ? WSTRIDE : FT_STRIDE;
+  double* srow = sT + (2 * lane) * SSTR + stage_shift(2 * lane) + (WARP_STAGE ? 0 : warp * 8);
 #pragma unroll 1
   for (int rr = 0; rr < 8; rr += 2) {
     if (!INTERIOR && r0 + rr >= p.n1) break;
@@ -250,7 +256,7 @@ __device__ __forceinline__ void fill_tile(const FillParams& p, long long ti, lon
     }
     if (mirror) {  // transposed staging tile: sT[column][row]
       *reinterpret_cast<double2*>(srow + rr) = make_double2(v00, v10);
-      *reinterpret_cast<double2*>(srow + FT_STRIDE + rr) = make_double2(v01, v11);
+      *reinterpret_cast<double2*>(srow + SSTR + rr) = make_double2(v01, v11);
     }
   }
 }
@@ -293,6 +299,29 @@ __global__ void __launch_bounds__(FILL_THREADS, 3) kfill_kernel(const FillParams
       ib = 0, ++ia;
     }
     const bool mirror = (p.mode == FVGP_FILL_SYMMETRIC) && (tj > ti);
+    if (p.bulk == 2) {  // per-warp mirror: no CTA barrier in the loop
+      double* wT = stage + warp * WSTAGE_DOUBLES;
+      if (mirror) {  // this warp's previous bulk stores must have finished READING its staging block
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        __syncwarp();
+      }
+      const bool interior2 = (ti + 1) * FT <= p.n1 && (tj + 1) * FT <= p.n2 && (p.noise == nullptr || ti != tj);
+      if (interior2) fill_tile<KIND, DIM, CENTRED, true, true>(p, ti, tj, mirror, wT, sRow, lane, warp);
+      else fill_tile<KIND, DIM, CENTRED, false, true>(p, ti, tj, mirror, wT, sRow, lane, warp);
+      if (mirror) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        const long long c0 = tj * FT;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = lane + 32 * h;
+          if (c0 + c < p.n2)
+            bulk_store_row(p.K + (c0 + c) * p.ldk + ti * FT + warp * 8, wT + c * WSTRIDE + stage_shift(c), 8 * 8);
+        }
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
+      continue;
+    }
     double* sT = stage + buf * STAGE_DOUBLES;
     if (mirror) {
       // the bulk stores that last used THIS staging buffer (two mirror tiles ago) must have finished reading it
@@ -328,14 +357,16 @@ __global__ void __launch_bounds__(FILL_THREADS, 3) kfill_kernel(const FillParams
       }
     }
   }
-  if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+  if (p.bulk == 2) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+  else if (p.bulk && tid < FT) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
 
 template <int KIND, int DIM, bool CENTRED>
 static void launch_fill_one(const FillParams& p, unsigned grid, cudaStream_t st) {
   constexpr int D = DIM > 0 ? DIM : kMaxDim;
   constexpr int DPAD = (D + 1) & ~1;
-  const size_t smem = (8 * 8 * DPAD + (p.mode == FVGP_FILL_SYMMETRIC ? 2 * STAGE_DOUBLES : 0)) * sizeof(double);
+  const size_t stage = p.mode != FVGP_FILL_SYMMETRIC ? 0 : (p.bulk == 2 ? 8 * WSTAGE_DOUBLES : 2 * STAGE_DOUBLES);
+  const size_t smem = (8 * 8 * DPAD + stage) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kfill_kernel<KIND, DIM, CENTRED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -934,10 +965,12 @@ int kfill_lower_batch_enqueue(int kind, const double* d_x, int64_t n, int dim, i
 
 extern "C" {
 
-// test / profiling hook: 0 = plain coalesced stores for the mirror tile, 1 = TMA bulk stores
+// test / profiling hook: mirror tile of the symmetric fill through 0 = plain coalesced stores (CTA barrier),
+// 1 = one 512-byte TMA bulk store per row (CTA barrier, double-buffered staging), 2 = per-warp 64-byte bulk stores,
+// no CTA barrier (default)
 int fvgp_set_bulk_store(int on) {
   const int old = g_use_bulk_store;
-  g_use_bulk_store = on ? 1 : 0;
+  g_use_bulk_store = on < 0 ? 0 : (on > 2 ? 2 : on);
   return old;
 }
 
@@ -954,7 +987,7 @@ int fvgp_kfill_dense(int kind, int mode, const double* d_x1, int64_t n1, const d
   p.tiles_j = (n2 + FT - 1) / FT;
   p.ntiles = mode == FVGP_FILL_FULL ? p.tiles_i * p.tiles_j : p.tiles_i * (p.tiles_i + 1) / 2;
   p.vec2 = (ldk % 2 == 0 && ((uintptr_t)d_K % 16 == 0)) ? 1 : 0;
-  p.bulk = (g_use_bulk_store && mode == FVGP_FILL_SYMMETRIC && p.vec2) ? 1 : 0;
+  p.bulk = (g_use_bulk_store && mode == FVGP_FILL_SYMMETRIC && p.vec2) ? g_use_bulk_store : 0;
   {
     static int band = -1;  // FVGP_FILL_BAND: tile rows per band of the symmetric fill's tile order (0 = column sweep)
     if (band < 0) {

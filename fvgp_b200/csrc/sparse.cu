@@ -1323,7 +1323,8 @@ static int lanczos_cols_variant() {
 
 template <int NB>
 static int lanczos_batch(int64_t n, const long long* ip, const int32_t* d_indices, const double* d_data, int degree,
-                         int probe0, uint64_t seed, double* d_work, double* h_alpha, double* h_beta, cudaStream_t st) {
+                         int probe0, uint64_t seed, double* d_work, double* h_alpha, double* h_beta, cudaStream_t st,
+                         int keep = NB) {  // keep < NB: a padded batch, only the first `keep` probes are returned
   const unsigned grid = krylov_grid();
   double* bufs[3] = {d_work, d_work + n * LZ_MAXB, d_work + 2 * n * LZ_MAXB};
   double* partials = d_work + 3 * n * LZ_MAXB;
@@ -1359,7 +1360,7 @@ static int lanczos_batch(int64_t n, const long long* ip, const int32_t* d_indice
   FVGP_CUDA_OK(cudaMemcpyAsync(ha, d_alpha, (size_t)degree * NB * sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaMemcpyAsync(hb, d_beta, (size_t)degree * NB * sizeof(double), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
-  for (int c = 0; c < NB; ++c)
+  for (int c = 0; c < keep; ++c)
     for (int j = 0; j < degree; ++j) {
       h_alpha[(size_t)c * degree + j] = ha[(size_t)j * NB + c];
       h_beta[(size_t)c * degree + j] = hb[(size_t)j * NB + c];
@@ -1376,21 +1377,39 @@ int fvgp_lanczos_tridiag(int64_t n, const int64_t* d_indptr, const int32_t* d_in
   cudaStream_t st = (cudaStream_t)stream;
   const long long* ip = (const long long*)d_indptr;
   int done = 0;
-  while (done < nprobes) {  // greedy batches of 16 / 8 / 4 / 2 / 1 probes
+  // One sweep over the matrix per Lanczos step costs about the same for 1 ... 16 probe columns (the SpMM is bound by
+  // streaming the matrix and by latency, not by the column count: 8 + 2 probes took the time of 4 + 1, r02 2-GPU
+  // run), so what counts is the NUMBER of batches: the remainder runs as ONE batch padded to the next power of two
+  // (the surplus columns are real probes of the stream that are simply not returned), e.g. 10 -> one batch of 16.
+  // FVGP_SLQ_GREEDY=1 restores the greedy 16 / 8 / 4 / 2 / 1 split (A/B).
+  static int greedy = -1;
+  if (greedy < 0) {
+    const char* e = getenv("FVGP_SLQ_GREEDY");
+    greedy = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  while (done < nprobes) {
     const int left = nprobes - done;
-    const int nb = left >= 16 ? 16 : left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
+    int nb, keep;
+    if (greedy) {
+      nb = left >= 16 ? 16 : left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
+      keep = nb;
+    } else {
+      nb = 1;
+      while (nb < left && nb < 16) nb *= 2;
+      keep = left < nb ? left : nb;
+    }
     double* ha = h_alpha + (size_t)done * degree;
     double* hb = h_beta + (size_t)done * degree;
     int r;
     switch (nb) {
-      case 16: r = lanczos_batch<16>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st); break;
-      case 8: r = lanczos_batch<8>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st); break;
-      case 4: r = lanczos_batch<4>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st); break;
-      case 2: r = lanczos_batch<2>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st); break;
-      default: r = lanczos_batch<1>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st); break;
+      case 16: r = lanczos_batch<16>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st, keep); break;
+      case 8: r = lanczos_batch<8>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st, keep); break;
+      case 4: r = lanczos_batch<4>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st, keep); break;
+      case 2: r = lanczos_batch<2>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st, keep); break;
+      default: r = lanczos_batch<1>(n, ip, d_indices, d_data, degree, probe0 + done, seed, d_work, ha, hb, st, keep); break;
     }
     if (r != 0) return r;
-    done += nb;
+    done += keep;
   }
   return 0;
 }

@@ -18,7 +18,11 @@ if "--after-gemm" in sys.argv:               # heat the chip with ~8 s of DMMA f
     torch.cuda.synchronize()
     del a, c
     print("after 30 DGEMMs of 16384^3")
-sizes = [int(a) for a in sys.argv[1:] if a.isdigit() and (sys.argv[sys.argv.index(a) - 1] != "--hog")]
+if "--bulk" in sys.argv:                     # mirror path of the symmetric fill: 0 plain, 1 CTA-wide bulk rows, 2 per-warp bulk
+    mode_b = int(sys.argv[sys.argv.index("--bulk") + 1])
+    L.load().fvgp_set_bulk_store(mode_b)
+    print("mirror store mode", mode_b)
+sizes = [int(a) for a in sys.argv[1:] if a.isdigit() and (sys.argv[sys.argv.index(a) - 1] not in ("--hog", "--bulk"))]
 for n in sizes or [30000, 50000]:
     rng = np.random.default_rng(0)
     x = L.to_dev(rng.random((n, 3)))
