@@ -321,18 +321,26 @@ class GPkv:
         hi = int(a.get("random_logdet_max_num_samples", 5000))
         rtol = float(a.get("random_logdet_error_rtol", 0.01))
         seed = int(a.get("random_logdet_seed", 0))
-        probes = lo
         if sharded:
-            def slq(csr, degree, probes, seed):
-                return self._sparse_eval.slq_logdet(csr, degree, probes, seed)
+            def draw(count, probe0):
+                return self._sparse_eval.slq_logdet(csr, degree, count, seed, probe0=probe0)[2]
         else:
-            slq = ops.slq_logdet
-        est, var, samples = slq(csr, degree=degree, probes=probes, seed=seed)
-        # imate stops when the standard error falls under error_rtol * |estimate|; extend in one step
-        if np.isfinite(var) and var > 0 and np.sqrt(var) > rtol * abs(est) and probes < hi:
-            need = int(min(hi, np.ceil(samples.var(ddof=1) / (rtol * abs(est)) ** 2)))
-            if need > probes:
-                est, var, samples = slq(csr, degree=degree, probes=need, seed=seed)
+            def draw(count, probe0):
+                return ops.slq_logdet(csr, degree=degree, probes=count, seed=seed, probe0=probe0)[2]
+        samples = np.asarray(draw(lo, 0), dtype=np.float64)
+        # imate's documented stopping rule: z_c * std / sqrt(ns) <= error_rtol * |mean| at confidence 0.95 (z_c = 1.96),
+        # checked from min_num_samples on; until it holds (or max_num_samples is reached) the SAME probe stream is
+        # extended by the number of samples the current variance asks for
+        z95 = 1.959963984540054
+        while len(samples) > 1 and len(samples) < hi:
+            mean, std = float(samples.mean()), float(samples.std(ddof=1))
+            if not (np.isfinite(std) and std > 0.0) or z95 * std / np.sqrt(len(samples)) <= rtol * abs(mean):
+                break
+            need = int(np.ceil((z95 * std / (rtol * abs(mean))) ** 2))
+            need = int(min(hi, max(need, len(samples) + 1)))
+            samples = np.concatenate([samples, draw(need - len(samples), len(samples))])
+        est = float(samples.mean())
+        var = float(samples.var(ddof=1) / len(samples)) if len(samples) > 1 else float("nan")
         self.last_logdet_variance = var
         self.last_logdet_info = {"variance": var, "num_samples_used": len(samples), "lanczos_degree": degree}
         return est

@@ -300,11 +300,12 @@ class ShardedSparseEvaluator:
         self._mark("pcg")
         return out
 
-    def slq_logdet(self, csr, degree, probes, seed):
-        """(estimate, variance of the mean, samples): the probes of the single-GPU stream, split over the ranks."""
+    def slq_logdet(self, csr, degree, probes, seed, probe0=0):
+        """(estimate, variance of the mean, samples): probes probe0 .. probe0 + probes - 1 of the single-GPU stream,
+        split over the ranks."""
         offs = split_probes(int(probes), self.world)
         self._mark(None)
-        mine = self.ops.slq_samples(csr, degree, offs[self.rank], offs[self.rank + 1] - offs[self.rank], seed)
+        mine = self.ops.slq_samples(csr, degree, int(probe0) + offs[self.rank], offs[self.rank + 1] - offs[self.rank], seed)
         self._mark("slq")
         samples = np.asarray(self.ops.gather_samples(mine, offs), dtype=np.float64)
         self._mark("gather_samples")

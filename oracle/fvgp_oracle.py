@@ -424,3 +424,77 @@ def dense_neg_log_likelihood_gradient_blocked(x, y, hps, noise, component=0, blo
     with cf.ThreadPoolExecutor(threads or os.cpu_count()) as ex:
         parts = list(ex.map(work, range(0, n, block)))
     return lml, -0.5 * np.sum(parts, axis=0)                             # -1/2 (b^T dK b - tr(KV^-1 dK))
+
+
+# --------------------------------------------------------------------------- a22: stochastic Lanczos quadrature
+# calculate_random_logdet (gp_lin_alg.py:1103-1181) hands the matrix to imate.logdet(method="slq", lanczos_degree=20,
+# min_num_samples=10, max_num_samples=5000, error_rtol=0.01, orthogonalize=0).  imate is an un-vendored, unpinned
+# dependency (pyproject.toml:56, `tests` extra) and is not installed here: PARITY UNPINNED against imate itself (its
+# probes come from its own RNG and the reference's tests only assert finiteness / rtol 0.1, tests/test_fvgp.py:1897,
+# :2282).  What CAN be pinned is the algorithm imate documents (Ubaru, Chen & Saad 2017, "Fast estimation of tr(f(A))
+# via stochastic Lanczos quadrature"; imate docs: logdet / slq): Hutchinson with Rademacher probes, m-step Lanczos
+# without re-orthogonalisation, Gauss quadrature on the tridiagonal, and the stopping rule
+#     z_c * std(samples) / sqrt(ns)  <=  max(error_atol, error_rtol * |mean|),   ns >= min_num_samples,
+# with z_c = sqrt(2) erfinv(confidence_level) = 1.96 at imate's default confidence_level = 0.95.
+# The probe STREAM below is the product's counter-based hash (splitmix64 of (seed, probe, row)), restated so that both
+# sides see identical probes and the comparison is deterministic.
+_MASK64 = (1 << 64) - 1
+
+
+def rademacher_probe(seed, probe, n):
+    """+-1 vector of probe number `probe`: bit 0 of splitmix64(seed + golden * (probe * FNV + i + 1))."""
+    i = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (np.uint64(probe) * np.uint64(0x100000001B3) + i + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return np.where((z & np.uint64(1)) == 1, 1.0, -1.0)
+
+
+def slq_samples(KV, degree=20, probes=10, seed=0, probe0=0):
+    """One SLQ sample of log det per probe: n * sum_k tau_k^2 log(theta_k) from the degree-step Lanczos tridiagonal."""
+    n = KV.shape[0]
+    out = np.empty(probes)
+    for p in range(probes):
+        z = rademacher_probe(seed, probe0 + p, n)
+        q_prev, q, beta = np.zeros(n), z / np.sqrt(n), 0.0
+        al, be = [], []
+        for _ in range(min(degree, n)):
+            w = KV @ q - beta * q_prev
+            a = float(q @ w)
+            w = w - a * q
+            beta = float(np.linalg.norm(w))
+            al.append(a), be.append(beta)
+            if beta < 1e-12 * max(1.0, abs(a)):
+                break
+            q_prev, q = q, w / beta
+        m = len(al)
+        T = np.diag(al) + np.diag(be[:m - 1], 1) + np.diag(be[:m - 1], -1)
+        lam, vec = np.linalg.eigh(T)
+        out[p] = n * np.sum(vec[0, :] ** 2 * np.log(lam))
+    return out
+
+
+SLQ_Z95 = 1.959963984540054          # sqrt(2) * erfinv(0.95)
+
+
+def slq_converged(samples, error_rtol=0.01, error_atol=0.0, min_num_samples=10):
+    """imate's documented stopping rule on the samples drawn so far."""
+    ns = len(samples)
+    if ns < max(2, min_num_samples):
+        return False
+    err = SLQ_Z95 * np.std(samples, ddof=1) / np.sqrt(ns)
+    return bool(err <= max(error_atol, error_rtol * abs(np.mean(samples))))
+
+
+def slq_logdet(KV, degree=20, min_num_samples=10, max_num_samples=5000, error_rtol=0.01, seed=0):
+    """(estimate, variance of the mean, samples): draw min_num_samples probes, then keep extending the stream by the
+    number the current variance says is needed (one step, capped) until the rule holds."""
+    samples = slq_samples(KV, degree, min_num_samples, seed)
+    while not slq_converged(samples, error_rtol, 0.0, min_num_samples) and len(samples) < max_num_samples:
+        need = int(np.ceil((SLQ_Z95 * np.std(samples, ddof=1) / (error_rtol * abs(np.mean(samples)))) ** 2))
+        need = min(max_num_samples, max(need, len(samples) + 1))
+        samples = np.concatenate([samples, slq_samples(KV, degree, need - len(samples), seed, probe0=len(samples))])
+    var = float(np.var(samples, ddof=1) / len(samples)) if len(samples) > 1 else float("nan")
+    return float(np.mean(samples)), var, samples

@@ -93,3 +93,33 @@ def test_c3_shape_through_fvgp_dense_sharded():
     import bench
     rec = bench.parity_c3(2000)
     assert rec["pass"], rec
+
+
+def test_slq_logdet_against_the_restated_algorithm():
+    """a22: the stochastic log-determinant.  imate is absent (parity unpinned against imate itself), so the product is
+    pinned to the oracle's restatement of the documented algorithm with IDENTICAL probes (same counter-based stream):
+    per-probe samples, the estimate and the number of samples the stopping rule draws."""
+    from fvgp_b200 import GP, ops
+    from fvgp_b200 import _lib as L
+    from oracle import fvgp_oracle as orc
+    rng = np.random.default_rng(5)
+    n = 3000
+    x = rng.random((n, 3))
+    y = np.sin(6 * x[:, 0]) + 0.1 * rng.standard_normal(n)
+    noise = np.full(n, 1e-2)
+    th = np.array([1.2, .16, .15, .17])
+    xd = L.to_dev(x)
+    csr = ops.wendland_csr(xd, xd, th, noise=L.to_dev(noise))
+    KV = csr.to_scipy()
+    for probe0, count in ((0, 10), (10, 3), (4, 5)):
+        ours = ops.slq_logdet(csr, degree=20, probes=count, seed=7, probe0=probe0)[2]
+        ref = orc.slq_samples(KV, 20, count, seed=7, probe0=probe0)
+        assert np.max(np.abs(ours - ref) / np.abs(ref)) <= 1e-7, (probe0, ours, ref)
+    args = {"random_logdet_seed": 7, "random_logdet_error_rtol": 0.002, "random_logdet_max_num_samples": 64,
+            "sparse_cg_tol": 1e-10}
+    gp = GP(x, y, init_hyperparameters=th, noise_variances=noise, gp2Scale=True, linalg_mode="sparseCG", args=args)
+    est, var, samples = orc.slq_logdet(KV, 20, 10, 64, 0.002, seed=7)
+    assert gp.kv.last_logdet_info["num_samples_used"] == len(samples) > 10
+    assert abs(gp.kv.logdet_KV / est - 1) <= 1e-8 and abs(gp.kv.last_logdet_variance / var - 1) <= 1e-5
+    exact = np.linalg.slogdet(KV.toarray())[1]
+    assert abs(est - exact) <= 4 * np.sqrt(var) + 0.02 * abs(exact)

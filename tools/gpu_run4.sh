@@ -2,7 +2,7 @@
 # GPU run 4 (round 2, 1 GPU): N=1 bench line (crash hunt with faulthandler), K-fill mirror A/B, parity suite on the new
 # fill / Lanczos paths, ncu launch list of POTRF at N = 8192
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_plugin.py -m gpu -x -q > gpurun_out/r02_v4_pytest_parity.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_plugin.py tests/test_gpu_parity_at_size.py -k 'not fifty and not benchmarked_n and not 16000' -m gpu -q > gpurun_out/r02_v4_pytest_parity.log 2>&1
 echo "parity rc=$?"; tail -3 gpurun_out/r02_v4_pytest_parity.log
 for B in 1 2; do timeout 300 python tools/kfill_sweep.py --bulk $B 30000 50000 >> gpurun_out/r02_v4_kfill_sweep.log 2>&1; done
 cat gpurun_out/r02_v4_kfill_sweep.log
