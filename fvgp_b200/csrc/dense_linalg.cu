@@ -792,6 +792,107 @@ __global__ void __launch_bounds__(TRSV_FUSED_THREADS) trsv_fused_kernel(const do
   }
 }
 
+// Block-range variants of the fused substitution for n > TRSV_FUSED_MAX: ONE launch walks all 64-wide tiles of a
+// VBLK-column diagonal block [b0, b1) (the step-per-launch chain was 782 launches per direction at N = 50 000, 32 ms for a
+// 20 GB read; 4.4 ms at N = 8192).  Rows / columns outside the block are left to the full-grid panel GEMVs of potrs_few.
+// Arithmetic per row / column is that of the step kernels (same accumulation order).
+__global__ void __launch_bounds__(TRSV_FUSED_THREADS) trsv_block_fwd_kernel(const double* __restrict__ L, long long ld,
+                                                                            int b0, int b1,
+                                                                            const double* __restrict__ dinv_base, double* w,
+                                                                            double* z, long long bstride) {
+  L += blockIdx.x * bstride, dinv_base += blockIdx.x * bstride, w += blockIdx.x * bstride, z += blockIdx.x * bstride;
+  __shared__ double S[VS][VSP];
+  __shared__ double yj[VS], zj[VS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = TRSV_FUSED_THREADS / 32;
+  for (int j0 = b0; j0 < b1; j0 += VS) {  // L z = b inside the block
+    const int t = j0 / VS, nt = min(VS, b1 - j0);
+    stage_inverse_block_wide(dinv_base + (long long)(t / 2) * TS * TS + (t % 2) * ((long long)VS * TS + VS), S, tid);
+    if (tid < VS) yj[tid] = tid < nt ? w[j0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < 4 * VS) {
+      const int r = tid >> 2, part = tid & 3;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int k = part; k <= r; k += 4) acc = fma(S[r][k], yj[k], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) {
+        zj[r] = acc;
+        if (r < nt) z[j0 + r] = acc;
+      }
+    }
+    __syncthreads();
+    const double z0 = zj[lane], z1 = zj[lane + 32];
+    for (int i0 = j0 + VS + warp * 4; i0 < b1; i0 += NW * 4) {  // four rows per warp in flight
+      double a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = min(i0 + u, b1 - 1);
+        const double* row = L + (long long)i * ld + j0;
+        a[u] = row[lane] * z0 + row[lane + 32] * z1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double acc = warp_sum(a[u]);
+        if (lane == 0 && i0 + u < b1) w[i0 + u] -= acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(TRSV_FUSED_THREADS) trsv_block_bwd_kernel(const double* __restrict__ L, long long ld,
+                                                                            int b0, int b1,
+                                                                            const double* __restrict__ dinv_base, double* z,
+                                                                            double* x, long long bstride) {
+  L += blockIdx.x * bstride, dinv_base += blockIdx.x * bstride, z += blockIdx.x * bstride, x += blockIdx.x * bstride;
+  __shared__ double S[VS][VSP];
+  __shared__ double yj[VS], zj[VS];
+  const int tid = threadIdx.x;
+  const int last = b0 + ((b1 - b0 - 1) / VS) * VS;
+  for (int j0 = last; j0 >= b0; j0 -= VS) {  // L^T x = z inside the block
+    const int t = j0 / VS, nt = min(VS, b1 - j0);
+    stage_inverse_block_wide(dinv_base + (long long)(t / 2) * TS * TS + (t % 2) * ((long long)VS * TS + VS), S, tid);
+    if (tid < VS) zj[tid] = tid < nt ? z[j0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < 4 * VS) {
+      const int c = tid >> 2, part = tid & 3;
+      double acc = 0.0;
+#pragma unroll 4
+      for (int r = c + part; r < VS; r += 4) acc = fma(S[r][c], zj[r], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) {
+        yj[c] = acc;
+        if (c < nt) x[j0 + c] = acc;
+      }
+    }
+    __syncthreads();
+    for (int c = b0 + tid; c < j0; c += TRSV_FUSED_THREADS) {
+      const double* col = L + (long long)j0 * ld + c;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int r = 0;
+      for (; r + 8 <= nt; r += 8) {
+        const double v0 = col[(long long)r * ld], v1 = col[(long long)(r + 1) * ld], v2 = col[(long long)(r + 2) * ld],
+                     v3 = col[(long long)(r + 3) * ld], v4 = col[(long long)(r + 4) * ld], v5 = col[(long long)(r + 5) * ld],
+                     v6 = col[(long long)(r + 6) * ld], v7 = col[(long long)(r + 7) * ld];
+        a0 = fma(v0, yj[r], a0), a1 = fma(v1, yj[r + 1], a1), a2 = fma(v2, yj[r + 2], a2), a3 = fma(v3, yj[r + 3], a3);
+        a0 = fma(v4, yj[r + 4], a0), a1 = fma(v5, yj[r + 5], a1), a2 = fma(v6, yj[r + 6], a2), a3 = fma(v7, yj[r + 7], a3);
+      }
+      for (; r + 4 <= nt; r += 4) {
+        a0 = fma(col[(long long)r * ld], yj[r], a0);
+        a1 = fma(col[(long long)(r + 1) * ld], yj[r + 1], a1);
+        a2 = fma(col[(long long)(r + 2) * ld], yj[r + 2], a2);
+        a3 = fma(col[(long long)(r + 3) * ld], yj[r + 3], a3);
+      }
+      for (; r < nt; ++r) a0 = fma(col[(long long)r * ld], yj[r], a0);
+      z[c] -= (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(1024) logdet_kernel(const double* __restrict__ L, long long ld, int n, double* out,
                                                       long long bstride) {
   L += blockIdx.x * bstride, out += blockIdx.x * bstride;
@@ -1157,12 +1258,17 @@ static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda,
       FVGP_CUDA_OK(cudaMemcpy2DAsync(w, bstride * sizeof(double), b, bstride * sizeof(double), n * sizeof(double), batch,
                                      cudaMemcpyDeviceToDevice, st));
     }
+    const bool fused_blocks = trsv_fused_enabled();
     for (int blk = 0; blk < nblocks; ++blk) {  // L z = b
       const int b0 = blk * VBLK, b1 = (int)std::min<int64_t>(n, b0 + VBLK);
-      for (int j0 = b0; j0 < b1; j0 += VS) {
-        const int rest = b1 - (j0 + VS);
-        const int grid = rest > 0 ? (rest + 63) / 64 : 1;
-        launch(fwd_step_kernel, dim3(grid, nb), 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), w, z, bstride);
+      if (fused_blocks) {
+        launch(trsv_block_fwd_kernel, nb, TRSV_FUSED_THREADS, 0, st, d_L, lda, b0, b1, d_tileinv, w, z, bstride);
+      } else {
+        for (int j0 = b0; j0 < b1; j0 += VS) {
+          const int rest = b1 - (j0 + VS);
+          const int grid = rest > 0 ? (rest + 63) / 64 : 1;
+          launch(fwd_step_kernel, dim3(grid, nb), 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), w, z, bstride);
+        }
       }
       if (b1 < n) {
         const int m = (int)n - b1;
@@ -1175,10 +1281,14 @@ static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda,
     for (int blk = nblocks - 1; blk >= 0; --blk) {  // L^T x = z
       const int b0 = blk * VBLK, b1 = (int)std::min<int64_t>(n, b0 + VBLK);
       const int last = b0 + ((b1 - b0 - 1) / VS) * VS;
-      for (int j0 = last; j0 >= b0; j0 -= VS) {
-        const int cols = j0 - b0;
-        const int grid = cols > 0 ? (cols + 255) / 256 : 1;
-        launch(bwd_step_kernel, dim3(grid, nb), 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), z, b, b0, bstride);
+      if (fused_blocks) {
+        launch(trsv_block_bwd_kernel, nb, TRSV_FUSED_THREADS, 0, st, d_L, lda, b0, b1, d_tileinv, z, b, bstride);
+      } else {
+        for (int j0 = last; j0 >= b0; j0 -= VS) {
+          const int cols = j0 - b0;
+          const int grid = cols > 0 ? (cols + 255) / 256 : 1;
+          launch(bwd_step_kernel, dim3(grid, nb), 256, 0, st, d_L, lda, b1, j0, block_inv(j0 / VS), z, b, b0, bstride);
+        }
       }
       if (b0 > 0) {  // z[0:b0] -= L[b0:b1, 0:b0]^T x[b0:b1]
         const int m = b1 - b0;
