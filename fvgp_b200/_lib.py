@@ -85,6 +85,11 @@ _SIGNATURES = {
     "fvgp_pcg_sharded_work_len": (c_int64, [c_int64]),
     "fvgp_pcg_sharded": (c_int, [_P, c_int64, POINTER(c_int64), _P, _P, _P, _P, _P, _P, c_double, c_int, _P,
                                  POINTER(c_int), POINTER(c_double), _P]),
+    "fvgp_ozaki_available": (c_int, []),
+    "fvgp_set_ozaki": (c_int, [c_int]),
+    "fvgp_ozaki_work_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int, c_int64]),
+    "fvgp_ozaki_gemm_nt": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_double, c_int, c_int64,
+                                   c_int, c_int, c_int64, _P, c_int64, _P]),
     "fvgp_bench_fp64_peak": (c_int, [c_int, c_int, c_int, _P, POINTER(c_double), _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

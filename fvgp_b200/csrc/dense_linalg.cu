@@ -1039,6 +1039,21 @@ static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
   return potrf_rec(c, A22, ld, n2, row0 + n1);
 }
 
+// INT8-slice (Ozaki) trailing updates: 0 = off (DMMA), S >= 6 = number of 6-bit slices (csrc/ozaki.cu).  Set by
+// fvgp_set_ozaki or the FVGP_OZAKI environment variable; used for trailing updates with at least OZAKI_MIN_M rows.
+static int g_ozaki_slices = -1;
+constexpr int OZAKI_MIN_M = 8192;
+constexpr int64_t OZAKI_NBLOCK = 4096;
+static int ozaki_slices() {
+  if (g_ozaki_slices < 0) {
+    const char* e = getenv("FVGP_OZAKI");
+    int v = e ? atoi(e) : 0;
+    if (v == 1) v = 8;
+    g_ozaki_slices = (v >= 6 && v <= 10 && fvgp_ozaki_available()) ? v : 0;
+  }
+  return g_ozaki_slices;
+}
+
 // Right-looking blocked Cholesky with one step of look-ahead on two streams.
 //
 // The recursion above is flop-optimal but strictly serial: the latency-bound work on the diagonal (tile
@@ -1067,6 +1082,17 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   Ctx cp = c;
   cp.st = P;
   int rc = 0;
+  // INT8-slice trailing updates: one scratch allocation for the largest update of this factorisation
+  const int oz = (nb % 16 == 0 && n - 2 * nb >= OZAKI_MIN_M) ? ozaki_slices() : 0;
+  void* oz_work = nullptr;
+  int64_t oz_bytes = 0;
+  if (oz) {
+    oz_bytes = fvgp_ozaki_work_bytes(n - 2 * nb, n - 2 * nb, nb, oz, OZAKI_NBLOCK);
+    if (cudaMallocAsync(&oz_work, (size_t)oz_bytes, S) != cudaSuccess) {
+      cudaGetLastError();
+      oz_work = nullptr;  // not enough memory: stay on the DMMA path
+    }
+  }
   auto panel = [&](int k) -> int {  // factor the diagonal block k, solve the blocks below it
     const int w = std::min(nb, rows_from(k));
     REC_OK(potrf_rec(cp, blk(k, k), ld, w, k * nb));
@@ -1083,8 +1109,12 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
     FVGP_CUDA_OK(cudaStreamWaitEvent(S, ev_panel[k], 0));
     if (k + 2 < nblk) {
       const int m2 = rows_from(k + 2);
-      rc = launch_gemm<false, false>(S, blk(k + 2, k), ld, blk(k + 2, k), ld, blk(k + 2, k + 2), ld, m2, m2, nb, -1.0, 1.0,
-                                     GEMM_LOWER);
+      if (oz_work != nullptr && m2 >= OZAKI_MIN_M)
+        rc = fvgp_ozaki_gemm_nt(blk(k + 2, k + 2), ld, blk(k + 2, k), ld, blk(k + 2, k), ld, m2, m2, nb, -1.0, 1, 0, 1, oz,
+                                OZAKI_NBLOCK, oz_work, oz_bytes, S);
+      else
+        rc = launch_gemm<false, false>(S, blk(k + 2, k), ld, blk(k + 2, k), ld, blk(k + 2, k + 2), ld, m2, m2, nb, -1.0, 1.0,
+                                       GEMM_LOWER);
       if (rc != 0) break;
     }
     FVGP_CUDA_OK(cudaEventRecord(ev_trail[k], S));
@@ -1109,6 +1139,7 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
     cudaEventDestroy(ev_panel[k]);
     cudaEventDestroy(ev_trail[k]);
   }
+  if (oz_work != nullptr) cudaFreeAsync(oz_work, S);
   cudaStreamDestroy(P);
   return rc;
 }
@@ -1185,6 +1216,14 @@ static inline int64_t round_up16(int64_t v) { return (v + 15) / 16 * 16; }
 extern "C" {
 
 int fvgp_version(void) { return 100; }
+
+// 0: DMMA trailing updates (default); 6..10: INT8-slice trailing updates with that many 6-bit slices (8 = FP64-grade
+// for the LML); returns the previous setting.  Ignored when the library was built without CUTLASS.
+int fvgp_set_ozaki(int slices) {
+  const int old = ozaki_slices();
+  g_ozaki_slices = (slices >= 6 && slices <= 10 && fvgp_ozaki_available()) ? slices : 0;
+  return old;
+}
 
 unsigned long long fvgp_launch_count(void) { return g_launches; }
 

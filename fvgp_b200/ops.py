@@ -309,6 +309,22 @@ def dgemm_nt(A, B, C, alpha=1.0, beta=0.0, lower=False):
     return C
 
 
+def ozaki_gemm_nt(C, A, B, sign=-1.0, lower=False, diag=0, slices=8, nblock=8192):
+    """C += sign * A B^T on the INT8 tensor cores at FP64 accuracy (include/fvgp_b200.h: fvgp_ozaki_gemm_nt).
+    C (m, n), A (m, k), B (n, k): row-major 2-D device tensors (strides taken from the tensors); B is A -> SYRK."""
+    lib = L.load()
+    torch = L._torch()
+    m, k = A.shape
+    n = B.shape[0]
+    same = int(A.data_ptr() == B.data_ptr() and A.shape == B.shape and A.stride(0) == B.stride(0))
+    nbytes = int(lib.fvgp_ozaki_work_bytes(m, n, k, int(slices), int(nblock)))
+    work = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    L.check(lib.fvgp_ozaki_gemm_nt(L.ptr(C), _ld(C), L.ptr(A), _ld(A), L.ptr(B), _ld(B), m, n, k, float(sign), int(lower),
+                                   int(diag), same, int(slices), int(nblock), L.ptr(work), nbytes, L.stream_ptr()),
+            "fvgp_ozaki_gemm_nt")
+    return C
+
+
 # ------------------------------------------------------------------------------ gp2Scale sparse
 class DeviceCSR:
     """Canonical CSR on the device: int64 indptr, int32 sorted indices, float64 data."""

@@ -304,6 +304,22 @@ int fvgp_pcg_sharded(void* comm, int64_t n, const int64_t* h_row_offsets, const 
                      double* d_x, double rtol, int maxiter, double* d_work, int* h_iters, double* h_relres,
                      void* stream);
 
+/* ---- FP64-accurate GEMM on the INT8 tensor cores (tcgen05.mma kind::i8 + TMEM; csrc/ozaki.cu): the trailing updates
+ * of calculate_Chol_factor (gp_lin_alg.py:237-269 -> LAPACK dpotrf) past the DMMA roof.  Ozaki-type splitting: rows
+ * scaled by powers of two, `slices` 6-bit digits per entry, exact int32 slice products grouped by scale into `slices`
+ * int8 GEMMs, FP64 recombination.  slices = 8: ~2^-47 relative to the row maxima, 36 integer MACs per FP64 MAC.
+ * C (m x n, ldc) += sign * A (m x k, lda) B (n x k, ldb)^T, FP64 row-major; lower != 0 updates only the entries with
+ * column <= row + diag; same_ab != 0: B is A (SYRK).  k % 16 == 0.  C is processed in column blocks of nblock.
+ * fvgp_ozaki_available() = 0 when the library was built without the CuTe / CUTLASS headers. */
+int fvgp_ozaki_available(void);
+/* 0: DMMA trailing updates in fvgp_potrf_lower (default); 6..10: INT8-slice updates with that many slices for updates
+ * of at least 8192 rows (environment default: FVGP_OZAKI).  Returns the previous setting. */
+int fvgp_set_ozaki(int slices);
+int64_t fvgp_ozaki_work_bytes(int64_t m, int64_t n, int64_t k, int slices, int64_t nblock);
+int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, int64_t m,
+                       int64_t n, int64_t k, double sign, int lower, int64_t diag, int same_ab, int slices, int64_t nblock,
+                       void* d_work, int64_t work_bytes, void* stream);
+
 /* ---- measurement only: register-resident FP64 issue-rate probes (which: 0 = DMMA.8x8x4,
  * 1 = DFMA) giving the FP64 roofline denominator of the box.  d_scratch: 148*8*256 doubles. */
 int fvgp_bench_fp64_peak(int which, int ctas_per_sm, int iters, double* d_scratch, double* h_tflops, void* stream);
