@@ -1075,6 +1075,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-blocks", type=int, default=12, help="C4 blocks compared with the oracle inside bench.py "
                     "(the -m gpu suite compares 50)")
+    ap.add_argument("--ozaki-slices", type=int, default=8)
     ap.add_argument("--c4-n", type=int, default=1000000)
     ap.add_argument("--c4-cpu-n", type=int, default=200000)
     ap.add_argument("--c3-points", type=int, default=20000)
@@ -1222,6 +1223,39 @@ def main():
                                               f"(--impl reference) times the unmodified reference over a ladder of sizes instead"}
 
     extras = not args.no_extras
+    # ---- the same step with the POTRF trailing updates on the INT8 tensor cores (Ozaki split, csrc/ozaki.cu) -------
+    if extras and rank == 0 and lib.fvgp_ozaki_available() and deadline.left() > 120:
+        def ozaki_section():
+            th = theta_k(4)
+            gp.kv._memo = None
+            ref_lml, ref_grad = gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
+            rec = {"slices": args.ozaki_slices, "what": "fvgp_set_ozaki: trailing updates of the look-ahead POTRF (>= 8192 rows) "
+                   "as INT8-slice GEMMs on tcgen05 (kind::i8, TMEM), everything else unchanged"}
+            old = lib.fvgp_set_ozaki(args.ozaki_slices)
+            try:
+                ops.start_phase_timing()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for k in range(3):
+                    o = step(100 + k)
+                torch.cuda.synchronize()
+                rec["seconds_per_step"] = (time.perf_counter() - t0) / 3
+                ph = ops.stop_phase_timing()
+                rec["potrf_seconds"] = ph.get("potrf", 0.0) / 3
+                rec["potrf_tflops_fp64_equivalent"] = n ** 3 / 3.0 / rec["potrf_seconds"] / 1e12
+                gp.kv._memo = None
+                lml, grad = gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
+                rec.update({"evals_per_s": 1.0 / rec["seconds_per_step"], "lml_rel_diff_vs_dmma": abs(lml / ref_lml - 1),
+                            "grad_max_rel_diff_vs_dmma": relerr(grad, ref_grad),
+                            "within_1e-8": bool(abs(lml / ref_lml - 1) <= 1e-8 and relerr(grad, ref_grad) <= 1e-8),
+                            "dmma_seconds_per_step": t_dev / args.steps,
+                            "dmma_potrf_seconds": phases.get("potrf", 0.0) / args.steps})
+                assert np.isfinite(o[0])
+            finally:
+                lib.fvgp_set_ozaki(old)
+                gp.kv._memo = None
+            return rec
+        guarded("ozaki_int8_trailing_updates", ozaki_section, line)
     # ---- parity at the benchmarked sizes (one GPU; the host needs its cores) ----------------------
     if extras and world == 1 and not args.no_parity:
         par = {}
