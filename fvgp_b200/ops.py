@@ -22,11 +22,13 @@ class _Phase:
         if PHASES is not None:
             torch = L._torch()
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.nvtx.range_push("fvgp/" + self.name)      # ncu / nsys --nvtx: per-phase ranges inside "timed/"
             self.e0.record()
 
     def __exit__(self, *exc):
         if PHASES is not None:
             self.e1.record()
+            L._torch().cuda.nvtx.range_pop()
             PHASES.setdefault(self.name, []).append((self.e0, self.e1))
 
 

@@ -235,3 +235,17 @@ def test_ctypes_signatures_match_the_header_prototypes():
     for ctype, d in zip(sig, decl):
         is_ptr = "*" in d
         assert is_ptr == (ctype is ctypes.c_void_p or hasattr(ctype, "contents") or ctype.__name__.startswith("LP_")), (d, ctype)
+
+
+def test_install_as_fvgp_registers_the_reference_import_names():
+    """`fvgp_b200.install_as_fvgp()`: unmodified `from fvgp import GP` / `from fvgp.kernels import ...` user code lands
+    on this package (run in a subprocess: the reference must not already be imported under that name)."""
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import fvgp_b200; fvgp_b200.install_as_fvgp();"
+            "from fvgp import GP, fvGP; from fvgp.kernels import squared_exponential_kernel, get_distance_matrix;"
+            "import fvgp.gp_kv as kv; import inspect;"
+            "assert GP is fvgp_b200.GP and kv.GPkv is fvgp_b200.gp_kv.GPkv;"
+            "assert inspect.signature(GP.__init__).parameters['compute_device'].default == 'cpu';"
+            "print('ok')") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip().endswith("ok"), out.stderr[-800:]
