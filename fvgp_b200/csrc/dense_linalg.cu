@@ -1088,9 +1088,16 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   int64_t oz_bytes = 0;
   if (oz) {
     oz_bytes = fvgp_ozaki_work_bytes(n - 2 * nb, n - 2 * nb, nb, oz, OZAKI_NBLOCK);
-    if (cudaMallocAsync(&oz_work, (size_t)oz_bytes, S) != cudaSuccess) {
+    const cudaError_t me = cudaMallocAsync(&oz_work, (size_t)oz_bytes, S);
+    if (me != cudaSuccess) {
       cudaGetLastError();
       oz_work = nullptr;  // not enough memory: stay on the DMMA path
+    }
+    static bool told = false;
+    if (!told) {
+      told = true;
+      fprintf(stderr, "[fvgp_b200] potrf n=%d nb=%d: INT8-slice trailing updates, %d slices, scratch %.2f GB: %s\n", n, nb, oz,
+              oz_bytes / 1e9, oz_work ? "on" : cudaGetErrorString(me));
     }
   }
   auto panel = [&](int k) -> int {  // factor the diagonal block k, solve the blocks below it

@@ -40,7 +40,7 @@ constexpr int STAGE_DOUBLES = FT * FT_STRIDE;
 constexpr int WSTRIDE = 10;
 constexpr int WSTAGE_DOUBLES = FT * WSTRIDE;  // per warp
 
-static int g_use_bulk_store = 2;
+static int g_use_bulk_store = 1;  // 2 (per-warp 64-byte bulk stores) measured SLOWER on B200: 6.22 vs 4.34 ms at N = 50 000
 
 struct FillParams {
   const double* x1;
@@ -966,8 +966,8 @@ int kfill_lower_batch_enqueue(int kind, const double* d_x, int64_t n, int dim, i
 extern "C" {
 
 // test / profiling hook: mirror tile of the symmetric fill through 0 = plain coalesced stores (CTA barrier),
-// 1 = one 512-byte TMA bulk store per row (CTA barrier, double-buffered staging), 2 = per-warp 64-byte bulk stores,
-// no CTA barrier (default)
+// 1 = one 512-byte TMA bulk store per row (CTA barrier, double-buffered staging; default), 2 = per-warp 64-byte bulk
+// stores without any CTA barrier (A/B: slower, the 64-byte pieces cost more in the store path than the barriers did)
 int fvgp_set_bulk_store(int on) {
   const int old = g_use_bulk_store;
   g_use_bulk_store = on < 0 ? 0 : (on > 2 ? 2 : on);

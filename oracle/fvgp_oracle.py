@@ -360,41 +360,75 @@ def posterior_mean_cov(x, y, hps, noise, x_pred, kernel=default_kernel):
 # that the oracle reaches the benchmarked sizes on the GPU box's host (N = 50 000 LML: 20 GB; the literal
 # formulation needs (3H+3) N^2 doubles for the gradient).  Pinned against the plain functions in
 # tests/test_oracle_golden.py, which are pinned against the reference's outputs.
-def _fill_upper_blocked(x, hps, noise, block=1024, threads=None):
-    """C-ordered A with A[r, c>=r] = default_kernel(x, x, hps)[r, c] + noise on the diagonal (gp_prior.py:376-400,
-    gp_kv.py:640-669); the strict lower triangle is left uninitialised."""
+def _fill_rows(x1, x2, hps, noise_diag=None, upper_only=False, block=1024, threads=None):
+    """C-ordered block default_kernel(x1, x2, hps) evaluated by row blocks in a thread pool (gp_prior.py:376-400);
+    noise_diag is added on the diagonal (gp_kv.py:640-669); upper_only skips the columns left of the diagonal."""
     import concurrent.futures as cf
     import os
-    n = len(x)
-    A = np.empty((n, n))
+    out = np.empty((len(x1), len(x2)))
 
     def work(r0):
-        r1 = min(r0 + block, n)
-        A[r0:r1, r0:] = default_kernel(x[r0:r1], x[r0:], hps)
-        idx = np.arange(r0, r1)
-        A[idx, idx] += noise[r0:r1]
+        r1 = min(r0 + block, len(x1))
+        c0 = r0 if upper_only else 0
+        out[r0:r1, c0:] = default_kernel(x1[r0:r1], x2[c0:], hps)
+        if noise_diag is not None:
+            idx = np.arange(r0, r1)
+            out[idx, idx] += noise_diag[r0:r1]
     with cf.ThreadPoolExecutor(threads or os.cpu_count()) as ex:
-        list(ex.map(work, range(0, n, block)))
-    return A
+        list(ex.map(work, range(0, len(x1), block)))
+    return out
 
 
-def dense_log_likelihood_blocked(x, y, hps, noise, block=1024, threads=None, return_factor=False):
-    """dense_log_likelihood for large N: blocked K-fill, in-place LAPACK dpotrf (what scipy cho_factor calls,
-    gp_lin_alg.py:237-269), dpotrs, 2 sum log diag (gp_lin_alg.py:289-360), LML (gp_marginal_likelihood.py:171-178)."""
+def _dpotrf_lower_of_transpose(B):
+    """In-place LAPACK dpotrf (what scipy cho_factor calls, gp_lin_alg.py:237-269) on the Fortran view B.T of a
+    C-ordered array whose UPPER triangle is filled; returns the factor as that view (lower triangle)."""
     from scipy.linalg import lapack
-    y = y.reshape(len(y), -1)
-    n = len(x)
-    A = _fill_upper_blocked(x, np.asarray(hps, dtype=float), noise, block, threads)
-    c, info = lapack.dpotrf(A.T, lower=1, overwrite_a=1, clean=0)        # A.T: Fortran view, lower triangle filled
+    c, info = lapack.dpotrf(B.T, lower=1, overwrite_a=1, clean=0)
     if info != 0:
         raise NonPositiveDefinite(f"dpotrf info = {info}")
-    assert np.shares_memory(c, A), "LAPACK copied the matrix"
+    assert np.shares_memory(c, B), "LAPACK copied the matrix"
+    return c
+
+
+def dense_log_likelihood_blocked(x, y, hps, noise, block=1024, threads=None, return_factor=False, split=None):
+    """dense_log_likelihood for large N: blocked K-fill, in-place LAPACK dpotrf, triangular solves, 2 sum log diag
+    (gp_lin_alg.py:289-360), LML (gp_marginal_likelihood.py:171-178).
+
+    N^2 < 2^31: one dpotrf / dpotrs on the whole matrix.  Beyond (N >= 46 341; `split` forces it): ONE level of the
+    2 x 2 block factorisation built from the same LAPACK / BLAS-3 routines on the half-size blocks
+        L11 = chol(K11),  X = L11^-1 K12 (= L21^T),  L22 = chol(K22 - X^T X)
+    because dpotrf on the whole N = 50 000 matrix crashed intermittently inside the threaded OpenBLAS of the GPU box
+    (element offsets past 2^31: 2 of 3 runs)."""
+    from scipy.linalg import blas, lapack
+    y = y.reshape(len(y), -1)
+    n = len(x)
+    hps = np.asarray(hps, dtype=float)
     m = np.full(n, np.mean(y))
     ym = y - m[:, None]
-    alpha, info = lapack.dpotrs(c, ym, lower=1)
-    logdet = 2.0 * np.sum(np.log(np.abs(np.diagonal(c))))
-    lml = log_likelihood_from(alpha, logdet, ym)
-    return (lml, c, alpha) if return_factor else lml
+    split = (n * n >= 2 ** 31) if split is None else split
+    if not split:
+        A = _fill_rows(x, x, hps, noise, upper_only=True, block=block, threads=threads)
+        c = _dpotrf_lower_of_transpose(A)
+        alpha, info = lapack.dpotrs(c, ym, lower=1)
+        logdet = 2.0 * np.sum(np.log(np.abs(np.diagonal(c))))
+        lml = log_likelihood_from(alpha, logdet, ym)
+        return (lml, c, alpha) if return_factor else lml
+    assert not return_factor, "the split factorisation does not return one factor array"
+    h = n // 2
+    L11 = _dpotrf_lower_of_transpose(_fill_rows(x[:h], x[:h], hps, noise[:h], upper_only=True, block=block, threads=threads))
+    X = _fill_rows(x[:h], x[h:], hps, block=block, threads=threads)                      # K12, h x (n - h)
+    X = sla.solve_triangular(L11, X, lower=True, overwrite_b=True, check_finite=False)   # L11^-1 K12 = L21^T
+    B22 = _fill_rows(x[h:], x[h:], hps, noise[h:], upper_only=True, block=block, threads=threads)
+    c22 = blas.dsyrk(-1.0, X, beta=1.0, c=B22.T, trans=1, lower=1, overwrite_c=1)        # lower(B22^T) -= X^T X
+    assert np.shares_memory(c22, B22), "BLAS copied the matrix"
+    L22 = _dpotrf_lower_of_transpose(B22)
+    z1 = sla.solve_triangular(L11, ym[:h], lower=True, check_finite=False)
+    z2 = sla.solve_triangular(L22, ym[h:] - X.T @ z1, lower=True, check_finite=False)
+    a2 = sla.solve_triangular(L22, z2, lower=True, trans="T", check_finite=False)
+    a1 = sla.solve_triangular(L11, z1 - X @ a2, lower=True, trans="T", check_finite=False)
+    alpha = np.vstack([a1, a2])
+    logdet = 2.0 * (np.sum(np.log(np.abs(np.diagonal(L11)))) + np.sum(np.log(np.abs(np.diagonal(L22)))))
+    return log_likelihood_from(alpha, logdet, ym)
 
 
 def dense_neg_log_likelihood_gradient_blocked(x, y, hps, noise, component=0, block=512, threads=None):

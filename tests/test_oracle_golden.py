@@ -125,6 +125,8 @@ def test_large_n_oracle_variants_equal_the_pinned_ones(golden):
         x, y, nz = g["x"], g["y"], g["noise"]
         for hk in ("h0", "h1"):
             assert abs(orc.dense_log_likelihood_blocked(x, y, g[hk], nz, block=97) / g["lml_" + hk] - 1) <= 1e-11
+            # the N^2 >= 2^31 branch (one level of the 2 x 2 block factorisation), forced at small N
+            assert abs(orc.dense_log_likelihood_blocked(x, y, g[hk], nz, block=97, split=True) / g["lml_" + hk] - 1) <= 1e-11
             lml, gr = orc.dense_neg_log_likelihood_gradient_blocked(x, y, g[hk], nz, block=53, threads=3)
             assert abs(lml / g["lml_" + hk] - 1) <= 1e-11
             assert rel(gr, g["grad_" + hk]) <= 1e-8, (tag, hk, gr, g["grad_" + hk])
