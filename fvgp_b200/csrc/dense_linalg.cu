@@ -1304,7 +1304,15 @@ static int potrs_few(cudaStream_t st, const double* d_L, int64_t n, int64_t lda,
       FVGP_CUDA_OK(cudaMemcpy2DAsync(w, bstride * sizeof(double), b, bstride * sizeof(double), n * sizeof(double), batch,
                                      cudaMemcpyDeviceToDevice, st));
     }
-    const bool fused_blocks = trsv_fused_enabled();
+    // FVGP_TRSV_BLOCKS=1: walk a whole 2048-column block in ONE single-CTA launch (trsv_block_*_kernel).  Measured on
+    // B200 it is SLOWER than one launch per 64-wide step (N = 8192: 5.13 vs 4.36 ms, N = 16 384: 11.4 vs 9.3 ms): the
+    // step kernels spread the update of the remaining rows over many CTAs, which outweighs their launch latency.
+    static int fused_env = -1;
+    if (fused_env < 0) {
+      const char* e = getenv("FVGP_TRSV_BLOCKS");
+      fused_env = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    const bool fused_blocks = fused_env == 1;
     for (int blk = 0; blk < nblocks; ++blk) {  // L z = b
       const int b0 = blk * VBLK, b1 = (int)std::min<int64_t>(n, b0 + VBLK);
       if (fused_blocks) {

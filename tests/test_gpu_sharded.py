@@ -36,8 +36,10 @@ def test_sharded_reports_non_positive_definite():
     from fvgp_b200 import _lib as L
     from fvgp_b200 import sharded
     x, y, noise, theta = _problem(600)
-    x[300] = x[10]                                    # duplicate point, no noise -> singular
-    ev = sharded.ShardedDenseEvaluator(x, y, np.zeros(600), nb=128, grid=(1, 1))
+    x[300] = x[10]                                    # duplicate point ...
+    bad = np.zeros(600)
+    bad[300] = -1e-6                                  # ... and a slightly negative "noise" there: pivot 301 is < 0 whatever
+    ev = sharded.ShardedDenseEvaluator(x, y, bad, nb=128, grid=(1, 1))      # the rounding of the exact-zero Schur complement
     with pytest.raises(L.NonPositiveDefiniteError):
         ev.evaluate(0, theta[0], 1.0 / theta[1:], 1.0, np.full(600, y.mean()))
 
