@@ -1100,6 +1100,16 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
               oz_bytes / 1e9, oz_work ? "on" : cudaGetErrorString(me));
     }
   }
+  if (oz_work != nullptr) {
+    // The int8 GEMMs are persistent kernels that hold every SM until they finish: next to them the latency-bound panel
+    // path on the high-priority stream only runs in the gaps between kernels, and the factorisation time became a
+    // lottery (1.13 ... 3.8 s at N = 50 000 against 1.30 s on the DMMA pipe, profiles/r02/ozaki_step_probe.v7.log).
+    // With the INT8 updates everything is therefore issued on ONE stream: update, look-ahead column, panel -- no
+    // overlap, but the updates themselves are 1.4x faster.
+    cudaStreamDestroy(P);
+    P = S;
+    cp.st = S;
+  }
   auto panel = [&](int k) -> int {  // factor the diagonal block k, solve the blocks below it
     const int w = std::min(nb, rows_from(k));
     REC_OK(potrf_rec(cp, blk(k, k), ld, w, k * nb));
@@ -1147,7 +1157,7 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
     cudaEventDestroy(ev_trail[k]);
   }
   if (oz_work != nullptr) cudaFreeAsync(oz_work, S);
-  cudaStreamDestroy(P);
+  if (P != S) cudaStreamDestroy(P);
   return rc;
 }
 

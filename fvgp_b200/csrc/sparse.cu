@@ -1377,10 +1377,11 @@ int fvgp_lanczos_tridiag(int64_t n, const int64_t* d_indptr, const int32_t* d_in
   cudaStream_t st = (cudaStream_t)stream;
   const long long* ip = (const long long*)d_indptr;
   int done = 0;
-  // One sweep over the matrix per Lanczos step costs about the same for 1 ... 16 probe columns (the SpMM is bound by
-  // streaming the matrix and by latency, not by the column count: 8 + 2 probes took the time of 4 + 1, r02 2-GPU
-  // run), so what counts is the NUMBER of batches: the remainder runs as ONE batch padded to the next power of two
-  // (the surplus columns are real probes of the stream that are simply not returned), e.g. 10 -> one batch of 16.
+  // Batch policy, from the B200 measurements at C4 (profiles/r02): one sweep over the matrix per Lanczos step costs
+  // about the same for 1 ... 8 probe columns (~0.7 ms: bound by streaming the matrix and by latency, not by the column
+  // count -- 8 + 2 probes took the time of 4 + 1), while the 16-column kernel is slower than two 8-column sweeps
+  // (1.8 vs 1.4 ms).  So: batches of at most 8, and a remainder runs as ONE batch padded to the next power of two
+  // (the surplus columns are later probes of the same stream that are not returned) instead of 4 + 2 + 1.
   // FVGP_SLQ_GREEDY=1 restores the greedy 16 / 8 / 4 / 2 / 1 split (A/B).
   static int greedy = -1;
   if (greedy < 0) {
@@ -1395,7 +1396,7 @@ int fvgp_lanczos_tridiag(int64_t n, const int64_t* d_indptr, const int32_t* d_in
       keep = nb;
     } else {
       nb = 1;
-      while (nb < left && nb < 16) nb *= 2;
+      while (nb < left && nb < 8) nb *= 2;
       keep = left < nb ? left : nb;
     }
     double* ha = h_alpha + (size_t)done * degree;

@@ -73,13 +73,14 @@ class GPprior:
             return self.kernel(x1, x2, hps, self.args)
         return self.kernel(x1, x2, hps)
 
-    def device_KV(self, hps, V):
+    def device_KV(self, hps, V, V_dev=None):
         """K(x_data, x_data; hps) + diag(V) on the device, ready to factor.
 
-        Returns ("dense", (buf, ld)) with the LOWER triangle filled, or ("sparse", DeviceCSR)."""
+        Returns ("dense", (buf, ld)) with the LOWER triangle filled, or ("sparse", DeviceCSR).  V_dev: the caller's
+        resident device copy of a vector V (saves the upload)."""
         x = self.x_data
         n = len(x)
-        Vd = L.to_dev(V) if (V is not None and np.ndim(V) == 1) else None
+        Vd = V_dev if V_dev is not None else (L.to_dev(V) if (V is not None and np.ndim(V) == 1) else None)
         res = self._call_kernel(x, x, np.asarray(hps, dtype=np.float64))
         xd = self.data.x_device() if self.data.Euclidean else None
         if isinstance(res, K.Radial):
