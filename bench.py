@@ -1081,7 +1081,7 @@ def main():
     ap.add_argument("--c3-points", type=int, default=20000)
     ap.add_argument("--c5-n", type=int, default=0)
     ap.add_argument("--no-c4", dest="with_c4", action="store_false", help="reference arm: skip the gp2Scale sub-record")
-    ap.add_argument("--budget", type=float, default=float(os.environ.get("FVGP_BENCH_BUDGET_S", "780")),
+    ap.add_argument("--budget", type=float, default=float(os.environ.get("FVGP_BENCH_BUDGET_S", "740")),
                     help="seconds after which optional sub-records are skipped")
     args = ap.parse_args()
     if args.workload == "c1":
@@ -1166,7 +1166,7 @@ def main():
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "last_lml": out[0], "last_grad": [float(g) for g in out[1]]}
     HOLD["line"] = line
-    start_watchdog(args.budget + 75.0, rank)
+    start_watchdog(args.budget + 60.0, rank)
 
     log(f"e2e region done: {t_e2e / args.steps:.3f} s per step")
     # ---- roofline of the dominant kernel (DMMA GEMM inside potrf + potri) ----------------------
