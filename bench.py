@@ -630,7 +630,7 @@ def sharded_dense_record(gp_factory, n, steps, warmup, with_grad, label):
            "gpu_launches_per_step": int(lib.fvgp_launch_count() - launches0) // steps,
            "constructor_seconds": t_ctor, "theta": [float(t) for t in th], "lml": lml,
            "grad": None if grad is None else [float(g) for g in grad],
-           "phase_seconds_last_step": getattr(E, "phase_seconds", None)}
+           "phase_seconds_last_step": E.phase_seconds() if hasattr(E, "phase_seconds") else None}
     return rec, gp
 
 

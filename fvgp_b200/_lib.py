@@ -39,6 +39,7 @@ _SIGNATURES = {
     "fvgp_chol_workspace_len": (c_int64, [c_int64]),
     "fvgp_potri_workspace_len": (c_int64, [c_int64]),
     "fvgp_potrf_lower": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
+    "fvgp_potrf_lower_enqueue": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "fvgp_potrs_work_len": (c_int64, [c_int64]),
     "fvgp_potrs_lower": (c_int, [_P, c_int64, c_int64, _P, _P, c_int, c_int64, _P, _P]),
     "fvgp_chol_logdet": (c_int, [_P, c_int64, c_int64, _P, POINTER(c_double), _P]),

@@ -1253,7 +1253,7 @@ int64_t fvgp_potri_workspace_len(int64_t n) {
   return h * h;
 }
 
-int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream) {
+static int potrf_lower_impl(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream, bool readback) {
   FVGP_REQUIRE(n > 0 && n < (1ll << 31) && lda >= n && lda % 2 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   Ctx c{st, d_tileinv, d_info, nullptr, 0};
@@ -1270,11 +1270,21 @@ int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int
   FVGP_CUDA_OK(cudaMemsetAsync(d_info, 0, sizeof(int), st));
   const int nb = potrf_block_width((int)n);
   int r = nb > 0 ? potrf_lookahead(c, d_A, lda, (int)n, nb) : potrf_rec(c, d_A, lda, (int)n, 0);
-  if (r != 0) return r;
+  if (r != 0 || !readback) return r;
   int info = 0;
   FVGP_CUDA_OK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
   FVGP_CUDA_OK(cudaStreamSynchronize(st));
   return info;
+}
+
+int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream) {
+  return potrf_lower_impl(d_A, n, lda, d_tileinv, d_info, stream, true);
+}
+
+// Same factorisation WITHOUT the host synchronisation: the status (0 or the 1-based failing pivot) stays in *d_info for
+// the caller to read when it next synchronises anyway (block-cyclic factorisation: one read for all panels).
+int fvgp_potrf_lower_enqueue(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream) {
+  return potrf_lower_impl(d_A, n, lda, d_tileinv, d_info, stream, false);
 }
 
 // Few right-hand sides: HBM-read bound (the lower triangle is read once per direction).  Blocks of VBLK

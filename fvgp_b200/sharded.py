@@ -132,6 +132,14 @@ class CudaLocalOps:
         return L.check(self.lib.fvgp_potrf_lower(L.ptr(A), n, self._ld(A), L.ptr(tileinv), L.ptr(info), L.stream_ptr()),
                        "fvgp_potrf_lower")
 
+    def potrf_enqueue(self, A, n, tileinv, info_slot):
+        """The same without a host synchronisation: the status is left in info_slot (1-element int32 device view)."""
+        L.check(self.lib.fvgp_potrf_lower_enqueue(L.ptr(A), n, self._ld(A), L.ptr(tileinv), L.ptr(info_slot),
+                                                  L.stream_ptr()), "fvgp_potrf_lower_enqueue")
+
+    def info_buffer(self, count):
+        return self.torch.zeros(count, dtype=self.torch.int32, device="cuda")
+
     def trsm_rlt(self, B, m, Lf, n, tileinv):
         L.check(self.lib.fvgp_trsm_right_lower_t(L.ptr(B), self._ld(B), m, L.ptr(Lf), self._ld(Lf), n, L.ptr(tileinv),
                                                  L.stream_ptr()), "fvgp_trsm_right_lower_t")
@@ -298,6 +306,7 @@ class ShardedSPD:
         self.panel = [ops.empty(maxm, nb) for _ in range(P)]          # the current block column, per process row
         self.diag = None                                              # replicated L_kk (nblk, nb, nb)
         self.diag_tinv = None
+        self.info_dev = None
         self.info = 0
         self.state = "empty"
 
@@ -372,9 +381,12 @@ class ShardedSPD:
         if comm.rank == owner:
             blk = self.block(k, k)
             D[:bk, :bk].copy_(blk)
-            st = ops.potrf(D, bk, T)
-            if st > 0:
-                info = k * nb + st
+            if self.info_dev is not None:                     # no host synchronisation per panel: flags read once at the end
+                ops.potrf_enqueue(D, bk, T, self.info_dev[k:k + 1])
+            else:
+                st = ops.potrf(D, bk, T)
+                if st > 0:
+                    info = k * nb + st
             blk.copy_(D[:bk, :bk])
         comm.broadcast(D, owner)
         comm.broadcast(T, owner)
@@ -421,6 +433,7 @@ class ShardedSPD:
             self.panel_b = [ops.empty(*t.shape) for t in self.panel]
         bufs = (self.panel, self.panel_b)
         ov = _Overlap(ops)
+        self.info_dev = ops.info_buffer(nblk) if hasattr(ops, "info_buffer") else None
         info_local = 0
         ov.fence_main_to_side()
         with ov.side():
@@ -437,6 +450,11 @@ class ShardedSPD:
             if st and not info_local:
                 info_local = st
             ov.fence_side_to_main()
+        if self.info_dev is not None:                         # first failing panel of this rank: ONE read for all panels
+            st = self.info_dev.cpu().numpy()
+            bad = np.nonzero(st)[0]
+            if bad.size:
+                info_local = int(bad[0]) * nb + int(st[bad[0]])
         flag = ops.zeros(1)
         flag[0] = float(info_local) if info_local else float("inf")
         if comm.world > 1:
@@ -555,15 +573,20 @@ class ShardedSPD:
         # the diagonal is still the original L there: steps j < k only touch columns J < j) -- one local GEMM per
         # owned block column, all ranks busy.  The loop keeps what is truly sequential: row-panel gather, panel
         # broadcast along the process row, accumulation into the columns to the left, M_kk times the block row.
+        # (A): L_kk and its tile inverses are replicated on every rank (solves, logdet), so the nblk independent diagonal
+        # inversions are dealt round-robin over ALL ranks -- with the owner doing each one and broadcasting it before the
+        # next started, this was a serial chain of nblk TRTRIs with every other rank waiting (0.2 s at C3 on 8 GPUs) --
+        # and the results are exchanged afterwards.
+        for k in range(nblk):
+            if comm.rank == k % comm.world:
+                ops.trtri(self.diag[k], lay.bsize(k), self.diag_tinv[k])
+                self.diag[k].tril_()
         for k in range(nblk):
             bk = lay.bsize(k)
-            owner = (k % lay.P) * lay.Q + (k % lay.Q)
             Dk = self.diag[k]
-            if comm.rank == owner:
-                ops.trtri(Dk, bk, self.diag_tinv[k])
-                Dk.tril_()
+            comm.broadcast(Dk, k % comm.world)
+            if comm.rank == (k % lay.P) * lay.Q + (k % lay.Q):
                 self.block(k, k).copy_(Dk[:bk, :bk])
-            comm.broadcast(Dk, owner)
         self.state = "inverting"                                     # self.diag no longer holds the factor
         for J in self.my_cols:
             bJ = lay.bsize(J)
@@ -767,14 +790,18 @@ class ShardedDenseEvaluator:
                 self.noise_dev = self.ops.upload(noise)
         A = self._matrix()
         centre = single.fill_centre(kind, inv_scale, length, self.bounds)
+        self._marks = [("start", self._event())]
         A.fill(kind, self.x_dev, self.x, amp, inv_scale, length, self.noise_dev, centre)
+        self._marks.append(("fill", self._event()))
         info = A.factor()
+        self._marks.append(("factor", self._event()))
         if info > 0:
             raise L.NonPositiveDefiniteError(info, self.n)
         ym = self.y - np.asarray(mean, dtype=np.float64).reshape(-1, 1)
         cols = []
         for c in range(ym.shape[1]):
             cols.append(A.solve(self.ops.upload(np.ascontiguousarray(ym[:, c]))))
+        self._marks.append(("solve", self._event()))
         alpha = np.stack([c.cpu().numpy() for c in cols], axis=1)
         logdet = A.logdet()
         r = ym.shape[1]
@@ -790,9 +817,38 @@ class ShardedDenseEvaluator:
         evaluate() -- or, with radial = (kind, amp, inv_scale, length), the traces against that descriptor's
         parameters; inverts the factored matrix in place on first use."""
         A = self._matrix()
+        marks = getattr(self, "_marks", None)
+        if marks is not None:
+            marks.append(("(host)", self._event()))
         if A.state == "factored":
             A.invert()
-        return A.grad_traces(None if theta is None else np.asarray(theta, dtype=np.float64), b_dev, radial=radial)
+        if marks is not None:
+            marks.append(("invert", self._event()))
+        out = A.grad_traces(None if theta is None else np.asarray(theta, dtype=np.float64), b_dev, radial=radial)
+        if marks is not None:
+            marks.append(("traces", self._event()))
+        return out
+
+    def _event(self):
+        """CUDA event on the current stream (None for the CPU ops of the gloo tests)."""
+        if getattr(self.ops, "device", "cpu") != "cuda":
+            return None
+        ev = self.ops.torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def phase_seconds(self):
+        """Device time of the phases of the LAST evaluation (+ gradient) on this rank, from CUDA events on the main
+        stream: {"fill", "factor", "solve", "invert", "traces"}; synchronises."""
+        marks = [m for m in getattr(self, "_marks", []) if m[1] is not None]
+        if len(marks) < 2:
+            return None
+        self.ops.torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            if name != "(host)":
+                out[name] = out.get(name, 0.0) + a.elapsed_time(b) * 1e-3
+        return out
 
     def solve(self, b):
         """KV^-1 b for host right-hand sides (N,) or (N, r) against the factor of the last evaluate()."""

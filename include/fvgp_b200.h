@@ -130,6 +130,9 @@ int64_t fvgp_potri_workspace_len(int64_t n); /* doubles: scratch panel of trtri 
  * triangle of d_A.  d_tileinv (fvgp_chol_workspace_len doubles) receives the inverses of the
  * 128x128 diagonal tiles (tile t at offset t*128*128) and must be passed unchanged to potrs / potri.  d_info: one int. */
 int fvgp_potrf_lower(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream);
+/* The same factorisation without the host synchronisation: the status stays in *d_info (0, or the 1-based failing
+ * pivot) for the caller to read later -- the block-cyclic factorisation reads all its panels' flags once at the end. */
+int fvgp_potrf_lower_enqueue(double* d_A, int64_t n, int64_t lda, double* d_tileinv, int* d_info, void* stream);
 
 /* calculate_Chol_solve (gp_lin_alg.py:289-328): solve (L L^T) X = B in place.  d_B holds
  * nrhs right-hand sides, each contiguous with stride ldb (i.e. B^T in C order).
