@@ -37,7 +37,7 @@ extern unsigned long long g_launches;
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   kernel<<<grid, block, smem, st>>>(std::forward<Args>(args)...);
-  ++g_launches;
+  __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);  // launches come from more than one host thread
 }
 
 constexpr int kMaxDim = 8;  // input-space dimensionality supported by the fused kernels

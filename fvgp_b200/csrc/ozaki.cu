@@ -70,7 +70,7 @@ static int i8_gemm(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, i
   if (Gemm::get_workspace_size(args) > ws_bytes) return FVGP_ERR_ARG;
   if (gemm.initialize(args, ws, st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
   if (gemm.run(st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
-  ++g_launches;
+  __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
   return 0;
 }
 

@@ -219,19 +219,64 @@ class GPkv:
         sol = np.empty_like(y_mean)
         cols = []
         solver = self._sparse_eval.pcg if shard is not None else ops.pcg      # row-sharded PCG over NCCL | one GPU
-        for c in range(r):
-            x0c = None if x0 is None else L.to_dev(np.ascontiguousarray(x0[:, c]))
-            x, info, iters, relres = solver(obj, self._dev_cached(("y_mean", c), y_mean[:, c]), x0=x0c, rtol=rtol,
-                                            maxiter=maxiter, precond=precond)
-            ev.info.setdefault("cg_iters", []).append(iters)
-            ev.info.setdefault("cg_relres", []).append(relres)
-            cols.append(x)
-            sol[:, c] = x.cpu().numpy()
+        # The solve and the stochastic log-determinant only READ the assembled matrix and are bound by different
+        # things (SpMV: HBM; the Lanczos SpMM: latency / L2 gathers), so on one GPU the log-determinant runs on a
+        # side stream from a helper thread (ctypes releases the GIL inside the C calls) while this thread runs the CG.
+        logdet_job = None
+        if want_logdet and shard is None and self._overlap_logdet():
+            logdet_job = self._start_logdet_job(obj, ev)
+        try:
+            for c in range(r):
+                x0c = None if x0 is None else L.to_dev(np.ascontiguousarray(x0[:, c]))
+                x, info, iters, relres = solver(obj, self._dev_cached(("y_mean", c), y_mean[:, c]), x0=x0c, rtol=rtol,
+                                                maxiter=maxiter, precond=precond)
+                ev.info.setdefault("cg_iters", []).append(iters)
+                ev.info.setdefault("cg_relres", []).append(relres)
+                cols.append(x)
+                sol[:, c] = x.cpu().numpy()
+        finally:
+            if logdet_job is not None:
+                ev.logdet = logdet_job()
         ev.alpha_dev = cols
         ev.KVinvY = sol
-        if want_logdet:
+        if want_logdet and logdet_job is None:
             ev.logdet = self._random_logdet(obj, ev, sharded=shard is not None)
         return ev
+
+    def _overlap_logdet(self):
+        import os
+        return os.environ.get("FVGP_SLQ_OVERLAP", "1") != "0" and not self.args.get("serial_logdet", False)
+
+    def _start_logdet_job(self, csr, ev):
+        """Run _random_logdet on a side stream in a helper thread; returns a function that joins it and hands back the
+        estimate (re-raising whatever the thread raised)."""
+        import threading
+        torch = L._torch()
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream()
+        side.wait_stream(main)                                  # the matrix is assembled on the main stream
+        box = {}
+        device = torch.cuda.current_device()
+
+        def work():
+            try:
+                torch.cuda.set_device(device)
+                with torch.cuda.stream(side):
+                    box["value"] = self._random_logdet(csr, ev)
+            except BaseException as e:                          # noqa: BLE001 -- handed to the caller's thread
+                box["error"] = e
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+
+        def join():
+            th.join()
+            main.wait_stream(side)
+            if "error" in box:
+                raise box["error"]
+            return box["value"]
+        return join
 
     # ---- multi-GPU gp2Scale (SURVEY 8e): CSR row slabs + SLQ probes over the ranks of torch.distributed -----------
     def _sparse_shard(self, hps, V):
@@ -517,6 +562,7 @@ class GPkv:
         state["_sharded_eval"] = state["_sharded_x"] = None
         state["_sparse_eval"] = None
         state["_dev_cache"] = {}
+        state["_side_stream"] = None
         return state
 
     def __setstate__(self, state):
