@@ -1126,10 +1126,22 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
     FVGP_CUDA_OK(cudaStreamWaitEvent(S, ev_panel[k], 0));
     if (k + 2 < nblk) {
       const int m2 = rows_from(k + 2);
-      if (oz_work != nullptr && m2 >= OZAKI_MIN_M)
-        rc = fvgp_ozaki_gemm_nt(blk(k + 2, k + 2), ld, blk(k + 2, k), ld, blk(k + 2, k), ld, m2, m2, nb, -1.0, 1, 0, 1, oz,
-                                OZAKI_NBLOCK, oz_work, oz_bytes, S);
-      else
+      bool done = false;
+      if (oz_work != nullptr && m2 >= OZAKI_MIN_M) {
+        // the INT8 path validates its arguments before it touches C: a refusal falls back to the DMMA update for good
+        const int orc = fvgp_ozaki_gemm_nt(blk(k + 2, k + 2), ld, blk(k + 2, k), ld, blk(k + 2, k), ld, m2, m2, nb, -1.0, 1, 0,
+                                           1, oz, OZAKI_NBLOCK, oz_work, oz_bytes, S);
+        done = orc == 0;
+        if (orc == -100) {  // failed after part of the block had been updated: not recoverable
+          rc = FVGP_ERR_CUDA;
+          break;
+        }
+        if (!done) {
+          fprintf(stderr, "[fvgp_b200] potrf: INT8-slice update refused (m = %d); continuing on the DMMA pipe\n", m2);
+          g_ozaki_slices = 0;
+        }
+      }
+      if (!done)
         rc = launch_gemm<false, false>(S, blk(k + 2, k), ld, blk(k + 2, k), ld, blk(k + 2, k + 2), ld, m2, m2, nb, -1.0, 1.0,
                                        GEMM_LOWER);
       if (rc != 0) break;

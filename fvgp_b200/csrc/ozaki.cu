@@ -146,6 +146,8 @@ extern "C" {
 
 int fvgp_ozaki_available(void) { return 1; }
 
+#define FVGP_OZAKI_PARTIAL (-100)  /* a GEMM failed after part of C had been updated: C is inconsistent */
+
 // scratch bytes for C (m x n) -= A (m x k) B^T (n x k) with S slices, processed in column blocks of `nblock`
 int64_t fvgp_ozaki_work_bytes(int64_t m, int64_t n, int64_t k, int slices, int64_t nblock) {
   const int64_t nb = nblock < n ? nblock : n;
@@ -193,6 +195,7 @@ int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda,
            (int8_t*)nullptr, b_rev, eb);
   }
   FVGP_LAUNCH_OK();
+  bool touched = false;  // has any entry of C been updated yet?  (a refusal before that leaves C intact)
   for (int64_t j0 = 0; j0 < n; j0 += nb) {
     const int64_t nj = (n - j0) < nb ? (n - j0) : nb;
     // rows that can touch this column block (lower: i + diag >= j0)
@@ -208,8 +211,9 @@ int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda,
       const int K = (int)((g - 1) * k);
       int rc = i8_gemm(a_fwd + i0 * rowbytes, rowbytes, b_rev + j0 * rowbytes + (int64_t)(S - g + 1) * k, rowbytes,
                        G + (int64_t)(S + 1 - g) * plane, ldg, (int)mi, (int)nj, K, ws, 8 << 20, st);
-      if (rc != 0) return rc;
+      if (rc != 0) return touched ? FVGP_OZAKI_PARTIAL : rc;
     }
+    touched = true;
     dim3 grid((unsigned)((nj + 255) / 256), (unsigned)((mi + 7) / 8));
     launch(oz_combine_kernel, grid, 256, 0, st, d_C + i0 * ldc + j0, (long long)ldc, (const int32_t*)G, (long long)ldg,
            (long long)plane, S, (long long)mi, (long long)nj, (const int*)(ea + i0), (const int*)(eb + j0), sign, lower,

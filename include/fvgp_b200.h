@@ -313,7 +313,9 @@ int fvgp_pcg_sharded(void* comm, int64_t n, const int64_t* h_row_offsets, const 
  * int8 GEMMs, FP64 recombination.  slices = 8: ~2^-47 relative to the row maxima, 36 integer MACs per FP64 MAC.
  * C (m x n, ldc) += sign * A (m x k, lda) B (n x k, ldb)^T, FP64 row-major; lower != 0 updates only the entries with
  * column <= row + diag; same_ab != 0: B is A (SYRK).  k % 16 == 0.  C is processed in column blocks of nblock.
- * fvgp_ozaki_available() = 0 when the library was built without the CuTe / CUTLASS headers. */
+ * fvgp_ozaki_available() = 0 when the library was built without the CuTe / CUTLASS headers.
+ * Returns 0; < 0 before any entry of C was touched (arguments / a GEMM the hardware path refuses: C is intact and the
+ * caller may fall back to fvgp_dgemm); -100 if a GEMM failed after part of C had been updated. */
 int fvgp_ozaki_available(void);
 /* 0: DMMA trailing updates in fvgp_potrf_lower (default); 6..10: INT8-slice updates with that many slices for updates
  * of at least 8192 rows (environment default: FVGP_OZAKI).  Returns the previous setting. */
