@@ -1088,6 +1088,22 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   int64_t oz_bytes = 0;
   if (oz) {
     oz_bytes = fvgp_ozaki_work_bytes(n - 2 * nb, n - 2 * nb, nb, oz, OZAKI_NBLOCK);
+    {
+      // The stream-ordered pool returns freed memory to the OS at the next synchronisation unless told otherwise; the
+      // 7.5 GB scratch then came back through the driver on every factorisation (0.3 ... 1.7 s each, the "lottery" of
+      // profiles/r02/ozaki_step_probe.v10.log).  Keep it in the pool.
+      static bool pool_set = false;
+      if (!pool_set) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long keep = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pool_set = true;
+      }
+    }
     const cudaError_t me = cudaMallocAsync(&oz_work, (size_t)oz_bytes, S);
     if (me != cudaSuccess) {
       cudaGetLastError();
@@ -1102,10 +1118,9 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   }
   if (oz_work != nullptr) {
     // The int8 GEMMs are persistent kernels that hold every SM until they finish: next to them the latency-bound panel
-    // path on the high-priority stream only runs in the gaps between kernels, and the factorisation time became a
-    // lottery (1.13 ... 3.8 s at N = 50 000 against 1.30 s on the DMMA pipe, profiles/r02/ozaki_step_probe.v7.log).
-    // With the INT8 updates everything is therefore issued on ONE stream: update, look-ahead column, panel -- no
-    // overlap, but the updates themselves are 1.4x faster.
+    // path on the high-priority stream only runs in the gaps between kernels.  With the INT8 updates everything is
+    // therefore issued on ONE stream: update, look-ahead column, panel -- no overlap, but a deterministic order, and the
+    // updates themselves are 1.4x faster.
     cudaStreamDestroy(P);
     P = S;
     cp.st = S;
