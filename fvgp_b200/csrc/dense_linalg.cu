@@ -1046,8 +1046,10 @@ constexpr int OZAKI_MIN_M = 8192;
 constexpr int64_t OZAKI_NBLOCK = 4096;
 static int ozaki_slices() {
   if (g_ozaki_slices < 0) {
+    // default ON with 8 slices (FVGP_OZAKI=0 switches it off): LML / gradient within 1.6e-12 / 2.7e-11 of the DMMA path
+    // and inside the 1e-8 oracle parity at N = 8000 / 16 000 / 50 000; POTRF at N = 50 000 1.305 -> 0.96 s
     const char* e = getenv("FVGP_OZAKI");
-    int v = e ? atoi(e) : 0;
+    int v = e ? atoi(e) : 8;
     if (v == 1) v = 8;
     g_ozaki_slices = (v >= 6 && v <= 10 && fvgp_ozaki_available()) ? v : 0;
   }
@@ -1083,7 +1085,13 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   cp.st = P;
   int rc = 0;
   // INT8-slice trailing updates: one scratch allocation for the largest update of this factorisation
-  const int oz = (nb % 16 == 0 && n - 2 * nb >= OZAKI_MIN_M) ? ozaki_slices() : 0;
+  // (measured with 2048-wide block columns only, i.e. N >= 40 000; smaller N stay on the DMMA pipe unless FVGP_OZAKI_ALL=1)
+  static int oz_all = -1;
+  if (oz_all < 0) {
+    const char* e = getenv("FVGP_OZAKI_ALL");
+    oz_all = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  const int oz = (nb % 16 == 0 && (nb >= 2048 || oz_all) && n - 2 * nb >= OZAKI_MIN_M) ? ozaki_slices() : 0;
   void* oz_work = nullptr;
   int64_t oz_bytes = 0;
   if (oz) {
@@ -1116,7 +1124,12 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
               oz_bytes / 1e9, oz_work ? "on" : cudaGetErrorString(me));
     }
   }
-  if (oz_work != nullptr) {
+  static int oz_streams = -1;  // FVGP_OZAKI_STREAMS=2: keep the panel path on its own stream next to the INT8 updates (A/B)
+  if (oz_streams < 0) {
+    const char* e = getenv("FVGP_OZAKI_STREAMS");
+    oz_streams = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  if (oz_work != nullptr && oz_streams == 1) {
     // The int8 GEMMs are persistent kernels that hold every SM until they finish: next to them the latency-bound panel
     // path on the high-priority stream only runs in the gaps between kernels.  With the INT8 updates everything is
     // therefore issued on ONE stream: update, look-ahead column, panel -- no overlap, but a deterministic order, and the
@@ -1199,8 +1212,11 @@ static int potrf_block_width(int n) {
     if (env > 0) env = std::max(BM, (env / BM) * BM);
   }
   if (env >= 0) return (env > 0 && n >= 4 * env) ? env : 0;
-  if (n >= 24576) return 2048;
-  if (n >= 6144) return 1024;
+  // round 2 sweep (profiles/r02/potrf_nb_sweep.v11.log, ms): N = 8192: recursion 18.2, nb 512 14.4, 1024 16.3, 2048 17.6;
+  // N = 12 288: 42.4 / 31.6 / 42.3 / 37.0;  N = 16 384: 73.2 / 62.6 / 61.0 / 72.3;  N = 24 576: 197.8 / 202.6 / 177.1 / 189.8
+  if (n >= 40000) return 2048;
+  if (n >= 14336) return 1024;
+  if (n >= 6144) return 512;
   return 0;
 }
 

@@ -38,40 +38,56 @@ using namespace cute;
 using LayoutA = cutlass::layout::RowMajor;     // A slices: M x K, K contiguous
 using LayoutB = cutlass::layout::ColumnMajor;  // B slices: N rows of K contiguous bytes = K x N column-major
 using LayoutC = cutlass::layout::RowMajor;
-using MmaTileShape = Shape<_128, _128, _128>;
-using ClusterShape = Shape<_1, _1, _1>;
+// Two tile configurations of the same collective: one SM per 128 x 128 x 128 tile, or a CTA pair (cta_group::2, cluster
+// 2 x 1) on a 256 x 128 x 128 tile.  FVGP_OZAKI_TILE=2 selects the pair.
+template <class MmaTileShape, class ClusterShape>
+struct I8Gemm {
+  // D (int32) = acc
+  using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTileShape, ClusterShape,
+      cutlass::epilogue::collective::EpilogueTileAuto, int32_t, int32_t, int32_t, LayoutC, 4, int32_t, LayoutC, 4,
+      cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
+  using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, int8_t, LayoutA, 16, int8_t, LayoutB, 16, int32_t, MmaTileShape,
+      ClusterShape,
+      cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
+      cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
+  using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
 
-// D (int32) = acc
-using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTileShape, ClusterShape,
-    cutlass::epilogue::collective::EpilogueTileAuto, int32_t, int32_t, int32_t, LayoutC, 4, int32_t, LayoutC, 4,
-    cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
-using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
-    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, int8_t, LayoutA, 16, int8_t, LayoutB, 16, int32_t, MmaTileShape,
-    ClusterShape,
-    cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
-    cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
-using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
-using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+  static int run(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* D, int64_t ldd, int m, int n, int K,
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
+    auto sa = cute::make_stride(lda, Int<1>{}, int64_t(0));
+    auto sb = cute::make_stride(ldb, Int<1>{}, int64_t(0));
+    auto sc = cute::make_stride(ldd, Int<1>{}, int64_t(0));
+    typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {m, n, K, 1}, {A, sa, B, sb},
+                                  {{1, 0}, D, sc, D, sc}};
+    Gemm gemm;
+    if (gemm.can_implement(args) != cutlass::Status::kSuccess) {
+      fprintf(stderr, "[fvgp_b200] ozaki: int8 GEMM %d x %d x %d cannot be implemented (alignment?)\n", m, n, K);
+      return FVGP_ERR_ARG;
+    }
+    if (Gemm::get_workspace_size(args) > ws_bytes) return FVGP_ERR_ARG;
+    if (gemm.initialize(args, ws, st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
+    if (gemm.run(st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
+    __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
+    return 0;
+  }
+};
+
+using I8Gemm1Sm = I8Gemm<Shape<_128, _128, _128>, Shape<_1, _1, _1>>;
+using I8Gemm2Sm = I8Gemm<Shape<_256, _128, _128>, Shape<_2, _1, _1>>;
 
 // D (m x n int32, ldd) = A (m x K int8, lda) B^T (n x K int8, ldb)
 static int i8_gemm(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* D, int64_t ldd, int m, int n, int K,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
-  auto sa = cute::make_stride(lda, Int<1>{}, int64_t(0));
-  auto sb = cute::make_stride(ldb, Int<1>{}, int64_t(0));
-  auto sc = cute::make_stride(ldd, Int<1>{}, int64_t(0));
-  typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {m, n, K, 1}, {A, sa, B, sb},
-                                {{1, 0}, D, sc, D, sc}};
-  Gemm gemm;
-  if (gemm.can_implement(args) != cutlass::Status::kSuccess) {
-    fprintf(stderr, "[fvgp_b200] ozaki: int8 GEMM %d x %d x %d cannot be implemented (alignment?)\n", m, n, K);
-    return FVGP_ERR_ARG;
+  static int tile = -1;
+  if (tile < 0) {
+    const char* e = getenv("FVGP_OZAKI_TILE");
+    tile = (e && atoi(e) == 2) ? 2 : 1;
   }
-  if (Gemm::get_workspace_size(args) > ws_bytes) return FVGP_ERR_ARG;
-  if (gemm.initialize(args, ws, st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
-  if (gemm.run(st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
-  __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
-  return 0;
+  if (tile == 2) return I8Gemm2Sm::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
+  return I8Gemm1Sm::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
 }
 
 constexpr int OZ_BITS = 6;

@@ -317,8 +317,9 @@ int fvgp_pcg_sharded(void* comm, int64_t n, const int64_t* h_row_offsets, const 
  * Returns 0; < 0 before any entry of C was touched (arguments / a GEMM the hardware path refuses: C is intact and the
  * caller may fall back to fvgp_dgemm); -100 if a GEMM failed after part of C had been updated. */
 int fvgp_ozaki_available(void);
-/* 0: DMMA trailing updates in fvgp_potrf_lower (default); 6..10: INT8-slice updates with that many slices for updates
- * of at least 8192 rows (environment default: FVGP_OZAKI).  Returns the previous setting. */
+/* 0: DMMA trailing updates in fvgp_potrf_lower; 6..10: INT8-slice updates with that many slices for updates of at
+ * least 8192 rows in factorisations with 2048-wide block columns (N >= 40 000).  Default 8 when the library was built
+ * with the CuTe / CUTLASS headers (FVGP_OZAKI=0 in the environment switches it off).  Returns the previous setting. */
 int fvgp_set_ozaki(int slices);
 int64_t fvgp_ozaki_work_bytes(int64_t m, int64_t n, int64_t k, int slices, int64_t nblock);
 int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, int64_t m,
