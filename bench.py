@@ -1077,6 +1077,7 @@ def main():
     ap.add_argument("--sharded", action="store_true", help="c4 only: shard CSR rows and SLQ probes over the ranks")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip parity / c4 / c1 / sharded sub-records")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-fresh-c4", action="store_true", help="skip the C4 measurement in a fresh subprocess")
     ap.add_argument("--parity-blocks", type=int, default=12, help="C4 blocks compared with the oracle inside bench.py "
                     "(the -m gpu suite compares 50)")
     ap.add_argument("--c4-n", type=int, default=1000000)
@@ -1302,6 +1303,20 @@ def main():
             guarded("c4", lambda: c4_record(args.c4_n, steps=max(5, min(args.steps, 10)), warmup=3), line)
         if deadline.allows(30):
             guarded("c1", lambda: c1_record(1000, 40, 20, 3), line)
+        if deadline.allows(90) and not args.no_fresh_c4:
+            # the same C4 workload in a fresh process of the same run: inside this process the step has been measured
+            # ~25 ms slower than standalone (host state after the dense phases and the host oracles); both are reported
+            def fresh_c4():
+                cmd = [sys.executable, os.path.abspath(__file__), "--workload", "c4", "--steps", "8", "--warmup", "3",
+                       "--size", str(args.c4_n)]
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=max(60.0, deadline.left()))
+                rows = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+                if not rows:
+                    raise RuntimeError("no JSON line from the C4 subprocess: " + out.stderr[-300:])
+                d = json.loads(rows[-1])
+                return {k: d.get(k) for k in ("value", "unit", "ms_per_step", "steps", "warmup", "last_lml", "log_likelihood_std",
+                                              "phases_seconds", "gpu_launches")}
+            guarded("c4_fresh_process", fresh_c4, line)
     if extras and world > 1:
         sh = sharded_section(args, deadline, rank, world)
         line["sharded"] = sh

@@ -582,6 +582,27 @@ __global__ void copy2d_kernel(double* dst, long long ldd, const double* src, lon
   for (int r = r0; r < min(r0 + 16, rows); ++r) dst[(long long)r * ldd + c] = src[(long long)r * lds + c];
 }
 
+// dst (cols x rows_pad, ldd) <- src (rows x cols, lds)^T, rows [rows, rows_pad) of the source read as zeros.  32 x 32
+// tiles through shared memory, both sides coalesced.
+__global__ void __launch_bounds__(256) transpose_pad_kernel(double* __restrict__ dst, long long ldd,
+                                                            const double* __restrict__ src, long long lds, int rows, int cols,
+                                                            int rows_pad) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < rows && c < cols) ? src[(long long)r * lds + c] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;  // dst row = source column
+    if (c < cols && r < rows_pad) dst[(long long)c * ldd + r] = tile[tx][ty + 8 * i];
+  }
+}
+
 // Zero the strict upper part inside every 128x128 diagonal block (the GEMM k-trims assume
 // triangular operands carry explicit zeros there).
 __global__ void zero_upper_diag_blocks_kernel(double* A, long long ld, int n, long long bstride) {
@@ -967,6 +988,9 @@ __global__ void __launch_bounds__(256) gemv_t_reduce_kernel(const double* __rest
 // ----------------------------------------------------------------------------------------------
 // Host-side recursion
 // ----------------------------------------------------------------------------------------------
+static int g_ozaki_lauum_min = 8192;      // smallest P11 (rows) whose SYRK update inside LAUUM goes through the INT8 path
+constexpr int64_t OZAKI_NBLOCK = 4096;     // column block of the INT8-slice GEMM's int32 planes
+
 struct Ctx {
   cudaStream_t st;
   double* dinv;        // per-64-tile inverses, tile t at dinv + t*4096
@@ -975,6 +999,10 @@ struct Ctx {
   int err;
   int batch = 1;       // > 1: every launch covers `batch` problems of identical shape (population evaluation) whose
   long long bstride = 0;  // buffers (matrix, tile inverses, scratch) sit `bstride` doubles apart; info is an int per problem
+  // INT8-slice SYRK inside LAUUM (fvgp_potri_lower): scratch for the transposed panel + the slices, 0 slices = off
+  int oz_slices = 0;
+  void* oz_work = nullptr;
+  long long oz_bytes = 0;
 };
 
 static inline int split(int n) {  // n > TS: first part is a multiple of 128, at least 128, less than n
@@ -1043,7 +1071,6 @@ static int potrf_rec(Ctx& c, double* A, long long ld, int n, int row0) {
 // fvgp_set_ozaki or the FVGP_OZAKI environment variable; used for trailing updates with at least OZAKI_MIN_M rows.
 static int g_ozaki_slices = -1;
 constexpr int OZAKI_MIN_M = 8192;
-constexpr int64_t OZAKI_NBLOCK = 4096;
 static int ozaki_slices() {
   if (g_ozaki_slices < 0) {
     // default ON with 8 slices (FVGP_OZAKI=0 switches it off): LML / gradient within 1.6e-12 / 2.7e-11 of the DMMA path
@@ -1124,16 +1151,16 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
               oz_bytes / 1e9, oz_work ? "on" : cudaGetErrorString(me));
     }
   }
-  static int oz_streams = -1;  // FVGP_OZAKI_STREAMS=2: keep the panel path on its own stream next to the INT8 updates (A/B)
+  // FVGP_OZAKI_STREAMS=1: issue everything on one stream.  Default 2 (panel path on its own high-priority stream next to
+  // the INT8 updates): N = 50 000 POTRF 836 vs 898 ms with the CTA-pair tile (profiles/r02/potrf_50k_ozaki_variants.v12.log).
+  static int oz_streams = -1;
   if (oz_streams < 0) {
     const char* e = getenv("FVGP_OZAKI_STREAMS");
-    oz_streams = (e && atoi(e) == 2) ? 2 : 1;
+    oz_streams = (e && atoi(e) == 1) ? 1 : 2;
   }
   if (oz_work != nullptr && oz_streams == 1) {
-    // The int8 GEMMs are persistent kernels that hold every SM until they finish: next to them the latency-bound panel
-    // path on the high-priority stream only runs in the gaps between kernels.  With the INT8 updates everything is
-    // therefore issued on ONE stream: update, look-ahead column, panel -- no overlap, but a deterministic order, and the
-    // updates themselves are 1.4x faster.
+    // one-stream order (A/B): update, look-ahead column, panel -- no overlap between the persistent int8 GEMMs and the
+    // latency-bound panel path
     cudaStreamDestroy(P);
     P = S;
     cp.st = S;
@@ -1247,7 +1274,27 @@ static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
   double* M22 = M21 + n1;
   REC_OK(lauum_rec(c, M, ld, n1));
   // P11 += M21^T M21
-  REC_OK((launch_gemm<true, true>(c.st, M21, ld, M21, ld, M, ld, n1, n1, n2, 1.0, 1.0, GEMM_LOWER, c.batch, c.bstride)));
+  bool syrk_done = false;
+  if (c.oz_slices > 0 && c.batch == 1 && n1 >= g_ozaki_lauum_min && n2 >= 1024) {
+    // INT8-slice path: the product is T T^T with T = M21^T (n1 x n2): transposed into scratch (k padded to 16 with zero
+    // columns), then the same SYRK as the POTRF trailing update.  No triangular operand here, so nothing is wasted.
+    const long long k16 = (n2 + 15) / 16 * 16;
+    const long long t_bytes = ((long long)n1 * k16 * (long long)sizeof(double) + 255) / 256 * 256;
+    const long long need = t_bytes + fvgp_ozaki_work_bytes(n1, n1, k16, c.oz_slices, OZAKI_NBLOCK);
+    if (need <= c.oz_bytes) {
+      double* T = (double*)c.oz_work;
+      launch(transpose_pad_kernel, dim3((n1 + 31) / 32, (unsigned)((k16 + 31) / 32)), 256, 0, c.st, T, k16, (const double*)M21, ld,
+             n2, n1, (int)k16);
+      FVGP_LAUNCH_OK();
+      const int orc = fvgp_ozaki_gemm_nt(M, ld, T, k16, T, k16, n1, n1, k16, 1.0, 1, 0, 1, c.oz_slices, OZAKI_NBLOCK,
+                                         (char*)c.oz_work + t_bytes, c.oz_bytes - t_bytes, c.st);
+      if (orc == -100) return FVGP_ERR_CUDA;
+      syrk_done = orc == 0;
+      if (!syrk_done) c.oz_slices = 0;  // refused before C was touched: DMMA from here on
+    }
+  }
+  if (!syrk_done)
+    REC_OK((launch_gemm<true, true>(c.st, M21, ld, M21, ld, M, ld, n1, n1, n2, 1.0, 1.0, GEMM_LOWER, c.batch, c.bstride)));
   // W = M22^T M21  (M22 lower: k >= row of the output)
   REC_OK((launch_gemm<true, true>(c.st, M22, ld, M21, ld, c.work, n1, n2, n1, n2, 1.0, 0.0, GEMM_KB_FROM_M, c.batch, c.bstride)));
   launch(copy2d_kernel, dim3((n1 + 255) / 256, (n2 + 15) / 16, c.batch), 256, 0, c.st, M21, ld, c.work, n1, n2, n1, c.bstride);
@@ -1460,7 +1507,35 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
   FVGP_LAUNCH_OK();
   int r = trtri_rec(c, d_L, lda, (int)n, 0);
   if (r != 0) return r;
-  return lauum_rec(c, d_L, lda, (int)n);
+  // INT8-slice SYRK updates inside LAUUM (P11 += M21^T M21, half of LAUUM's flops): FVGP_OZAKI_LAUUM=1, needs the same
+  // switch as the POTRF updates (fvgp_set_ozaki) and a top-level P11 of at least OZAKI_LAUUM_MIN rows.
+  static int lauum_oz = -1;
+  if (lauum_oz < 0) {
+    const char* e = getenv("FVGP_OZAKI_LAUUM");
+    lauum_oz = e ? atoi(e) : 0;
+    if (lauum_oz > 1) g_ozaki_lauum_min = lauum_oz;  // FVGP_OZAKI_LAUUM=<rows>: also sets the threshold (tests at smaller N)
+  }
+  const int n1_top = split((int)n);
+  if (lauum_oz > 0 && ozaki_slices() > 0 && n > TS && n1_top >= g_ozaki_lauum_min) {
+    const long long k16 = ((n - n1_top) + 15) / 16 * 16;
+    c.oz_bytes = ((long long)n1_top * k16 * (long long)sizeof(double) + 255) / 256 * 256 +
+                 fvgp_ozaki_work_bytes(n1_top, n1_top, k16, ozaki_slices(), OZAKI_NBLOCK) + 4096;
+    if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) == cudaSuccess) {
+      c.oz_slices = ozaki_slices();
+    } else {
+      cudaGetLastError();
+      c.oz_work = nullptr, c.oz_bytes = 0;
+    }
+    static bool told = false;
+    if (!told) {
+      told = true;
+      fprintf(stderr, "[fvgp_b200] potri n=%lld: INT8-slice SYRK updates inside LAUUM, scratch %.2f GB: %s\n", (long long)n,
+              c.oz_bytes / 1e9, c.oz_work ? "on" : "allocation failed, DMMA");
+    }
+  }
+  r = lauum_rec(c, d_L, lda, (int)n);
+  if (c.oz_work != nullptr) cudaFreeAsync(c.oz_work, st);
+  return r;
 }
 
 int fvgp_dgemm_nt(const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C, int64_t ldc, int m,

@@ -39,7 +39,8 @@ using LayoutA = cutlass::layout::RowMajor;     // A slices: M x K, K contiguous
 using LayoutB = cutlass::layout::ColumnMajor;  // B slices: N rows of K contiguous bytes = K x N column-major
 using LayoutC = cutlass::layout::RowMajor;
 // Two tile configurations of the same collective: one SM per 128 x 128 x 128 tile, or a CTA pair (cta_group::2, cluster
-// 2 x 1) on a 256 x 128 x 128 tile.  FVGP_OZAKI_TILE=2 selects the pair.
+// 2 x 1) on a 256 x 128 x 128 tile (default; SASS UTCIMMA.2CTA): 1.92 vs 1.68 PMAC/s on the 32768^2 x 2048 SYRK
+// (profiles/r02/ozaki_probe_tiles.v12.log).  FVGP_OZAKI_TILE=1 selects the single-SM tile.
 template <class MmaTileShape, class ClusterShape>
 struct I8Gemm {
   // D (int32) = acc
@@ -84,7 +85,7 @@ static int i8_gemm(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, i
   static int tile = -1;
   if (tile < 0) {
     const char* e = getenv("FVGP_OZAKI_TILE");
-    tile = (e && atoi(e) == 2) ? 2 : 1;
+    tile = (e && atoi(e) == 1) ? 1 : 2;
   }
   if (tile == 2) return I8Gemm2Sm::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
   return I8Gemm1Sm::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
