@@ -683,12 +683,26 @@ def sharded_section(args, deadline, rank, world):
         parallel.barrier()
         if 10.0 * n * n < 0.85 * 180e9 and deadline.allows(150):           # fits one GPU: agreement + strong-scaling baseline
             if rank == 0:
-                l1, g1, dt = single_gpu_check(lambda: fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise,
-                                                           args={"dense_sharded": False}), th)
+                from fvgp_b200 import _lib as L_
+                lib_ = L_.load()
+
+                def one():
+                    return fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise, args={"dense_sharded": False})
+                old = lib_.fvgp_set_ozaki(0)                                # the block-cyclic path is all-DMMA: same arithmetic
+                try:
+                    l1, g1, dt = single_gpu_check(one, th)
+                finally:
+                    lib_.fvgp_set_ozaki(old)
                 rec["single_gpu"] = {"seconds_per_step": dt, "lml": l1, "grad": [float(g) for g in g1],
+                                     "arithmetic": "DMMA only (fvgp_set_ozaki(0)), as on the block-cyclic path",
                                      "lml_rel_diff": abs(rec["lml"] / l1 - 1), "grad_rel_diff": relerr(rec["grad"], g1),
                                      "agree_1e-8": bool(abs(rec["lml"] / l1 - 1) <= 1e-8 and relerr(rec["grad"], g1) <= 1e-8)}
                 rec["strong_scaling_efficiency"] = dt / (world * rec["seconds_per_step"])
+                if old and deadline.left() > 120:                           # the single-GPU default (INT8-slice SYRK updates)
+                    l2, g2, dt2 = single_gpu_check(one, th)
+                    rec["single_gpu_default_int8"] = {"seconds_per_step": dt2, "lml_rel_diff": abs(rec["lml"] / l2 - 1),
+                                                      "grad_rel_diff": relerr(rec["grad"], g2),
+                                                      "strong_scaling_efficiency_vs_it": dt2 / (world * rec["seconds_per_step"])}
             parallel.barrier()
         return rec
     if deadline.allows(200):
@@ -1018,10 +1032,10 @@ def workload_config(args):
     return {"workload": f"C2: single-task GP, 3-D input, N={args.n}, anisotropic Matern-3/2 (default kernel), dense FP64 "
                         f"Cholesky, LML + hyperparameter gradient per step",
             "n": args.n, "dim": 3, "hyperparameters": 4, "parallelism": f"replicas x{args.gpus} (one theta proposal per GPU)",
-            "arithmetic": "IEEE FP64 throughout; for N >= 40 000 the trailing updates of the Cholesky factorisation run as "
-                          "error-free INT8-slice products (8 x 6-bit slices, exact int32 accumulation, FP64 recombination; "
-                          "FVGP_OZAKI=0 keeps them on the FP64 tensor pipe): LML / gradient within 2e-12 / 3e-11 of the pure "
-                          "FP64 path, oracle parity at N = 50 000 in `parity`",
+            "arithmetic": "IEEE FP64 throughout; for N >= 40 000 the SYRK updates of the Cholesky factorisation and of LAUUM run "
+                          "as error-free INT8-slice products (8 x 6-bit slices, exact int32 accumulation, FP64 recombination; "
+                          "FVGP_OZAKI=0 keeps everything on the FP64 tensor pipe): LML / gradient within 2e-12 / 6e-10 of the "
+                          "pure FP64 path (`int8_trailing_updates_ab`), oracle parity at N = 50 000 in `parity`",
             "l2_policy": f"inputs larger than L2: K is {8 * args.n ** 2 / 1e9:.1f} GB"}
 
 
@@ -1187,14 +1201,15 @@ def main():
         int8_on = bool(lib.fvgp_ozaki_available()) and n >= 40000 and os.environ.get("FVGP_OZAKI", "8") not in ("0",)
         line["roofline"] = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri",
                             "achieved": achieved, "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
-                            "dmma_kernel_only": {"what": "POTRI (TRTRI + LAUUM, 2 N^3 / 3 flop), every flop on the DMMA pipe",
-                                                 "achieved": potri_tflops, "frac": potri_tflops / pk.value},
+                            "potri": {"what": "TRTRI + LAUUM, 2 N^3 / 3 flop; on the DMMA pipe except (N >= 40 000) the SYRK half "
+                                              "of LAUUM (N^3 / 6), which runs as INT8-slice GEMMs: FP64-equivalent",
+                                      "achieved": potri_tflops, "frac": potri_tflops / pk.value},
                             "potrf": {"seconds": t_potrf, "achieved_fp64_equivalent": n ** 3 / 3.0 / t_potrf / 1e12,
                                       "int8_trailing_updates": int8_on,
                                       "note": "with the INT8-slice trailing updates (csrc/ozaki.cu, default for N >= 40 000) the "
                                               "N^3/3 flop of POTRF are FP64-EQUIVALENT: most of them run as int8 MMAs on the "
                                               "tcgen05 pipe, so `achieved` of the whole phase pair can approach or pass the DMMA "
-                                              "peak; `dmma_kernel_only` is the figure for the DMMA kernel alone"},
+                                              "peak; the all-DMMA figures are in `int8_trailing_updates_ab` (and in round 1's line)"},
                             "whole_step": {"achieved": step_tflops, "frac": step_tflops / pk.value,
                                            "note": "N^3 flop over ms_per_step (fill, solves, traces and host time included)"},
                             # dram__bytes_read.sum + dram__bytes_write.sum summed over every dgemm_mma_kernel launch of ONE
@@ -1245,8 +1260,8 @@ def main():
             gp.kv._memo = None
             on_lml, on_grad = gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
             old = lib.fvgp_set_ozaki(0)
-            rec = {"slices_default": int(old), "what": "trailing SYRK updates of the look-ahead POTRF (>= 8192 rows, N >= 40 000) as "
-                   "INT8-slice GEMMs on tcgen05 (kind::i8, TMEM) vs everything on the DMMA pipe (fvgp_set_ozaki(0))"}
+            rec = {"slices_default": int(old), "what": "SYRK updates of the look-ahead POTRF and of LAUUM (>= 8192 rows, N >= 40 000) "
+                   "as INT8-slice GEMMs on tcgen05 (kind::i8, TMEM) vs everything on the DMMA pipe (fvgp_set_ozaki(0))"}
             try:
                 ops.start_phase_timing()
                 torch.cuda.synchronize()
@@ -1257,6 +1272,8 @@ def main():
                 rec["dmma_seconds_per_step"] = (time.perf_counter() - t0) / 3
                 ph = ops.stop_phase_timing()
                 rec["dmma_potrf_seconds"] = ph.get("potrf", 0.0) / 3
+                rec["dmma_potri_seconds"] = ph.get("potri", 0.0) / 3
+                rec["int8_potri_seconds"] = phases.get("potri", 0.0) / args.steps
                 gp.kv._memo = None
                 lml, grad = gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
                 rec.update({"int8_seconds_per_step": t_dev / args.steps, "int8_potrf_seconds": phases.get("potrf", 0.0) / args.steps,

@@ -1507,16 +1507,19 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
   FVGP_LAUNCH_OK();
   int r = trtri_rec(c, d_L, lda, (int)n, 0);
   if (r != 0) return r;
-  // INT8-slice SYRK updates inside LAUUM (P11 += M21^T M21, half of LAUUM's flops): FVGP_OZAKI_LAUUM=1, needs the same
-  // switch as the POTRF updates (fvgp_set_ozaki) and a top-level P11 of at least OZAKI_LAUUM_MIN rows.
+  // INT8-slice SYRK updates inside LAUUM (P11 += M21^T M21, half of LAUUM's flops), under the same switch as the POTRF
+  // updates (fvgp_set_ozaki) and, like them, by default for N >= 40 000: POTRI at N = 50 000 2.479 -> 2.29 s, gradient
+  // within 5.7e-10 of the DMMA path (LML unaffected), oracle parity at N = 16 000 with the threshold lowered
+  // (profiles/r02/ozaki_lauum_step_probe.v13.log).  FVGP_OZAKI_LAUUM=0 switches it off, =<rows> sets the smallest P11
+  // and lifts the N >= 40 000 gate (tests at smaller N).
   static int lauum_oz = -1;
   if (lauum_oz < 0) {
     const char* e = getenv("FVGP_OZAKI_LAUUM");
-    lauum_oz = e ? atoi(e) : 0;
-    if (lauum_oz > 1) g_ozaki_lauum_min = lauum_oz;  // FVGP_OZAKI_LAUUM=<rows>: also sets the threshold (tests at smaller N)
+    lauum_oz = e ? atoi(e) : 1;
+    if (lauum_oz > 1) g_ozaki_lauum_min = lauum_oz;
   }
   const int n1_top = split((int)n);
-  if (lauum_oz > 0 && ozaki_slices() > 0 && n > TS && n1_top >= g_ozaki_lauum_min) {
+  if (lauum_oz > 0 && (n >= 40000 || lauum_oz > 1) && ozaki_slices() > 0 && n > TS && n1_top >= g_ozaki_lauum_min) {
     const long long k16 = ((n - n1_top) + 15) / 16 * 16;
     c.oz_bytes = ((long long)n1_top * k16 * (long long)sizeof(double) + 255) / 256 * 256 +
                  fvgp_ozaki_work_bytes(n1_top, n1_top, k16, ozaki_slices(), OZAKI_NBLOCK) + 4096;
