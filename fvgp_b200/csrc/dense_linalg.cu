@@ -584,16 +584,18 @@ __global__ void copy2d_kernel(double* dst, long long ldd, const double* src, lon
 
 // dst (cols x rows_pad, ldd) <- src (rows x cols, lds)^T, rows [rows, rows_pad) of the source read as zeros.  32 x 32
 // tiles through shared memory, both sides coalesced.
+// lower != 0: only the lower triangle of the (square) source is read (r >= c), everything above it counts as zero --
+// the strict upper triangle of the factor / inverse buffer is never written and holds garbage.
 __global__ void __launch_bounds__(256) transpose_pad_kernel(double* __restrict__ dst, long long ldd,
                                                             const double* __restrict__ src, long long lds, int rows, int cols,
-                                                            int rows_pad) {
+                                                            int rows_pad, int lower) {
   __shared__ double tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + ty + 8 * i, c = c0 + tx;
-    tile[ty + 8 * i][tx] = (r < rows && c < cols) ? src[(long long)r * lds + c] : 0.0;
+    tile[ty + 8 * i][tx] = (r < rows && c < cols && (!lower || r >= c)) ? src[(long long)r * lds + c] : 0.0;
   }
   __syncthreads();
 #pragma unroll
@@ -601,6 +603,17 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(double* __restrict__
     const int c = c0 + ty + 8 * i, r = r0 + tx;  // dst row = source column
     if (c < cols && r < rows_pad) dst[(long long)c * ldd + r] = tile[tx][ty + 8 * i];
   }
+}
+
+// dst (rows x cols, ldd) <- src rows [row0, row0 + rows) of a lower-triangular matrix, columns [0, cols): entries right
+// of the diagonal (c > row0 + r) are written as zeros instead of being read.
+__global__ void __launch_bounds__(256) copy_lower_rows_kernel(double* __restrict__ dst, long long ldd,
+                                                              const double* __restrict__ src, long long lds, int rows, int cols,
+                                                              int row0) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * 16;
+  if (c >= cols) return;
+  for (int r = r0; r < min(r0 + 16, rows); ++r) dst[(long long)r * ldd + c] = (c <= row0 + r) ? src[(long long)r * lds + c] : 0.0;
 }
 
 // Zero the strict upper part inside every 128x128 diagonal block (the GEMM k-trims assume
@@ -1003,6 +1016,7 @@ struct Ctx {
   int oz_slices = 0;
   void* oz_work = nullptr;
   long long oz_bytes = 0;
+  int oz_tri = 0;      // > 0: also the products with a triangular operand, contraction range cut into this many chunks
 };
 
 static inline int split(int n) {  // n > TS: first part is a multiple of 128, at least 128, less than n
@@ -1081,6 +1095,17 @@ static int ozaki_slices() {
     g_ozaki_slices = (v >= 6 && v <= 10 && fvgp_ozaki_available()) ? v : 0;
   }
   return g_ozaki_slices;
+}
+
+// Chunk count of the INT8-slice products with a triangular operand inside POTRI (0 = those stay on DMMA).
+static int g_ozaki_tri = -1;
+static int ozaki_tri_chunks() {
+  if (g_ozaki_tri < 0) {
+    const char* e = getenv("FVGP_OZAKI_TRI");
+    const int v = e ? atoi(e) : 0;
+    g_ozaki_tri = v < 0 ? 0 : (v > 16 ? 16 : v);
+  }
+  return g_ozaki_tri;
 }
 
 // Right-looking blocked Cholesky with one step of look-ahead on two streams.
@@ -1248,6 +1273,79 @@ static int potrf_block_width(int n) {
 }
 
 // L -> L^-1 in place (lower).  Needs explicit zeros above the diagonal inside diagonal blocks.
+// ---- INT8-slice versions of the POTRI products that have a TRIANGULAR operand (csrc/ozaki.cu; opt-in, Ctx::oz_tri).
+// A full-K int8 GEMM would do twice the useful work, so the output is cut into `chunks` blocks along the triangular
+// operand and every block only multiplies the part of the contraction range that operand reaches (waste (c+1)/(2c)
+// instead of 1/2 ... i.e. 25 % extra at 4 chunks).  All products are brought into the NT form of fvgp_ozaki_gemm_nt by
+// transposing the triangular operand into scratch with its never-written upper triangle masked to zero.
+// Return 0 = done, 1 = refused before anything was modified (caller falls back to the DMMA products), < 0 = error.
+static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
+
+static int oz_chunk(int n, int chunks) {
+  int cb = ((n + chunks - 1) / chunks + BM - 1) / BM * BM;
+  return cb < BM ? BM : cb;
+}
+
+// TRTRI: L21 <- -M22 L21 M11 (M11 = L[0:n1,0:n1], M22 already inverted in place, both lower).
+static int trtri_products_int8(Ctx& c, double* L, long long ld, int n1, int n2) {
+  double* L21 = L + (long long)n1 * ld;
+  double* L22 = L21 + n1;
+  const int cb1 = oz_chunk(n1, c.oz_tri), cb2 = oz_chunk(n2, c.oz_tri);
+  const long long bt_bytes = align256((long long)n1 * n1 * 8), ab_bytes = align256((long long)cb2 * n2 * 8);
+  const long long head = bt_bytes > ab_bytes ? bt_bytes : ab_bytes;
+  const long long need = head + fvgp_ozaki_work_bytes(cb1 > cb2 ? cb1 : cb2, n1 > n2 ? n1 : n2, n1 > n2 ? n1 : n2, c.oz_slices,
+                                                       OZAKI_NBLOCK);
+  if (need > c.oz_bytes || n2 % 16 != 0) return 1;
+  double* Bt = (double*)c.oz_work;  // Bt[j][k] = M11[k][j] for k >= j, 0 otherwise
+  void* ow = (char*)c.oz_work + head;
+  const long long ob = c.oz_bytes - head;
+  double* Wt = c.work;  // n1 x n2: Wt = M11^T L21^T
+  launch(transpose_pad_kernel, dim3((n1 + 31) / 32, (n1 + 31) / 32), 256, 0, c.st, Bt, (long long)n1, (const double*)L, ld, n1, n1,
+         n1, 1);
+  FVGP_LAUNCH_OK();
+  FVGP_CUDA_OK(cudaMemsetAsync(Wt, 0, (size_t)n1 * n2 * sizeof(double), c.st));
+  for (int jb = 0; jb < n1; jb += cb1) {  // rows [jb, je) of Wt only see k >= jb
+    const int je = std::min(jb + cb1, n1);
+    const int rc = fvgp_ozaki_gemm_nt(Wt + (long long)jb * n2, n2, Bt + (long long)jb * n1 + jb, n1, L21 + jb, ld, je - jb, n2,
+                                      n1 - jb, 1.0, 0, 0, 0, c.oz_slices, OZAKI_NBLOCK, ow, ob, c.st);
+    if (rc != 0) return (jb == 0 && rc != -100) ? 1 : FVGP_ERR_CUDA;  // only scratch was written so far
+  }
+  // L21 <- -M22 Wt^T: row block [ib, ie) only sees k < ie; the block of M22 goes through a zero-masked copy
+  double* Ab = (double*)c.oz_work;
+  FVGP_CUDA_OK(cudaMemset2DAsync(L21, ld * sizeof(double), 0, (size_t)n1 * sizeof(double), n2, c.st));
+  for (int ib = 0; ib < n2; ib += cb2) {
+    const int ie = std::min(ib + cb2, n2);
+    launch(copy_lower_rows_kernel, dim3((ie + 255) / 256, (ie - ib + 15) / 16), 256, 0, c.st, Ab, (long long)ie,
+           (const double*)(L22 + (long long)ib * ld), ld, ie - ib, ie, ib);
+    FVGP_LAUNCH_OK();
+    const int rc = fvgp_ozaki_gemm_nt(L21 + (long long)ib * ld, ld, Ab, ie, Wt, n2, ie - ib, n1, ie, -1.0, 0, 0, 0, c.oz_slices,
+                                      OZAKI_NBLOCK, ow, ob, c.st);
+    if (rc != 0) return FVGP_ERR_CUDA;  // L21 has been overwritten: no way back
+  }
+  return 0;
+}
+
+// LAUUM: W = M22^T M21 (n2 x n1) into c.work, given T = M21^T (n1 x k16, zero-padded) already in scratch at `T`.
+static int lauum_w_int8(Ctx& c, const double* M22, long long ld, int n1, int n2, const double* T, long long k16, void* free_work,
+                        long long free_bytes) {
+  const int cb = oz_chunk(n2, c.oz_tri);
+  const long long u_bytes = align256((long long)n2 * n2 * 8);
+  if (u_bytes + fvgp_ozaki_work_bytes(cb, n1, n2, c.oz_slices, OZAKI_NBLOCK) > free_bytes || n2 % 16 != 0) return 1;
+  double* U = (double*)free_work;  // U[i][k] = M22[k][i] for k >= i, 0 otherwise
+  void* ow = (char*)free_work + u_bytes;
+  const long long ob = free_bytes - u_bytes;
+  launch(transpose_pad_kernel, dim3((n2 + 31) / 32, (n2 + 31) / 32), 256, 0, c.st, U, (long long)n2, M22, ld, n2, n2, n2, 1);
+  FVGP_LAUNCH_OK();
+  FVGP_CUDA_OK(cudaMemsetAsync(c.work, 0, (size_t)n2 * n1 * sizeof(double), c.st));
+  for (int ib = 0; ib < n2; ib += cb) {  // rows [ib, ie) of W only see k >= ib
+    const int ie = std::min(ib + cb, n2);
+    const int rc = fvgp_ozaki_gemm_nt(c.work + (long long)ib * n1, n1, U + (long long)ib * n2 + ib, n2, T + ib, k16, ie - ib, n1,
+                                      n2 - ib, 1.0, 0, 0, 0, c.oz_slices, OZAKI_NBLOCK, ow, ob, c.st);
+    if (rc != 0) return (ib == 0 && rc != -100) ? 1 : FVGP_ERR_CUDA;
+  }
+  return 0;
+}
+
 static int trtri_rec(Ctx& c, double* L, long long ld, int n, int row0) {
   if (n <= TS) {
     const double* tile = c.dinv + (long long)(row0 / TS) * TS * TS;
@@ -1260,6 +1358,10 @@ static int trtri_rec(Ctx& c, double* L, long long ld, int n, int row0) {
   double* L22 = L21 + n1;
   REC_OK(trtri_rec(c, L, ld, n1, row0));
   REC_OK(trtri_rec(c, L22, ld, n2, row0 + n1));
+  if (c.oz_tri > 0 && c.oz_slices > 0 && c.batch == 1 && n1 >= g_ozaki_lauum_min && n2 >= g_ozaki_lauum_min / 2) {
+    const int rc = trtri_products_int8(c, L, ld, n1, n2);
+    if (rc <= 0) return rc;  // done, or failed for good; 1 = refused untouched: DMMA products below
+  }
   // W = L21 * M11   (M11 lower: k >= column)
   REC_OK((launch_gemm<false, true>(c.st, L21, ld, L, ld, c.work, n1, n2, n1, n1, 1.0, 0.0, GEMM_KB_FROM_N, c.batch, c.bstride)));
   // L21 = -M22 * W  (M22 lower: k <= row)
@@ -1274,7 +1376,7 @@ static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
   double* M22 = M21 + n1;
   REC_OK(lauum_rec(c, M, ld, n1));
   // P11 += M21^T M21
-  bool syrk_done = false;
+  bool syrk_done = false, w_done = false;
   if (c.oz_slices > 0 && c.batch == 1 && n1 >= g_ozaki_lauum_min && n2 >= 1024) {
     // INT8-slice path: the product is T T^T with T = M21^T (n1 x n2): transposed into scratch (k padded to 16 with zero
     // columns), then the same SYRK as the POTRF trailing update.  No triangular operand here, so nothing is wasted.
@@ -1284,19 +1386,26 @@ static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
     if (need <= c.oz_bytes) {
       double* T = (double*)c.oz_work;
       launch(transpose_pad_kernel, dim3((n1 + 31) / 32, (unsigned)((k16 + 31) / 32)), 256, 0, c.st, T, k16, (const double*)M21, ld,
-             n2, n1, (int)k16);
+             n2, n1, (int)k16, 0);
       FVGP_LAUNCH_OK();
       const int orc = fvgp_ozaki_gemm_nt(M, ld, T, k16, T, k16, n1, n1, k16, 1.0, 1, 0, 1, c.oz_slices, OZAKI_NBLOCK,
                                          (char*)c.oz_work + t_bytes, c.oz_bytes - t_bytes, c.st);
       if (orc == -100) return FVGP_ERR_CUDA;
       syrk_done = orc == 0;
-      if (!syrk_done) c.oz_slices = 0;  // refused before C was touched: DMMA from here on
+      if (!syrk_done) {
+        c.oz_slices = 0;  // refused before C was touched: DMMA from here on
+      } else if (c.oz_tri > 0 && n2 >= g_ozaki_lauum_min / 2) {
+        const int wrc = lauum_w_int8(c, M22, ld, n1, n2, T, k16, (char*)c.oz_work + t_bytes, c.oz_bytes - t_bytes);
+        if (wrc < 0) return wrc;
+        w_done = wrc == 0;
+      }
     }
   }
   if (!syrk_done)
     REC_OK((launch_gemm<true, true>(c.st, M21, ld, M21, ld, M, ld, n1, n1, n2, 1.0, 1.0, GEMM_LOWER, c.batch, c.bstride)));
   // W = M22^T M21  (M22 lower: k >= row of the output)
-  REC_OK((launch_gemm<true, true>(c.st, M22, ld, M21, ld, c.work, n1, n2, n1, n2, 1.0, 0.0, GEMM_KB_FROM_M, c.batch, c.bstride)));
+  if (!w_done)
+    REC_OK((launch_gemm<true, true>(c.st, M22, ld, M21, ld, c.work, n1, n2, n1, n2, 1.0, 0.0, GEMM_KB_FROM_M, c.batch, c.bstride)));
   launch(copy2d_kernel, dim3((n1 + 255) / 256, (n2 + 15) / 16, c.batch), 256, 0, c.st, M21, ld, c.work, n1, n2, n1, c.bstride);
   FVGP_LAUNCH_OK();
   return lauum_rec(c, M22, ld, n2);
@@ -1329,6 +1438,12 @@ int fvgp_version(void) { return 100; }
 int fvgp_set_ozaki(int slices) {
   const int old = ozaki_slices();
   g_ozaki_slices = (slices >= 6 && slices <= 10 && fvgp_ozaki_available()) ? slices : 0;
+  return old;
+}
+
+int fvgp_set_ozaki_tri(int chunks) {
+  const int old = ozaki_tri_chunks();
+  g_ozaki_tri = chunks < 0 ? 0 : (chunks > 16 ? 16 : chunks);
   return old;
 }
 
@@ -1505,36 +1620,51 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
   Ctx c{st, const_cast<double*>(d_tileinv), nullptr, d_work, 0};
   launch(zero_upper_diag_blocks_kernel, (unsigned)((n + BM - 1) / BM), 256, 0, st, d_L, lda, (int)n, 0ll);
   FVGP_LAUNCH_OK();
-  int r = trtri_rec(c, d_L, lda, (int)n, 0);
-  if (r != 0) return r;
   // INT8-slice SYRK updates inside LAUUM (P11 += M21^T M21, half of LAUUM's flops), under the same switch as the POTRF
   // updates (fvgp_set_ozaki) and, like them, by default for N >= 40 000: POTRI at N = 50 000 2.479 -> 2.29 s, gradient
   // within 5.7e-10 of the DMMA path (LML unaffected), oracle parity at N = 16 000 with the threshold lowered
   // (profiles/r02/ozaki_lauum_step_probe.v13.log).  FVGP_OZAKI_LAUUM=0 switches it off, =<rows> sets the smallest P11
-  // and lifts the N >= 40 000 gate (tests at smaller N).
+  // and lifts the N >= 40 000 gate (tests at smaller N).  FVGP_OZAKI_TRI=<chunks> (fvgp_set_ozaki_tri) additionally
+  // sends the products with a triangular operand (both TRTRI products, W = M22^T M21 of LAUUM) through chunked INT8
+  // GEMMs: trtri_products_int8 / lauum_w_int8 above.
   static int lauum_oz = -1;
   if (lauum_oz < 0) {
     const char* e = getenv("FVGP_OZAKI_LAUUM");
     lauum_oz = e ? atoi(e) : 1;
     if (lauum_oz > 1) g_ozaki_lauum_min = lauum_oz;
   }
-  const int n1_top = split((int)n);
+  const int n1_top = split((int)n), n2_top = (int)n - n1_top;
   if (lauum_oz > 0 && (n >= 40000 || lauum_oz > 1) && ozaki_slices() > 0 && n > TS && n1_top >= g_ozaki_lauum_min) {
-    const long long k16 = ((n - n1_top) + 15) / 16 * 16;
-    c.oz_bytes = ((long long)n1_top * k16 * (long long)sizeof(double) + 255) / 256 * 256 +
-                 fvgp_ozaki_work_bytes(n1_top, n1_top, k16, ozaki_slices(), OZAKI_NBLOCK) + 4096;
+    const int S = ozaki_slices(), tri = ozaki_tri_chunks();
+    const long long k16 = (n2_top + 15) / 16 * 16;
+    const long long t_bytes = align256((long long)n1_top * k16 * 8);
+    c.oz_bytes = t_bytes + fvgp_ozaki_work_bytes(n1_top, n1_top, k16, S, OZAKI_NBLOCK);
+    if (tri > 0) {
+      const int cb1 = oz_chunk(n1_top, tri), cb2 = oz_chunk(n2_top, tri), cbm = std::max(cb1, cb2), nm = std::max(n1_top, n2_top);
+      const long long trtri_need = std::max(align256((long long)n1_top * n1_top * 8), align256((long long)cb2 * n2_top * 8)) +
+                                   fvgp_ozaki_work_bytes(cbm, nm, nm, S, OZAKI_NBLOCK);
+      const long long w_need = t_bytes + align256((long long)n2_top * n2_top * 8) + fvgp_ozaki_work_bytes(cb2, n1_top, n2_top, S, OZAKI_NBLOCK);
+      c.oz_bytes = std::max(c.oz_bytes, std::max(trtri_need, w_need));
+    }
+    c.oz_bytes += 4096;
     if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) == cudaSuccess) {
-      c.oz_slices = ozaki_slices();
+      c.oz_slices = S;
+      c.oz_tri = tri;
     } else {
       cudaGetLastError();
       c.oz_work = nullptr, c.oz_bytes = 0;
     }
-    static bool told = false;
-    if (!told) {
-      told = true;
-      fprintf(stderr, "[fvgp_b200] potri n=%lld: INT8-slice SYRK updates inside LAUUM, scratch %.2f GB: %s\n", (long long)n,
-              c.oz_bytes / 1e9, c.oz_work ? "on" : "allocation failed, DMMA");
+    static int told = -1;
+    if (told != tri) {
+      told = tri;
+      fprintf(stderr, "[fvgp_b200] potri n=%lld: INT8-slice SYRK updates inside LAUUM%s, scratch %.2f GB: %s\n", (long long)n,
+              tri > 0 ? " + chunked triangular products" : "", c.oz_bytes / 1e9, c.oz_work ? "on" : "allocation failed, DMMA");
     }
+  }
+  int r = trtri_rec(c, d_L, lda, (int)n, 0);
+  if (r != 0) {
+    if (c.oz_work != nullptr) cudaFreeAsync(c.oz_work, st);
+    return r;
   }
   r = lauum_rec(c, d_L, lda, (int)n);
   if (c.oz_work != nullptr) cudaFreeAsync(c.oz_work, st);

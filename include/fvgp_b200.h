@@ -321,6 +321,11 @@ int fvgp_ozaki_available(void);
  * least 8192 rows in factorisations with 2048-wide block columns (N >= 40 000).  Default 8 when the library was built
  * with the CuTe / CUTLASS headers (FVGP_OZAKI=0 in the environment switches it off).  Returns the previous setting. */
 int fvgp_set_ozaki(int slices);
+/* 0 (default): inside fvgp_potri_lower only the SYRK half of LAUUM uses the INT8-slice path; c > 0: also the products
+ * with a triangular operand (both TRTRI products and W = M22^T M21 of LAUUM, see SURVEY.md 8 a7: np.linalg.inv of the
+ * gradient path), with the contraction range cut into c chunks so that an int8 GEMM only multiplies the part the
+ * triangle reaches.  FVGP_OZAKI_TRI in the environment sets the start value.  Returns the previous setting. */
+int fvgp_set_ozaki_tri(int chunks);
 int64_t fvgp_ozaki_work_bytes(int64_t m, int64_t n, int64_t k, int slices, int64_t nblock);
 int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, int64_t m,
                        int64_t n, int64_t k, double sign, int lower, int64_t diag, int same_ab, int slices, int64_t nblock,
