@@ -89,6 +89,8 @@ _SIGNATURES = {
     "fvgp_ozaki_available": (c_int, []),
     "fvgp_set_ozaki": (c_int, [c_int]),
     "fvgp_set_ozaki_tri": (c_int, [c_int]),
+    "fvgp_set_ozaki_gate": (c_int, [c_int, c_int]),
+    "fvgp_ozaki_i8_seconds": (c_double, [c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "fvgp_ozaki_work_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int, c_int64]),
     "fvgp_ozaki_gemm_nt": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_double, c_int, c_int64,
                                    c_int, c_int, c_int64, _P, c_int64, _P]),

@@ -1001,6 +1001,8 @@ __global__ void __launch_bounds__(256) gemv_t_reduce_kernel(const double* __rest
 // ----------------------------------------------------------------------------------------------
 // Host-side recursion
 // ----------------------------------------------------------------------------------------------
+static int g_ozaki_all = -1;               // 1: INT8-slice POTRF updates also with block columns narrower than 2048 (N < 40 000)
+static int g_ozaki_potri_min_n = 40000;   // smallest N whose POTRI uses the INT8-slice path at all (fvgp_set_ozaki_gate)
 static int g_ozaki_lauum_min = 8192;      // smallest P11 (rows) whose SYRK update inside LAUUM goes through the INT8 path
 constexpr int64_t OZAKI_NBLOCK = 4096;     // column block of the INT8-slice GEMM's int32 planes
 
@@ -1097,13 +1099,15 @@ static int ozaki_slices() {
   return g_ozaki_slices;
 }
 
-// Chunk count of the INT8-slice products with a triangular operand inside POTRI (0 = those stay on DMMA).
+// Chunk count of the INT8-slice products with a triangular operand inside POTRI (0 = those stay on DMMA).  Default 8:
+// POTRI at N = 50 000 2.30 s (SYRK half only) -> 1.97 (4 chunks) / 1.67 (8) / 1.73 (12) / 1.76 (16) / 1.87 s (24),
+// gradient within 7e-10 of the all-DMMA path at every setting (profiles/r02/ozaki_tri_probe.v15.log, .v16.log).
 static int g_ozaki_tri = -1;
 static int ozaki_tri_chunks() {
   if (g_ozaki_tri < 0) {
     const char* e = getenv("FVGP_OZAKI_TRI");
-    const int v = e ? atoi(e) : 0;
-    g_ozaki_tri = v < 0 ? 0 : (v > 16 ? 16 : v);
+    const int v = e ? atoi(e) : 8;
+    g_ozaki_tri = v < 0 ? 0 : (v > 32 ? 32 : v);
   }
   return g_ozaki_tri;
 }
@@ -1138,11 +1142,11 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   int rc = 0;
   // INT8-slice trailing updates: one scratch allocation for the largest update of this factorisation
   // (measured with 2048-wide block columns only, i.e. N >= 40 000; smaller N stay on the DMMA pipe unless FVGP_OZAKI_ALL=1)
-  static int oz_all = -1;
-  if (oz_all < 0) {
+  if (g_ozaki_all < 0) {
     const char* e = getenv("FVGP_OZAKI_ALL");
-    oz_all = (e && atoi(e) == 1) ? 1 : 0;
+    g_ozaki_all = (e && atoi(e) == 1) ? 1 : 0;
   }
+  const int oz_all = g_ozaki_all;
   const int oz = (nb % 16 == 0 && (nb >= 2048 || oz_all) && n - 2 * nb >= OZAKI_MIN_M) ? ozaki_slices() : 0;
   void* oz_work = nullptr;
   int64_t oz_bytes = 0;
@@ -1275,8 +1279,8 @@ static int potrf_block_width(int n) {
 // L -> L^-1 in place (lower).  Needs explicit zeros above the diagonal inside diagonal blocks.
 // ---- INT8-slice versions of the POTRI products that have a TRIANGULAR operand (csrc/ozaki.cu; opt-in, Ctx::oz_tri).
 // A full-K int8 GEMM would do twice the useful work, so the output is cut into `chunks` blocks along the triangular
-// operand and every block only multiplies the part of the contraction range that operand reaches (waste (c+1)/(2c)
-// instead of 1/2 ... i.e. 25 % extra at 4 chunks).  All products are brought into the NT form of fvgp_ozaki_gemm_nt by
+// operand and every block only multiplies the part of the contraction range that operand reaches: (c + 1) / c times
+// the useful work at c chunks (25 % extra at 4, 12.5 % at 8) instead of 2x.  All products are brought into the NT form of fvgp_ozaki_gemm_nt by
 // transposing the triangular operand into scratch with its never-written upper triangle masked to zero.
 // Return 0 = done, 1 = refused before anything was modified (caller falls back to the DMMA products), < 0 = error.
 static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
@@ -1441,9 +1445,17 @@ int fvgp_set_ozaki(int slices) {
   return old;
 }
 
+int fvgp_set_ozaki_gate(int min_n, int min_rows) {
+  if (min_n < 0 || min_rows < 2 * BM) return FVGP_ERR_ARG;
+  g_ozaki_potri_min_n = min_n;
+  g_ozaki_lauum_min = min_rows;
+  g_ozaki_all = min_n < 40000 ? 1 : 0;
+  return 0;
+}
+
 int fvgp_set_ozaki_tri(int chunks) {
   const int old = ozaki_tri_chunks();
-  g_ozaki_tri = chunks < 0 ? 0 : (chunks > 16 ? 16 : chunks);
+  g_ozaki_tri = chunks < 0 ? 0 : (chunks > 32 ? 32 : chunks);
   return old;
 }
 
@@ -1631,14 +1643,15 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
   if (lauum_oz < 0) {
     const char* e = getenv("FVGP_OZAKI_LAUUM");
     lauum_oz = e ? atoi(e) : 1;
-    if (lauum_oz > 1) g_ozaki_lauum_min = lauum_oz;
+    if (lauum_oz > 1) g_ozaki_lauum_min = lauum_oz, g_ozaki_potri_min_n = 0;
   }
   const int n1_top = split((int)n), n2_top = (int)n - n1_top;
-  if (lauum_oz > 0 && (n >= 40000 || lauum_oz > 1) && ozaki_slices() > 0 && n > TS && n1_top >= g_ozaki_lauum_min) {
+  if (lauum_oz > 0 && n >= g_ozaki_potri_min_n && ozaki_slices() > 0 && n > TS && n1_top >= g_ozaki_lauum_min) {
     const int S = ozaki_slices(), tri = ozaki_tri_chunks();
     const long long k16 = (n2_top + 15) / 16 * 16;
     const long long t_bytes = align256((long long)n1_top * k16 * 8);
-    c.oz_bytes = t_bytes + fvgp_ozaki_work_bytes(n1_top, n1_top, k16, S, OZAKI_NBLOCK);
+    const long long syrk_bytes = t_bytes + fvgp_ozaki_work_bytes(n1_top, n1_top, k16, S, OZAKI_NBLOCK);
+    c.oz_bytes = syrk_bytes;
     if (tri > 0) {
       const int cb1 = oz_chunk(n1_top, tri), cb2 = oz_chunk(n2_top, tri), cbm = std::max(cb1, cb2), nm = std::max(n1_top, n2_top);
       const long long trtri_need = std::max(align256((long long)n1_top * n1_top * 8), align256((long long)cb2 * n2_top * 8)) +
@@ -1647,18 +1660,25 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
       c.oz_bytes = std::max(c.oz_bytes, std::max(trtri_need, w_need));
     }
     c.oz_bytes += 4096;
-    if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) == cudaSuccess) {
+    int tri_on = tri;
+    if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) != cudaSuccess && tri > 0) {
+      cudaGetLastError();  // not enough HBM for the triangular products' scratch: the SYRK half alone needs less
+      c.oz_work = nullptr, tri_on = 0;
+      c.oz_bytes = syrk_bytes + 4096;
+      if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) != cudaSuccess) c.oz_work = nullptr;
+    }
+    if (c.oz_work != nullptr) {
       c.oz_slices = S;
-      c.oz_tri = tri;
+      c.oz_tri = tri_on;
     } else {
       cudaGetLastError();
-      c.oz_work = nullptr, c.oz_bytes = 0;
+      c.oz_bytes = 0;
     }
     static int told = -1;
     if (told != tri) {
       told = tri;
       fprintf(stderr, "[fvgp_b200] potri n=%lld: INT8-slice SYRK updates inside LAUUM%s, scratch %.2f GB: %s\n", (long long)n,
-              tri > 0 ? " + chunked triangular products" : "", c.oz_bytes / 1e9, c.oz_work ? "on" : "allocation failed, DMMA");
+              c.oz_tri > 0 ? " + chunked triangular products" : "", c.oz_bytes / 1e9, c.oz_work ? "on" : "allocation failed, DMMA");
     }
   }
   int r = trtri_rec(c, d_L, lda, (int)n, 0);

@@ -38,9 +38,12 @@ using namespace cute;
 using LayoutA = cutlass::layout::RowMajor;     // A slices: M x K, K contiguous
 using LayoutB = cutlass::layout::ColumnMajor;  // B slices: N rows of K contiguous bytes = K x N column-major
 using LayoutC = cutlass::layout::RowMajor;
-// Two tile configurations of the same collective: one SM per 128 x 128 x 128 tile, or a CTA pair (cta_group::2, cluster
-// 2 x 1) on a 256 x 128 x 128 tile (default; SASS UTCIMMA.2CTA): 1.92 vs 1.68 PMAC/s on the 32768^2 x 2048 SYRK
-// (profiles/r02/ozaki_probe_tiles.v12.log).  FVGP_OZAKI_TILE=1 selects the single-SM tile.
+// Tile configurations of the same collective (FVGP_OZAKI_TILE): 1 = one SM per 128 x 128 x 128 tile; 2 = a CTA pair
+// (cta_group::2, cluster 2 x 1; SASS UTCIMMA.2CTA) on 256 x 128 x 128; 3 (default) = a CTA pair on 256 x 256 x 128;
+// 4 = tile 2 in a 2 x 2 cluster.  Raw GEMM rate (tools/i8_rate_probe.py, profiles/r02/i8_rate_probe.v17.log; nominal
+// dense INT8 peak 2.25 PMAC/s): 32768 x 4096 x 16384: 1.42 / 1.71 / 2.00 / 1.56 PMAC/s; the POTRI shape
+// 6272 x 24912 x 100352: 1.38 / 1.23 / 2.03 / 1.47 -- the wide tile halves the operand traffic per MAC, which is what
+// bounds the narrower ones once the operands stop fitting L2.
 template <class MmaTileShape, class ClusterShape>
 struct I8Gemm {
   // D (int32) = acc
@@ -78,16 +81,22 @@ struct I8Gemm {
 
 using I8Gemm1Sm = I8Gemm<Shape<_128, _128, _128>, Shape<_1, _1, _1>>;
 using I8Gemm2Sm = I8Gemm<Shape<_256, _128, _128>, Shape<_2, _1, _1>>;
+using I8Gemm2SmWide = I8Gemm<Shape<_256, _256, _128>, Shape<_2, _1, _1>>;  // FVGP_OZAKI_TILE=3
+using I8Gemm2SmCl4 = I8Gemm<Shape<_256, _128, _128>, Shape<_2, _2, _1>>;   // FVGP_OZAKI_TILE=4
+
+static int g_tile = -1;
 
 // D (m x n int32, ldd) = A (m x K int8, lda) B^T (n x K int8, ldb)
 static int i8_gemm(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* D, int64_t ldd, int m, int n, int K,
                    void* ws, size_t ws_bytes, cudaStream_t st) {
-  static int tile = -1;
-  if (tile < 0) {
+  if (g_tile < 0) {
     const char* e = getenv("FVGP_OZAKI_TILE");
-    tile = (e && atoi(e) == 1) ? 1 : 2;
+    const int v = e ? atoi(e) : 3;
+    g_tile = (v >= 1 && v <= 4) ? v : 3;
   }
-  if (tile == 2) return I8Gemm2Sm::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
+  if (g_tile == 2) return I8Gemm2Sm::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
+  if (g_tile == 3) return I8Gemm2SmWide::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
+  if (g_tile == 4) return I8Gemm2SmCl4::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
   return I8Gemm1Sm::run(A, lda, B, ldb, D, ldd, m, n, K, ws, ws_bytes, st);
 }
 
@@ -240,6 +249,45 @@ int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda,
   return 0;
 }
 
+// Measurement hook (tools/i8_rate_probe.py): seconds per launch of the raw int8 GEMM m x n x K (operands filled with
+// a fixed byte pattern, int32 output) for tile configuration `tile` (1..4, see i8_gemm), best of `reps`; < 0 on error.
+double fvgp_ozaki_i8_seconds(int64_t m, int64_t n, int64_t K, int tile, int reps, void* stream) {
+  using namespace fvgp::oz;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m <= 0 || n <= 0 || K <= 0 || K % 16 != 0 || tile < 1 || tile > 4) return -1.0;
+  int8_t *A = nullptr, *B = nullptr;
+  int32_t* D = nullptr;
+  void* ws = nullptr;
+  const int64_t ldd = (n + 3) / 4 * 4;
+  if (cudaMalloc(&A, m * K) != cudaSuccess || cudaMalloc(&B, n * K) != cudaSuccess ||
+      cudaMalloc(&D, m * ldd * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&ws, 8 << 20) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(A), cudaFree(B), cudaFree(D), cudaFree(ws);
+    return -2.0;
+  }
+  cudaMemsetAsync(A, 3, m * K, st);
+  cudaMemsetAsync(B, 5, n * K, st);
+  const int old = g_tile;
+  g_tile = tile;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  double best = 1e30;
+  int rc = 0;
+  for (int r = 0; r < reps + 1 && rc == 0; ++r) {  // first launch = warm-up
+    cudaEventRecord(e0, st);
+    rc = i8_gemm(A, K, B, K, D, ldd, (int)m, (int)n, (int)K, ws, 8 << 20, st);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms * 1e-3 < best) best = ms * 1e-3;
+  }
+  g_tile = old;
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(A), cudaFree(B), cudaFree(D), cudaFree(ws);
+  return rc == 0 ? best : -3.0;
+}
+
 }  // extern "C"
 
 #else  // built without the CUTLASS headers: the entry points exist and report that the path is unavailable
@@ -252,5 +300,6 @@ int fvgp_ozaki_gemm_nt(double*, int64_t, const double*, int64_t, const double*, 
   fprintf(stderr, "[fvgp_b200] built without CUTLASS headers: the INT8-slice GEMM is not available\n");
   return FVGP_ERR_ARG;
 }
+double fvgp_ozaki_i8_seconds(int64_t, int64_t, int64_t, int, int, void*) { return -1.0; }
 }
 #endif

@@ -321,11 +321,19 @@ int fvgp_ozaki_available(void);
  * least 8192 rows in factorisations with 2048-wide block columns (N >= 40 000).  Default 8 when the library was built
  * with the CuTe / CUTLASS headers (FVGP_OZAKI=0 in the environment switches it off).  Returns the previous setting. */
 int fvgp_set_ozaki(int slices);
-/* 0 (default): inside fvgp_potri_lower only the SYRK half of LAUUM uses the INT8-slice path; c > 0: also the products
+/* 0: inside fvgp_potri_lower only the SYRK half of LAUUM uses the INT8-slice path; c > 0 (default 8): also the products
  * with a triangular operand (both TRTRI products and W = M22^T M21 of LAUUM, see SURVEY.md 8 a7: np.linalg.inv of the
  * gradient path), with the contraction range cut into c chunks so that an int8 GEMM only multiplies the part the
  * triangle reaches.  FVGP_OZAKI_TRI in the environment sets the start value.  Returns the previous setting. */
 int fvgp_set_ozaki_tri(int chunks);
+/* Which factorisations / inversions use the INT8-slice products: N >= min_n (default 40 000, the range it was measured
+ * to pay in; below it fvgp_potrf_lower also needs an update of >= 8192 rows) and, inside fvgp_potri_lower, per recursion
+ * level a leading block of at least min_rows rows (default 8192, >= 256).  Lowered by the parity tests so that the path
+ * is compared with the oracle at sizes the oracle finishes in seconds. */
+int fvgp_set_ozaki_gate(int min_n, int min_rows);
+/* Measurement hook: seconds per launch of the raw int8 GEMM (m x n x K, int32 output) behind fvgp_ozaki_gemm_nt for
+ * tile configuration 1..4 (FVGP_OZAKI_TILE), best of reps; < 0 on error.  Allocates its own buffers. */
+double fvgp_ozaki_i8_seconds(int64_t m, int64_t n, int64_t K, int tile, int reps, void* stream);
 int64_t fvgp_ozaki_work_bytes(int64_t m, int64_t n, int64_t k, int slices, int64_t nblock);
 int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, int64_t m,
                        int64_t n, int64_t k, double sign, int lower, int64_t diag, int same_ab, int slices, int64_t nblock,

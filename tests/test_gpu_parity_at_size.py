@@ -123,3 +123,43 @@ def test_slq_logdet_against_the_restated_algorithm():
     assert abs(gp.kv.logdet_KV / est - 1) <= 1e-8 and abs(gp.kv.last_logdet_variance / var - 1) <= 1e-5
     exact = np.linalg.slogdet(KV.toarray())[1]
     assert abs(est - exact) <= 4 * np.sqrt(var) + 0.02 * abs(exact)
+
+
+def test_int8_slice_factorisation_and_inverse_against_the_oracle():
+    """The INT8-slice path (POTRF trailing updates, LAUUM SYRK, chunked triangular products of TRTRI / LAUUM) is on by
+    default only for N >= 40 000, where the oracle's gradient does not fit the host.  Here the gate is lowered so that
+    the same code runs at N = 16 000 and is compared with the oracle (1e-8) -- and with the all-DMMA path, from which it
+    must differ in the last digits (otherwise the gate did not open and the test would prove nothing)."""
+    import bench
+    from fvgp_b200 import GP
+    from fvgp_b200 import _lib as L
+    from oracle import fvgp_oracle as orc
+    lib = L.load()
+    if not lib.fvgp_ozaki_available():
+        pytest.skip("library built without the CuTe / CUTLASS headers")
+    n = 16000
+    x, y, noise = bench.synthetic_c2(n)
+    th = bench.theta_k(2)
+    gp = GP(x, y, init_hyperparameters=bench.theta_k(0), noise_variances=noise)
+    old = lib.fvgp_set_ozaki(0)
+    try:
+        lml_d, grad_d = gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
+        lib.fvgp_set_ozaki(8)
+        assert lib.fvgp_set_ozaki_gate(0, 2048) == 0
+        res = {}
+        for chunks in (0, 4, 8):
+            lib.fvgp_set_ozaki_tri(chunks)
+            gp.kv._memo = None
+            res[chunks] = (gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th))
+    finally:
+        lib.fvgp_set_ozaki(old)
+        lib.fvgp_set_ozaki_tri(8)
+        lib.fvgp_set_ozaki_gate(40000, 8192)
+    bench.release(gp)
+    lml_ref, grad_ref = orc.dense_neg_log_likelihood_gradient_blocked(x, y, th, noise)
+    assert abs(lml_d / lml_ref - 1) <= 1e-8 and bench.relerr(grad_d, grad_ref) <= 1e-8
+    for chunks, (lml, grad) in res.items():
+        assert abs(lml / lml_ref - 1) <= 1e-8, (chunks, lml, lml_ref)
+        assert bench.relerr(grad, grad_ref) <= 1e-8, (chunks, grad, grad_ref)
+        assert not np.array_equal(grad, grad_d), chunks
+    assert not np.array_equal(res[0][1], res[8][1])

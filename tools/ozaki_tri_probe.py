@@ -19,7 +19,7 @@ n = int(os.environ.get("PROBE_N", "50000"))
 x, y, noise = bench.synthetic_c2(n)
 gp = GP(x, y, init_hyperparameters=bench.theta_k(0), noise_variances=noise)
 res = {}
-modes = [(0, 0), (8, 0), (8, 4), (8, 8), (8, 0), (8, 4), (8, 8)]
+modes = [(0, 0)] + [(8, int(t)) for t in os.environ.get('PROBE_TRI', '0,4,8,0,4,8').split(',')]
 for oz, tri in modes:
     lib.fvgp_set_ozaki(oz)
     lib.fvgp_set_ozaki_tri(tri)
@@ -39,7 +39,7 @@ for oz, tri in modes:
         print(f"ozaki={oz} tri={tri} step {k}: LML {t1 - t0:.3f} s (potrf {ph.get('potrf', 0):.3f}), gradient {t2 - t1:.3f} s "
               f"(potri {ph.get('potri', 0):.3f}); free HBM {torch.cuda.mem_get_info()[0] / 1e9:.0f} GB", flush=True)
         res[(oz, tri, k)] = (lml, grad)
-for oz, tri in modes[1:4]:
+for oz, tri in sorted(set(modes[1:])):
     for k in range(2):
         a, b = res[(0, 0, k)], res[(oz, tri, k)]
         print(f"ozaki={oz} tri={tri} theta {k}: LML rel diff {abs(a[0] / b[0] - 1):.2e}, "
