@@ -688,21 +688,22 @@ def sharded_section(args, deadline, rank, world):
 
                 def one():
                     return fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise, args={"dense_sharded": False})
-                old = lib_.fvgp_set_ozaki(0)                                # the block-cyclic path is all-DMMA: same arithmetic
-                try:
-                    l1, g1, dt = single_gpu_check(one, th)
-                finally:
-                    lib_.fvgp_set_ozaki(old)
+                # both paths in their default arithmetic: INT8-slice trailing updates (tcgen05) where the blocks are large
+                # enough, DMMA elsewhere
+                l1, g1, dt = single_gpu_check(one, th)
                 rec["single_gpu"] = {"seconds_per_step": dt, "lml": l1, "grad": [float(g) for g in g1],
-                                     "arithmetic": "DMMA only (fvgp_set_ozaki(0)), as on the block-cyclic path",
+                                     "arithmetic": "default (INT8-slice trailing updates on both paths)",
                                      "lml_rel_diff": abs(rec["lml"] / l1 - 1), "grad_rel_diff": relerr(rec["grad"], g1),
                                      "agree_1e-8": bool(abs(rec["lml"] / l1 - 1) <= 1e-8 and relerr(rec["grad"], g1) <= 1e-8)}
                 rec["strong_scaling_efficiency"] = dt / (world * rec["seconds_per_step"])
-                if old and deadline.left() > 120:                           # the single-GPU default (INT8-slice SYRK updates)
-                    l2, g2, dt2 = single_gpu_check(one, th)
-                    rec["single_gpu_default_int8"] = {"seconds_per_step": dt2, "lml_rel_diff": abs(rec["lml"] / l2 - 1),
-                                                      "grad_rel_diff": relerr(rec["grad"], g2),
-                                                      "strong_scaling_efficiency_vs_it": dt2 / (world * rec["seconds_per_step"])}
+                if lib_.fvgp_ozaki_slices() > 0 and deadline.left() > 150:  # the all-DMMA single-GPU step, for reference
+                    old = lib_.fvgp_set_ozaki(0)
+                    try:
+                        l2, g2, dt2 = single_gpu_check(one, th)
+                    finally:
+                        lib_.fvgp_set_ozaki(old)
+                    rec["single_gpu_dmma_only"] = {"seconds_per_step": dt2, "lml_rel_diff": abs(rec["lml"] / l2 - 1),
+                                                   "grad_rel_diff": relerr(rec["grad"], g2)}
             parallel.barrier()
         return rec
     if deadline.allows(200):
@@ -1032,10 +1033,12 @@ def workload_config(args):
     return {"workload": f"C2: single-task GP, 3-D input, N={args.n}, anisotropic Matern-3/2 (default kernel), dense FP64 "
                         f"Cholesky, LML + hyperparameter gradient per step",
             "n": args.n, "dim": 3, "hyperparameters": 4, "parallelism": f"replicas x{args.gpus} (one theta proposal per GPU)",
-            "arithmetic": "IEEE FP64 throughout; for N >= 40 000 the SYRK updates of the Cholesky factorisation and of LAUUM run "
-                          "as error-free INT8-slice products (8 x 6-bit slices, exact int32 accumulation, FP64 recombination; "
-                          "FVGP_OZAKI=0 keeps everything on the FP64 tensor pipe): LML / gradient within 2e-12 / 6e-10 of the "
-                          "pure FP64 path (`int8_trailing_updates_ab`), oracle parity at N = 50 000 in `parity`",
+            "arithmetic": "FP64 results throughout; for N >= 40 000 the large products of the Cholesky factorisation (trailing "
+                          "updates) and of the inversion (TRTRI products, LAUUM) run as error-free INT8-slice products on the "
+                          "tcgen05 tensor cores (8 x 6-bit slices per entry, exact int32 accumulation, FP64 recombination; "
+                          "FVGP_OZAKI=0 keeps everything on the FP64 tensor pipe): LML / gradient within 2e-12 / 7e-10 of the "
+                          "pure FP64 path (`int8_trailing_updates_ab`), oracle parity at N = 50 000 in `parity` and, with the "
+                          "size gate lowered, at N = 16 000 in tests/test_gpu_parity_at_size.py",
             "l2_policy": f"inputs larger than L2: K is {8 * args.n ** 2 / 1e9:.1f} GB"}
 
 
@@ -1144,6 +1147,7 @@ def main():
     torch.cuda.synchronize()
     sampler.start()
     launches0 = lib.fvgp_launch_count()
+    macs0 = lib.fvgp_ozaki_mac_count()
     ops.start_phase_timing()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" lists exactly these launches
@@ -1156,6 +1160,7 @@ def main():
     parallel.barrier()
     phases = ops.stop_phase_timing()
     launches = lib.fvgp_launch_count() - launches0
+    i8_macs = (lib.fvgp_ozaki_mac_count() - macs0) / args.steps       # int8 multiply-accumulates per step (counted per launch)
     clocks = sampler.summary()
     t_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
@@ -1198,26 +1203,69 @@ def main():
         achieved = n ** 3 / t_tensor / 1e12
         step_tflops = n ** 3 / (t_dev / args.steps) / 1e12
         potri_tflops = 2.0 * n ** 3 / 3.0 / t_potri / 1e12
-        int8_on = bool(lib.fvgp_ozaki_available()) and n >= 40000 and os.environ.get("FVGP_OZAKI", "8") not in ("0",)
-        line["roofline"] = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri",
-                            "achieved": achieved, "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
-                            "potri": {"what": "TRTRI + LAUUM, 2 N^3 / 3 flop; on the DMMA pipe except (N >= 40 000) the SYRK half "
-                                              "of LAUUM (N^3 / 6), which runs as INT8-slice GEMMs: FP64-equivalent",
-                                      "achieved": potri_tflops, "frac": potri_tflops / pk.value},
-                            "potrf": {"seconds": t_potrf, "achieved_fp64_equivalent": n ** 3 / 3.0 / t_potrf / 1e12,
-                                      "int8_trailing_updates": int8_on,
-                                      "note": "with the INT8-slice trailing updates (csrc/ozaki.cu, default for N >= 40 000) the "
-                                              "N^3/3 flop of POTRF are FP64-EQUIVALENT: most of them run as int8 MMAs on the "
-                                              "tcgen05 pipe, so `achieved` of the whole phase pair can approach or pass the DMMA "
-                                              "peak; the all-DMMA figures are in `int8_trailing_updates_ab` (and in round 1's line)"},
-                            "whole_step": {"achieved": step_tflops, "frac": step_tflops / pk.value,
-                                           "note": "N^3 flop over ms_per_step (fill, solves, traces and host time included)"},
-                            # dram__bytes_read.sum + dram__bytes_write.sum summed over every dgemm_mma_kernel launch of ONE
-                            # timed evaluation (ncu launch list of this command, profiles/*/launches_bench_n50k.*.json)
-                            "traffic": gemm_dram_traffic(n)[0], "traffic_note": gemm_dram_traffic(n)[1],
-                            "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)",
-                            "algorithmic_flops_per_step": float(n) ** 3,
-                            "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
+        int8_on = i8_macs > 0
+        peaks = load_peaks()
+        fp64 = {"what": "N^3 flop of POTRF + POTRI over their time, against the DMMA (FP64 tensor pipe) issue rate measured live "
+                        "(fvgp_bench_fp64_peak).  With the INT8-slice products on, these are FP64-EQUIVALENT flop: most of "
+                        "them are executed as int8 MMAs, so the fraction can pass 1; the all-DMMA figures are in "
+                        "`int8_trailing_updates_ab` (and in round 1's line)",
+                "achieved": achieved, "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
+                "potrf": {"seconds": t_potrf, "achieved": n ** 3 / 3.0 / t_potrf / 1e12},
+                "potri": {"seconds": t_potri, "achieved": potri_tflops},
+                "whole_step": {"achieved": step_tflops, "frac": step_tflops / pk.value,
+                               "note": "N^3 flop over ms_per_step (fill, solves, traces and host time included)"},
+                "peak_source": "measured live: register-resident DMMA.8x8x4 issue rate (fvgp_bench_fp64_peak)"}
+        if int8_on:
+            # dominant kernel: the int8 GEMM (tcgen05.mma kind::i8, CTA pair, 256 x 256 x 128 tile) behind the INT8-slice
+            # products.  achieved = 2 x the multiply-accumulates actually launched per step (counted per GEMM launch in
+            # csrc/ozaki.cu) over the time of the two phases that contain them -- slicing, recombination, panels, tile
+            # kernels and the remaining DMMA products included, i.e. a LOWER bound on the kernel's own rate.  peak: the
+            # dense int8 rate is twice the bf16 rate on this part; MEASURED_PEAKS.json holds the bf16 figures.
+            bf16 = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+            peak8, src8 = ((2.0 * bf16, "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside a long step)")
+                           if bf16 else (4500.0, "fallback: nominal dense INT8 rate of B200"))
+            ach8 = 2.0 * i8_macs / t_tensor / 1e12
+            burst = lib.fvgp_ozaki_i8_seconds(6272, 24912, 100352, 3, 3, None)
+            line["roofline"] = {"bound": "tensor",
+                                "kernel": "int8 GEMM of the INT8-slice products (CuTe/CUTLASS sm100 collective: TMA + tcgen05.mma "
+                                          "kind::i8 cta_group::2, 256x256x128, int32 accumulators in TMEM) inside potrf + potri",
+                                "achieved": ach8, "peak": peak8, "unit": "TFLOP/s", "frac": ach8 / peak8,
+                                "op": "int8 multiply-accumulate = 2 ops (TOP/s)", "peak_source": src8,
+                                "nominal_peak": 4500.0, "frac_of_nominal": ach8 / 4500.0,
+                                "int8_macs_per_step": i8_macs,
+                                "algorithmic_note": "36 int8 MACs per FP64 MAC (8 slices: 8*9/2 slice pairs); the step's FP64 "
+                                                    "work is N^3/2 MACs, of which the INT8 path covers the products with >= 8192 "
+                                                    "rows; chunking of the triangular products adds 1/8 on those",
+                                "kernel_alone": ({"shape_mnk": [6272, 24912, 100352], "seconds": burst,
+                                                  "achieved": 2.0 * 6272 * 24912 * 100352 / burst / 1e12,
+                                                  "frac_of_nominal": 2.0 * 6272 * 24912 * 100352 / burst / 1e12 / 4500.0,
+                                                  "note": "one TRTRI-chunk-shaped launch timed alone with CUDA events (burst clocks)"}
+                                                 if burst > 0 else None),
+                                "fp64_equivalent": fp64,
+                                "potrf": {"seconds": t_potrf, "achieved_fp64_equivalent": n ** 3 / 3.0 / t_potrf / 1e12,
+                                          "int8_trailing_updates": True},
+                                "potri": {"seconds": t_potri, "achieved": potri_tflops, "frac": potri_tflops / pk.value,
+                                          "what": "TRTRI + LAUUM, 2 N^3 / 3 flop, FP64-equivalent"},
+                                "whole_step": fp64["whole_step"],
+                                "traffic": None,
+                                "traffic_note": "no ncu --set full capture of the int8 GEMM this round; the DMMA GEMM's DRAM "
+                                                "traffic (round 1 capture): " + str(gemm_dram_traffic(n)[1]),
+                                "algorithmic_flops_per_step": float(n) ** 3,
+                                "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
+        else:
+            line["roofline"] = {"bound": "tensor", "kernel": "dgemm_mma_kernel (DMMA.8x8x4) inside potrf + potri",
+                                "achieved": achieved, "peak": pk.value, "unit": "TFLOP/s", "frac": achieved / pk.value,
+                                "potri": {"what": "TRTRI + LAUUM, 2 N^3 / 3 flop", "achieved": potri_tflops,
+                                          "frac": potri_tflops / pk.value},
+                                "potrf": {"seconds": t_potrf, "achieved_fp64_equivalent": n ** 3 / 3.0 / t_potrf / 1e12,
+                                          "int8_trailing_updates": False},
+                                "whole_step": fp64["whole_step"],
+                                # dram__bytes_read.sum + dram__bytes_write.sum summed over every dgemm_mma_kernel launch of
+                                # ONE timed evaluation (ncu launch list, profiles/*/launches_bench_n50k.*.json)
+                                "traffic": gemm_dram_traffic(n)[0], "traffic_note": gemm_dram_traffic(n)[1],
+                                "peak_source": fp64["peak_source"],
+                                "algorithmic_flops_per_step": float(n) ** 3,
+                                "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
         log("fp64 peak probe done; K-fill rooflines ...")
         line["roofline_kfill"] = kfill_rooflines(n, gp, x, noise)
         log("same-N point ...")
@@ -1260,8 +1308,9 @@ def main():
             gp.kv._memo = None
             on_lml, on_grad = gp.log_likelihood(th), gp.neg_log_likelihood_gradient(th)
             old = lib.fvgp_set_ozaki(0)
-            rec = {"slices_default": int(old), "what": "SYRK updates of the look-ahead POTRF and of LAUUM (>= 8192 rows, N >= 40 000) "
-                   "as INT8-slice GEMMs on tcgen05 (kind::i8, TMEM) vs everything on the DMMA pipe (fvgp_set_ozaki(0))"}
+            rec = {"slices_default": int(old), "what": "trailing updates of the look-ahead POTRF, SYRK of LAUUM and the chunked "
+                   "triangular products of TRTRI / LAUUM (>= 8192 rows, N >= 40 000) as INT8-slice GEMMs on tcgen05 (kind::i8, "
+                   "TMEM) vs everything on the DMMA pipe (fvgp_set_ozaki(0))"}
             try:
                 ops.start_phase_timing()
                 torch.cuda.synchronize()

@@ -89,6 +89,11 @@ _SIGNATURES = {
     "fvgp_ozaki_available": (c_int, []),
     "fvgp_set_ozaki": (c_int, [c_int]),
     "fvgp_set_ozaki_tri": (c_int, [c_int]),
+    "fvgp_ozaki_slices": (c_int, []),
+    "fvgp_ozaki_mac_count": (c_uint64, []),
+    "fvgp_ozaki_gemm_work_bytes": (c_int64, [c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int64]),
+    "fvgp_ozaki_gemm": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_double,
+                                c_int, c_int, c_int64, _P, c_int64, _P]),
     "fvgp_set_ozaki_gate": (c_int, [c_int, c_int]),
     "fvgp_ozaki_i8_seconds": (c_double, [c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "fvgp_ozaki_work_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int, c_int64]),

@@ -1700,6 +1700,48 @@ int fvgp_dgemm_nt(const double* d_A, int64_t lda, const double* d_B, int64_t ldb
 
 /* ---- building blocks of the block-cyclic multi-GPU factorisation (fvgp_b200/sharded.py) ---- */
 
+int fvgp_ozaki_slices(void) { return ozaki_slices(); }
+
+// fvgp_dgemm's operand layouts on the INT8-slice path: operands stored k x rows are transposed into scratch (k padded
+// to a multiple of 16 with zero columns) so that the product takes the NT form of fvgp_ozaki_gemm_nt.
+int64_t fvgp_ozaki_gemm_work_bytes(int a_mn, int b_mn, int64_t m, int64_t n, int64_t k, int slices, int64_t nblock) {
+  const int64_t k16 = (k + 15) / 16 * 16;
+  return fvgp_ozaki_work_bytes(m, n, k16, slices, nblock) + (a_mn ? align256(m * k16 * 8) : 0) +
+         (b_mn ? align256(n * k16 * 8) : 0);
+}
+
+int fvgp_ozaki_gemm(int a_mn, int b_mn, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C,
+                    int64_t ldc, int64_t m, int64_t n, int64_t k, double sign, int zero_c, int slices, int64_t nblock,
+                    void* d_work, int64_t work_bytes, void* stream) {
+  FVGP_REQUIRE(m > 0 && n > 0 && k > 0 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31));
+  FVGP_REQUIRE(work_bytes >= fvgp_ozaki_gemm_work_bytes(a_mn, b_mn, m, n, k, slices, nblock));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t k16 = (k + 15) / 16 * 16;
+  if ((!a_mn || !b_mn) && k16 != k) return FVGP_ERR_ARG;  // a K-major operand cannot be padded in place
+  char* w = (char*)d_work;
+  const double *A = d_A, *B = d_B;
+  int64_t la = lda, lb = ldb;
+  if (a_mn) {  // stored k x m -> m x k16
+    double* At = (double*)w;
+    w += align256(m * k16 * 8);
+    launch(transpose_pad_kernel, dim3((unsigned)((m + 31) / 32), (unsigned)((k16 + 31) / 32)), 256, 0, st, At, (long long)k16, d_A,
+           (long long)lda, (int)k, (int)m, (int)k16, 0);
+    A = At, la = k16;
+  }
+  if (b_mn) {  // stored k x n -> n x k16
+    double* Bt = (double*)w;
+    w += align256(n * k16 * 8);
+    launch(transpose_pad_kernel, dim3((unsigned)((n + 31) / 32), (unsigned)((k16 + 31) / 32)), 256, 0, st, Bt, (long long)k16, d_B,
+           (long long)ldb, (int)k, (int)n, (int)k16, 0);
+    B = Bt, lb = k16;
+  }
+  FVGP_LAUNCH_OK();
+  if (zero_c) FVGP_CUDA_OK(cudaMemset2DAsync(d_C, (size_t)ldc * sizeof(double), 0, (size_t)n * sizeof(double), (size_t)m, st));
+  const int rc = fvgp_ozaki_gemm_nt(d_C, ldc, A, la, B, lb, m, n, k16, sign, 0, 0, 0, slices, nblock, w,
+                                    work_bytes - (int64_t)(w - (char*)d_work), st);
+  return rc;  // a refusal (< 0, not -100) after zero_c is still safe to redo with fvgp_dgemm and beta = 0
+}
+
 int fvgp_dgemm(int a_mn, int b_mn, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C,
                int64_t ldc, int m, int n, int k, double alpha, double beta, int flags, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

@@ -44,6 +44,8 @@ using LayoutC = cutlass::layout::RowMajor;
 // dense INT8 peak 2.25 PMAC/s): 32768 x 4096 x 16384: 1.42 / 1.71 / 2.00 / 1.56 PMAC/s; the POTRI shape
 // 6272 x 24912 x 100352: 1.38 / 1.23 / 2.03 / 1.47 -- the wide tile halves the operand traffic per MAC, which is what
 // bounds the narrower ones once the operands stop fitting L2.
+static unsigned long long g_i8_macs = 0;  // int8 multiply-accumulates launched so far (m n K per GEMM): bench.py's roofline
+
 template <class MmaTileShape, class ClusterShape>
 struct I8Gemm {
   // D (int32) = acc
@@ -75,6 +77,7 @@ struct I8Gemm {
     if (gemm.initialize(args, ws, st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
     if (gemm.run(st) != cutlass::Status::kSuccess) return FVGP_ERR_CUDA;
     __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&g_i8_macs, (unsigned long long)m * (unsigned long long)n * (unsigned long long)K, __ATOMIC_RELAXED);
     return 0;
   }
 };
@@ -249,6 +252,8 @@ int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda,
   return 0;
 }
 
+unsigned long long fvgp_ozaki_mac_count(void) { return fvgp::oz::g_i8_macs; }
+
 // Measurement hook (tools/i8_rate_probe.py): seconds per launch of the raw int8 GEMM m x n x K (operands filled with
 // a fixed byte pattern, int32 output) for tile configuration `tile` (1..4, see i8_gemm), best of `reps`; < 0 on error.
 double fvgp_ozaki_i8_seconds(int64_t m, int64_t n, int64_t K, int tile, int reps, void* stream) {
@@ -301,5 +306,6 @@ int fvgp_ozaki_gemm_nt(double*, int64_t, const double*, int64_t, const double*, 
   return FVGP_ERR_ARG;
 }
 double fvgp_ozaki_i8_seconds(int64_t, int64_t, int64_t, int, int, void*) { return -1.0; }
+unsigned long long fvgp_ozaki_mac_count(void) { return 0; }
 }
 #endif

@@ -144,7 +144,38 @@ class CudaLocalOps:
         L.check(self.lib.fvgp_trsm_right_lower_t(L.ptr(B), self._ld(B), m, L.ptr(Lf), self._ld(Lf), n, L.ptr(tileinv),
                                                  L.stream_ptr()), "fvgp_trsm_right_lower_t")
 
+    # Trailing updates of at least this many rows (and block edges of at least int8_min_block) go through the INT8-slice
+    # GEMM on tcgen05 (fvgp_ozaki_gemm: 2-3x the DMMA rate at FP64-grade accuracy, csrc/ozaki.cu) while fvgp_set_ozaki
+    # is on; everything else -- and every product the INT8 path refuses -- runs on the DMMA pipe.
+    int8_min_rows = 4096
+    int8_min_block = 1024
+    INT8_NBLOCK = 4096
+
+    def _gemm_int8(self, a_mn, b_mn, A, B, C, m, n, k, alpha, beta):
+        slices = self.lib.fvgp_ozaki_slices()
+        if slices <= 0:
+            return False
+        need = int(self.lib.fvgp_ozaki_gemm_work_bytes(int(a_mn), int(b_mn), m, n, k, slices, self.INT8_NBLOCK))
+        if need <= 0:
+            return False
+        key = L.stream_ptr().value or 0                           # one scratch buffer per stream: updates on the main and on
+        pool = self.__dict__.setdefault("_int8_work", {})      # the look-ahead stream may be in flight together
+        buf = pool.get(key)
+        if buf is None or buf.numel() < need:
+            pool[key] = None
+            buf = pool[key] = self.torch.empty(need + (need >> 3), dtype=self.torch.uint8, device="cuda")
+        rc = self.lib.fvgp_ozaki_gemm(int(a_mn), int(b_mn), L.ptr(A), self._ld(A), L.ptr(B), self._ld(B), L.ptr(C),
+                                      self._ld(C), m, n, k, float(alpha), int(beta == 0.0), slices, self.INT8_NBLOCK,
+                                      L.ptr(buf), buf.numel(), L.stream_ptr())
+        if rc == -100:
+            raise RuntimeError("fvgp_ozaki_gemm failed after part of the block had been updated")
+        self.int8_calls = getattr(self, "int8_calls", 0) + (rc == 0)
+        return rc == 0
+
     def gemm(self, a_mn, b_mn, A, B, C, m, n, k, alpha, beta, flags=0):
+        if (flags == 0 and m >= self.int8_min_rows and min(n, k) >= self.int8_min_block and abs(alpha) == 1.0
+                and beta in (0.0, 1.0) and self._gemm_int8(a_mn, b_mn, A, B, C, m, n, k, alpha, beta)):
+            return
         L.check(self.lib.fvgp_dgemm(int(a_mn), int(b_mn), L.ptr(A), self._ld(A), L.ptr(B), self._ld(B), L.ptr(C),
                                     self._ld(C), m, n, k, float(alpha), float(beta), int(flags), L.stream_ptr()),
                 "fvgp_dgemm")

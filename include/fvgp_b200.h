@@ -331,9 +331,21 @@ int fvgp_set_ozaki_tri(int chunks);
  * level a leading block of at least min_rows rows (default 8192, >= 256).  Lowered by the parity tests so that the path
  * is compared with the oracle at sizes the oracle finishes in seconds. */
 int fvgp_set_ozaki_gate(int min_n, int min_rows);
+/* The INT8-slice product with fvgp_dgemm's operand layouts (a_mn / b_mn as there; (1, 0) is accepted here), for the
+ * trailing updates of the block-cyclic multi-GPU factorisation and inversion (fvgp_b200/sharded.py):
+ * C (m x n) = sign * op(A) op(B) + (zero_c ? 0 : C).  Operands stored k x rows are transposed into scratch (k padded
+ * to 16); a K-major operand needs k % 16 == 0.  Return values as fvgp_ozaki_gemm_nt (after a refusal with zero_c the
+ * caller redoes the product with fvgp_dgemm and beta = 0).  fvgp_ozaki_slices(): the current fvgp_set_ozaki setting. */
+int fvgp_ozaki_slices(void);
+int64_t fvgp_ozaki_gemm_work_bytes(int a_mn, int b_mn, int64_t m, int64_t n, int64_t k, int slices, int64_t nblock);
+int fvgp_ozaki_gemm(int a_mn, int b_mn, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, double* d_C,
+                    int64_t ldc, int64_t m, int64_t n, int64_t k, double sign, int zero_c, int slices, int64_t nblock,
+                    void* d_work, int64_t work_bytes, void* stream);
 /* Measurement hook: seconds per launch of the raw int8 GEMM (m x n x K, int32 output) behind fvgp_ozaki_gemm_nt for
  * tile configuration 1..4 (FVGP_OZAKI_TILE), best of reps; < 0 on error.  Allocates its own buffers. */
 double fvgp_ozaki_i8_seconds(int64_t m, int64_t n, int64_t K, int tile, int reps, void* stream);
+/* int8 multiply-accumulates launched by the INT8-slice path since the library was loaded (m n K per GEMM). */
+unsigned long long fvgp_ozaki_mac_count(void);
 int64_t fvgp_ozaki_work_bytes(int64_t m, int64_t n, int64_t k, int slices, int64_t nblock);
 int fvgp_ozaki_gemm_nt(double* d_C, int64_t ldc, const double* d_A, int64_t lda, const double* d_B, int64_t ldb, int64_t m,
                        int64_t n, int64_t k, double sign, int lower, int64_t diag, int same_ab, int slices, int64_t nblock,

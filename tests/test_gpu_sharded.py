@@ -32,6 +32,32 @@ def test_sharded_single_rank_matches_oracle(n, nb):
     assert np.max(np.abs(0.5 * out["traces"] - grad_ref) / np.abs(grad_ref)) < 1e-8
 
 
+def test_sharded_single_rank_int8_slice_updates_match_oracle():
+    """The block-cyclic path sends updates of >= 4096 rows through the INT8-slice GEMM (fvgp_ozaki_gemm: all three
+    operand layouts of factor / invert); here the thresholds are lowered so that the same routing is exercised at a
+    size the oracle covers.  n is not a multiple of the block: the ragged last block (k % 16 != 0) must fall back."""
+    from fvgp_b200 import _lib as L
+    from fvgp_b200 import sharded
+    from oracle import fvgp_oracle as orc
+    if not L.load().fvgp_ozaki_slices():
+        pytest.skip("INT8-slice path not available / switched off")
+    n, nb = 4200, 512
+    x, y, noise, theta = _problem(n)
+    res = {}
+    for int8 in (False, True):
+        ops = sharded.CudaLocalOps()
+        ops.int8_min_rows, ops.int8_min_block = (1024, 256) if int8 else (1 << 30, 1 << 30)
+        ev = sharded.ShardedDenseEvaluator(x, y, noise, nb=nb, grid=(1, 1), ops=ops)
+        res[int8] = ev.evaluate(0, theta[0], 1.0 / theta[1:], 1.0, np.full(n, y.mean()), want_gradient_theta=theta)
+        assert (getattr(ops, "int8_calls", 0) > 20) == int8
+    lml_ref = orc.dense_log_likelihood(x, y, theta, noise)
+    grad_ref = orc.dense_neg_log_likelihood_gradient(x, y, theta, noise, economical=True)
+    for out in res.values():
+        assert abs(out["lml"] / lml_ref - 1) < 1e-8
+        assert np.max(np.abs(0.5 * out["traces"] - grad_ref) / np.abs(grad_ref)) < 1e-8
+    assert not np.array_equal(res[True]["traces"], res[False]["traces"])
+
+
 def test_sharded_reports_non_positive_definite():
     from fvgp_b200 import _lib as L
     from fvgp_b200 import sharded
@@ -74,6 +100,7 @@ def _worker(rank, world, port, n, nb, q):
     from fvgp_b200 import sharded
     x, y, noise, theta = _problem(n)
     ev = sharded.ShardedDenseEvaluator(x, y, noise, nb=nb)
+    ev.ops.int8_min_rows, ev.ops.int8_min_block = 512, 128      # INT8-slice updates at this size too (default: >= 4096 rows)
     out = ev.evaluate(0, theta[0], 1.0 / theta[1:], 1.0, np.full(n, y.mean()), want_gradient_theta=theta)
     torch.cuda.synchronize()
     # the same through the public API: every rank holds a replica of the (small) host data and calls collectively
