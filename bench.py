@@ -1042,6 +1042,21 @@ def workload_config(args):
             "l2_policy": f"inputs larger than L2: K is {8 * args.n ** 2 / 1e9:.1f} GB"}
 
 
+def i8_gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the int8 GEMM at the `kernel_alone` shape, from the
+    committed ncu --set full capture (profiles/r02/ncu_i8_gemm.v19.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02", "ncu_i8_gemm.v19.json")) as fh:
+            d = json.load(fh)
+        return float(d["dram_bytes"]), (f"per launch at m, n, K = {d['shape_mnk']} (the `kernel_alone` shape): {d['dram_bytes'] / 1e9:.1f} GB "
+                                        f"of DRAM traffic vs {d['algorithmic_bytes'] / 1e9:.2f} GB algorithmic (operands once + int32 "
+                                        f"output): operand panels are re-read across tiles (L2 hit rate {d['l2_hit_rate_pct']:.0f} %), "
+                                        f"DRAM at {d['dram_throughput_pct']:.0f} % of peak, tensor pipe active "
+                                        f"{d['tensor_pipe_active_pct_elapsed']:.1f} % of the launch: tensor-bound ({d['source']})")
+    except Exception as exc:
+        return None, f"no capture on file ({exc})"
+
+
 def kfill_rooflines(n, gp, x, noise):
     """K-assembly against HBM: the symmetric mode (full square + noise diagonal, 8 N^2 bytes written) and FILL_LOWER,
     the mode the LML path uses (tiles on / below the diagonal only: 4 N^2 + 256 N bytes)."""
@@ -1247,9 +1262,7 @@ def main():
                                 "potri": {"seconds": t_potri, "achieved": potri_tflops, "frac": potri_tflops / pk.value,
                                           "what": "TRTRI + LAUUM, 2 N^3 / 3 flop, FP64-equivalent"},
                                 "whole_step": fp64["whole_step"],
-                                "traffic": None,
-                                "traffic_note": "no ncu --set full capture of the int8 GEMM this round; the DMMA GEMM's DRAM "
-                                                "traffic (round 1 capture): " + str(gemm_dram_traffic(n)[1]),
+                                "traffic": i8_gemm_traffic()[0], "traffic_note": i8_gemm_traffic()[1],
                                 "algorithmic_flops_per_step": float(n) ** 3,
                                 "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()}}
         else:
