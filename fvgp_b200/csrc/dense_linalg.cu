@@ -1004,6 +1004,7 @@ __global__ void __launch_bounds__(256) gemv_t_reduce_kernel(const double* __rest
 static int g_ozaki_all = -1;               // 1: INT8-slice POTRF updates also with block columns narrower than 2048 (N < 40 000)
 static int g_ozaki_potri_min_n = 40000;   // smallest N whose POTRI uses the INT8-slice path at all (fvgp_set_ozaki_gate)
 static int g_ozaki_lauum_min = 8192;      // smallest P11 (rows) whose SYRK update inside LAUUM goes through the INT8 path
+constexpr int OZAKI_MIN_CHUNK = 1536;      // fewest rows per chunk of a triangular INT8 product (multiple of BM)
 constexpr int64_t OZAKI_NBLOCK = 4096;     // column block of the INT8-slice GEMM's int32 planes
 
 struct Ctx {
@@ -1148,8 +1149,8 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   }
   const int oz_all = g_ozaki_all;
   const int oz = (nb % 16 == 0 && (nb >= 2048 || oz_all) && n - 2 * nb >= OZAKI_MIN_M) ? ozaki_slices() : 0;
-  void* oz_work = nullptr;
-  int64_t oz_bytes = 0;
+  void *oz_work = nullptr, *ozp_work = nullptr;  // scratch of the updates on S / of the look-ahead column on P
+  int64_t oz_bytes = 0, ozp_bytes = 0;
   if (oz) {
     oz_bytes = fvgp_ozaki_work_bytes(n - 2 * nb, n - 2 * nb, nb, oz, OZAKI_NBLOCK);
     {
@@ -1173,11 +1174,24 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
       cudaGetLastError();
       oz_work = nullptr;  // not enough memory: stay on the DMMA path
     }
+    // FVGP_OZAKI_PANEL=0: keep the look-ahead column update (m x nb x nb, panel stream) on the DMMA pipe
+    static int oz_panel = -1;
+    if (oz_panel < 0) {
+      const char* e = getenv("FVGP_OZAKI_PANEL");
+      oz_panel = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (oz_work != nullptr && oz_panel) {
+      ozp_bytes = fvgp_ozaki_work_bytes(n - 2 * nb, nb, nb, oz, OZAKI_NBLOCK);
+      if (cudaMallocAsync(&ozp_work, (size_t)ozp_bytes, S) != cudaSuccess) {
+        cudaGetLastError();
+        ozp_work = nullptr;
+      }
+    }
     static bool told = false;
     if (!told) {
       told = true;
-      fprintf(stderr, "[fvgp_b200] potrf n=%d nb=%d: INT8-slice trailing updates, %d slices, scratch %.2f GB: %s\n", n, nb, oz,
-              oz_bytes / 1e9, oz_work ? "on" : cudaGetErrorString(me));
+      fprintf(stderr, "[fvgp_b200] potrf n=%d nb=%d: INT8-slice trailing updates, %d slices, scratch %.2f + %.2f GB: %s\n", n, nb,
+              oz, oz_bytes / 1e9, ozp_work ? ozp_bytes / 1e9 : 0.0, oz_work ? "on" : cudaGetErrorString(me));
     }
   }
   // FVGP_OZAKI_STREAMS=1: issue everything on one stream.  Default 2 (panel path on its own high-priority stream next to
@@ -1236,9 +1250,22 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
     const int w1 = std::min(nb, rows_from(k + 1));
     rc = launch_gemm<false, false>(P, blk(k + 1, k), ld, blk(k + 1, k), ld, blk(k + 1, k + 1), ld, w1, w1, nb, -1.0, 1.0,
                                    GEMM_LOWER);
-    if (rc == 0 && k + 2 < nblk)
-      rc = launch_gemm<false, false>(P, blk(k + 2, k), ld, blk(k + 1, k), ld, blk(k + 2, k + 1), ld, rows_from(k + 2), w1,
-                                     nb, -1.0, 1.0, 0);
+    if (rc == 0 && k + 2 < nblk) {
+      const int m2 = rows_from(k + 2);
+      bool done = false;
+      if (ozp_work != nullptr && g_ozaki_slices > 0 && m2 >= OZAKI_MIN_M && w1 == nb) {
+        // the block column below the diagonal block (m2 x nb x nb): the same INT8 route, own scratch on the panel stream
+        const int orc = fvgp_ozaki_gemm_nt(blk(k + 2, k + 1), ld, blk(k + 2, k), ld, blk(k + 1, k), ld, m2, w1, nb, -1.0, 0, 0, 0,
+                                           oz, OZAKI_NBLOCK, ozp_work, ozp_bytes, P);
+        if (orc == -100) {
+          rc = FVGP_ERR_CUDA;
+          break;
+        }
+        done = orc == 0;
+      }
+      if (!done)
+        rc = launch_gemm<false, false>(P, blk(k + 2, k), ld, blk(k + 1, k), ld, blk(k + 2, k + 1), ld, m2, w1, nb, -1.0, 1.0, 0);
+    }
     if (rc == 0) rc = panel(k + 1);
   }
   // the caller's stream continues only after the last panel
@@ -1253,6 +1280,7 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
     cudaEventDestroy(ev_trail[k]);
   }
   if (oz_work != nullptr) cudaFreeAsync(oz_work, S);
+  if (ozp_work != nullptr) cudaFreeAsync(ozp_work, S);  // after ev_panel[last]: S waits for everything queued on P
   if (P != S) cudaStreamDestroy(P);
   return rc;
 }
@@ -1287,7 +1315,7 @@ static inline long long align256(long long b) { return (b + 255) / 256 * 256; }
 
 static int oz_chunk(int n, int chunks) {
   int cb = ((n + chunks - 1) / chunks + BM - 1) / BM * BM;
-  return cb < BM ? BM : cb;
+  return cb < OZAKI_MIN_CHUNK ? OZAKI_MIN_CHUNK : cb;  // short row blocks leave the 256 x 256 tiles' last wave half empty
 }
 
 // TRTRI: L21 <- -M22 L21 M11 (M11 = L[0:n1,0:n1], M22 already inverted in place, both lower).

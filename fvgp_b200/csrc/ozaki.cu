@@ -114,8 +114,18 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= m) return;
   const double* a = A + row * lda;
+  // rows are 16-byte aligned (lda even, column offsets even) and k % 16 == 0: 16 entries per lane and trip, one 16-byte
+  // store per slice (the 4-entry version ran at half the HBM rate: profiles/r02/launches_bench_n50k.v21.txt)
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && (k % 16 == 0);
   double mx = 0.0;
-  for (int c = lane; c < k; c += 32) mx = fmax(mx, fabs(a[c]));
+  if (vec) {
+    for (int c = lane * 2; c < k; c += 64) {
+      const double2 t = *reinterpret_cast<const double2*>(a + c);
+      mx = fmax(mx, fmax(fabs(t.x), fabs(t.y)));
+    }
+  } else {
+    for (int c = lane; c < k; c += 32) mx = fmax(mx, fabs(a[c]));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   int e = 0;
@@ -124,6 +134,31 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   const long long rowbytes = (long long)S * k;
   int8_t* f = fwd != nullptr ? fwd + row * rowbytes : nullptr;
   int8_t* r = rev != nullptr ? rev + row * rowbytes : nullptr;
+  if (vec) {
+    for (int c0 = lane * 16; c0 < k; c0 += 512) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; u += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(a + c0 + u);
+        v[u] = scalbn(t.x, -e);
+        v[u + 1] = scalbn(t.y, -e);
+      }
+      for (int s = 0; s < S; ++s) {
+        int4 q;
+        signed char* qq = reinterpret_cast<signed char*>(&q);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const double t = v[u] * 64.0;
+          const double d = rint(t);
+          v[u] = t - d;  // exact: |t| < 2^7 with at most 53 significant bits, d its nearest integer
+          qq[u] = (signed char)(int)d;
+        }
+        if (f != nullptr) *reinterpret_cast<int4*>(f + (long long)s * k + c0) = q;
+        if (r != nullptr) *reinterpret_cast<int4*>(r + (long long)(S - 1 - s) * k + c0) = q;
+      }
+    }
+    return;
+  }
   for (int c0 = lane * 4; c0 < k; c0 += 128) {
     double v[4];
 #pragma unroll

@@ -20,6 +20,9 @@ x, y, noise = bench.synthetic_c2(n)
 gp = GP(x, y, init_hyperparameters=bench.theta_k(0), noise_variances=noise)
 res = {}
 modes = [(0, 0)] + [(8, int(t)) for t in os.environ.get('PROBE_TRI', '0,4,8,0,4,8').split(',')]
+min_rows = int(os.environ.get('PROBE_MIN_ROWS', '8192'))
+assert lib.fvgp_set_ozaki_gate(40000, min_rows) == 0
+print('smallest leading block on the INT8 path inside POTRI:', min_rows, 'rows')
 for oz, tri in modes:
     lib.fvgp_set_ozaki(oz)
     lib.fvgp_set_ozaki_tri(tri)
