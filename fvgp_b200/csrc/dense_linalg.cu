@@ -1414,14 +1414,25 @@ static int lauum_rec(Ctx& c, double* M, long long ld, int n) {
     // columns), then the same SYRK as the POTRF trailing update.  No triangular operand here, so nothing is wasted.
     const long long k16 = (n2 + 15) / 16 * 16;
     const long long t_bytes = ((long long)n1 * k16 * (long long)sizeof(double) + 255) / 256 * 256;
-    const long long need = t_bytes + fvgp_ozaki_work_bytes(n1, n1, k16, c.oz_slices, OZAKI_NBLOCK);
-    if (need <= c.oz_bytes) {
+    // the contraction range is cut into `parts` pieces when the slices of the whole range do not fit the scratch
+    // (N ~ 100 000 on one GPU: 40 GB of slices next to the 80 GB matrix); every piece accumulates into P11
+    int parts = 1;
+    long long kc = k16;
+    while (parts < 32 && t_bytes + fvgp_ozaki_work_bytes(n1, n1, kc, c.oz_slices, OZAKI_NBLOCK) > c.oz_bytes) {
+      parts *= 2;
+      kc = ((k16 + parts - 1) / parts + 15) / 16 * 16;
+    }
+    if (t_bytes + fvgp_ozaki_work_bytes(n1, n1, kc, c.oz_slices, OZAKI_NBLOCK) <= c.oz_bytes) {
       double* T = (double*)c.oz_work;
       launch(transpose_pad_kernel, dim3((n1 + 31) / 32, (unsigned)((k16 + 31) / 32)), 256, 0, c.st, T, k16, (const double*)M21, ld,
              n2, n1, (int)k16, 0);
       FVGP_LAUNCH_OK();
-      const int orc = fvgp_ozaki_gemm_nt(M, ld, T, k16, T, k16, n1, n1, k16, 1.0, 1, 0, 1, c.oz_slices, OZAKI_NBLOCK,
-                                         (char*)c.oz_work + t_bytes, c.oz_bytes - t_bytes, c.st);
+      int orc = 0;
+      for (long long k0 = 0; k0 < k16 && orc == 0; k0 += kc) {
+        orc = fvgp_ozaki_gemm_nt(M, ld, T + k0, k16, T + k0, k16, n1, n1, std::min(kc, k16 - k0), 1.0, 1, 0, 1, c.oz_slices,
+                                 OZAKI_NBLOCK, (char*)c.oz_work + t_bytes, c.oz_bytes - t_bytes, c.st);
+        if (orc != 0 && k0 > 0) orc = -100;  // an earlier piece is already in P11
+      }
       if (orc == -100) return FVGP_ERR_CUDA;
       syrk_done = orc == 0;
       if (!syrk_done) {
@@ -1687,19 +1698,25 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
       const long long w_need = t_bytes + align256((long long)n2_top * n2_top * 8) + fvgp_ozaki_work_bytes(cb2, n1_top, n2_top, S, OZAKI_NBLOCK);
       c.oz_bytes = std::max(c.oz_bytes, std::max(trtri_need, w_need));
     }
-    c.oz_bytes += 4096;
-    int tri_on = tri;
-    if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) != cudaSuccess && tri > 0) {
-      cudaGetLastError();  // not enough HBM for the triangular products' scratch: the SYRK half alone needs less
-      c.oz_work = nullptr, tri_on = 0;
-      c.oz_bytes = syrk_bytes + 4096;
-      if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) != cudaSuccess) c.oz_work = nullptr;
+    // scratch ladder: everything, the SYRK half alone, then the SYRK with its contraction range in 2 / 4 / 8 pieces
+    // (lauum_rec cuts it to whatever it is given; the triangular products refuse when their share does not fit)
+    const long long full = c.oz_bytes;
+    long long ladder[5] = {full, syrk_bytes, 0, 0, 0};
+    for (int i = 2, parts = 2; i < 5; ++i, parts *= 2)
+      ladder[i] = t_bytes + fvgp_ozaki_work_bytes(n1_top, n1_top, ((k16 + parts - 1) / parts + 15) / 16 * 16, S, OZAKI_NBLOCK);
+    c.oz_work = nullptr;
+    for (int i = 0; i < 5 && c.oz_work == nullptr; ++i) {
+      if (i > 0 && ladder[i] >= ladder[i - 1]) continue;
+      c.oz_bytes = ladder[i] + 4096;
+      if (cudaMallocAsync(&c.oz_work, (size_t)c.oz_bytes, st) != cudaSuccess) {
+        cudaGetLastError();
+        c.oz_work = nullptr;
+      }
     }
     if (c.oz_work != nullptr) {
       c.oz_slices = S;
-      c.oz_tri = tri_on;
+      c.oz_tri = tri;
     } else {
-      cudaGetLastError();
       c.oz_bytes = 0;
     }
     static int told = -1;
