@@ -683,27 +683,36 @@ def sharded_section(args, deadline, rank, world):
         parallel.barrier()
         if 10.0 * n * n < 0.85 * 180e9 and deadline.allows(150):           # fits one GPU: agreement + strong-scaling baseline
             if rank == 0:
-                from fvgp_b200 import _lib as L_
-                lib_ = L_.load()
+                try:                                                # a failure here must not keep rank 0 from the barrier
+                    from fvgp_b200 import _lib as L_
+                    lib_ = L_.load()
 
-                def one():
-                    return fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise, args={"dense_sharded": False})
-                # both paths in their default arithmetic: INT8-slice trailing updates (tcgen05) where the blocks are large
-                # enough, DMMA elsewhere
-                l1, g1, dt = single_gpu_check(one, th)
-                rec["single_gpu"] = {"seconds_per_step": dt, "lml": l1, "grad": [float(g) for g in g1],
-                                     "arithmetic": "default (INT8-slice trailing updates on both paths)",
-                                     "lml_rel_diff": abs(rec["lml"] / l1 - 1), "grad_rel_diff": relerr(rec["grad"], g1),
-                                     "agree_1e-8": bool(abs(rec["lml"] / l1 - 1) <= 1e-8 and relerr(rec["grad"], g1) <= 1e-8)}
-                rec["strong_scaling_efficiency"] = dt / (world * rec["seconds_per_step"])
-                if lib_.fvgp_ozaki_slices() > 0 and deadline.left() > 150:  # the all-DMMA single-GPU step, for reference
-                    old = lib_.fvgp_set_ozaki(0)
-                    try:
-                        l2, g2, dt2 = single_gpu_check(one, th)
-                    finally:
-                        lib_.fvgp_set_ozaki(old)
-                    rec["single_gpu_dmma_only"] = {"seconds_per_step": dt2, "lml_rel_diff": abs(rec["lml"] / l2 - 1),
-                                                   "grad_rel_diff": relerr(rec["grad"], g2)}
+                    def one():
+                        return fvGP(x, y, init_hyperparameters=THETA_C3, noise_variances=noise, args={"dense_sharded": False})
+                    # both paths in their default arithmetic: INT8-slice trailing updates (tcgen05) where the blocks are large
+                    # enough, DMMA elsewhere
+                    l1, g1, dt = single_gpu_check(one, th)
+                    rec["single_gpu"] = {"seconds_per_step": dt, "lml": l1, "grad": [float(g) for g in g1],
+                                         "arithmetic": "default (INT8-slice trailing updates on both paths)",
+                                         "lml_rel_diff": abs(rec["lml"] / l1 - 1), "grad_rel_diff": relerr(rec["grad"], g1),
+                                         "agree_1e-8": bool(abs(rec["lml"] / l1 - 1) <= 1e-8 and relerr(rec["grad"], g1) <= 1e-8)}
+                    rec["strong_scaling_efficiency"] = dt / (world * rec["seconds_per_step"])
+                    if lib_.fvgp_ozaki_slices() > 0 and deadline.left() > 150:  # the all-DMMA single-GPU step, for reference
+                        old = lib_.fvgp_set_ozaki(0)
+                        try:
+                            l2, g2, dt2 = single_gpu_check(one, th)
+                        finally:
+                            lib_.fvgp_set_ozaki(old)
+                        rec["single_gpu_dmma_only"] = {"seconds_per_step": dt2, "lml_rel_diff": abs(rec["lml"] / l2 - 1),
+                                                       "grad_rel_diff": relerr(rec["grad"], g2)}
+                except Exception as exc:
+                    import traceback
+                    traceback.print_exc()
+                    rec["single_gpu_error"] = f"{type(exc).__name__}: {exc}"[:300]
+                    import gc
+                    import torch as _t
+                    gc.collect()
+                    _t.cuda.empty_cache()
             parallel.barrier()
         return rec
     if deadline.allows(200):

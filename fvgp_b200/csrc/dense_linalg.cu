@@ -1113,6 +1113,32 @@ static int ozaki_tri_chunks() {
   return g_ozaki_tri;
 }
 
+// The INT8 scratch comes from the stream-ordered pool, which by default returns freed memory to the OS at the next
+// synchronisation: the 7.5 GB of an N = 50 000 factorisation then came back through the driver on every call (0.3 ... 1.7 s
+// each, the "lottery" of profiles/r02/ozaki_step_probe.v10.log).  While the matrices leave room the pool keeps what it
+// has; when they do not (two N x N buffers + workspace beyond ~40 % of the device: N ~ 100 000 on one GPU) cached scratch
+// would starve the caller's own allocator (torch ran out of memory for the POTRI workspace with 19 GB idle in the pool:
+// profiles/r02/v26_c3_single_gpu_probe.log), so the pool goes back to releasing and is trimmed at once.
+static void pool_retention(long long n) {
+  int dev = 0;
+  cudaMemPool_t pool;
+  size_t free_b = 0, total_b = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess ||
+      cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  const int roomy = 2.5 * 8.0 * (double)n * (double)n < (double)total_b ? 1 : 0;
+  static int state = -1;
+  if (state != roomy) {
+    unsigned long long keep = roomy ? ~0ull : 0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (!roomy) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+    state = roomy;
+  }
+}
+
 // Right-looking blocked Cholesky with one step of look-ahead on two streams.
 //
 // The recursion above is flop-optimal but strictly serial: the latency-bound work on the diagonal (tile
@@ -1153,22 +1179,7 @@ static int potrf_lookahead(Ctx& c, double* A, long long ld, int n, int nb) {
   int64_t oz_bytes = 0, ozp_bytes = 0;
   if (oz) {
     oz_bytes = fvgp_ozaki_work_bytes(n - 2 * nb, n - 2 * nb, nb, oz, OZAKI_NBLOCK);
-    {
-      // The stream-ordered pool returns freed memory to the OS at the next synchronisation unless told otherwise; the
-      // 7.5 GB scratch then came back through the driver on every factorisation (0.3 ... 1.7 s each, the "lottery" of
-      // profiles/r02/ozaki_step_probe.v10.log).  Keep it in the pool.
-      static bool pool_set = false;
-      if (!pool_set) {
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-          unsigned long long keep = ~0ull;
-          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-        pool_set = true;
-      }
-    }
+    pool_retention(n);
     const cudaError_t me = cudaMallocAsync(&oz_work, (size_t)oz_bytes, S);
     if (me != cudaSuccess) {
       cudaGetLastError();
@@ -1698,6 +1709,7 @@ int fvgp_potri_lower(double* d_L, int64_t n, int64_t lda, const double* d_tilein
       const long long w_need = t_bytes + align256((long long)n2_top * n2_top * 8) + fvgp_ozaki_work_bytes(cb2, n1_top, n2_top, S, OZAKI_NBLOCK);
       c.oz_bytes = std::max(c.oz_bytes, std::max(trtri_need, w_need));
     }
+    pool_retention(n);
     // scratch ladder: everything, the SYRK half alone, then the SYRK with its contraction range in 2 / 4 / 8 pieces
     // (lauum_rec cuts it to whatever it is given; the triangular products refuse when their share does not fit)
     const long long full = c.oz_bytes;

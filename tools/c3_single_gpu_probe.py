@@ -15,9 +15,10 @@ from fvgp_b200 import fvGP, ops  # noqa: E402
 
 pts = int(os.environ.get("PROBE_POINTS", "20000"))
 x, y, noise = bench.synthetic_c3(pts)
+torch.cuda.empty_cache()
 gp = fvGP(x, y, init_hyperparameters=bench.THETA_C3, noise_variances=noise, args={"dense_sharded": False})
-for k in range(2):
-    th = bench.THETA_C3 * (1.0 + 0.01 * k)
+for k in range(int(os.environ.get('PROBE_STEPS', '1'))):
+    th = bench.THETA_C3 * (1.01 + 0.01 * k)            # not the constructor's theta: a full fill + POTRF + POTRI
     ops.start_phase_timing()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
