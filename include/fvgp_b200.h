@@ -322,9 +322,10 @@ int fvgp_ozaki_available(void);
  * with the CuTe / CUTLASS headers (FVGP_OZAKI=0 in the environment switches it off).  Returns the previous setting. */
 int fvgp_set_ozaki(int slices);
 /* 0: inside fvgp_potri_lower only the SYRK half of LAUUM uses the INT8-slice path; c > 0 (default 8): also the products
- * with a triangular operand (both TRTRI products and W = M22^T M21 of LAUUM, see SURVEY.md 8 a7: np.linalg.inv of the
- * gradient path), with the contraction range cut into c chunks so that an int8 GEMM only multiplies the part the
- * triangle reaches.  FVGP_OZAKI_TRI in the environment sets the start value.  Returns the previous setting. */
+ * with a triangular operand (both TRTRI products and W = M22^T M21 of LAUUM; the inverse is the reference's
+ * calculate_inv_from_chol / np.linalg.inv, gp_lin_alg.py:1540-1558, used by the trace term of the gradient at
+ * gp_marginal_likelihood.py:273-274), with the contraction range cut into c chunks so that an int8 GEMM only multiplies
+ * the part the triangle reaches.  FVGP_OZAKI_TRI in the environment sets the start value.  Returns the previous setting. */
 int fvgp_set_ozaki_tri(int chunks);
 /* Which factorisations / inversions use the INT8-slice products: N >= min_n (default 40 000, the range it was measured
  * to pay in; below it fvgp_potrf_lower also needs an update of >= 8192 rows) and, inside fvgp_potri_lower, per recursion
